@@ -1,0 +1,16 @@
+"""emlight_b200 -- B200 (sm_100a) implementation of EMLight's illumination-estimation hot path.
+
+Public surface mirrors the reference's:
+
+    from emlight_b200 import DenseNet            # RegressionNetwork/DenseNet.py: DenseNet
+    from emlight_b200 import SamplesLoss         # RegressionNetwork/geomloss: SamplesLoss  (gmloss: GMSamplesLoss)
+    from emlight_b200 import sphere_points, convert_to_panorama     # RegressionNetwork/util.py
+
+Module-name shims for unchanged reference scripts live in ``emlight_b200/dropin`` (put it on sys.path).
+All arithmetic runs in hand-written CUDA reached through the C ABI of include/emlight_b200.h.
+"""
+from .panorama import convert_to_panorama, render_from_params, sphere_points  # noqa: F401
+from .samples_loss import GMSamplesLoss, SamplesLoss  # noqa: F401
+from .densenet import DenseNet  # noqa: F401
+
+__all__ = ["DenseNet", "SamplesLoss", "GMSamplesLoss", "sphere_points", "convert_to_panorama", "render_from_params"]

@@ -1,0 +1,89 @@
+"""ctypes binding of libemlight_b200.so (include/emlight_b200.h).  No CPU fallback: a missing library raises."""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_long, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libemlight_b200.so")
+ABI_VERSION = 1
+
+EML_CONV_1x1, EML_CONV_3x3, EML_CONV_POOL2 = 0, 1, 2
+EML_PREC_BF16, EML_PREC_BF16X3, EML_PREC_FP32 = 0, 1, 2
+PRECISIONS = {"bf16": EML_PREC_BF16, "bf16x3": EML_PREC_BF16X3, "fp32": EML_PREC_FP32}
+
+
+class ConvParams(Structure):
+    _fields_ = [("in_", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("w_oihw", c_void_p),
+                ("wpack", c_void_p), ("out", c_void_p), ("stats", c_void_p), ("stats_stride", c_long),
+                ("B", c_int), ("H", c_int), ("W", c_int), ("C_in", c_int), ("in_pitch", c_int),
+                ("C_out", c_int), ("out_pitch", c_int), ("out_choff", c_int),
+                ("mode", c_int), ("relu", c_int), ("precision", c_int)]
+
+
+# name -> (restype, argtypes); must list every symbol include/emlight_b200.h declares
+SIGNATURES = {
+    "eml_version": (c_int, []),
+    "eml_error_string": (c_char_p, [c_int]),
+    "eml_device_ok": (c_int, []),
+    "eml_sg_render_fwd": (c_int, [c_void_p, c_long, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "eml_sg_render_params_fwd": (c_int, [c_void_p, c_long, c_void_p, c_long, c_void_p, c_long, c_void_p, c_long,
+                                         c_void_p, c_long, c_float, c_void_p, c_long, c_void_p, c_int, c_int, c_void_p]),
+    "eml_sg_render_bwd": (c_int, [c_void_p, c_long, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_int, c_int, c_void_p]),
+    "eml_sinkhorn_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "eml_sinkhorn_fwdbwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float,
+                                    c_float, c_void_p, c_size_t, c_void_p]),
+    "eml_conv_wpack_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "eml_conv_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "eml_conv_forward": (c_int, [POINTER(ConvParams), c_void_p]),
+    "eml_stem_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_long,
+                                 c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "eml_bn_fold": (c_int, [c_void_p, c_long, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
+    "eml_head_pool": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "eml_linear_fp32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "emlight_b200: %s is missing -- build it with `python -m emlight_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.eml_version() != ABI_VERSION:
+        raise RuntimeError("emlight_b200: ABI version mismatch (library %d, binding %d)" % (lib.eml_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(code, what=""):
+    if code != 0:
+        msg = load().eml_error_string(code)
+        raise RuntimeError("%s failed: %s (code %d)" % (what or "emlight_b200 call", msg.decode() if msg else "?", code))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("emlight_b200 runs on CUDA tensors only (sm_100a kernels; no CPU fallback)")

@@ -1,0 +1,410 @@
+"""EMLight regression network -- drop-in for ``RegressionNetwork/DenseNet.py`` running on sm_100a kernels.
+
+Same constructor signature, same module / parameter / buffer names (``features.denseblock{b}.denselayer{l}.
+{norm1,conv1,norm2,conv2}``, ``features.transition{b}.{norm,conv}``, ``features.last_norm{b}``, ``fc*``) and the same
+default initialisation order as DenseNet.py:82-133, so ``state_dict()`` / ``load_state_dict()`` interoperate with
+reference checkpoints and ``torch.manual_seed(s); DenseNet()`` yields the reference's initial weights.  ``forward(x)``
+returns the dict of DenseNet.py:153-157.  The nn.Conv2d / nn.BatchNorm2d / nn.Linear children only *own* the
+parameters; forward never calls them -- it drives the C ABI of include/emlight_b200.h:
+
+  stem   conv0+norm0+relu        -> eml_stem_forward                      (NCHW image -> NHWC concat buffer)
+  layer  norm1+relu+conv1        -> eml_conv_forward(1x1, relu=1)         reads the concat buffer in place
+         norm2+conv2 (NO relu,   -> eml_conv_forward(3x3, relu=0)         writes its 12 channels in place
+         DenseNet.py:41-43)
+  trans  norm+relu+conv+avgpool  -> eml_conv_forward(POOL2)               pooling commuted in front of the 1x1 conv
+  last_norm{b}                   -> folded into every consumer's scale/shift (affine o affine), never materialised
+  head   relu+avgpool4+fc+4 fc   -> eml_head_pool, eml_linear_fp32 x2     (fc columns permuted NCHW->NHWC at pack time)
+
+BatchNorm follows ``self.training`` like the reference: batch statistics (accumulated by the producing kernels'
+epilogues, folded by eml_bn_fold) + running-stat update in train mode -- which is what the reference's test.py
+actually runs -- running statistics in eval mode.
+
+Backward through the network is not implemented in this round: outputs carry a grad_fn that raises.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import ConvParams
+
+_EPS = 1e-5
+
+
+def _up4(n):
+    return (n + 3) & ~3
+
+
+class _Transition(nn.Sequential):
+    def __init__(self, c_in, c_out):
+        super().__init__()
+        self.add_module("norm", nn.BatchNorm2d(c_in))
+        self.add_module("relu", nn.ReLU(inplace=True))
+        self.add_module("conv", nn.Conv2d(c_in, c_out, kernel_size=1, stride=1, bias=False))
+        self.add_module("pool", nn.AvgPool2d(kernel_size=2, stride=2))
+
+
+class _DenseLayer(nn.Sequential):
+    def __init__(self, c_in, growth_rate, bn_size, drop_rate):
+        super().__init__()
+        if bn_size <= 0:
+            raise ValueError("emlight_b200.DenseNet implements the bottleneck (bn_size > 0) variant the reference uses")
+        if drop_rate:
+            raise ValueError("drop_rate != 0 is not implemented (the reference trains with drop_rate=0)")
+        inter = 4 * growth_rate                       # DenseNet.py:37: hard-wired, bn_size only gates it
+        self.add_module("norm1", nn.BatchNorm2d(c_in))
+        self.add_module("relu1", nn.ReLU(inplace=True))
+        self.add_module("conv1", nn.Conv2d(c_in, inter, kernel_size=1, stride=1, bias=False))
+        self.add_module("norm2", nn.BatchNorm2d(inter))
+        self.add_module("conv2", nn.Conv2d(inter, growth_rate, kernel_size=3, padding=1, bias=False))
+        self.drop_rate = drop_rate
+
+
+class _DenseBlock(nn.Sequential):
+    def __init__(self, num_layers, c_in, bn_size, growth_rate, drop_rate):
+        super().__init__()
+        for i in range(num_layers):
+            self.add_module("denselayer%d" % (i + 1), _DenseLayer(c_in + i * growth_rate, growth_rate, bn_size, drop_rate))
+
+
+class _ForwardOnly(torch.autograd.Function):
+    """Marks the outputs as differentiable-in-principle so that a training script fails loudly, not silently."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        outs = module._run(x)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise NotImplementedError(
+            "emlight_b200.DenseNet: backward (dgrad/wgrad kernels) is not implemented in this round; "
+            "run inference under torch.no_grad() or use the reference module for training")
+
+
+class DenseNet(nn.Module):
+    def __init__(self, growth_rate=12, block_config=(16, 16, 16), compression=0.5, num_init_features=24, bn_size=4,
+                 drop_rate=0, avgpool_size=4, *, n_anchors=96, precision="bf16x3"):
+        super().__init__()
+        if precision not in _lib.PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(_lib.PRECISIONS))
+        self.avgpool_size = avgpool_size
+        self.precision = precision
+        self.growth_rate = growth_rate
+        self.block_config = tuple(block_config)
+        self.features = nn.Sequential(OrderedDict([
+            ("conv0", nn.Conv2d(3, num_init_features, kernel_size=3, stride=1, padding=1, bias=False)),
+            ("norm0", nn.BatchNorm2d(num_init_features)),
+            ("relu0", nn.ReLU(inplace=True)),
+        ]))
+        c = num_init_features
+        self._plan = []                                # (block, c_in, c_out, c_tr)
+        for i, n in enumerate(self.block_config):
+            self.features.add_module("denseblock%d" % (i + 1), _DenseBlock(n, c, bn_size, growth_rate, drop_rate))
+            c_out = c + n * growth_rate
+            c_tr = int(math.floor(c_out * compression))
+            # DenseNet.py:110: `i != len(block_config)` is always true -> a transition follows EVERY block
+            self.features.add_module("transition%d" % (i + 1), _Transition(c_out, c_tr))
+            self.features.add_module("last_norm%d" % (i + 1), nn.BatchNorm2d(c_tr))
+            self._plan.append((i + 1, c, c_out, c_tr))
+            c = c_tr
+        self.fc = nn.Linear(8208, 1024)
+        self.fc_dist = nn.Linear(1024, n_anchors)
+        self.fc_intensity = nn.Linear(1024, 1)
+        self.fc_rgb_ratio = nn.Linear(1024, 3)
+        self.fc_ambient = nn.Linear(1024, 3)
+        self.sigmoid = nn.Sigmoid()                    # parameter-free members the reference also registers
+        self.tanh = nn.Tanh()
+        self.softmax = nn.Softmax(dim=1)
+        self.relu = nn.ReLU()
+        self._cache = None                             # packed weights + folded eval-mode BN, keyed on param versions
+        self._ws = {}                                  # activation workspaces keyed on (B,H,W,device)
+
+    # ------------------------------------------------------------------ reference-facing API
+    def forward(self, x):
+        _lib.require_cuda(x)
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("expected input (B,3,H,W), got %s" % (tuple(x.shape),))
+        params = [p for p in self.parameters() if p.requires_grad]
+        if torch.is_grad_enabled() and (x.requires_grad or params):
+            d, i, r, a = _ForwardOnly.apply(self, x, *params)
+        else:
+            d, i, r, a = self._run(x)
+        return {"distribution": d, "intensity": i, "rgb_ratio": r, "ambient": a}
+
+    # ------------------------------------------------------------------ packing
+    def _bns(self):
+        """[(name, module)] of every BatchNorm in execution order."""
+        out = [("norm0", self.features.norm0)]
+        for b, _, _, _ in self._plan:
+            blk = getattr(self.features, "denseblock%d" % b)
+            for l, layer in enumerate(blk.children()):
+                out.append(("b%d.l%d.norm1" % (b, l), layer.norm1))
+                out.append(("b%d.l%d.norm2" % (b, l), layer.norm2))
+            out.append(("t%d.norm" % b, getattr(self.features, "transition%d" % b).norm))
+            out.append(("ln%d" % b, getattr(self.features, "last_norm%d" % b)))
+        return out
+
+    def _convs(self):
+        out = []
+        for b, _, _, _ in self._plan:
+            blk = getattr(self.features, "denseblock%d" % b)
+            for l, layer in enumerate(blk.children()):
+                out.append(("b%d.l%d.conv1" % (b, l), layer.conv1, 1))
+                out.append(("b%d.l%d.conv2" % (b, l), layer.conv2, 9))
+            out.append(("t%d.conv" % b, getattr(self.features, "transition%d" % b).conv, 1))
+        return out
+
+    def _state_key(self, device):
+        vs = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        bs = tuple((b.data_ptr(), b._version) for b in self.buffers())
+        return (str(device), self.precision, vs, bs if not self.training else None)
+
+    @torch.no_grad()
+    def _pack(self, device):
+        """(Re)build the derived cache: packed bf16 hi/lo weight images, permuted fc weight, eval-mode BN folds."""
+        lib = _lib.load()
+        key = self._state_key(device)
+        if self._cache is not None and self._cache["key"] == key:
+            return self._cache
+        st = _lib.stream_ptr()
+        c = {"key": key, "wpack": {}, "w": {}}
+        for name, conv, taps in self._convs():
+            w = conv.weight.detach().contiguous().float()
+            c["w"][name] = w
+            if self.precision != "fp32":
+                nbytes = lib.eml_conv_wpack_bytes(w.shape[0], w.shape[1], taps)
+                buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+                _lib.check(lib.eml_conv_pack_weights(_lib.ptr(w), _lib.ptr(buf), w.shape[0], w.shape[1], taps, st),
+                           "eml_conv_pack_weights")
+                c["wpack"][name] = buf
+        c["w0"] = self.features.conv0.weight.detach().contiguous().float()
+        # fc consumes the pooled map flattened in NCHW order (DenseNet.py:138); ours is NHWC -> permute its columns once
+        c_tr = self._plan[-1][3]
+        P = self.fc.in_features // c_tr
+        c["fc_w"] = self.fc.weight.detach().float().view(-1, c_tr, P).permute(0, 2, 1).reshape(self.fc.out_features, -1).contiguous()
+        c["fc_b"] = self.fc.bias.detach().float().contiguous()
+        heads = (self.fc_dist, self.fc_intensity, self.fc_rgb_ratio, self.fc_ambient)
+        c["head_w"] = torch.cat([h.weight.detach().float() for h in heads], 0).contiguous()
+        c["head_b"] = torch.cat([h.bias.detach().float() for h in heads], 0).contiguous()
+        c["head_split"] = [h.out_features for h in heads]
+        # affine table: one [scale | shift] pair (each padded to 4 floats) per BatchNorm
+        offs, total = {}, 0
+        for name, bn in self._bns():
+            cp = _up4(bn.num_features)
+            offs[name] = (total, cp)
+            total += 2 * cp
+        c["aff_offs"] = offs
+        c["aff"] = torch.zeros(total, dtype=torch.float32, device=device)
+        # identity pre-affine rows (scale 1, shift 0) for channels that are stored post-activation
+        cmax = _up4(max(p[2] for p in self._plan))
+        c["pre"] = torch.zeros(len(self._plan), 2, cmax, dtype=torch.float32, device=device)
+        c["pre"][:, 0, :] = 1.0
+        if not self.training:
+            self._fold_eval(c)
+        self._cache = c
+        return c
+
+    def _aff(self, c, name):
+        off, cp = c["aff_offs"][name]
+        return c["aff"][off:off + cp], c["aff"][off + cp:off + 2 * cp]
+
+    def _fold(self, c, name, bn, stats=None, stride=0, count=0.0, pre=None, mean_var=None):
+        lib = _lib.load()
+        sc, sh = self._aff(c, name)
+        ps, pt = (None, None) if pre is None else pre
+        mv_m, mv_v = (None, None) if mean_var is None else mean_var
+        _lib.check(lib.eml_bn_fold(_lib.ptr(stats), stride, float(count),
+                                   _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var), _lib.ptr(bn.weight),
+                                   _lib.ptr(bn.bias), _lib.ptr(ps), _lib.ptr(pt), _lib.ptr(sc), _lib.ptr(sh),
+                                   _lib.ptr(mv_m), _lib.ptr(mv_v), bn.num_features, _EPS, _lib.stream_ptr()),
+                   "eml_bn_fold(%s)" % name)
+
+    def _fold_eval(self, c):
+        """Eval mode: every BN's scale/shift from running statistics; last_norm{b} composed into block b+1's consumers."""
+        f = self.features
+        self._fold(c, "norm0", f.norm0)
+        pre = None
+        for bi, (b, c_in, c_out, c_tr) in enumerate(self._plan):
+            blk = getattr(f, "denseblock%d" % b)
+            for l, layer in enumerate(blk.children()):
+                self._fold(c, "b%d.l%d.norm1" % (b, l), layer.norm1, pre=pre)
+                self._fold(c, "b%d.l%d.norm2" % (b, l), layer.norm2)
+            tr = getattr(f, "transition%d" % b)
+            self._fold(c, "t%d.norm" % b, tr.norm, pre=pre)
+            ln = getattr(f, "last_norm%d" % b)
+            self._fold(c, "ln%d" % b, ln)
+            if bi + 1 < len(self._plan):
+                a, s = self._aff(c, "ln%d" % b)
+                c["pre"][bi + 1, 0, :c_tr] = a[:c_tr]
+                c["pre"][bi + 1, 1, :c_tr] = s[:c_tr]
+                pre = (c["pre"][bi + 1, 0], c["pre"][bi + 1, 1])
+
+    # ------------------------------------------------------------------ workspaces
+    def _workspace(self, B, H, W, device):
+        key = (B, H, W, str(device))
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        if H % 32 or W % 32:
+            raise ValueError("input height/width must be multiples of 32 (three /2 transitions and a /4 pool)")
+        c_last = self._plan[-1][3]
+        if c_last * (H // 32) * (W // 32) != self.fc.in_features:
+            raise ValueError("input %dx%d gives %d pooled features but fc expects %d (the reference network is built "
+                             "for 192x256 crops, SURVEY F2)" % (H, W, c_last * (H // 32) * (W // 32), self.fc.in_features))
+        ws = {"slab": [], "geom": []}
+        h, w = H, W
+        for b, c_in, c_out, c_tr in self._plan:
+            ws["slab"].append(torch.empty(B, h, w, _up4(c_out), dtype=torch.float32, device=device))
+            ws["geom"].append((h, w))
+            h, w = h // 2, w // 2
+        ws["bott"] = torch.empty(B, H, W, 4 * self.growth_rate, dtype=torch.float32, device=device)
+        ws["t_last"] = torch.empty(B, h, w, _up4(c_last), dtype=torch.float32, device=device)
+        ws["pooled"] = torch.empty(B, self.fc.in_features, dtype=torch.float32, device=device)
+        ws["fc"] = torch.empty(B, self.fc.out_features, dtype=torch.float32, device=device)
+        # batch-statistics accumulators (train mode): per slab (2, pitch) + per conv1 output (2, 48) + stem raw + last
+        n = 2 * 32
+        so = {"stem_raw": 0}
+        for bi, (b, c_in, c_out, c_tr) in enumerate(self._plan):
+            so["slab%d" % b] = n; n += 2 * _up4(c_out)
+            for l in range(self.block_config[bi]):
+                so["b%d.l%d.mid" % (b, l)] = n; n += 2 * 4 * self.growth_rate
+        so["t_last"] = n; n += 2 * _up4(c_last)
+        ws["stats"] = torch.zeros(n, dtype=torch.float64, device=device)
+        ws["stats_offs"] = so
+        nb = sum(bn.num_features for _, bn in self._bns())
+        ws["bmean"] = torch.zeros(nb, dtype=torch.float32, device=device)
+        ws["bvar"] = torch.zeros(nb, dtype=torch.float32, device=device)
+        self._ws = {key: ws}                            # keep one geometry resident
+        return ws
+
+    # ------------------------------------------------------------------ execution
+    def _conv(self, c, name, src, src_pitch, H, W, B, c_in, dst, dst_pitch, choff, c_out, mode, relu, aff, stats, stride):
+        lib = _lib.load()
+        p = ConvParams()
+        p.in_ = src.data_ptr()
+        p.scale = aff[0].data_ptr()
+        p.shift = aff[1].data_ptr()
+        p.w_oihw = c["w"][name].data_ptr()
+        p.wpack = c["wpack"][name].data_ptr() if name in c["wpack"] else None
+        p.out = dst.data_ptr()
+        p.stats = stats.data_ptr() if stats is not None else None
+        p.stats_stride = stride
+        p.B, p.H, p.W = B, H, W
+        p.C_in, p.in_pitch = c_in, src_pitch
+        p.C_out, p.out_pitch, p.out_choff = c_out, dst_pitch, choff
+        p.mode, p.relu, p.precision = mode, relu, _lib.PRECISIONS[self.precision]
+        _lib.check(lib.eml_conv_forward(p, _lib.stream_ptr()), "eml_conv_forward(%s)" % name)
+
+    @torch.no_grad()
+    def _run(self, x):
+        lib = _lib.load()
+        dev = x.device
+        B, _, H, W = x.shape
+        x = x.contiguous().float()
+        c = self._pack(dev)
+        ws = self._workspace(B, H, W, dev)
+        st = _lib.stream_ptr()
+        train = self.training
+        f = self.features
+        g = 4 * self.growth_rate
+        so = ws["stats_offs"]
+        stats = ws["stats"]
+        bm_off = [0]
+        updates = []                                    # (bn, mean_view, var_view, count) for the running-stat update
+
+        def mv(bn, count):
+            o = bm_off[0]
+            bm_off[0] += bn.num_features
+            m, v = ws["bmean"][o:o + bn.num_features], ws["bvar"][o:o + bn.num_features]
+            updates.append((bn, m, v, count))
+            return m, v
+
+        if train:
+            stats.zero_()
+        # ---- stem (DenseNet.py:89-92)
+        slab = ws["slab"][0]
+        pitch = slab.shape[3]
+        s1 = stats[so["slab1"]:]
+        if train:
+            raw = stats[so["stem_raw"]:]
+            _lib.check(lib.eml_stem_forward(_lib.ptr(x), _lib.ptr(c["w0"]), None, None, None, pitch, _lib.ptr(raw), None, 0,
+                                            B, H, W, f.conv0.out_channels, 0, st), "eml_stem_forward(stats)")
+            self._fold(c, "norm0", f.norm0, stats=raw, stride=f.conv0.out_channels, count=B * H * W,
+                       mean_var=mv(f.norm0, B * H * W))
+        a0 = self._aff(c, "norm0")
+        _lib.check(lib.eml_stem_forward(_lib.ptr(x), _lib.ptr(c["w0"]), _lib.ptr(a0[0]), _lib.ptr(a0[1]), _lib.ptr(slab), pitch,
+                                        None, _lib.ptr(s1) if train else None, pitch, B, H, W, f.conv0.out_channels, 1, st),
+                   "eml_stem_forward")
+        # ---- dense blocks + transitions
+        pre = None
+        for bi, (b, c_in, c_out, c_tr) in enumerate(self._plan):
+            slab = ws["slab"][bi]
+            pitch = slab.shape[3]
+            h, w = ws["geom"][bi]
+            count = B * h * w
+            sstat = stats[so["slab%d" % b]:]
+            blk = getattr(f, "denseblock%d" % b)
+            for l, layer in enumerate(blk.children()):
+                ci = c_in + l * self.growth_rate
+                n1, n2 = "b%d.l%d.norm1" % (b, l), "b%d.l%d.norm2" % (b, l)
+                mid = stats[so["b%d.l%d.mid" % (b, l)]:]
+                if train:
+                    self._fold(c, n1, layer.norm1, stats=sstat, stride=pitch, count=count, pre=pre, mean_var=mv(layer.norm1, count))
+                self._conv(c, "b%d.l%d.conv1" % (b, l), slab, pitch, h, w, B, ci, ws["bott"], g, 0, g, _lib.EML_CONV_1x1, 1,
+                           self._aff(c, n1), mid if train else None, g)
+                if train:
+                    self._fold(c, n2, layer.norm2, stats=mid, stride=g, count=count, mean_var=mv(layer.norm2, count))
+                self._conv(c, "b%d.l%d.conv2" % (b, l), ws["bott"], g, h, w, B, g, slab, pitch, ci, self.growth_rate,
+                           _lib.EML_CONV_3x3, 0, self._aff(c, n2), sstat[ci:] if train else None, pitch)
+            tr = getattr(f, "transition%d" % b)
+            tn = "t%d.norm" % b
+            if train:
+                self._fold(c, tn, tr.norm, stats=sstat, stride=pitch, count=count, pre=pre, mean_var=mv(tr.norm, count))
+            last = bi + 1 == len(self._plan)
+            dst = ws["t_last"] if last else ws["slab"][bi + 1]
+            dpitch = dst.shape[3]
+            dstat = stats[so["t_last"]:] if last else stats[so["slab%d" % (b + 1)]:]
+            self._conv(c, "t%d.conv" % b, slab, pitch, h, w, B, c_out, dst, dpitch, 0, c_tr, _lib.EML_CONV_POOL2, 1,
+                       self._aff(c, tn), dstat if train else None, dpitch)
+            ln = getattr(f, "last_norm%d" % b)
+            if train:
+                cnt2 = B * (h // 2) * (w // 2)
+                self._fold(c, "ln%d" % b, ln, stats=dstat, stride=dpitch, count=cnt2, mean_var=mv(ln, cnt2))
+                if not last:
+                    a, s = self._aff(c, "ln%d" % b)
+                    c["pre"][bi + 1, 0, :c_tr] = a[:c_tr]
+                    c["pre"][bi + 1, 1, :c_tr] = s[:c_tr]
+            if not last:
+                pre = (c["pre"][bi + 1, 0], c["pre"][bi + 1, 1])
+        # ---- head (DenseNet.py:136-150): last_norm affine + relu + avgpool -> fc -> 4 heads
+        hl, wl = ws["t_last"].shape[1], ws["t_last"].shape[2]
+        a, s = self._aff(c, "ln%d" % self._plan[-1][0])
+        _lib.check(lib.eml_head_pool(_lib.ptr(ws["t_last"]), ws["t_last"].shape[3], _lib.ptr(a), _lib.ptr(s), _lib.ptr(ws["pooled"]),
+                                     B, hl, wl, self._plan[-1][3], self.avgpool_size, st), "eml_head_pool")
+        _lib.check(lib.eml_linear_fp32(_lib.ptr(ws["pooled"]), _lib.ptr(c["fc_w"]), _lib.ptr(c["fc_b"]), _lib.ptr(ws["fc"]),
+                                       B, self.fc.out_features, self.fc.in_features, st), "eml_linear_fp32(fc)")
+        nh = c["head_w"].shape[0]
+        heads = torch.empty(B, nh, dtype=torch.float32, device=dev)
+        _lib.check(lib.eml_linear_fp32(_lib.ptr(ws["fc"]), _lib.ptr(c["head_w"]), _lib.ptr(c["head_b"]), _lib.ptr(heads),
+                                       B, nh, self.fc.out_features, st), "eml_linear_fp32(heads)")
+        if train:
+            self._update_running_stats(updates)
+        outs, o = [], 0
+        for n in c["head_split"]:
+            outs.append(heads[:, o:o + n])
+            o += n
+        return outs
+
+    @torch.no_grad()
+    def _update_running_stats(self, updates):
+        """running = (1-m)*running + m*batch, unbiased variance, num_batches_tracked += 1 (nn.BatchNorm2d semantics)."""
+        for bn, mean, var, count in updates:
+            if not bn.track_running_stats or bn.running_mean is None:
+                continue
+            bn.num_batches_tracked += 1
+            m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+            bn.running_var.mul_(1 - m).add_(var, alpha=m * count / max(count - 1, 1))

@@ -1,0 +1,158 @@
+/*
+ * emlight_b200 -- C ABI of the B200 (sm_100a) implementation of EMLight's illumination hot path.
+ *
+ * One shared object (libemlight_b200.so), plain `extern "C"` entry points, raw DEVICE pointers,
+ * explicit sizes, a CUDA stream passed as `void*` (a cudaStream_t; NULL = legacy default stream).
+ * No torch types, no allocation, no implicit synchronisation, no global mutable state: every call
+ * is re-entrant and enqueues work on the caller's stream.
+ *
+ * Return value: 0 = ok; negative = argument error (EML_E_*); positive = cudaError_t of the launch.
+ * `eml_error_string()` renders either.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference repo).
+ */
+#ifndef EMLIGHT_B200_H
+#define EMLIGHT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EML_OK 0
+#define EML_E_NULL (-1)      /* required pointer is NULL */
+#define EML_E_SHAPE (-2)     /* unsupported size / shape */
+#define EML_E_ALIGN (-3)     /* pointer or pitch not aligned as documented */
+#define EML_E_ARG (-4)       /* invalid scalar argument */
+#define EML_E_WORKSPACE (-5) /* workspace too small */
+
+int eml_version(void);                 /* ABI version, bumped on any signature change */
+const char *eml_error_string(int code); /* static string, never NULL */
+int eml_device_ok(void);               /* 0 iff the current device is compute capability 10.x */
+
+/* ------------------------------------------------------------------------------------------------
+ * R2/R3 -- spherical-Gaussian -> 128x256 equirect panorama.
+ * Replaces  RegressionNetwork/util.py:222-245 `convert_to_panorama(dirs, sizes, colors)`
+ * (copies: representation/util.py:205-228, GenProjector/util.py:346-369, Needlets/utils.py:10-33).
+ *   out[b,ch,r,c] = sum_k colors[b,3k+ch] * exp((dirs[b,3k:3k+3] . p(r,c) - 1) / sizes[b,k])  (+ ambient[b,ch])
+ * dirs   (B,3N) fp32, row stride `dirs_bstride` floats (0 => one (3N) vector shared by the batch)
+ * sizes  (B,N)  fp32, row stride `sizes_bstride` floats (0 => shared)
+ * colors (B,3N) fp32 contiguous, k-major / channel-minor
+ * ambient NULL or (B,3): added to every pixel (GenProjector/data.py:100)
+ * out    (B,3,128,256) fp32 contiguous NCHW, 16-byte aligned.   1 <= N <= 512.
+ */
+int eml_sg_render_fwd(const float *dirs, long dirs_bstride, const float *sizes, long sizes_bstride,
+                      const float *colors, const float *ambient, float *out, int B, int N, void *stream);
+
+/* Same render with the light colours composed on the fly from the regression heads
+ * (RegressionNetwork/train.py:117-121; GenProjector/data.py:86-98):
+ *   colors[b,k,ch] = dist[b,k] * intensity[b] * gain * rgb_ratio[b,ch]
+ * dist (B,N) row stride dist_bstride; intensity (B) stride int_bstride; rgb_ratio (B,3) stride rgb_bstride
+ * (strides in floats, so the three can alias one packed head-output matrix). */
+int eml_sg_render_params_fwd(const float *dirs, long dirs_bstride, const float *sizes, long sizes_bstride,
+                             const float *dist, long dist_bstride, const float *intensity, long int_bstride,
+                             const float *rgb_ratio, long rgb_bstride, float gain, const float *ambient,
+                             long amb_bstride, float *out, int B, int N, void *stream);
+
+/* Backward of eml_sg_render_fwd w.r.t. dirs, sizes, colors (any of the three outputs may be NULL).
+ * Outputs are (B,3N),(B,N),(B,3N) contiguous and are OVERWRITTEN (zeroed inside the call, then accumulated). */
+int eml_sg_render_bwd(const float *dirs, long dirs_bstride, const float *sizes, long sizes_bstride,
+                      const float *colors, const float *grad_out, float *g_dirs, float *g_sizes,
+                      float *g_colors, int B, int N, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * S1-S5 -- debiased Sinkhorn divergence over N anchors, forward value and d/dx in one launch.
+ * Replaces  RegressionNetwork/geomloss/samples_loss.py:35-46,79-93 `SamplesLoss.forward(x, y)` with
+ * loss="sinkhorn", p=2, reach=None, uniform weights (samples_loss.py:62-70), cost
+ * C_ij = (0.1 (a_i-b_j)^2 + M_ij)/2 (geomloss/utils.py:85-99), the eps-scaling loop of
+ * sinkhorn_divergence.py:72-109 and the cost of :65-69; gmloss/* only changes M.
+ *   x, y   (B,N) fp32 contiguous (the reference's (B,N,1))
+ *   M      (N,N) fp32 symmetric anchor distance matrix shared by the batch
+ *   loss   (B)   out
+ *   grad_x (B,N) out or NULL:  d loss[b] / d x[b,i]
+ *   diameter <= 0  => computed on the device as |max - min| over all of x and y
+ *                     (sinkhorn_divergence.py:9-18,28-31; replaces the reference's .item() host sync)
+ *   workspace: eml_sinkhorn_workspace_bytes(B,N) bytes of device scratch, 16-byte aligned.
+ * 8 <= N <= 160.
+ */
+size_t eml_sinkhorn_workspace_bytes(int B, int N);
+int eml_sinkhorn_fwdbwd(const float *x, const float *y, const float *M, float *loss, float *grad_x, int B,
+                        int N, float blur, float scaling, float diameter, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * D1-D5 -- DenseNet-BC convolutions as implicit GEMMs on NHWC fp32 activations.
+ * Replaces the ATen conv2d/batch_norm/relu/cat/avg_pool2d chain issued by
+ * RegressionNetwork/DenseNet.py:14-21 (_Transition), :26-55 (_DenseLayer), :88-93 (stem).
+ *
+ *   out[m, n] = sum_{tap, c} W[n, tap, c] * act( scale[c] * in[src(m, tap), c] + shift[c] )
+ *
+ * with act = ReLU or identity, src() the 1x1 / 3x3(pad 1) / 2x2-average-pool gather, out-of-image taps
+ * contributing exactly 0 (zero padding is applied AFTER the affine, like the reference's BN -> conv).
+ * `in` is an NHWC tensor whose pixel pitch (`in_pitch` floats) may exceed C_in: the dense block's
+ * concatenation buffer is read in place and the 12 new channels are written in place at `out_choff`
+ * (this is what removes the reference's torch.cat, DenseNet.py:55).
+ */
+typedef struct eml_conv_params {
+    const float *in;        /* (B,H,W,in_pitch) fp32 NHWC, 16-byte aligned */
+    const float *scale;     /* (C_in) per-channel multiplier of the fused BatchNorm (NULL => 1), 16-byte aligned */
+    const float *shift;     /* (C_in) per-channel offset (NULL => 0), 16-byte aligned */
+    const float *w_oihw;    /* (C_out,C_in,kh,kw) fp32 weights, reference layout (read by EML_PREC_FP32) */
+    const void *wpack;      /* the same weights packed by eml_conv_pack_weights() (read by the tensor-core modes) */
+    float *out;             /* (B,Ho,Wo,out_pitch) fp32 NHWC; channels [out_choff, out_choff+C_out) written */
+    double *stats;          /* NULL or accumulators: stats[n] += sum, stats[stats_stride + n] += sum of squares */
+    long stats_stride;      /* doubles between the sum row and the sum-of-squares row (0 => C_out) */
+    int B, H, W;            /* input spatial size */
+    int C_in, in_pitch;     /* channels read / pixel pitch in floats (multiple of 4) */
+    int C_out, out_pitch, out_choff;
+    int mode;               /* EML_CONV_1x1, EML_CONV_3x3, EML_CONV_POOL2 (act -> 2x2 average -> 1x1) */
+    int relu;               /* 1: act = ReLU, 0: identity */
+    int precision;          /* EML_PREC_BF16 (1 MMA pass), EML_PREC_BF16X3 (hi/lo split, fp32-grade), EML_PREC_FP32 (SIMT) */
+} eml_conv_params;
+
+#define EML_CONV_1x1 0
+#define EML_CONV_3x3 1
+#define EML_CONV_POOL2 2
+#define EML_PREC_BF16 0
+#define EML_PREC_BF16X3 1
+#define EML_PREC_FP32 2
+
+/* Bytes of the packed weight image for (C_out, C_in, taps); w is OIHW fp32 on the DEVICE. */
+size_t eml_conv_wpack_bytes(int C_out, int C_in, int taps);
+int eml_conv_pack_weights(const float *w_oihw, void *wpack, int C_out, int C_in, int taps, void *stream);
+int eml_conv_forward(const eml_conv_params *p, void *stream);
+
+/* Stem: conv0 3x3 (3 -> C_out<=32) on the NCHW input image, fused affine+ReLU, NHWC output at channel 0.
+ * Replaces DenseNet.py:89-92 (conv0, norm0, relu0).  scale/shift NULL => raw convolution output.
+ * stats_raw: NULL or (2,C_out) double accumulators of the pre-affine values; stats_out: NULL or accumulators of
+ * the written values with the sum-of-squares row `stats_out_stride` doubles after the sum row (0 => C_out). */
+int eml_stem_forward(const float *x_nchw, const float *w_oihw, const float *scale, const float *shift,
+                     float *out, int out_pitch, double *stats_raw, double *stats_out, long stats_out_stride,
+                     int B, int H, int W, int C_out, int write_out, void *stream);
+
+/* BatchNorm bookkeeping (DenseNet.py:17,30,41,91,122; eps 1e-5).
+ * Given per-channel accumulators stats=(sum, sumsq) over `count` values of the STORED tensor t, an optional
+ * upstream affine u = pre_scale*t + pre_shift (the folded last_norm of the previous transition), and this
+ * norm's gamma/beta, writes scale/shift such that  BN_batchstat(u) = scale*t + shift.
+ * stats[c] is the sum and stats[stats_stride + c] the sum of squares (stats_stride 0 => C).
+ * With stats == NULL uses running_mean/running_var (eval mode) instead of batch statistics. */
+int eml_bn_fold(const double *stats, long stats_stride, double count, const float *running_mean, const float *running_var,
+                const float *gamma, const float *beta, const float *pre_scale, const float *pre_shift,
+                float *scale, float *shift, float *batch_mean, float *batch_var, int C, float eps,
+                void *stream);
+
+/* Head: relu(scale*t+shift) -> 4x4 average pool -> (B, Hp*Wp*C) in NHWC order (DenseNet.py:136-138;
+ * the fc weight columns are permuted to this order at pack time). */
+int eml_head_pool(const float *in, int in_pitch, const float *scale, const float *shift, float *out, int B,
+                  int H, int W, int C, int pool, void *stream);
+
+/* out (M,N) = a (M,K) @ w (N,K)^T + bias (N), fp32 FFMA (DenseNet.py:139-150 fc and the four heads). */
+int eml_linear_fp32(const float *a, const float *w, const float *bias, float *out, int M, int N, int K,
+                    void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMLIGHT_B200_H */
