@@ -1,0 +1,248 @@
+#!/usr/bin/env python
+"""Benchmark of the EMLight illumination hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+Workload (BASELINE.json configs[2], the one the metric "illumination maps/sec (crop -> 128x256 HDR pano)" describes):
+    B=256 LDR crops (3x192x256) per GPU -> DenseNet-BC regression (eval-mode BN, fp32 storage,
+    bf16x3 split tensor-core MMAs) -> light composition -> spherical-Gaussian render -> (B,3,128,256) fp32 panoramas.
+Weak scaling: every rank processes its own B crops; the path is per-sample independent, so there is no data-path collective.
+
+One JSON line on rank 0.  `--impl reference` times the CPU restatement of the reference (oracle/, the same ATen CPU ops the
+reference issues) on the host cores instead.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "illumination maps/sec (256x192 crop -> 128x256 HDR pano)"
+N_ANCHORS = 128
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:      # noqa: BLE001
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def cpu_reference_step(batch, sd, x, dirs, threads):
+    """One pass of the reference path on the CPU: DenseNet forward (eval BN) -> colour composition -> SG render."""
+    import numpy as np
+    import torch
+    from oracle import densenet_oracle as DO, render_oracle as RO
+    torch.set_num_threads(threads)
+    with torch.no_grad():
+        out = DO.densenet_forward(sd, x, training=False)
+    # train.py:115-122: colours from the heads, shared anchors, size 0.0025, then the reference's light-by-light render
+    cols = (out["distribution"][:, :, None] * (out["intensity"][:, :, None] * 500.0) * out["rgb_ratio"][:, None, :]).reshape(batch, -1)
+    sizes = torch.full((batch, N_ANCHORS), 0.0025)
+    return RO.convert_to_panorama_torch(torch.from_numpy(dirs).repeat(batch, 1), sizes, cols)
+
+
+def time_cpu(sample, steps, warmup):
+    """Times the CPU path with the intra-op thread count that serves it best (torch's CPU convolutions stop scaling --
+    and regress -- well below a large host's core count, so every power of two up to the core count is tried once)."""
+    import numpy as np
+    import torch
+    from oracle import densenet_oracle as DO, render_oracle as RO
+    ncpu = os.cpu_count() or 1
+    sd = DO.init_state_dict(seed=0, n_anchors=N_ANCHORS)
+    x = torch.rand(sample, 3, 192, 256, generator=torch.Generator().manual_seed(1234))
+    dirs = RO.sphere_points(N_ANCHORS).astype(np.float32).reshape(1, -1)
+    cands = sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)})
+    best, threads = None, ncpu
+    for c in cands:
+        cpu_reference_step(1, sd, x[:1], dirs, c)
+        t0 = time.perf_counter()
+        cpu_reference_step(sample, sd, x, dirs, c)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, threads = dt, c
+    for _ in range(warmup):
+        cpu_reference_step(sample, sd, x, dirs, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(sample, sd, x, dirs, threads)
+    dt = (time.perf_counter() - t0) / steps
+    return sample / dt, dt, threads
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="crops per GPU per step")
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
+    ap.add_argument("--cpu-sample", type=int, default=8, help="crops per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    config = {"workload": "BASELINE configs[2]: DenseNet-BC regression fwd (eval BN) + SG render -> 128x256 pano",
+              "batch_per_gpu": args.batch, "global_batch": args.batch * world, "input": "3x192x256 fp32 NCHW",
+              "anchors": N_ANCHORS, "parallelism": "dp%d (independent shards, no collective)" % world,
+              "l2": "per-step inputs (151 MB) and activations (>10 GB) exceed the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = args.cpu_sample
+        v, dt, threads = time_cpu(sample, max(args.steps, 1), warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "maps/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": dict(config, batch_per_gpu=sample, global_batch=sample),
+                "cpu_baseline": {"value": v, "unit": "maps/s", "cores": threads, "kind": "port",
+                                 "sample": "best of {8,16,32,64,all} intra-op threads; %d crops per step, oracle/ DenseNet forward + light-by-light SG render, torch CPU ATen ops (eval BN)" % sample},
+                "e2e": {"value": v, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import emlight_b200 as E
+    from emlight_b200 import build
+    build.build()
+    B = args.batch
+    torch.manual_seed(0)
+    net = E.DenseNet(n_anchors=N_ANCHORS, precision=args.precision).to(dev).eval()
+    gen = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.rand(B, 3, 192, 256, generator=gen).pin_memory()
+    x = x_host.to(dev)
+    dirs = torch.from_numpy(E.sphere_points(N_ANCHORS)).float().to(dev)
+    pano_host = torch.empty(B, 3, 128, 256, dtype=torch.float32).pin_memory()
+
+    def step(inp):
+        with torch.no_grad():
+            o = net(inp)
+            return E.render_from_params(o["distribution"], o["intensity"], o["rgb_ratio"], dirs=dirs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(warmup):
+        step(x)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(lambda: step(x), args.steps)
+    # end to end through the public API with host buffers: pinned H2D of the crops, D2H of the panoramas, every step
+    def e2e_step():
+        xi = x_host.to(dev, non_blocking=True)
+        pano_host.copy_(step(xi), non_blocking=True)
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    value = B * world * args.steps / (ms / 1e3)
+    e2e_value = B * world * args.steps / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel family, measured live with CUDA events on the launching stream
+    net.launch_log = []
+    torch.cuda.synchronize()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(); step(x); t1.record()
+    torch.cuda.synchronize()
+    fam = {}
+    for family, name, abytes, flops, a, b in net.launch_log:
+        f = fam.setdefault(family, {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0})
+        f["ms"] += a.elapsed_time(b); f["bytes"] += abytes; f["flops"] += flops; f["launches"] += 1
+    net.launch_log = None
+    step_ms = t0.elapsed_time(t1)
+    hbm_peak, tf_peak, peak_kind = peaks()
+    top = max(fam, key=lambda k: fam[k]["ms"])
+    roofs = {k: {"ms_per_step": round(v["ms"], 3), "launches": v["launches"], "share_of_step": round(v["ms"] / step_ms, 3),
+                 "GBps": round(v["bytes"] / v["ms"] / 1e6, 1), "TFLOPs": round(v["flops"] / v["ms"] / 1e9, 2)} for k, v in fam.items()}
+    achieved = fam[top]["bytes"] / fam[top]["ms"] / 1e6
+    roofline = {"kernel": {"conv1x1": "conv_gemm_kernel<0,SPLIT>", "conv3x3": "conv_gemm_kernel<1,SPLIT>",
+                           "pool1x1": "conv_gemm_kernel<2,SPLIT>"}[top],
+                "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(achieved / hbm_peak, 4), "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                "traffic": None, "families": roofs,
+                "note": "achieved = algorithmic bytes (inputs read once + outputs written once, fp32) / CUDA-event time, summed over the family's launches in one step"}
+    launches_per_step = 1 + sum(v["launches"] for v in fam.values()) + 1 + 2 + 1   # stem + convs + head_pool + 2 linear + render
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt, threads = time_cpu(args.cpu_sample, 3, 1)
+        cpu = {"value": v, "unit": "maps/s", "cores": threads, "kind": "port",
+               "sample": "best of {8,16,32,64,all} intra-op threads; %d crops per step x 3 steps, oracle/ DenseNet forward + light-by-light SG render, torch CPU ATen ops (eval BN)" % args.cpu_sample}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "maps/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"bf16x3": "f32 storage, bf16x3 split tensor-core MMA (fp32-grade)", "bf16": "f32 storage, bf16 MMA",
+                          "fp32": "f32 FFMA"}[args.precision],
+                "data": "synthetic", "config": config,
+                "e2e": {"value": e2e_value, "unit": "maps/s", "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": pano_host.numel() * 4},
+                "gpu_launches": launches_per_step * args.steps, "clocks": sampler.summary(), "roofline": roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -24,113 +24,17 @@
 // These kernels are HBM-bound by design (DESIGN.md section "roofline"): per 128-pixel tile the gather moves
 // 128*C_in*4 bytes while the MMAs take ~24 cycles per k-step at N=48.
 #include "common.cuh"
-#include <cuda_bf16.h>
+#include "umma.cuh"
 
 namespace {
+using namespace eml;
 
 constexpr int TILE_M = 128;
 constexpr int CHUNK_K = 64;
-constexpr int NTHREADS = 128;
+constexpr int NTHREADS = 256;
+constexpr int ROWS_PER_THREAD = TILE_M / (NTHREADS / 16);   // 8
 constexpr int STAGES = 2;
 constexpr int A_TILE_BYTES = TILE_M * CHUNK_K * 2;   // 16 KB: 128 rows x 128 B
-
-// ------------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    long long t0 = 0;
-    int spins = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) break;
-        if (++spins == 1024) t0 = clock64();
-        if (spins > 1024 && (spins & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start address >> 4 | [16,30) LBO >> 4 (=1, unused for swizzled K-major) | [32,46) SBO >> 4 (8 rows x 128 B)
-//   [46,48) version = 1 (sm_100) | [61,64) layout type = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
-    d |= static_cast<uint64_t>(1) << 16;
-    d |= static_cast<uint64_t>(1024 >> 4) << 32;
-    d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>(2) << 61;
-    return d;
-}
-// cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major A and B,
-// N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
-           (static_cast<uint32_t>(M >> 4) << 24);
-}
-
-// Byte offset of element (row, k) inside a [rows][64 bf16] K-major SWIZZLE_128B tile whose base is 1024-aligned
-// (Swizzle<3,4,3>: the 16-byte chunk index is XORed with the row index modulo 8).
-__host__ __device__ constexpr uint32_t sw128_offset(int row, int k) {
-    return static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
-}
 
 // ------------------------------------------------------------------------------------------------ kernel
 struct GemmArgs {
@@ -174,25 +78,6 @@ __device__ __forceinline__ float4 load_quad_guarded(const float *p, int ch, int 
     return r;
 }
 
-// Store 4 consecutive channels of one row as bf16 hi (and lo) into the swizzled A tile.
-template <bool SPLIT>
-__device__ __forceinline__ void store_quad(unsigned char *a_hi, unsigned char *a_lo, uint32_t off, float4 v) {
-    __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y);
-    __nv_bfloat162 h23 = __floats2bfloat162_rn(v.z, v.w);
-    uint2 hv;
-    hv.x = *reinterpret_cast<uint32_t *>(&h01);
-    hv.y = *reinterpret_cast<uint32_t *>(&h23);
-    *reinterpret_cast<uint2 *>(a_hi + off) = hv;
-    if (SPLIT) {
-        __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __low2float(h01), v.y - __high2float(h01));
-        __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __low2float(h23), v.w - __high2float(h23));
-        uint2 lv;
-        lv.x = *reinterpret_cast<uint32_t *>(&l01);
-        lv.y = *reinterpret_cast<uint32_t *>(&l23);
-        *reinterpret_cast<uint2 *>(a_lo + off) = lv;
-    }
-}
-
 // MODE 0: 1x1 | 1: 3x3 pad 1 | 2: act -> 2x2 average pool -> 1x1
 template <int MODE, bool SPLIT>
 __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(const GemmArgs a) {
@@ -225,14 +110,14 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(const GemmArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
 
-    // ---- gather geometry: thread -> (channel quad `sub`, row group `rgrp`); rows r = rgrp + 8*i, i < 16.
+    // ---- gather geometry: thread -> (channel quad `sub`, row group `rgrp` < 16); rows r = rgrp + 16*i, i < 8.
     const int sub = tid & 15, rgrp = tid >> 4;
     // source pixel index per row (-1: row beyond M); for 3x3 also the (x, y) of the centre pixel.
-    int pix[16];
-    int xy[MODE == 1 ? 16 : 1];
+    int pix[ROWS_PER_THREAD];
+    int xy[MODE == 1 ? ROWS_PER_THREAD : 1];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        long m = m0 + rgrp + 8 * i;
+    for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+        long m = m0 + rgrp + 16 * i;
         if (m >= a.M) { pix[i] = -1; if (MODE == 1) xy[i] = 0; continue; }
         if (MODE == 0) {
             pix[i] = static_cast<int>(m);
@@ -250,8 +135,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(const GemmArgs a) {
             pix[i] = static_cast<int>((b * a.H + 2 * yo) * a.W + 2 * xo);
         }
     }
-    // per-thread constant part of the swizzled store offset: row = rgrp + 8*i  ->  i*1024 + rgrp*128 + ...
-    const uint32_t st_off = static_cast<uint32_t>(rgrp * 128 + ((((sub >> 1) ^ rgrp) & 7) << 4) + (sub & 1) * 8);
+    // per-thread constant part of the swizzled store offset: row = rgrp + 16*i  ->  (2i + rgrp/8)*1024 + (rgrp%8)*128 + ...
+    const uint32_t st_off = static_cast<uint32_t>((rgrp >> 3) * 1024 + (rgrp & 7) * 128 + ((((sub >> 1) ^ rgrp) & 7) << 4) + (sub & 1) * 8);
     const uint32_t idesc = make_idesc_bf16(TILE_M, a.N_pad);
     const size_t wchunk_bytes = static_cast<size_t>(2) * b_tile_bytes;     // hi image then lo image
 
@@ -283,14 +168,13 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(const GemmArgs a) {
             }
             int dy = 0, dx = 0;
             if (MODE == 1) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            {
                 if (MODE != 2) {
                     float4 v[8];
                     bool ok[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int i = half * 8 + j;
+                        const int i = j;
                         ok[j] = ch_ok && pix[i] >= 0;
                         long src = pix[i];
                         if (MODE == 1) {
@@ -303,10 +187,9 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(const GemmArgs a) {
                     }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int i = half * 8 + j;
                         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);      // zero padding is applied AFTER the affine
                         if (ok[j]) o = act4(v[j], sc, sh, a.relu, nvalid);
-                        store_quad<SPLIT>(a_hi, a_lo, st_off + i * 1024, o);
+                        store_quad<SPLIT>(a_hi, a_lo, st_off + j * 2048, o);
                     }
                 } else {
 #pragma unroll
@@ -315,7 +198,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(const GemmArgs a) {
                         bool ok[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const int i = half * 8 + q * 4 + j;
+                            const int i = q * 4 + j;
                             ok[j] = ch_ok && pix[i] >= 0;
                             const float *p = a.in + static_cast<long>(pix[i]) * a.in_pitch + ch;
 #pragma unroll
@@ -326,7 +209,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(const GemmArgs a) {
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const int i = half * 8 + q * 4 + j;
+                            const int i = q * 4 + j;
                             float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (ok[j]) {
 #pragma unroll
@@ -336,7 +219,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(const GemmArgs a) {
                                 }
                                 o.x *= 0.25f; o.y *= 0.25f; o.z *= 0.25f; o.w *= 0.25f;
                             }
-                            store_quad<SPLIT>(a_hi, a_lo, st_off + i * 1024, o);
+                            store_quad<SPLIT>(a_hi, a_lo, st_off + i * 2048, o);
                         }
                     }
                 }
@@ -368,16 +251,17 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(const GemmArgs a) {
     mbar_wait(bar_acc, 0);
     __syncwarp();                                           // tcgen05.ld is .sync.aligned
     tc_fence_after();
-    const int row = warp * 32 + lane;
+    const int row = (warp & 3) * 32 + lane;
     const long m = m0 + row;
     const bool row_ok = m < a.M;
     float *orow = a.out + (row_ok ? m : 0) * a.out_pitch + a.out_choff;
     const bool vec_ok = ((a.out_pitch | a.out_choff) & 3) == 0;
     float *tile = reinterpret_cast<float *>(smem);         // [128][N_pad+1] staging for the statistics
     const int tp = a.N_pad + 1;
-    for (int g = 0; g < a.N_pad; g += 16) {
+    // warps w and w+4 share TMEM lanes [32(w%4), +32) and split the 16-column groups between them
+    for (int g = (warp >> 2) * 16; g < a.N_pad; g += 32) {
         float v[16];
-        tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(g), v);
+        tmem_ld16(tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(g), v);
         if (row_ok) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -460,10 +344,22 @@ int launch(const GemmArgs &a, cudaStream_t st) {
 
 }  // namespace
 
-extern "C" size_t eml_conv_wpack_bytes(int C_out, int C_in, int taps) {
-    if (C_out <= 0 || C_in <= 0 || taps <= 0) return 0;
+int eml_conv_forward_simt(const eml_conv_params *p, cudaStream_t st);   // conv_simt.cu
+// conv3x3_rows.cu: planar no-im2col 3x3 kernel
+size_t eml_rows_wpack_bytes(int C_out, int C_in);
+int eml_rows_pack(const float *w_oihw, unsigned char *dst, int C_out, int C_in, cudaStream_t st);
+bool eml_rows_supported(const eml_conv_params *p);
+int eml_rows_forward(const eml_conv_params *p, const unsigned char *wplanar, cudaStream_t st);
+
+static size_t generic_wpack_bytes(int C_out, int C_in, int taps) {
     const int cpt = (C_in + CHUNK_K - 1) / CHUNK_K;
     return static_cast<size_t>(taps) * cpt * 2 * pad16(C_out) * 128;
+}
+
+extern "C" size_t eml_conv_wpack_bytes(int C_out, int C_in, int taps) {
+    if (C_out <= 0 || C_in <= 0 || taps <= 0) return 0;
+    // generic SWIZZLE_128B chunk images, followed (3x3 only) by the planar image of conv3x3_rows.cu
+    return generic_wpack_bytes(C_out, C_in, taps) + (taps == 9 ? eml_rows_wpack_bytes(C_out, C_in) : 0);
 }
 
 extern "C" int eml_conv_pack_weights(const float *w_oihw, void *wpack, int C_out, int C_in, int taps, void *stream) {
@@ -473,10 +369,13 @@ extern "C" int eml_conv_pack_weights(const float *w_oihw, void *wpack, int C_out
     const int cpt = (C_in + CHUNK_K - 1) / CHUNK_K;
     pack_weights_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         w_oihw, static_cast<unsigned char *>(wpack), C_out, C_in, taps, pad16(C_out), cpt);
-    return eml_launch_status();
+    int rc = eml_launch_status();
+    if (rc == EML_OK && taps == 9 && eml_rows_wpack_bytes(C_out, C_in) > 0)
+        rc = eml_rows_pack(w_oihw, static_cast<unsigned char *>(wpack) + generic_wpack_bytes(C_out, C_in, taps), C_out, C_in,
+                           static_cast<cudaStream_t>(stream));
+    return rc;
 }
 
-int eml_conv_forward_simt(const eml_conv_params *p, cudaStream_t st);   // conv_simt.cu
 
 extern "C" int eml_conv_forward(const eml_conv_params *p, void *stream) {
     EML_CHECK_PTR(p); EML_CHECK_PTR(p->in); EML_CHECK_PTR(p->out);
@@ -494,6 +393,8 @@ extern "C" int eml_conv_forward(const eml_conv_params *p, void *stream) {
     EML_CHECK_PTR(p->wpack);
     EML_CHECK_ALIGN16(p->wpack);
     if (static_cast<long>(p->B) * p->H * p->W >= (1L << 31)) return EML_E_SHAPE;
+    if (eml_rows_supported(p))
+        return eml_rows_forward(p, static_cast<const unsigned char *>(p->wpack) + generic_wpack_bytes(p->C_out, p->C_in, 9), st);
 
     GemmArgs a{};
     a.in = p->in; a.scale = p->scale; a.shift = p->shift;

@@ -121,6 +121,7 @@ class DenseNet(nn.Module):
         self.relu = nn.ReLU()
         self._cache = None                             # packed weights + folded eval-mode BN, keyed on param versions
         self._ws = {}                                  # activation workspaces keyed on (B,H,W,device)
+        self.launch_log = None                         # set to a list to collect (kernel family, name, shape info, start, end events)
 
     # ------------------------------------------------------------------ reference-facing API
     def forward(self, x):
@@ -296,7 +297,17 @@ class DenseNet(nn.Module):
         p.C_in, p.in_pitch = c_in, src_pitch
         p.C_out, p.out_pitch, p.out_choff = c_out, dst_pitch, choff
         p.mode, p.relu, p.precision = mode, relu, _lib.PRECISIONS[self.precision]
+        if self.launch_log is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _lib.check(lib.eml_conv_forward(p, _lib.stream_ptr()), "eml_conv_forward(%s)" % name)
+        if self.launch_log is not None:
+            e1.record()
+            m_out = B * H * W // (4 if mode == _lib.EML_CONV_POOL2 else 1)
+            # algorithmic bytes: every input element read once, every output element written once (fp32)
+            abytes = 4 * (B * H * W * c_in + m_out * c_out)
+            flops = 2 * m_out * c_out * c_in * (9 if mode == _lib.EML_CONV_3x3 else 1)
+            self.launch_log.append((("conv1x1", "conv3x3", "pool1x1")[mode], name, abytes, flops, e0, e1))
 
     @torch.no_grad()
     def _run(self, x):

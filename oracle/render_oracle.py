@@ -77,3 +77,17 @@ def compose_colors(dist, intensity, rgb_ratio, gain=500.0):
     """(B,N),(B,1),(B,3) -> (B,3N) k-major (train.py:117-121)."""
     c = dist[:, :, None] * (intensity[:, :, None] * np.float32(gain)) * rgb_ratio[:, None, :]
     return c.reshape(dist.shape[0], -1).astype(np.float32)
+
+
+def convert_to_panorama_torch(dirs, sizes, colors):
+    """The same light-by-light accumulation written with torch CPU ops (what the reference executes, util.py:222-245);
+    used as the timed CPU baseline.  dirs (B,3N), sizes (B,N), colors (B,3N) torch fp32 tensors."""
+    import torch
+    xyz = torch.from_numpy(pixel_dirs(np.float32)).reshape(3, -1)
+    B = colors.shape[0]
+    n = colors.shape[1] // 3
+    out = torch.zeros(B, 3, PANO_H, PANO_W, dtype=dirs.dtype)
+    for k in range(n):
+        d = torch.matmul(dirs[:, 3 * k:3 * k + 3], xyz).view(-1, PANO_H, PANO_W)
+        out = out + colors[:, 3 * k:3 * k + 3][:, :, None, None] * torch.exp((d - 1) / sizes[:, k].view(-1, 1, 1))[:, None, :, :]
+    return out

@@ -59,6 +59,9 @@ CASES = [
     ("pool", 1, 16, 16, 216, 216, 108, 300, 0, True),     # transition1
     ("pool", 2, 4, 8, 342, 344, 171, 172, 0, True),       # transition3: N_pad 176, odd C_out (scalar stores)
     ("1x1", 3, 24, 32, 204, 216, 48, 48, 0, True),        # 18 tiles
+    ("3x3", 1, 4, 128, 48, 48, 12, 216, 24, False),       # planar no-im2col kernel (W % 128 == 0): block-2 geometry
+    ("3x3", 2, 3, 256, 48, 48, 12, 344, 150, False),      # block-1 geometry, two tiles per row, top/bottom borders
+    ("3x3", 1, 1, 128, 48, 48, 12, 12, 0, True),          # single row: both vertical neighbours are padding
 ]
 
 
