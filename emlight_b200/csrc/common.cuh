@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "../../include/emlight_b200.h"
 
 #define EML_CHECK_PTR(p) do { if ((p) == nullptr) return EML_E_NULL; } while (0)
@@ -31,4 +32,10 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Debug / A-B switches read from the environment (e.g. EML_NO_PERSIST=1 selects the non-persistent kernels).
+static inline bool eml_env_flag(const char *name) {
+    const char *v = getenv(name);
+    return v != nullptr && v[0] != '\0' && v[0] != '0';
 }

@@ -209,6 +209,271 @@ __global__ void __launch_bounds__(ROWS_THREADS) conv3x3_rows_kernel(const RowsAr
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent ROLLING-ROW variant (no statistics epilogue).
+// A CTA owns a vertical band (image b, 128-pixel column block, RB consecutive output rows) and walks down it: output row
+// y needs input rows y-1, y, y+1, of which y-1 and y are already staged from the previous step -- so every new output row
+// stages exactly ONE new halo row (130 px) into a 4-slot ring instead of three (3x fewer loads, conversions and
+// shared-memory stores, and no 3x L2 re-read of the bottleneck tensor).  Tap (dy,dx) of output row r reads ring slot
+// (r+dy) mod 4 through a shifted no-swizzle descriptor, exactly as in the kernel above.
+// Tensor-side shared-memory traffic is cut as well: the weights are staged as one N=32 operand [B_hi ; B_lo], so
+//     D[:, 0:16]  += A_hi * B_hi      D[:, 16:32] += A_hi * B_lo      (ONE M128 N32 K16 MMA, A_hi read once)
+//     D[:, 0:16]  += A_lo * B_hi                                       (one M128 N16 K16 MMA)
+// and the epilogue adds the two 16-column halves.  2 MMAs and 76 operand wavefronts per k-step instead of 3 and 108.
+// Roles: warps 0-7 producers, warp 8 MMA issuer, warps 9-12 epilogue; TMEM 2 x 32 columns.
+constexpr int RP_THREADS = 256 + 32 + 128;
+constexpr int RING = 4;
+
+__device__ __forceinline__ void rows_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+struct RollArgs {
+    RowsArgs r;
+    const unsigned char *wcat;     // SPLIT: [tap][kc][32 rows (hi 0-15, lo 16-31)][16 B]; else planar hi image
+    int rb;                        // output rows per band
+    int bands_y;                   // bands per image column block
+    long nunits;                   // B * tiles_x * bands_y
+};
+
+template <int C_IN, bool SPLIT>
+__global__ void __launch_bounds__(RP_THREADS, 1) conv3x3_roll_kernel(const RollArgs ra) {
+    const RowsArgs &a = ra.r;
+    constexpr int KC = C_IN / 8;
+    constexpr int CQ = C_IN / 4;
+    constexpr int PLANE = ROWS_PP * 16;
+    constexpr int SLOT_BYTES = KC * PLANE;                 // one staged row, one image (hi or lo)
+    constexpr int IMG_BYTES = RING * SLOT_BYTES;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long s_bar[1 + 2 * RING + 4];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(16) float s_scale[C_IN];
+    __shared__ __align__(16) float s_shift[C_IN];
+
+    unsigned char *ring_hi = smem;
+    unsigned char *ring_lo = smem + IMG_BYTES;             // only when SPLIT
+    unsigned char *w_sm = smem + (SPLIT ? 2 : 1) * IMG_BYTES;
+    const int wn = SPLIT ? 32 : a.N_pad;                   // rows of the staged weight operand
+    const int w_bytes = 9 * KC * wn * 16;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar_w = smem_u32(&s_bar[0]);
+    const uint32_t bar_rfull = smem_u32(&s_bar[1]);                 // [RING] row staged
+    const uint32_t bar_rempty = smem_u32(&s_bar[1 + RING]);         // [RING] last MMA reading the row retired
+    const uint32_t bar_accfull = smem_u32(&s_bar[1 + 2 * RING]);    // [2]
+    const uint32_t bar_accempty = smem_u32(&s_bar[3 + 2 * RING]);   // [2]
+
+    if (tid == 0) {
+        mbar_init(bar_w, 1);
+        for (int i = 0; i < RING; ++i) { mbar_init(bar_rfull + 8 * i, 8); mbar_init(bar_rempty + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_accfull + 8 * i, 1); mbar_init(bar_accempty + 8 * i, 4); }
+        fence_mbar_init();
+    }
+    if (warp == 8) {
+        __syncwarp();
+        tmem_alloc(smem_u32(&s_tmem), 64);
+    }
+    for (int i = tid; i < C_IN; i += RP_THREADS) {
+        s_scale[i] = a.scale ? a.scale[i] : 1.f;
+        s_shift[i] = a.shift ? a.shift[i] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+    const int tiles_x = (a.W + ROWS_TILE - 1) / ROWS_TILE;
+
+    // unit -> (b, tx, band); rows of the band: y0 .. y0+nrows-1
+    auto decode = [&](long unit, long &b, int &x0, int &y0, int &nrows) {
+        const int band = static_cast<int>(unit % ra.bands_y);
+        const long t = unit / ra.bands_y;
+        x0 = static_cast<int>(t % tiles_x) * ROWS_TILE;
+        b = t / tiles_x;
+        y0 = band * ra.rb;
+        nrows = min(ra.rb, a.H - y0);
+    };
+
+    if (warp < 8) {
+        // ======================================================= PRODUCERS: one halo row per step
+        constexpr int SLOTS = 256 / CQ;
+        constexpr int NPX = (130 + SLOTS - 1) / SLOTS;
+        const int q = tid % CQ, ps = tid / CQ;
+        const bool active = ps < SLOTS;
+        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + q * 4);
+        const float4 sh = *reinterpret_cast<const float4 *>(s_shift + q * 4);
+        const uint32_t soff0 = static_cast<uint32_t>(((q >> 1) * ROWS_PP + ps) * 16 + (q & 1) * 8);
+        const long gstride = static_cast<long>(SLOTS) * a.in_pitch;
+        uint32_t R = 0;                                         // rows staged so far by this CTA
+        for (long unit = blockIdx.x; unit < ra.nunits; unit += gridDim.x) {
+            long b; int x0, y0, nrows;
+            decode(unit, b, x0, y0, nrows);
+            float4 v[2][NPX];
+            unsigned okm[2];
+            auto load_row = [&](int iy, float4 (&dst)[NPX], unsigned &m) {
+                const bool row_ok = active && iy >= 0 && iy < a.H;
+                const float *rp = a.in + ((b * a.H + iy) * static_cast<long>(a.W) + (x0 - 1 + ps)) * a.in_pitch + q * 4;
+                m = 0;
+#pragma unroll
+                for (int i = 0; i < NPX; ++i) {
+                    const int px = ps + i * SLOTS;
+                    const int ix = x0 - 1 + px;
+                    const bool ok = row_ok && px < 130 && ix >= 0 && ix < a.W;
+                    dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) { dst[i] = __ldg(reinterpret_cast<const float4 *>(rp + i * gstride)); m |= 1u << i; }
+                }
+            };
+            auto store_row = [&](uint32_t Rg, const float4 (&src)[NPX], unsigned m) {
+                const uint32_t slot = Rg % RING, ph = (Rg / RING) & 1;
+                mbar_wait(bar_rempty + 8 * slot, ph ^ 1);
+                unsigned char *hi = ring_hi + slot * SLOT_BYTES;
+                unsigned char *lo = ring_lo + slot * SLOT_BYTES;
+#pragma unroll
+                for (int i = 0; i < NPX; ++i) {
+                    if (!active || ps + i * SLOTS >= 130) continue;
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);           // zero padding is applied AFTER the affine
+                    if ((m >> i) & 1u) {
+                        o.x = fmaf(src[i].x, sc.x, sh.x); o.y = fmaf(src[i].y, sc.y, sh.y);
+                        o.z = fmaf(src[i].z, sc.z, sh.z); o.w = fmaf(src[i].w, sc.w, sh.w);
+                        if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    }
+                    store_quad<SPLIT>(hi, lo, soff0 + static_cast<uint32_t>(i * SLOTS * 16), o);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) rows_mbar_arrive(bar_rfull + 8 * slot);
+            };
+            // rows y0-1 .. y0+nrows (nrows+2 rows), software-pipelined: row k+1's loads fly while row k is converted
+            const int total = nrows + 2;
+            load_row(y0 - 1, v[0], okm[0]);
+            for (int k = 0; k < total; ++k) {
+                const int cur = k & 1;
+                if (k + 1 < total) {
+                    if (cur == 0) load_row(y0 + k, v[1], okm[1]); else load_row(y0 + k, v[0], okm[0]);
+                }
+                if (cur == 0) store_row(R, v[0], okm[0]); else store_row(R, v[1], okm[1]);
+                ++R;
+            }
+        }
+    } else if (warp == 8) {
+        // ======================================================= MMA ISSUER
+        if (lane == 0) {
+            mbar_expect_tx(bar_w, static_cast<uint32_t>(w_bytes));
+            bulk_g2s(smem_u32(w_sm), ra.wcat, static_cast<uint32_t>(w_bytes), bar_w);
+            mbar_wait(bar_w, 0);
+            const uint32_t idesc_cat = make_idesc_bf16(ROWS_TILE, SPLIT ? 32 : a.N_pad);
+            const uint32_t idesc_16 = make_idesc_bf16(ROWS_TILE, 16);
+            const uint32_t wlbo = static_cast<uint32_t>(wn * 16);
+            const uint32_t w_s = smem_u32(w_sm), hi_s = smem_u32(ring_hi), lo_s = smem_u32(ring_lo);
+            uint32_t R0 = 0, j = 0;
+            for (long unit = blockIdx.x; unit < ra.nunits; unit += gridDim.x) {
+                long b; int x0, y0, nrows;
+                decode(unit, b, x0, y0, nrows);
+                // rows R0 (y0-1) and R0+1 (y0) must be present before the first output row
+                for (int r = 0; r < 2; ++r) mbar_wait(bar_rfull + 8 * ((R0 + r) % RING), ((R0 + r) / RING) & 1);
+                for (int i = 0; i < nrows; ++i, ++j) {
+                    const uint32_t buf = j & 1, aph = (j >> 1) & 1;
+                    const uint32_t Rn = R0 + i + 2;                                  // newest row needed (y+1)
+                    mbar_wait(bar_rfull + 8 * (Rn % RING), (Rn / RING) & 1);
+                    mbar_wait(bar_accempty + 8 * buf, aph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * 32;
+                    uint32_t acc = 0;
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int dy = tap / 3, dx = tap - dy * 3;
+                        const uint32_t slot = (R0 + i + dy) % RING;
+#pragma unroll
+                        for (int ks = 0; ks < KC / 2; ++ks) {
+                            const uint32_t aoff = slot * SLOT_BYTES + static_cast<uint32_t>((2 * ks * ROWS_PP + dx) * 16);
+                            const uint32_t woff = static_cast<uint32_t>((tap * KC + 2 * ks) * wn * 16);
+                            const uint64_t dah = make_nosw_desc(hi_s + aoff, PLANE, 128);
+                            const uint64_t dbw = make_nosw_desc(w_s + woff, wlbo, 128);
+                            umma_bf16(d_tmem, dah, dbw, idesc_cat, acc);          // hi*[hi|lo] -> cols 0..31
+                            if (SPLIT) {
+                                const uint64_t dal = make_nosw_desc(lo_s + aoff, PLANE, 128);
+                                umma_bf16(d_tmem, dal, dbw, idesc_16, 1u);            // lo*hi -> cols 0..15 (first 16 rows of the operand)
+                            }
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(bar_rempty + 8 * ((R0 + i) % RING));                 // row y-1 is dead after this output row
+                    if (i == nrows - 1) {                                            // band ends: rows y and y+1 die as well
+                        umma_commit(bar_rempty + 8 * ((R0 + i + 1) % RING));
+                        umma_commit(bar_rempty + 8 * ((R0 + i + 2) % RING));
+                    }
+                    umma_commit(bar_accfull + 8 * buf);
+                }
+                R0 += static_cast<uint32_t>(nrows + 2);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ======================================================= EPILOGUE
+        const int q4 = warp & 3;
+        const bool vec_ok = ((a.out_pitch | a.out_choff) & 3) == 0;
+        uint32_t j = 0;
+        for (long unit = blockIdx.x; unit < ra.nunits; unit += gridDim.x) {
+            long b; int x0, y0, nrows;
+            decode(unit, b, x0, y0, nrows);
+            for (int i = 0; i < nrows; ++i, ++j) {
+                const uint32_t buf = j & 1, aph = (j >> 1) & 1;
+                mbar_wait(bar_accfull + 8 * buf, aph);
+                __syncwarp();
+                tc_fence_after();
+                const int x = x0 + q4 * 32 + lane;
+                float v[16];
+                tmem_ld16(tmem_base + buf * 32 + (static_cast<uint32_t>(q4 * 32) << 16), v);
+                if (SPLIT) {
+                    float w2[16];
+                    tmem_ld16(tmem_base + buf * 32 + 16 + (static_cast<uint32_t>(q4 * 32) << 16), w2);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] += w2[e];
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) rows_mbar_arrive(bar_accempty + 8 * buf);            // TMEM drained: release before the stores
+                if (x < a.W) {
+                    float *orow = a.out + ((b * a.H + (y0 + i)) * static_cast<long>(a.W) + x) * a.out_pitch + a.out_choff;
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const int n = qq * 4;
+                        if (vec_ok && n + 3 < a.C_out) {
+                            *reinterpret_cast<float4 *>(orow + n) = make_float4(v[n], v[n + 1], v[n + 2], v[n + 3]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (n + e < a.C_out) orow[n + e] = v[n + e];
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, 64);
+    }
+}
+
+// OIHW fp32 -> [tap][kc][32 rows: n<16 hi(n), n>=16 lo(n-16)][8 bf16]  (the N=32 concatenated operand of the rolling kernel)
+__global__ void pack_cat_kernel(const float *__restrict__ w, unsigned char *__restrict__ out, int C_out, int C_in) {
+    const int KC = C_in / 8;
+    const int total = 9 * KC * 32 * 8;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int e = idx & 7;
+        const int n = (idx >> 3) & 31;
+        const int kc = (idx / 256) % KC;
+        const int tap = idx / (256 * KC);
+        const int c = kc * 8 + e, nn = n & 15;
+        float v = 0.f;
+        if (nn < C_out) v = w[(static_cast<long>(nn) * C_in + c) * 9 + tap];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        *reinterpret_cast<__nv_bfloat16 *>(out + static_cast<size_t>(idx) * 2) = n < 16 ? hi : lo;
+    }
+}
+
 // OIHW fp32 -> planar [tap][kc][n][8 bf16], hi image then lo image.
 __global__ void pack_planar_kernel(const float *__restrict__ w, unsigned char *__restrict__ out, int C_out, int C_in,
                                    int N_pad) {
@@ -234,20 +499,27 @@ __global__ void pack_planar_kernel(const float *__restrict__ w, unsigned char *_
 }  // namespace
 
 // ---- entry points used by conv_gemm.cu's dispatcher
-size_t eml_rows_wpack_bytes(int C_out, int C_in) {
-    if (C_in % 8) return 0;
+static size_t rows_planar_bytes(int C_out, int C_in) {
     const int N_pad = (C_out + 15) & ~15;
     return static_cast<size_t>(2) * 9 * (C_in / 8) * N_pad * 16;
+}
+
+size_t eml_rows_wpack_bytes(int C_out, int C_in) {
+    if (C_in % 8) return 0;
+    // planar hi|lo image (non-persistent kernel) followed by the N=32 concatenated image (rolling kernel, C_out <= 16)
+    return rows_planar_bytes(C_out, C_in) + (C_out <= 16 ? static_cast<size_t>(9) * (C_in / 8) * 32 * 16 : 0);
 }
 
 int eml_rows_pack(const float *w_oihw, unsigned char *dst, int C_out, int C_in, cudaStream_t st) {
     const int N_pad = (C_out + 15) & ~15;
     pack_planar_kernel<<<32, 256, 0, st>>>(w_oihw, dst, C_out, C_in, N_pad);
+    if (C_out <= 16) pack_cat_kernel<<<32, 256, 0, st>>>(w_oihw, dst + rows_planar_bytes(C_out, C_in), C_out, C_in);
     return eml_launch_status();
 }
 
 bool eml_rows_supported(const eml_conv_params *p) {
-    return p->mode == EML_CONV_3x3 && p->C_in == 48 && p->C_out <= 16 && (p->W % ROWS_TILE) == 0 &&
+    return p->mode == EML_CONV_3x3 && p->C_in == 48 && p->C_out <= 16 &&
+           ((p->W % ROWS_TILE) == 0 || (p->stats == nullptr && !eml_env_flag("EML_NO_PERSIST"))) &&
            (p->precision == EML_PREC_BF16 || p->precision == EML_PREC_BF16X3);
 }
 
@@ -267,6 +539,35 @@ int eml_rows_forward(const eml_conv_params *p, const unsigned char *wplanar, cud
     const long tiles = static_cast<long>(p->B) * p->H * (p->W / ROWS_TILE);
     if (tiles >= (1L << 31)) return EML_E_SHAPE;
     cudaError_t e;
+    if (a.stats == nullptr && !eml_env_flag("EML_NO_PERSIST")) {
+        RollArgs ra{};
+        ra.r = a;
+        ra.wcat = split ? wplanar + rows_planar_bytes(p->C_out, p->C_in) : wplanar;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int tiles_x = (p->W + ROWS_TILE - 1) / ROWS_TILE;
+        // band height: 32 rows (6 % halo overhead) unless that leaves fewer than ~8 units per SM, then 16
+        int rb = 32;
+        if (static_cast<long>(p->B) * tiles_x * ((p->H + rb - 1) / rb) < 8L * sms) rb = 16;
+        if (rb > p->H) rb = p->H;
+        ra.rb = rb;
+        ra.bands_y = (p->H + rb - 1) / rb;
+        ra.nunits = static_cast<long>(p->B) * tiles_x * ra.bands_y;
+        const size_t ring = static_cast<size_t>(RING) * KC * ROWS_PP * 16;
+        const size_t psm = (split ? 2 : 1) * ring + static_cast<size_t>(9) * KC * (split ? 32 : a.N_pad) * 16;
+        const unsigned grid = static_cast<unsigned>(ra.nunits < sms ? ra.nunits : sms);
+        if (split) {
+            e = cudaFuncSetAttribute(conv3x3_roll_kernel<48, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psm));
+            if (e != cudaSuccess) return static_cast<int>(e);
+            conv3x3_roll_kernel<48, true><<<grid, RP_THREADS, psm, st>>>(ra);
+        } else {
+            e = cudaFuncSetAttribute(conv3x3_roll_kernel<48, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psm));
+            if (e != cudaSuccess) return static_cast<int>(e);
+            conv3x3_roll_kernel<48, false><<<grid, RP_THREADS, psm, st>>>(ra);
+        }
+        return eml_launch_status();
+    }
     if (split) {
         e = cudaFuncSetAttribute(conv3x3_rows_kernel<48, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);

@@ -349,6 +349,9 @@ int eml_conv_forward_simt(const eml_conv_params *p, cudaStream_t st);   // conv_
 size_t eml_rows_wpack_bytes(int C_out, int C_in);
 int eml_rows_pack(const float *w_oihw, unsigned char *dst, int C_out, int C_in, cudaStream_t st);
 bool eml_rows_supported(const eml_conv_params *p);
+// conv1x1_persist.cu: persistent warp-specialised 1x1 kernel (no statistics epilogue)
+bool eml_persist_supported(const eml_conv_params *p);
+int eml_persist_forward(const eml_conv_params *p, cudaStream_t st);
 int eml_rows_forward(const eml_conv_params *p, const unsigned char *wplanar, cudaStream_t st);
 
 static size_t generic_wpack_bytes(int C_out, int C_in, int taps) {
@@ -393,6 +396,7 @@ extern "C" int eml_conv_forward(const eml_conv_params *p, void *stream) {
     EML_CHECK_PTR(p->wpack);
     EML_CHECK_ALIGN16(p->wpack);
     if (static_cast<long>(p->B) * p->H * p->W >= (1L << 31)) return EML_E_SHAPE;
+    if (eml_persist_supported(p) && !eml_env_flag("EML_NO_PERSIST")) return eml_persist_forward(p, st);
     if (eml_rows_supported(p))
         return eml_rows_forward(p, static_cast<const unsigned char *>(p->wpack) + generic_wpack_bytes(p->C_out, p->C_in, 9), st);
 

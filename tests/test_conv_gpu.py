@@ -93,6 +93,30 @@ def test_conv_matches_reference(lib, cuda, case, precision):
     assert stats[:choff].abs().max() == 0 if choff else True
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] != "pool"] + [("1x1", 40, 48, 64, 132, 216, 48, 48, 0, True)],
+                         ids=lambda c: "%s-B%d-%dx%d-c%d" % (c[0], c[1], c[2], c[3], c[4]))
+def test_conv_persistent_kernels(lib, cuda, case, precision):
+    """Without a statistics epilogue the dispatcher picks the persistent warp-specialised kernels (one CTA per SM walking
+    the tiles); the last case has 960 tiles so every CTA loops > 6 times and the stage/accumulator rings wrap."""
+    mode, B, H, W, c_in, pitch, c_out, out_pitch, choff, relu = case
+    g = torch.Generator().manual_seed((hash(case) + 17) & 0xffff)
+    x = torch.randn(B, H, W, pitch, generator=g)
+    x[..., c_in:] = float("nan")
+    scale = 0.5 + torch.rand(c_in, generator=g)
+    shift = 0.3 * torch.randn(c_in, generator=g)
+    taps = 3 if mode == "3x3" else 1
+    w = torch.randn(c_out, c_in, taps, taps, generator=g) / np.sqrt(c_in * taps * taps)
+    out, _ = run_conv(lib, cuda, x, c_in, scale, shift, w, mode, relu, precision, out_pitch, choff, False)
+    ref = conv_ref(x, c_in, scale, shift, w, mode, relu)
+    got = out[..., choff:choff + c_out].double()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= TOL[precision], err
+    rest = torch.cat([out[..., :choff], out[..., choff + c_out:]], -1)
+    assert torch.isnan(rest).all()
+
+
 def test_conv_argument_errors(lib, cuda):
     from emlight_b200._lib import ConvParams
     x = torch.zeros(1, 8, 8, 24, device=cuda); o = torch.zeros(1, 8, 8, 48, device=cuda)
