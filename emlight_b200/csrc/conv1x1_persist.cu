@@ -3,12 +3,14 @@
 // Same math and shared-memory layouts as conv_gemm_kernel<0,SPLIT> (conv_gemm.cu) -- that kernel stays as the
 // general path (statistics epilogue, wide N, pooling) -- but organised so that nothing serialises per tile:
 //   grid = one CTA per SM, each walking tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...
-//   warps 0-7  PRODUCERS  gather 128 x 64 slab elements per K-chunk with coalesced float4 loads, apply the layer's
+//   warps 0-15 PRODUCERS  gather 128 x 64 slab elements per K-chunk with coalesced float4 loads, apply the layer's
 //                         BN affine + ReLU, split to bf16 hi/lo, store into a 4-stage SWIZZLE_128B ring (full/empty
 //                         mbarriers); they run ahead across tile boundaries, so HBM loads are always in flight
-//   warp  8    MMA        one lane issues tcgen05.mma against the RESIDENT weights (all K-chunks, <= 72 KB, one
+//   warp  16   MMA        one lane issues tcgen05.mma against the RESIDENT weights (all K-chunks, <= 72 KB, one
 //                         cp.async.bulk per CTA lifetime); tcgen05.commit frees ring stages / publishes accumulators
-//   warps 9-12 EPILOGUE   tcgen05.ld the finished accumulator (TMEM double-buffered: 2 x 64 columns) and store NHWC
+//   warps 17-20 EPILOGUE  tcgen05.ld the finished accumulator (TMEM double-buffered: 2 x 64 columns), stage it in shared
+//                         memory as 16-byte planes and write it out with fully coalesced float4 stores (a thread's own
+//                         row is 192 B at a 192..1376 B pitch: storing it directly costs 32 L1 wavefronts per instruction)
 // Barrier-init, TMEM allocation and the weight fetch are paid once per SM instead of once per 128 pixels.
 #include "common.cuh"
 #include "umma.cuh"
@@ -18,8 +20,10 @@ using namespace eml;
 
 constexpr int P_TILE_M = 128;
 constexpr int P_CHUNK_K = 64;
-constexpr int P_STAGES = 4;
-constexpr int P_PRODUCERS = 256;                // warps 0..7
+constexpr int P_MAX_STAGES = 4;
+constexpr int P_PRODUCERS = 512;                // warps 0..15 (4 per scheduler: latency hiding for the gather)
+constexpr int P_PWARPS = P_PRODUCERS / 32;
+constexpr int P_NROWS = P_TILE_M * 16 / P_PRODUCERS;   // rows per producer thread per chunk (4)
 constexpr int P_THREADS = P_PRODUCERS + 32 + 128;   // + MMA warp + 4 epilogue warps
 constexpr int P_A_TILE = P_TILE_M * P_CHUNK_K * 2;
 constexpr int P_ACC_COLS = 64;                  // TMEM columns per accumulator buffer (N_pad <= 64)
@@ -35,6 +39,7 @@ struct PArgs {
     int C_out, N_pad, out_pitch, out_choff;
     int nchunks;
     int relu;
+    int stages;          // A-ring depth (3 or 4, whatever fits next to the resident weights and the output staging)
     long ntiles;
 };
 
@@ -50,29 +55,31 @@ __device__ __forceinline__ float p_act(float x, float s, float t, int relu) {
 template <bool SPLIT, bool RELU>
 __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PArgs a) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long s_bar[2 * P_STAGES + 1 + 4];
+    __shared__ __align__(8) unsigned long long s_bar[2 * P_MAX_STAGES + 1 + 4];
     __shared__ uint32_t s_tmem;
 
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * P_A_TILE;
+    const int P_STAGES = a.stages;
     unsigned char *w_sm = smem + P_STAGES * STAGE_BYTES;
     const int b_tile_bytes = a.N_pad * 128;
     const int w_chunk_sm = (SPLIT ? 2 : 1) * b_tile_bytes;          // bytes per chunk kept in smem
+    const size_t out_stage_off = static_cast<size_t>(P_STAGES) * STAGE_BYTES + static_cast<size_t>(a.nchunks) * w_chunk_sm;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     const uint32_t bar_full = smem_u32(&s_bar[0]);
-    const uint32_t bar_empty = smem_u32(&s_bar[P_STAGES]);
-    const uint32_t bar_w = smem_u32(&s_bar[2 * P_STAGES]);
-    const uint32_t bar_accfull = smem_u32(&s_bar[2 * P_STAGES + 1]);    // [2]
-    const uint32_t bar_accempty = smem_u32(&s_bar[2 * P_STAGES + 3]);   // [2]
+    const uint32_t bar_empty = smem_u32(&s_bar[P_MAX_STAGES]);
+    const uint32_t bar_w = smem_u32(&s_bar[2 * P_MAX_STAGES]);
+    const uint32_t bar_accfull = smem_u32(&s_bar[2 * P_MAX_STAGES + 1]);    // [2]
+    const uint32_t bar_accempty = smem_u32(&s_bar[2 * P_MAX_STAGES + 3]);   // [2]
 
     if (tid == 0) {
-        for (int s = 0; s < P_STAGES; ++s) { mbar_init(bar_full + 8 * s, P_PRODUCERS / 32); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < P_MAX_STAGES; ++s) { mbar_init(bar_full + 8 * s, P_PRODUCERS / 32); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_w, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(bar_accfull + 8 * i, 1); mbar_init(bar_accempty + 8 * i, 4); }
         fence_mbar_init();
     }
-    if (warp == 8) {
+    if (warp == P_PWARPS) {
         __syncwarp();
         tmem_alloc(smem_u32(&s_tmem), 2 * P_ACC_COLS);
     }
@@ -81,13 +88,16 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
 
-    if (warp < 8) {
+    if (warp < P_PWARPS) {
         // =========================================================== PRODUCERS
-        const int sub = tid & 15, rgrp = tid >> 4;                   // channel quad, row group (rows rgrp + 16 i)
+        const int sub = tid & 15, rgrp = tid >> 4;                   // channel quad, row group (rows rgrp + 32 i, i < 4)
         const uint32_t st_off = static_cast<uint32_t>((rgrp >> 3) * 1024 + (rgrp & 7) * 128 + ((((sub >> 1) ^ rgrp) & 7) << 4) + (sub & 1) * 8);
+        constexpr int RSTEP = P_PRODUCERS / 16;                      // 32 rows between a thread's consecutive rows
+        constexpr uint32_t SSTEP = RSTEP / 8 * 1024;                 // = 4096 bytes in the swizzled tile
+        constexpr unsigned FULLM = (1u << P_NROWS) - 1;
         // Register double-buffering: the loads of chunk g+1 are issued before chunk g is converted and stored, so every
         // producer thread keeps 8-16 float4 (128-256 B) in flight through the transform and the barrier waits.
-        auto issue = [&](long tile, int c, float4 (&v)[8]) -> unsigned {
+        auto issue = [&](long tile, int c, float4 (&v)[P_NROWS]) -> unsigned {
             const long m0 = tile * P_TILE_M;
             const int c0 = c * P_CHUNK_K;
             const int ksteps = (min(P_CHUNK_K, a.C_in - c0) + 15) >> 4;
@@ -96,16 +106,16 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
             const float *rowp = a.in + (m0 + rgrp) * a.in_pitch + ch;
             unsigned m = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < P_NROWS; ++i) {
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lane_ok && (m0 + rgrp + 16 * i) < a.M) {
-                    v[i] = __ldg(reinterpret_cast<const float4 *>(rowp + static_cast<long>(16 * i) * a.in_pitch));
+                if (lane_ok && (m0 + rgrp + RSTEP * i) < a.M) {
+                    v[i] = __ldg(reinterpret_cast<const float4 *>(rowp + static_cast<long>(RSTEP * i) * a.in_pitch));
                     m |= 1u << i;
                 }
             }
             return m;
         };
-        auto process = [&](int c, const float4 (&v)[8], unsigned okm, int s) {
+        auto process = [&](int c, const float4 (&v)[P_NROWS], unsigned okm, int s) {
             const int c0 = c * P_CHUNK_K;
             const int ksteps = (min(P_CHUNK_K, a.C_in - c0) + 15) >> 4;
             if (sub * 4 >= ksteps * 16) return;                      // this lane's 8-byte slot is never read by the MMA
@@ -121,20 +131,20 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
             }
             unsigned char *a_hi = smem + static_cast<size_t>(s) * STAGE_BYTES;
             unsigned char *a_lo = a_hi + P_A_TILE;
-            if (nvalid >= 4 && okm == 0xFFu) {
+            if (nvalid >= 4 && okm == FULLM) {
                 // fast path (all 8 rows inside M, all 4 channels inside C_in): no predicates, no selects
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < P_NROWS; ++i) {
                     float4 o;
                     o.x = fmaf(v[i].x, sc.x, sh.x); o.y = fmaf(v[i].y, sc.y, sh.y);
                     o.z = fmaf(v[i].z, sc.z, sh.z); o.w = fmaf(v[i].w, sc.w, sh.w);
                     if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                    store_quad<SPLIT>(a_hi, a_lo, st_off + i * 2048, o);
+                    store_quad<SPLIT>(a_hi, a_lo, st_off + i * SSTEP, o);
                 }
                 return;
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < P_NROWS; ++i) {
                 float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                 if ((okm >> i) & 1u) {
                     o.x = p_act(v[i].x, sc.x, sh.x, RELU);
@@ -142,10 +152,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
                     o.z = nvalid > 2 ? p_act(v[i].z, sc.z, sh.z, RELU) : 0.f;
                     o.w = nvalid > 3 ? p_act(v[i].w, sc.w, sh.w, RELU) : 0.f;
                 }
-                store_quad<SPLIT>(a_hi, a_lo, st_off + i * 2048, o);
+                store_quad<SPLIT>(a_hi, a_lo, st_off + i * SSTEP, o);
             }
         };
-        float4 cur[8], nxt[8];
+        float4 cur[P_NROWS], nxt[P_NROWS];
         long tile = blockIdx.x;
         int c = 0;
         bool have = tile < a.ntiles;
@@ -166,10 +176,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full + 8 * s);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+            for (int i = 0; i < P_NROWS; ++i) cur[i] = nxt[i];
             curm = nxtm; tile = ntile; c = nc; have = nhave; ++g;
         }
-    } else if (warp == 8) {
+    } else if (warp == P_PWARPS) {
         // =========================================================== MMA ISSUER
         if (lane == 0) {
             // resident weights: every K-chunk's packed image, one bulk copy (SPLIT) or one per chunk (hi halves only)
@@ -216,43 +226,70 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
         }
         __syncwarp();
     } else {
-        // =========================================================== EPILOGUE (warps 9..12 -> TMEM lane quarter warp % 4)
+        // =========================================================== EPILOGUE (4 warps -> TMEM lane quarter warp % 4)
         const int q = warp & 3;
-        const bool vec_ok = ((a.out_pitch | a.out_choff) & 3) == 0;
+        const int et = tid - (P_PRODUCERS + 32);                       // 0..127 within the epilogue group
+        const int nq = a.N_pad >> 2;                                   // float4 quads per staged row
+        const bool direct = !(((a.out_pitch | a.out_choff) & 3) == 0 && (a.C_out & 3) == 0);
+        float *stage = reinterpret_cast<float *>(smem + out_stage_off);      // [nq planes][129 x 16 B]
+        constexpr int PLANE_F = 129 * 4;                               // floats per plane (one 16-byte pad slot)
         uint32_t j = 0;
         for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++j) {
             const uint32_t buf = j & 1, aph = (j >> 1) & 1;
             mbar_wait(bar_accfull + 8 * buf, aph);
             __syncwarp();
             tc_fence_after();
-            const long m = tile * P_TILE_M + q * 32 + lane;
-            const bool row_ok = m < a.M;
-            float *orow = a.out + (row_ok ? m : 0) * a.out_pitch + a.out_choff;
+            const int row = q * 32 + lane;
+            const long m0 = tile * P_TILE_M;
+            if (direct) {
+                // odd channel counts / unaligned destinations: plain per-row stores
+                const long m = m0 + row;
+                const bool row_ok = m < a.M;
+                float *orow = a.out + (row_ok ? m : 0) * a.out_pitch + a.out_choff;
+                for (int g16 = 0; g16 < a.N_pad; g16 += 16) {
+                    float v[16];
+                    tmem_ld16(tmem_base + buf * P_ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g16), v);
+                    if (row_ok) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e)
+                            if (g16 + e < a.C_out) orow[g16 + e] = v[e];
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_accempty + 8 * buf);
+                continue;
+            }
+            // 1. TMEM -> registers -> shared planes: plane p holds quad p of all 128 rows, 16 B per row (conflict-free)
             for (int g16 = 0; g16 < a.N_pad; g16 += 16) {
                 float v[16];
                 tmem_ld16(tmem_base + buf * P_ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g16), v);
-                if (row_ok) {
 #pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        const int n = g16 + qq * 4;
-                        if (vec_ok && n + 3 < a.C_out) {
-                            *reinterpret_cast<float4 *>(orow + n) = make_float4(v[qq * 4], v[qq * 4 + 1], v[qq * 4 + 2], v[qq * 4 + 3]);
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (n + e < a.C_out) orow[n + e] = v[qq * 4 + e];
-                        }
-                    }
-                }
+                for (int qq = 0; qq < 4; ++qq)
+                    *reinterpret_cast<float4 *>(stage + ((g16 >> 2) + qq) * PLANE_F + row * 4) =
+                        make_float4(v[qq * 4], v[qq * 4 + 1], v[qq * 4 + 2], v[qq * 4 + 3]);
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_accempty + 8 * buf);
+            if (lane == 0) mbar_arrive(bar_accempty + 8 * buf);            // accumulator drained: the MMA warp may reuse it
+            asm volatile("bar.sync 1, 128;" ::: "memory");               // staging complete (epilogue warps only)
+            // 2. coalesced write-out: consecutive threads take consecutive float4 of the (row, quad) stream
+            const int cq = a.C_out >> 2;                                  // valid quads per row
+            const int total = P_TILE_M * cq;
+            for (int f = et; f < total; f += 128) {
+                const int r = f / cq, qd = f - r * cq;
+                const long m = m0 + r;
+                if (m < a.M) {
+                    const float4 val = *reinterpret_cast<const float4 *>(stage + qd * PLANE_F + r * 4);
+                    *reinterpret_cast<float4 *>(a.out + m * a.out_pitch + a.out_choff + qd * 4) = val;
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");               // staging buffer free for the next tile
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == P_PWARPS) {
         __syncwarp();
         tmem_dealloc(tmem_base, 2 * P_ACC_COLS);
     }
@@ -260,14 +297,22 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
 
 }  // namespace
 
+static size_t persist_smem(int nchunks, int N_pad, bool split, int stages) {
+    return static_cast<size_t>(stages) * (split ? 2 : 1) * P_A_TILE + static_cast<size_t>(nchunks) * (split ? 2 : 1) * N_pad * 128 +
+           static_cast<size_t>(N_pad / 4) * 129 * 16 + 1024;
+}
+static int persist_stages(int nchunks, int N_pad, bool split) {
+    for (int st = P_MAX_STAGES; st >= 2; --st)
+        if (persist_smem(nchunks, N_pad, split, st) <= 226 * 1024) return st;
+    return 0;
+}
+
 bool eml_persist_supported(const eml_conv_params *p) {
     if (p->mode != EML_CONV_1x1 || p->stats != nullptr) return false;
     if (p->precision != EML_PREC_BF16 && p->precision != EML_PREC_BF16X3) return false;
     const int N_pad = (p->C_out + 15) & ~15;
     const int nchunks = (p->C_in + P_CHUNK_K - 1) / P_CHUNK_K;
-    const bool split = p->precision == EML_PREC_BF16X3;
-    const size_t smem = static_cast<size_t>(P_STAGES) * (split ? 2 : 1) * P_A_TILE + static_cast<size_t>(nchunks) * (split ? 2 : 1) * N_pad * 128 + 1024;
-    return N_pad <= P_ACC_COLS && smem <= 225 * 1024;
+    return N_pad <= P_ACC_COLS && persist_stages(nchunks, N_pad, p->precision == EML_PREC_BF16X3) >= 3;
 }
 
 int eml_persist_forward(const eml_conv_params *p, cudaStream_t st) {
@@ -281,7 +326,8 @@ int eml_persist_forward(const eml_conv_params *p, cudaStream_t st) {
     a.relu = p->relu;
     a.ntiles = (a.M + P_TILE_M - 1) / P_TILE_M;
     const bool split = p->precision == EML_PREC_BF16X3;
-    const size_t smem = static_cast<size_t>(P_STAGES) * (split ? 2 : 1) * P_A_TILE + static_cast<size_t>(a.nchunks) * (split ? 2 : 1) * a.N_pad * 128 + 1024;
+    a.stages = persist_stages(a.nchunks, a.N_pad, split);
+    const size_t smem = persist_smem(a.nchunks, a.N_pad, split, a.stages);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -8,6 +8,6 @@ d=json.loads(open('gpurun_out/bench_n1.json').read().strip().split('\n')[-1])
 print('value',d['value'],'e2e',d['e2e']['value'],'ms',d['ms_per_step'],'cpu',d['cpu_baseline'])
 print(json.dumps(d['roofline']['families']))
 PY
-KF='regex:conv_gemm|conv3x3_rows|conv1x1_persist|stem_kernel|head_pool|linear_kernel|sg_render|conv_simt'
+KF='regex:conv|stem_kernel|head_pool|linear_kernel|sg_render'
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KF" -s 312 -c 104 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches exit $?"
