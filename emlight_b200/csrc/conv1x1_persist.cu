@@ -180,8 +180,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
             curm = nxtm; tile = ntile; c = nc; have = nhave; ++g;
         }
     } else if (warp == P_PWARPS) {
-        // =========================================================== MMA ISSUER
-        if (lane == 0) {
+        // =========================================================== MMA ISSUER (warp-uniform loops, one elected lane issues)
+        const bool leader = elect_one();
+        if (leader) {
             // resident weights: every K-chunk's packed image, one bulk copy (SPLIT) or one per chunk (hi halves only)
             if (SPLIT) {
                 const uint32_t bytes = static_cast<uint32_t>(a.nchunks) * w_chunk_sm;
@@ -192,25 +193,28 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
                 for (int c = 0; c < a.nchunks; ++c)
                     bulk_g2s(smem_u32(w_sm + c * b_tile_bytes), a.wpack + static_cast<size_t>(c) * 2 * b_tile_bytes, b_tile_bytes, bar_w);
             }
-            mbar_wait(bar_w, 0);
-            const uint32_t idesc = make_idesc_bf16(P_TILE_M, a.N_pad);
-            uint32_t g = 0, j = 0;
-            for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++j) {
-                const uint32_t buf = j & 1, aph = (j >> 1) & 1;
-                mbar_wait(bar_accempty + 8 * buf, aph ^ 1);           // epilogue drained this accumulator
+        }
+        mbar_wait(bar_w, 0);
+        const uint32_t idesc = make_idesc_bf16(P_TILE_M, a.N_pad);
+        const uint64_t dA0 = make_sw128_desc(smem_u32(smem));                 // stage 0, hi image
+        const uint64_t dB0 = make_sw128_desc(smem_u32(w_sm));                 // chunk 0, hi image
+        const uint32_t stage16 = STAGE_BYTES >> 4, alo16 = P_A_TILE >> 4;     // 16-byte units for the address field
+        const uint32_t wchunk16 = static_cast<uint32_t>(w_chunk_sm) >> 4, blo16 = static_cast<uint32_t>(b_tile_bytes) >> 4;
+        uint32_t g = 0, j = 0;
+        for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++j) {
+            const uint32_t buf = j & 1, aph = (j >> 1) & 1;
+            mbar_wait(bar_accempty + 8 * buf, aph ^ 1);                       // epilogue drained this accumulator
+            const uint32_t d_tmem = tmem_base + buf * P_ACC_COLS;
+            for (int c = 0; c < a.nchunks; ++c, ++g) {
+                const uint32_t s = g % P_STAGES;
+                const uint32_t ph = (g / P_STAGES) & 1;
+                mbar_wait(bar_full + 8 * s, ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * P_ACC_COLS;
-                for (int c = 0; c < a.nchunks; ++c, ++g) {
-                    const int s = g % P_STAGES;
-                    const uint32_t ph = (g / P_STAGES) & 1;
-                    mbar_wait(bar_full + 8 * s, ph);
-                    tc_fence_after();
+                if (leader) {
                     const int kvalid = min(P_CHUNK_K, a.C_in - c * P_CHUNK_K);
                     const int ksteps = (kvalid + 15) >> 4;
-                    const uint32_t a_hi_s = smem_u32(smem + static_cast<size_t>(s) * STAGE_BYTES);
-                    const uint32_t b_hi_s = smem_u32(w_sm + static_cast<size_t>(c) * w_chunk_sm);
-                    const uint64_t da_hi = make_sw128_desc(a_hi_s), db_hi = make_sw128_desc(b_hi_s);
-                    const uint64_t da_lo = make_sw128_desc(a_hi_s + P_A_TILE), db_lo = make_sw128_desc(b_hi_s + b_tile_bytes);
+                    const uint64_t da_hi = dA0 + static_cast<uint64_t>(s * stage16), da_lo = da_hi + alo16;
+                    const uint64_t db_hi = dB0 + static_cast<uint64_t>(static_cast<uint32_t>(c) * wchunk16), db_lo = db_hi + blo16;
                     for (int k = 0; k < ksteps; ++k) {
                         const uint64_t adv = static_cast<uint64_t>(k * 2);
                         umma_bf16(d_tmem, da_hi + adv, db_hi + adv, idesc, (c | k) != 0 ? 1u : 0u);
@@ -220,11 +224,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
                         }
                     }
                     umma_commit(bar_empty + 8 * s);
+                    if (c == a.nchunks - 1) umma_commit(bar_accfull + 8 * buf);
                 }
-                umma_commit(bar_accfull + 8 * buf);
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else {
         // =========================================================== EPILOGUE (4 warps -> TMEM lane quarter warp % 4)
         const int q = warp & 3;

@@ -354,58 +354,60 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv3x3_roll_kernel(const RollA
             }
         }
     } else if (warp == 8) {
-        // ======================================================= MMA ISSUER
-        if (lane == 0) {
+        // ======================================================= MMA ISSUER (warp-uniform loops, one elected lane issues)
+        const bool leader = elect_one();
+        if (leader) {
             mbar_expect_tx(bar_w, static_cast<uint32_t>(w_bytes));
             bulk_g2s(smem_u32(w_sm), ra.wcat, static_cast<uint32_t>(w_bytes), bar_w);
-            mbar_wait(bar_w, 0);
-            const uint32_t idesc_cat = make_idesc_bf16(ROWS_TILE, SPLIT ? 32 : a.N_pad);
-            const uint32_t idesc_16 = make_idesc_bf16(ROWS_TILE, 16);
-            const uint32_t wlbo = static_cast<uint32_t>(wn * 16);
-            const uint32_t w_s = smem_u32(w_sm), hi_s = smem_u32(ring_hi), lo_s = smem_u32(ring_lo);
-            uint32_t R0 = 0, j = 0;
-            for (long unit = blockIdx.x; unit < ra.nunits; unit += gridDim.x) {
-                long b; int x0, y0, nrows;
-                decode(unit, b, x0, y0, nrows);
-                // rows R0 (y0-1) and R0+1 (y0) must be present before the first output row
-                for (int r = 0; r < 2; ++r) mbar_wait(bar_rfull + 8 * ((R0 + r) % RING), ((R0 + r) / RING) & 1);
-                for (int i = 0; i < nrows; ++i, ++j) {
-                    const uint32_t buf = j & 1, aph = (j >> 1) & 1;
-                    const uint32_t Rn = R0 + i + 2;                                  // newest row needed (y+1)
-                    mbar_wait(bar_rfull + 8 * (Rn % RING), (Rn / RING) & 1);
-                    mbar_wait(bar_accempty + 8 * buf, aph ^ 1);
-                    tc_fence_after();
+        }
+        mbar_wait(bar_w, 0);
+        const uint32_t idesc_cat = make_idesc_bf16(ROWS_TILE, SPLIT ? 32 : a.N_pad);
+        const uint32_t idesc_16 = make_idesc_bf16(ROWS_TILE, 16);
+        // descriptor bases; per MMA only the 14-bit start-address field (16-byte units) moves
+        const uint64_t dA_hi = make_nosw_desc(smem_u32(ring_hi), PLANE, 128);
+        const uint64_t dA_lo = make_nosw_desc(smem_u32(ring_lo), PLANE, 128);
+        const uint64_t dW = make_nosw_desc(smem_u32(w_sm), static_cast<uint32_t>(wn * 16), 128);
+        uint32_t R0 = 0, j = 0;
+        for (long unit = blockIdx.x; unit < ra.nunits; unit += gridDim.x) {
+            long b; int x0, y0, nrows;
+            decode(unit, b, x0, y0, nrows);
+            // rows R0 (y0-1) and R0+1 (y0) must be present before the first output row
+            for (int r = 0; r < 2; ++r) mbar_wait(bar_rfull + 8 * ((R0 + r) % RING), ((R0 + r) / RING) & 1);
+            for (int i = 0; i < nrows; ++i, ++j) {
+                const uint32_t buf = j & 1, aph = (j >> 1) & 1;
+                const uint32_t Rn = R0 + i + 2;                                      // newest row needed (y+1)
+                mbar_wait(bar_rfull + 8 * (Rn % RING), (Rn / RING) & 1);
+                mbar_wait(bar_accempty + 8 * buf, aph ^ 1);
+                tc_fence_after();
+                if (leader) {
                     const uint32_t d_tmem = tmem_base + buf * 32;
                     uint32_t acc = 0;
-#pragma unroll 1
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int dy = tap / 3, dx = tap - dy * 3;
-                        const uint32_t slot = (R0 + i + dy) % RING;
 #pragma unroll
-                        for (int ks = 0; ks < KC / 2; ++ks) {
-                            const uint32_t aoff = slot * SLOT_BYTES + static_cast<uint32_t>((2 * ks * ROWS_PP + dx) * 16);
-                            const uint32_t woff = static_cast<uint32_t>((tap * KC + 2 * ks) * wn * 16);
-                            const uint64_t dah = make_nosw_desc(hi_s + aoff, PLANE, 128);
-                            const uint64_t dbw = make_nosw_desc(w_s + woff, wlbo, 128);
-                            umma_bf16(d_tmem, dah, dbw, idesc_cat, acc);          // hi*[hi|lo] -> cols 0..31
-                            if (SPLIT) {
-                                const uint64_t dal = make_nosw_desc(lo_s + aoff, PLANE, 128);
-                                umma_bf16(d_tmem, dal, dbw, idesc_16, 1u);            // lo*hi -> cols 0..15 (first 16 rows of the operand)
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const uint32_t slot16 = ((R0 + i + dy) % RING) * (SLOT_BYTES / 16);
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                            for (int ks = 0; ks < KC / 2; ++ks) {
+                                const uint64_t aoff = slot16 + static_cast<uint32_t>(2 * ks * ROWS_PP + dx);
+                                const uint64_t woff = static_cast<uint32_t>(((dy * 3 + dx) * KC + 2 * ks) * wn);
+                                umma_bf16(d_tmem, dA_hi + aoff, dW + woff, idesc_cat, acc);       // hi*[hi|lo] -> cols 0..31
+                                if (SPLIT) umma_bf16(d_tmem, dA_lo + aoff, dW + woff, idesc_16, 1u);  // lo*hi -> cols 0..15
+                                acc = 1;
                             }
-                            acc = 1;
                         }
                     }
-                    umma_commit(bar_rempty + 8 * ((R0 + i) % RING));                 // row y-1 is dead after this output row
-                    if (i == nrows - 1) {                                            // band ends: rows y and y+1 die as well
+                    umma_commit(bar_rempty + 8 * ((R0 + i) % RING));                     // row y-1 is dead after this output row
+                    if (i == nrows - 1) {                                                // band ends: rows y and y+1 die as well
                         umma_commit(bar_rempty + 8 * ((R0 + i + 1) % RING));
                         umma_commit(bar_rempty + 8 * ((R0 + i + 2) % RING));
                     }
                     umma_commit(bar_accfull + 8 * buf);
                 }
-                R0 += static_cast<uint32_t>(nrows + 2);
+                __syncwarp();
             }
+            R0 += static_cast<uint32_t>(nrows + 2);
         }
-        __syncwarp();
     } else {
         // ======================================================= EPILOGUE
         const int q4 = warp & 3;

@@ -104,6 +104,19 @@ __host__ __device__ constexpr uint32_t sw128_offset(int row, int k) {
 }
 
 
+// One elected lane of a converged warp (elect.sync).  Issue loops are written warp-uniformly and only the tcgen05
+// instructions are predicated with this: inside `if (lane == 0)` ptxas must treat every descriptor as thread-varying and
+// emits an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~17 dependent instructions) in front of each UTCHMMA.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // K-major NO-SWIZZLE ("interleave") descriptor: 8-row x 16-byte core matrices; rows inside a core matrix are 16 B
 // apart, core matrices are SBO bytes apart along M/N and LBO bytes apart along K (cute: ((8,n),2):((1,SBO),LBO) in
 // 16-byte units).  With SBO = 128 the M rows are uniformly 16 B apart, so a row shift is just a start-address shift.
