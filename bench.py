@@ -146,10 +146,9 @@ def main():
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     import emlight_b200 as E
-    from emlight_b200 import build
+    from emlight_b200 import build, parallel
+    parallel.init("nccl", dev)
     build.build()
     B = args.batch
     torch.manual_seed(0)
@@ -178,10 +177,7 @@ def main():
             fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return parallel.max_over_ranks(e0.elapsed_time(e1), dev)
 
     for _ in range(warmup):
         step(x)
