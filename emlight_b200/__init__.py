@@ -5,6 +5,7 @@ Public surface mirrors the reference's:
     from emlight_b200 import DenseNet            # RegressionNetwork/DenseNet.py: DenseNet
     from emlight_b200 import SamplesLoss         # RegressionNetwork/geomloss: SamplesLoss  (gmloss: GMSamplesLoss)
     from emlight_b200 import sphere_points, convert_to_panorama     # RegressionNetwork/util.py
+    from emlight_b200 import SphereConv2D, SPADE, SPADEResnetBlock, SPADEGenerator   # GenProjector/models/networks/*
 
 Module-name shims for unchanged reference scripts live in ``emlight_b200/dropin`` (put it on sys.path).
 All arithmetic runs in hand-written CUDA reached through the C ABI of include/emlight_b200.h.
@@ -12,5 +13,7 @@ All arithmetic runs in hand-written CUDA reached through the C ABI of include/em
 from .panorama import convert_to_panorama, render_from_params, sphere_points  # noqa: F401
 from .samples_loss import GMSamplesLoss, SamplesLoss  # noqa: F401
 from .densenet import DenseNet  # noqa: F401
+from .genprojector import SPADE, ConvEncoder, SPADEGenerator, SPADEResnetBlock, SphereConv2D  # noqa: F401
 
-__all__ = ["DenseNet", "SamplesLoss", "GMSamplesLoss", "sphere_points", "convert_to_panorama", "render_from_params"]
+__all__ = ["DenseNet", "SamplesLoss", "GMSamplesLoss", "sphere_points", "convert_to_panorama", "render_from_params",
+           "SphereConv2D", "SPADE", "SPADEResnetBlock", "ConvEncoder", "SPADEGenerator"]

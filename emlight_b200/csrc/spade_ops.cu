@@ -1,0 +1,283 @@
+// GenProjector (SPADE / SphereNet generator) support kernels, sm_100a.  All activations NHWC fp32.
+//
+// SphereConv2D (GenProjector/models/networks/spherenet/sphere_cnn.py:87-124) = bilinear resampling on a per-pixel
+// tangent-plane 3x3 pattern + a stride-3 3x3 convolution, i.e.  y[m, o] = b_o + sum_{tap,c} W[o,c,tap] * S[m,tap,c]
+// with S[m,tap,c] = sum_{t<4} w_t(m,tap) * x[src_t(m,tap), c].  The reference materialises S as a 9x larger image with
+// grid_sample; here `eml_im2col_lut` builds the (M, 9*Cp) operand of the tcgen05 GEMM (eml_conv_forward, 1x1 mode)
+// straight from a per-(H,W,stride) lookup table of 4 taps + weights per (pixel, tap) -- the same kernel serves the
+// regular stride-2 3x3 convolutions of the ConvEncoder with a one-tap table.  The producer's per-channel bias and the
+// consumer's activation (ReLU of mlp_shared, LeakyReLU(0.2) of the SPADE blocks) are applied to the source values
+// before blending, so those intermediate tensors are never written.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return v > 0.f ? v : 0.2f * v;
+    return v;
+}
+
+// A[m, tap*Cp + c] = sum_t w[m,tap,t] * act(x[b, idx[m,tap,t], c] + bias[c]);  one thread = one float4 of channels.
+__global__ void __launch_bounds__(256) im2col_lut_kernel(const float *__restrict__ x, int x_pitch, int C, int Cp,
+                                                         const int *__restrict__ idx, const float *__restrict__ wgt,
+                                                         const float *__restrict__ bias, int act, float *__restrict__ A,
+                                                         long Mo_img, long in_img_pixels, long total_quads) {
+    const int cq = Cp >> 2;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total_quads;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int q = static_cast<int>(i % cq);
+        const long mt = i / cq;                       // (m, tap)
+        const int tap = static_cast<int>(mt % 9);
+        const long m = mt / 9;
+        const long b = m / Mo_img;
+        const long mp = m - b * Mo_img;               // pixel within the output image
+        const int c = q * 4;
+        const int4 id = *reinterpret_cast<const int4 *>(idx + (mp * 9 + tap) * 4);
+        const float4 w = *reinterpret_cast<const float4 *>(wgt + (mp * 9 + tap) * 4);
+        float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias != nullptr) {
+            bs.x = bias[c];
+            if (c + 1 < C) bs.y = bias[c + 1];
+            if (c + 2 < C) bs.z = bias[c + 2];
+            if (c + 3 < C) bs.w = bias[c + 3];
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float *xb = x + b * in_img_pixels * x_pitch + c;
+        const int ids[4] = {id.x, id.y, id.z, id.w};
+        const float ws[4] = {w.x, w.y, w.z, w.w};
+        const bool full = c + 3 < C && (x_pitch & 3) == 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (ids[t] < 0) continue;                 // zero padding (grid_sample padding_mode='zeros' / conv padding)
+            const float *p = xb + static_cast<long>(ids[t]) * x_pitch;
+            float4 v;
+            if (full) {
+                v = __ldg(reinterpret_cast<const float4 *>(p));
+            } else {
+                v.x = p[0];
+                v.y = c + 1 < C ? p[1] : 0.f;
+                v.z = c + 2 < C ? p[2] : 0.f;
+                v.w = c + 3 < C ? p[3] : 0.f;
+            }
+            acc.x = fmaf(ws[t], apply_act(v.x + bs.x, act), acc.x);
+            acc.y = fmaf(ws[t], apply_act(v.y + bs.y, act), acc.y);
+            acc.z = fmaf(ws[t], apply_act(v.z + bs.z, act), acc.z);
+            acc.w = fmaf(ws[t], apply_act(v.w + bs.w, act), acc.w);
+        }
+        if (c + 1 >= C) acc.y = 0.f;
+        if (c + 2 >= C) acc.z = 0.f;
+        if (c + 3 >= C) acc.w = 0.f;
+        *reinterpret_cast<float4 *>(A + (m * 9 + tap) * Cp + c) = acc;
+    }
+}
+
+// out = ((x - mean_c) * inv_c) * (1 + g + bg_c) + (b + bb_c), optional LeakyReLU(0.2)   (normalization.py:101-115)
+// gb holds gamma in channels [0,C) and beta in [C,2C) of each pixel (one GEMM with concatenated weights).
+__global__ void __launch_bounds__(256) spade_modulate_kernel(const float *__restrict__ x, int x_pitch,
+                                                             const float *__restrict__ mean, const float *__restrict__ inv,
+                                                             const float *__restrict__ gb, int gb_pitch,
+                                                             const float *__restrict__ bias_g, const float *__restrict__ bias_b,
+                                                             float *__restrict__ out, int out_pitch, long M, int C, int lrelu) {
+    const long total = M * C;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        const long m = i / C;
+        const float n = (x[m * x_pitch + c] - mean[c]) * inv[c];
+        const float g = gb[m * gb_pitch + c] + bias_g[c];
+        const float b = gb[m * gb_pitch + C + c] + bias_b[c];
+        float v = fmaf(n, 1.f + g, b);
+        if (lrelu) v = v > 0.f ? v : 0.2f * v;
+        out[m * out_pitch + c] = v;
+    }
+}
+
+// out = a + bias_a (+ r + bias_r)     (SPADEResnetBlock output x_s + dx, architecture.py:51-58)
+__global__ void __launch_bounds__(256) bias_residual_kernel(const float *__restrict__ a, int a_pitch, const float *__restrict__ bias_a,
+                                                            const float *__restrict__ r, int r_pitch, const float *__restrict__ bias_r,
+                                                            float *__restrict__ out, int out_pitch, long M, int C) {
+    const long total = M * C;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        const long m = i / C;
+        float v = a[m * a_pitch + c] + (bias_a ? bias_a[c] : 0.f);
+        if (r != nullptr) v += r[m * r_pitch + c] + (bias_r ? bias_r[c] : 0.f);
+        out[m * out_pitch + c] = v;
+    }
+}
+
+// nearest-neighbour resize NHWC -> NHWC (F.interpolate(mode='nearest'): src = floor(dst * in / out)); also the x2 upsample
+__global__ void __launch_bounds__(256) resize_nearest_kernel(const float *__restrict__ x, int x_pitch, int Hi, int Wi,
+                                                             float *__restrict__ out, int out_pitch, int Ho, int Wo, int C, long B,
+                                                             int src_nchw) {
+    const long total = B * Ho * Wo * C;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        long t = i / C;
+        const int xo = static_cast<int>(t % Wo); t /= Wo;
+        const int yo = static_cast<int>(t % Ho);
+        const long b = t / Ho;
+        // PyTorch: src = min(floor(dst * scale), in - 1) with scale = in / out evaluated in float
+        const int ys = min(static_cast<int>(floorf(yo * (static_cast<float>(Hi) / Ho))), Hi - 1);
+        const int xs = min(static_cast<int>(floorf(xo * (static_cast<float>(Wi) / Wo))), Wi - 1);
+        const float v = src_nchw ? x[((b * C + c) * Hi + ys) * static_cast<long>(Wi) + xs]
+                                 : x[((b * Hi + ys) * static_cast<long>(Wi) + xs) * x_pitch + c];
+        out[((b * Ho + yo) * static_cast<long>(Wo) + xo) * out_pitch + c] = v;
+    }
+}
+
+// bilinear resize NCHW -> NHWC, align_corners=False (F.interpolate(mode='bilinear'), generator.py:116)
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(const float *__restrict__ x, int Hi, int Wi, float *__restrict__ out,
+                                                              int out_pitch, int Ho, int Wo, int C, long B) {
+    const long total = B * Ho * Wo * C;
+    const float sy = static_cast<float>(Hi) / Ho, sx = static_cast<float>(Wi) / Wo;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        long t = i / C;
+        const int xo = static_cast<int>(t % Wo); t /= Wo;
+        const int yo = static_cast<int>(t % Ho);
+        const long b = t / Ho;
+        const float fy = fmaxf((yo + 0.5f) * sy - 0.5f, 0.f), fx = fmaxf((xo + 0.5f) * sx - 0.5f, 0.f);
+        const int y0 = min(static_cast<int>(fy), Hi - 1), x0 = min(static_cast<int>(fx), Wi - 1);
+        const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
+        const float ly = fy - y0, lx = fx - x0;
+        const float *p = x + (b * C + c) * static_cast<long>(Hi) * Wi;
+        const float v = (1.f - ly) * ((1.f - lx) * p[y0 * static_cast<long>(Wi) + x0] + lx * p[y0 * static_cast<long>(Wi) + x1]) +
+                        ly * ((1.f - lx) * p[y1 * static_cast<long>(Wi) + x0] + lx * p[y1 * static_cast<long>(Wi) + x1]);
+        out[((b * Ho + yo) * static_cast<long>(Wo) + xo) * out_pitch + c] = v;
+    }
+}
+
+// InstanceNorm2d(affine=False, eps) + optional LeakyReLU(0.2): one block per (b, 32-channel group); two passes over H*W.
+__global__ void __launch_bounds__(256) instance_norm_kernel(const float *__restrict__ x, int x_pitch, float *__restrict__ out,
+                                                            int out_pitch, int HW, int C, float eps, int lrelu) {
+    __shared__ double s1[8][32], s2[8][32];
+    __shared__ float s_mean[32], s_inv[32];
+    const long b = blockIdx.y;
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int row = threadIdx.x >> 5;                              // 8 pixel lanes
+    const float *xb = x + b * HW * static_cast<long>(x_pitch);
+    double a1 = 0.0, a2 = 0.0;
+    if (c < C)
+        for (int p = row; p < HW; p += 8) {
+            const double v = xb[static_cast<long>(p) * x_pitch + c];
+            a1 += v; a2 += v * v;
+        }
+    s1[row][threadIdx.x & 31] = a1; s2[row][threadIdx.x & 31] = a2;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int r = 0; r < 8; ++r) { t1 += s1[r][threadIdx.x]; t2 += s2[r][threadIdx.x]; }
+        const double mean = t1 / HW;
+        double var = t2 / HW - mean * mean;                       // biased variance, like F.instance_norm
+        if (var < 0.0) var = 0.0;
+        s_mean[threadIdx.x] = static_cast<float>(mean);
+        s_inv[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+    __syncthreads();
+    if (c < C) {
+        const float mean = s_mean[threadIdx.x & 31], inv = s_inv[threadIdx.x & 31];
+        float *ob = out + b * HW * static_cast<long>(out_pitch);
+        for (int p = row; p < HW; p += 8) {
+            float v = (xb[static_cast<long>(p) * x_pitch + c] - mean) * inv;
+            if (lrelu) v = v > 0.f ? v : 0.2f * v;
+            ob[static_cast<long>(p) * out_pitch + c] = v;
+        }
+    }
+}
+
+// out_nchw[b,c,p] = (tanh(x[b,p,c] + bias[c]) + 1) * scale      (generator.py:85-86)
+__global__ void __launch_bounds__(256) tanh_out_kernel(const float *__restrict__ x, int x_pitch, const float *__restrict__ bias,
+                                                       float *__restrict__ out, long B, int HW, int C, float scale) {
+    const long total = B * C * HW;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(i % HW);
+        long t = i / HW;
+        const int c = static_cast<int>(t % C);
+        const long b = t / C;
+        out[i] = (tanhf(x[(b * HW + p) * x_pitch + c] + (bias ? bias[c] : 0.f)) + 1.f) * scale;
+    }
+}
+
+inline unsigned grid_for(long total, int per_block = 256) {
+    long b = (total + per_block - 1) / per_block;
+    const long cap = 148L * 16;
+    return static_cast<unsigned>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+extern "C" int eml_im2col_lut(const float *x, int x_pitch, int C, int Cp, const int *lut_idx, const float *lut_w,
+                              const float *bias, int act, float *A, int B, long out_pixels, long in_pixels, void *stream) {
+    EML_CHECK_PTR(x); EML_CHECK_PTR(lut_idx); EML_CHECK_PTR(lut_w); EML_CHECK_PTR(A);
+    EML_CHECK_ALIGN16(lut_idx); EML_CHECK_ALIGN16(lut_w); EML_CHECK_ALIGN16(A);
+    if (B <= 0 || C <= 0 || Cp < C || (Cp & 3) || x_pitch < C || out_pixels <= 0 || in_pixels <= 0) return EML_E_SHAPE;
+    if (act < 0 || act > 2) return EML_E_ARG;
+    if ((x_pitch & 3) == 0) EML_CHECK_ALIGN16(x);
+    const long total = static_cast<long>(B) * out_pixels * 9 * (Cp / 4);
+    im2col_lut_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_pitch, C, Cp, lut_idx, lut_w, bias, act, A,
+                                                                                   out_pixels, in_pixels, total);
+    return eml_launch_status();
+}
+
+extern "C" int eml_spade_modulate(const float *x, int x_pitch, const float *mean, const float *inv_std, const float *gamma_beta,
+                                  int gb_pitch, const float *bias_gamma, const float *bias_beta, float *out, int out_pitch,
+                                  long M, int C, int leaky_relu, void *stream) {
+    EML_CHECK_PTR(x); EML_CHECK_PTR(mean); EML_CHECK_PTR(inv_std); EML_CHECK_PTR(gamma_beta); EML_CHECK_PTR(bias_gamma);
+    EML_CHECK_PTR(bias_beta); EML_CHECK_PTR(out);
+    if (M <= 0 || C <= 0 || x_pitch < C || gb_pitch < 2 * C || out_pitch < C) return EML_E_SHAPE;
+    spade_modulate_kernel<<<grid_for(M * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_pitch, mean, inv_std, gamma_beta, gb_pitch,
+                                                                                       bias_gamma, bias_beta, out, out_pitch, M, C, leaky_relu);
+    return eml_launch_status();
+}
+
+extern "C" int eml_bias_residual(const float *a, int a_pitch, const float *bias_a, const float *r, int r_pitch, const float *bias_r,
+                                 float *out, int out_pitch, long M, int C, void *stream) {
+    EML_CHECK_PTR(a); EML_CHECK_PTR(out);
+    if (M <= 0 || C <= 0 || a_pitch < C || out_pitch < C || (r != nullptr && r_pitch < C)) return EML_E_SHAPE;
+    bias_residual_kernel<<<grid_for(M * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, a_pitch, bias_a, r, r_pitch, bias_r, out,
+                                                                                      out_pitch, M, C);
+    return eml_launch_status();
+}
+
+extern "C" int eml_resize_nearest(const float *x, int x_pitch, int Hi, int Wi, float *out, int out_pitch, int Ho, int Wo, int C, int B,
+                                  int src_is_nchw, void *stream) {
+    EML_CHECK_PTR(x); EML_CHECK_PTR(out);
+    if (B <= 0 || C <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0 || out_pitch < C || (!src_is_nchw && x_pitch < C)) return EML_E_SHAPE;
+    const long total = static_cast<long>(B) * Ho * Wo * C;
+    resize_nearest_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_pitch, Hi, Wi, out, out_pitch, Ho, Wo, C, B,
+                                                                                       src_is_nchw);
+    return eml_launch_status();
+}
+
+extern "C" int eml_resize_bilinear_nchw(const float *x, int Hi, int Wi, float *out, int out_pitch, int Ho, int Wo, int C, int B,
+                                        void *stream) {
+    EML_CHECK_PTR(x); EML_CHECK_PTR(out);
+    if (B <= 0 || C <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0 || out_pitch < C) return EML_E_SHAPE;
+    const long total = static_cast<long>(B) * Ho * Wo * C;
+    resize_bilinear_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, Hi, Wi, out, out_pitch, Ho, Wo, C, B);
+    return eml_launch_status();
+}
+
+extern "C" int eml_instance_norm(const float *x, int x_pitch, float *out, int out_pitch, int B, int HW, int C, float eps,
+                                 int leaky_relu, void *stream) {
+    EML_CHECK_PTR(x); EML_CHECK_PTR(out);
+    if (B <= 0 || C <= 0 || HW <= 0 || x_pitch < C || out_pitch < C) return EML_E_SHAPE;
+    dim3 grid((C + 31) / 32, B);
+    instance_norm_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_pitch, out, out_pitch, HW, C, eps, leaky_relu);
+    return eml_launch_status();
+}
+
+extern "C" int eml_tanh_to_nchw(const float *x, int x_pitch, const float *bias, float *out, int B, int HW, int C, float scale,
+                                void *stream) {
+    EML_CHECK_PTR(x); EML_CHECK_PTR(out);
+    if (B <= 0 || C <= 0 || HW <= 0 || x_pitch < C) return EML_E_SHAPE;
+    const long total = static_cast<long>(B) * C * HW;
+    tanh_out_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_pitch, bias, out, B, HW, C, scale);
+    return eml_launch_status();
+}

@@ -1,0 +1,483 @@
+"""GenProjector SPADE / SphereNet generator -- drop-in for ``GenProjector/models/networks`` (inference path), sm_100a.
+
+Classes keep the reference's names, constructor arguments and ``state_dict`` keys:
+
+  SphereConv2D(in_c, out_c, stride=1, bias=True, mode='bilinear')      spherenet/sphere_cnn.py:87-124
+  SPADE(config_text, norm_nc, label_nc)                                normalization.py:68-115
+  SPADEResnetBlock(fin, fout, opt)                                     architecture.py:22-69
+  ConvEncoder(opt)                                                     generator.py:90-126
+  SPADEGenerator(opt).forward(input, crop) -> (B,3,128,256) in [0,50]  generator.py:17-88
+
+Spectral-normalised layers carry ``weight_orig / weight_u / weight_v`` exactly like ``torch.nn.utils.spectral_norm`` so
+reference checkpoints load; in eval mode the weight is ``weight_orig / (u . W v)`` (no power iteration), folded into the
+packed bf16 hi/lo weight images at pack time.  Every convolution is LUT gather (``eml_im2col_lut``) + tcgen05 GEMM
+(``eml_conv_forward``); normalisation / modulation / resize / tanh are the small kernels of ``csrc/spade_ops.cu``.
+
+This round implements the eval-mode forward (what ``GenProjector/test.py:21-39`` runs: running-statistics BatchNorm inside
+SPADE, stored spectral-norm vectors).  Training-mode forward (batch-statistic SyncBN, power iteration) and backward raise.
+"""
+import math
+import re
+from functools import lru_cache
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.nn.parameter import Parameter
+
+from . import _lib
+from ._lib import ConvParams
+
+_NHIDDEN = 128
+_MAX_N = 256          # output channels per GEMM launch (TMEM columns of the generic implicit-GEMM kernel)
+
+
+def _up4(n):
+    return (n + 3) & ~3
+
+
+# ----------------------------------------------------------------------------------------------------- sampling tables
+@lru_cache(maxsize=None)
+def _sphere_coords(h, w, stride):
+    """(Ho,Wo,3,3,2) float64 (row, col) sample positions of SphereConv2D (sphere_cnn.py:11-58): gnomonic projection of a
+    3x3 tangent patch with d_phi = pi/h, d_theta = 2pi/w around every `stride`-th pixel; centre forced to the pixel itself
+    (:57), longitude wrapped modulo w (:55)."""
+    dphi, dth = math.pi / h, 2 * math.pi / w
+    tx, ty = math.tan(dth), math.tan(dphi)
+    sy = ty / math.cos(dth)
+    px = np.array([[-tx, 0.0, tx]] * 3)                                  # get_xy(): x offsets per column
+    px[1, 1] = 1.0
+    py = np.array([[sy, ty, sy], [0.0, 1.0, 0.0], [-sy, -ty, -sy]])
+    rr = np.arange(0, h, stride, dtype=np.float64).reshape(-1, 1, 1, 1)
+    cc = np.arange(0, w, stride, dtype=np.float64).reshape(1, -1, 1, 1)
+    phi = -((rr + 0.5) / h * math.pi - math.pi / 2)
+    theta = (cc + 0.5) / w * 2 * math.pi - math.pi
+    rho = np.sqrt(px ** 2 + py ** 2)
+    nu = np.arctan(rho)
+    nphi = np.arcsin(np.cos(nu) * np.sin(phi) + py * np.sin(nu) * np.cos(phi) / rho)
+    nth = theta + np.arctan(px * np.sin(nu) / (rho * np.cos(phi) * np.cos(nu) - py * np.sin(phi) * np.sin(nu)))
+    r = (-nphi + math.pi / 2) * h / math.pi - 0.5
+    c = ((nth + math.pi) * w / 2 / math.pi - 0.5 + w) % w
+    r, c = np.broadcast_arrays(r, c)
+    out = np.stack((r, c), -1).copy()
+    out[:, :, 1, 1, 0] = np.arange(0, h, stride).reshape(-1, 1)
+    out[:, :, 1, 1, 1] = np.arange(0, w, stride).reshape(1, -1)
+    return out
+
+
+@lru_cache(maxsize=None)
+def _sphere_lut(h, w, stride):
+    """4 bilinear taps per (output pixel, filter tap) reproducing grid_sample(bilinear, zeros, align_corners=False) on the
+    grid the reference builds (sphere_cnn.py:75-84): normalised g = 2p/size - 1 in fp32, un-normalised ((g+1)*size-1)/2."""
+    co = _sphere_coords(h, w, stride)
+    gy = (co[..., 0] * 2 / h - 1).astype(np.float32)
+    gx = (co[..., 1] * 2 / w - 1).astype(np.float32)
+    iy = ((gy + np.float32(1)) * np.float32(h) - np.float32(1)) / np.float32(2)
+    ix = ((gx + np.float32(1)) * np.float32(w) - np.float32(1)) / np.float32(2)
+    y0 = np.floor(iy); x0 = np.floor(ix)
+    wy1 = (iy - y0).astype(np.float32); wx1 = (ix - x0).astype(np.float32)
+    wy0 = (y0 + np.float32(1) - iy).astype(np.float32); wx0 = (x0 + np.float32(1) - ix).astype(np.float32)
+    y0 = y0.astype(np.int64); x0 = x0.astype(np.int64)
+    idx = np.full(co.shape[:4] + (4,), -1, np.int32)
+    wgt = np.zeros(co.shape[:4] + (4,), np.float32)
+    for t, (yy, xx, ww) in enumerate(((y0, x0, wy0 * wx0), (y0, x0 + 1, wy0 * wx1), (y0 + 1, x0, wy1 * wx0), (y0 + 1, x0 + 1, wy1 * wx1))):
+        ok = (yy >= 0) & (yy < h) & (xx >= 0) & (xx < w)
+        idx[..., t] = np.where(ok, yy * w + xx, -1)
+        wgt[..., t] = np.where(ok, ww, 0)
+    ho, wo = co.shape[:2]
+    return idx.reshape(ho * wo, 9, 4), wgt.reshape(ho * wo, 9, 4), ho, wo
+
+
+@lru_cache(maxsize=None)
+def _conv_s2_lut(h, w):
+    """Regular 3x3, stride 2, padding 1 convolution (ConvEncoder, generator.py:100-104) as a one-tap table."""
+    ho, wo = (h + 1) // 2, (w + 1) // 2
+    yo, xo = np.meshgrid(np.arange(ho), np.arange(wo), indexing="ij")
+    idx = np.full((ho, wo, 9, 4), -1, np.int32)
+    wgt = np.zeros((ho, wo, 9, 4), np.float32)
+    for ky in range(3):
+        for kx in range(3):
+            yy, xx = 2 * yo + ky - 1, 2 * xo + kx - 1
+            ok = (yy >= 0) & (yy < h) & (xx >= 0) & (xx < w)
+            idx[:, :, ky * 3 + kx, 0] = np.where(ok, yy * w + xx, -1)
+            wgt[:, :, ky * 3 + kx, 0] = ok
+    return idx.reshape(ho * wo, 9, 4), wgt.reshape(ho * wo, 9, 4), ho, wo
+
+
+class _Luts:
+    def __init__(self):
+        self.cache = {}
+
+    def get(self, kind, h, w, stride, device):
+        key = (kind, h, w, stride, str(device))
+        if key not in self.cache:
+            idx, wgt, ho, wo = _sphere_lut(h, w, stride) if kind == "sphere" else _conv_s2_lut(h, w)
+            self.cache[key] = (torch.from_numpy(idx).to(device), torch.from_numpy(wgt).to(device), ho, wo)
+        return self.cache[key]
+
+
+_LUTS = _Luts()
+
+
+# ----------------------------------------------------------------------------------------------------- low-level ops
+class _PackedConv:
+    """A 3x3 (sphere or regular) convolution's weights as GEMM operands: K = 9*Cp, output sliced into <= 256 channels."""
+
+    def __init__(self, weight, precision):
+        lib = _lib.load()
+        O, C = weight.shape[0], weight.shape[1]
+        self.C, self.Cp, self.O = C, _up4(C), O
+        K = 9 * self.Cp
+        wk = torch.zeros(O, 9, self.Cp, dtype=torch.float32, device=weight.device)
+        wk[:, :, :C] = weight.detach().float().permute(0, 2, 3, 1).reshape(O, 9, C)      # (O, tap, c)
+        self.wk = wk.reshape(O, K).contiguous()
+        self.K = K
+        self.slices = []
+        st = _lib.stream_ptr()
+        for n0 in range(0, O, _MAX_N):
+            n = min(_MAX_N, O - n0)
+            w_s = self.wk[n0:n0 + n].contiguous()
+            pack = None
+            if precision != "fp32":
+                pack = torch.empty(lib.eml_conv_wpack_bytes(n, K, 1), dtype=torch.uint8, device=weight.device)
+                _lib.check(lib.eml_conv_pack_weights(_lib.ptr(w_s), _lib.ptr(pack), n, K, 1, st), "eml_conv_pack_weights")
+            self.slices.append((n0, n, w_s, pack))
+
+
+def _gemm(A, M, pc, out, out_pitch, choff, precision):
+    """out[:, choff:choff+O] = A (M,K) @ W^T via eml_conv_forward (1x1 mode), sliced over the output channels."""
+    lib = _lib.load()
+    for n0, n, w_s, pack in pc.slices:
+        p = ConvParams()
+        p.in_ = A.data_ptr(); p.scale = None; p.shift = None
+        p.w_oihw = w_s.data_ptr(); p.wpack = pack.data_ptr() if pack is not None else None
+        p.out = out.data_ptr(); p.stats = None; p.stats_stride = 0
+        p.B, p.H, p.W = 1, 1, M
+        p.C_in, p.in_pitch = pc.K, pc.K
+        p.C_out, p.out_pitch, p.out_choff = n, out_pitch, choff + n0
+        p.mode, p.relu, p.precision = _lib.EML_CONV_1x1, 0, _lib.PRECISIONS[precision]
+        _lib.check(lib.eml_conv_forward(p, _lib.stream_ptr()), "eml_conv_forward(GEMM %dx%dx%d)" % (M, n, pc.K))
+
+
+def _im2col(x, B, H, W, C, lut, bias, act):
+    """x NHWC (B,H,W,pitch) -> A (B*Ho*Wo, 9*Cp) fp32."""
+    lib = _lib.load()
+    idx, wgt, ho, wo = lut
+    Cp = _up4(C)
+    A = torch.empty(B * ho * wo, 9 * Cp, dtype=torch.float32, device=x.device)
+    _lib.check(lib.eml_im2col_lut(_lib.ptr(x), x.shape[-1], C, Cp, _lib.ptr(idx), _lib.ptr(wgt), _lib.ptr(bias), act, _lib.ptr(A),
+                                  B, ho * wo, H * W, _lib.stream_ptr()), "eml_im2col_lut")
+    return A, ho, wo
+
+
+def _sphere_conv_raw(x, B, H, W, pc, stride, bias_in, act, precision):
+    """Bias-free SphereConv2D on an NHWC tensor: returns (B,Ho,Wo,up4(O)) holding W * S(act(x + bias_in))."""
+    A, ho, wo = _im2col(x, B, H, W, pc.C, _LUTS.get("sphere", H, W, stride, x.device), bias_in, act)
+    out = torch.empty(B, ho, wo, _up4(pc.O), dtype=torch.float32, device=x.device)
+    _gemm(A, B * ho * wo, pc, out, out.shape[-1], 0, precision)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------- modules
+class SphereConv2D(nn.Module):
+    """Drop-in for sphere_cnn.SphereConv2D (3x3 only, bilinear).  NCHW in / NCHW out like the reference."""
+
+    def __init__(self, in_c, out_c, stride=1, bias=True, mode="bilinear"):
+        super().__init__()
+        if mode != "bilinear":
+            raise ValueError("only mode='bilinear' is implemented (the mode EMLight uses)")
+        self.in_c, self.out_c, self.stride, self.mode = in_c, out_c, stride, mode
+        self.weight = Parameter(torch.Tensor(out_c, in_c, 3, 3))
+        if bias:
+            self.bias = Parameter(torch.Tensor(out_c))
+        else:
+            self.register_parameter("bias", None)
+        self.precision = "bf16x3"
+        self.reset_parameters()
+        self._pc = None
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.weight, a=np.sqrt(5))
+        if self.bias is not None:
+            self.bias.data.zero_()
+
+    def effective_weight(self):
+        return self.weight
+
+    def _tracked(self):
+        return (self.weight,)
+
+    def packed(self, precision):
+        key = (precision,) + tuple((t.data_ptr(), t._version, str(t.device)) for t in self._tracked())
+        if self._pc is None or self._pc[0] != key:
+            with torch.no_grad():
+                self._pc = (key, _PackedConv(self.effective_weight(), precision))
+        return self._pc[1]
+
+    @torch.no_grad()
+    def forward(self, x):
+        _lib.require_cuda(x)
+        lib = _lib.load()
+        B, C, H, W = x.shape
+        xn = x.float().permute(0, 2, 3, 1).contiguous()
+        pc = self.packed(self.precision)
+        raw = _sphere_conv_raw(xn, B, H, W, pc, self.stride, None, 0, self.precision)
+        ho, wo = raw.shape[1], raw.shape[2]
+        out = torch.empty_like(raw)
+        _lib.check(lib.eml_bias_residual(_lib.ptr(raw), raw.shape[-1], _lib.ptr(self.bias), None, 0, None, _lib.ptr(out), out.shape[-1],
+                                         B * ho * wo, self.out_c, _lib.stream_ptr()), "eml_bias_residual")
+        return out[..., :self.out_c].permute(0, 3, 1, 2).contiguous()
+
+
+class _SpectralSphereConv2D(SphereConv2D):
+    """SphereConv2D under torch.nn.utils.spectral_norm naming: weight_orig (parameter), weight_u / weight_v (buffers)."""
+
+    def __init__(self, in_c, out_c):
+        super().__init__(in_c, out_c)
+        w = self.weight
+        del self._parameters["weight"]
+        self.register_parameter("weight_orig", Parameter(w.data))
+        self.register_buffer("weight_u", nn.functional.normalize(torch.randn(out_c), dim=0))
+        self.register_buffer("weight_v", nn.functional.normalize(torch.randn(in_c * 9), dim=0))
+
+    def effective_weight(self):
+        w = self.weight_orig
+        sigma = torch.dot(self.weight_u, torch.mv(w.reshape(w.shape[0], -1), self.weight_v))
+        return w / sigma
+
+    def _tracked(self):
+        return (self.weight_orig, self.weight_u, self.weight_v)
+
+
+class _SpectralConv2d(nn.Module):
+    """nn.Conv2d(3x3, stride 2, padding 1, no bias) under spectral_norm naming (ConvEncoder layers, generator.py:100-104)."""
+
+    def __init__(self, in_c, out_c):
+        super().__init__()
+        self.in_channels, self.out_channels = in_c, out_c
+        w = torch.empty(out_c, in_c, 3, 3)
+        nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+        self.register_parameter("bias", None)
+        self.weight_orig = Parameter(w)
+        self.register_buffer("weight_u", nn.functional.normalize(torch.randn(out_c), dim=0))
+        self.register_buffer("weight_v", nn.functional.normalize(torch.randn(in_c * 9), dim=0))
+        self._pc = None
+
+    def packed(self, precision):
+        w = self.weight_orig
+        key = (w.data_ptr(), w._version, self.weight_u._version, self.weight_v._version, precision, str(w.device))
+        if self._pc is None or self._pc[0] != key:
+            with torch.no_grad():
+                sigma = torch.dot(self.weight_u, torch.mv(w.reshape(w.shape[0], -1), self.weight_v))
+                self._pc = (key, _PackedConv(w / sigma, precision))
+        return self._pc[1]
+
+
+class _ParamFreeBN(nn.Module):
+    """SynchronizedBatchNorm2d(affine=False) as SPADE uses it: buffers only (normalization.py:80)."""
+
+    def __init__(self, c, eps=1e-5, momentum=0.1):
+        super().__init__()
+        self.num_features, self.eps, self.momentum = c, eps, momentum
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+
+class SPADE(nn.Module):
+    def __init__(self, config_text, norm_nc, label_nc):
+        super().__init__()
+        parsed = re.search(r"spade(\D+)(\d)x\d", config_text)
+        if parsed is None or parsed.group(1) not in ("syncbatch", "batch"):
+            raise ValueError("only the spade(sync)batch3x3 configuration EMLight uses is implemented, got %r" % config_text)
+        self.norm_nc, self.label_nc = norm_nc, label_nc
+        self.param_free_norm = _ParamFreeBN(norm_nc)
+        self.mlp_shared = nn.Sequential(SphereConv2D(label_nc, _NHIDDEN), nn.ReLU())
+        self.mlp_gamma = SphereConv2D(_NHIDDEN, norm_nc)
+        self.mlp_beta = SphereConv2D(_NHIDDEN, norm_nc)
+        self._gb = None
+
+    def _packed_gb(self, precision):
+        g, b = self.mlp_gamma.weight, self.mlp_beta.weight
+        key = (g.data_ptr(), g._version, b.data_ptr(), b._version, precision, str(g.device))
+        if self._gb is None or self._gb[0] != key:
+            with torch.no_grad():
+                self._gb = (key, _PackedConv(torch.cat([g, b], 0), precision))       # one GEMM: gamma | beta
+        return self._gb[1]
+
+    @torch.no_grad()
+    def apply_nhwc(self, x, B, H, W, seg, x_bias, lrelu, precision):
+        """x (B,H,W,pitch) raw conv output whose bias `x_bias` (or None) has not been added yet; seg (B,H,W,4) resized guide."""
+        lib = _lib.load()
+        C = self.norm_nc
+        bn = self.param_free_norm
+        mean = bn.running_mean if x_bias is None else bn.running_mean - x_bias            # (x + b - m) = x - (m - b)
+        inv = torch.rsqrt(bn.running_var + bn.eps)
+        shared = self.mlp_shared[0]
+        actv = _sphere_conv_raw(seg, B, H, W, shared.packed(precision), 1, None, 0, precision)
+        gb = _sphere_conv_raw(actv, B, H, W, self._packed_gb(precision), 1, shared.bias, 1, precision)      # relu(actv + bias)
+        out = torch.empty(B, H, W, _up4(C), dtype=torch.float32, device=x.device)
+        _lib.check(lib.eml_spade_modulate(_lib.ptr(x), x.shape[-1], _lib.ptr(mean.contiguous()), _lib.ptr(inv.contiguous()), _lib.ptr(gb),
+                                          gb.shape[-1], _lib.ptr(self.mlp_gamma.bias), _lib.ptr(self.mlp_beta.bias), _lib.ptr(out),
+                                          out.shape[-1], B * H * W, C, int(lrelu), _lib.stream_ptr()), "eml_spade_modulate")
+        return out
+
+
+class SPADEResnetBlock(nn.Module):
+    def __init__(self, fin, fout, opt):
+        super().__init__()
+        self.learned_shortcut = fin != fout
+        fmiddle = min(fin, fout)
+        spectral = "spectral" in opt.norm_G
+        conv = _SpectralSphereConv2D if spectral else SphereConv2D
+        self.conv_0 = conv(fin, fmiddle)
+        self.conv_1 = conv(fmiddle, fout)
+        if self.learned_shortcut:
+            self.conv_s = conv(fin, fout)
+        cfg = opt.norm_G.replace("spectral", "")
+        self.norm_0 = SPADE(cfg, fin, opt.semantic_nc)
+        self.norm_1 = SPADE(cfg, fmiddle, opt.semantic_nc)
+        if self.learned_shortcut:
+            self.norm_s = SPADE(cfg, fin, opt.semantic_nc)
+        self.fin, self.fout, self.fmiddle = fin, fout, fmiddle
+
+    @torch.no_grad()
+    def apply_nhwc(self, x, B, H, W, seg, precision):
+        """x (B,H,W,pitch) finished activations -> (B,H,W,up4(fout))."""
+        lib = _lib.load()
+        r, r_bias = x, None
+        if self.learned_shortcut:
+            s = self.norm_s.apply_nhwc(x, B, H, W, seg, None, False, precision)
+            r = _sphere_conv_raw(s, B, H, W, self.conv_s.packed(precision), 1, None, 0, precision)
+            r_bias = self.conv_s.bias
+        h = self.norm_0.apply_nhwc(x, B, H, W, seg, None, True, precision)
+        d0 = _sphere_conv_raw(h, B, H, W, self.conv_0.packed(precision), 1, None, 0, precision)
+        h = self.norm_1.apply_nhwc(d0, B, H, W, seg, self.conv_0.bias, True, precision)
+        d1 = _sphere_conv_raw(h, B, H, W, self.conv_1.packed(precision), 1, None, 0, precision)
+        out = torch.empty(B, H, W, _up4(self.fout), dtype=torch.float32, device=x.device)
+        _lib.check(lib.eml_bias_residual(_lib.ptr(d1), d1.shape[-1], _lib.ptr(self.conv_1.bias), _lib.ptr(r), r.shape[-1], _lib.ptr(r_bias),
+                                         _lib.ptr(out), out.shape[-1], B * H * W, self.fout, _lib.stream_ptr()), "eml_bias_residual")
+        return out
+
+
+class ConvEncoder(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        ndf = opt.ngf
+        if getattr(opt, "norm_E", "spectralinstance") != "spectralinstance":
+            raise ValueError("only norm_E='spectralinstance' (the reference default) is implemented")
+        chans = [3, ndf, ndf * 2, ndf * 4, ndf * 8, ndf * 8]
+        for i in range(1, 6):
+            setattr(self, "layer%d" % i, nn.Sequential(_SpectralConv2d(chans[i - 1], chans[i]), nn.InstanceNorm2d(chans[i], affine=False)))
+        self.fc = nn.Linear(ndf * 8 * 4 * 4, 16 * ndf * 2 * 1)
+        self.actvn = nn.LeakyReLU(0.2, False)
+        self.opt = opt
+        self._fc = None
+
+    @torch.no_grad()
+    def encode(self, crop, precision):
+        """crop (B,3,Hc,Wc) NCHW -> z (B, 32*ngf)."""
+        lib = _lib.load()
+        B = crop.shape[0]
+        dev = crop.device
+        st = _lib.stream_ptr()
+        x = torch.empty(B, 128, 128, 4, dtype=torch.float32, device=dev)
+        _lib.check(lib.eml_resize_bilinear_nchw(_lib.ptr(crop.contiguous().float()), crop.shape[2], crop.shape[3], _lib.ptr(x), 4, 128, 128, 3, B, st),
+                   "eml_resize_bilinear_nchw")
+        H = W = 128
+        C = 3
+        for i in range(1, 6):
+            conv = getattr(self, "layer%d" % i)[0]
+            pc = conv.packed(precision)
+            A, ho, wo = _im2col(x, B, H, W, C, _LUTS.get("conv_s2", H, W, 2, dev), None, 0)    # LeakyReLU already applied by the norm below
+            raw = torch.empty(B, ho, wo, _up4(pc.O), dtype=torch.float32, device=dev)
+            _gemm(A, B * ho * wo, pc, raw, raw.shape[-1], 0, precision)
+            x = torch.empty_like(raw)
+            _lib.check(lib.eml_instance_norm(_lib.ptr(raw), raw.shape[-1], _lib.ptr(x), x.shape[-1], B, ho * wo, pc.O, 1e-5, 1, st),
+                       "eml_instance_norm")
+            H, W, C = ho, wo, pc.O
+        # fc consumes the NCHW flattening (generator.py:124); ours is NHWC -> permute the weight columns once
+        key = (self.fc.weight.data_ptr(), self.fc.weight._version, str(dev))
+        if self._fc is None or self._fc[0] != key:
+            wf = self.fc.weight.detach().float().view(self.fc.out_features, C, H * W).permute(0, 2, 1).reshape(self.fc.out_features, -1).contiguous()
+            self._fc = (key, wf)
+        flat = x[..., :C].reshape(B, -1) if x.shape[-1] != C else x.reshape(B, -1)
+        z = torch.empty(B, self.fc.out_features, dtype=torch.float32, device=dev)
+        _lib.check(lib.eml_linear_fp32(_lib.ptr(flat.contiguous()), _lib.ptr(self._fc[1]), _lib.ptr(self.fc.bias), _lib.ptr(z), B,
+                                       self.fc.out_features, flat.shape[1], st), "eml_linear_fp32(netE.fc)")
+        return z
+
+
+class SPADEGenerator(nn.Module):
+    """opt needs: ngf, norm_G ('spectralspadesyncbatch3x3'), semantic_nc (3), num_upsampling_layers ('normal'), crop_size, aspect_ratio."""
+
+    def __init__(self, opt, precision="bf16x3"):
+        super().__init__()
+        if precision not in _lib.PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(_lib.PRECISIONS))
+        if getattr(opt, "num_upsampling_layers", "normal") != "normal":
+            raise ValueError("only num_upsampling_layers='normal' (the reference default) is implemented")
+        self.opt = opt
+        self.precision = precision
+        nf = opt.ngf
+        self.sw = opt.crop_size // 32
+        self.sh = round(self.sw / opt.aspect_ratio)
+        self.head_0 = SPADEResnetBlock(16 * nf, 16 * nf, opt)
+        self.G_middle_0 = SPADEResnetBlock(16 * nf, 16 * nf, opt)
+        self.G_middle_1 = SPADEResnetBlock(16 * nf, 16 * nf, opt)
+        self.up_0 = SPADEResnetBlock(16 * nf, 8 * nf, opt)
+        self.up_1 = SPADEResnetBlock(8 * nf, 4 * nf, opt)
+        self.up_2 = SPADEResnetBlock(4 * nf, 2 * nf, opt)
+        self.up_3 = SPADEResnetBlock(2 * nf, 1 * nf, opt)
+        self.up = nn.Upsample(scale_factor=2)
+        self.sphere_conv1 = SphereConv2D(nf, 3, stride=1)
+        self.netE = ConvEncoder(opt)
+
+    def forward(self, input, crop):
+        if self.training:
+            raise NotImplementedError("emlight_b200.SPADEGenerator: training-mode forward (batch-statistic SyncBN, spectral-norm power "
+                                      "iteration) and backward are not implemented in this round; call .eval() for inference")
+        _lib.require_cuda(input, crop)
+        with torch.no_grad():
+            return self._run(input, crop)
+
+    def _run(self, guide, crop):
+        lib = _lib.load()
+        prec = self.precision
+        B = guide.shape[0]
+        dev = guide.device
+        st = _lib.stream_ptr()
+        guide = guide.contiguous().float()
+        gh, gw = guide.shape[2], guide.shape[3]
+        segs = {}
+
+        def seg(h, w):
+            if (h, w) not in segs:
+                s = torch.zeros(B, h, w, 4, dtype=torch.float32, device=dev)
+                _lib.check(lib.eml_resize_nearest(_lib.ptr(guide), 0, gh, gw, _lib.ptr(s), 4, h, w, guide.shape[1], B, 1, st), "eml_resize_nearest(guide)")
+                segs[(h, w)] = s
+            return segs[(h, w)]
+
+        def upsample(x, H, W, C):
+            out = torch.empty(B, 2 * H, 2 * W, x.shape[-1], dtype=torch.float32, device=dev)
+            _lib.check(lib.eml_resize_nearest(_lib.ptr(x), x.shape[-1], H, W, _lib.ptr(out), out.shape[-1], 2 * H, 2 * W, C, B, 0, st), "eml_resize_nearest(x2)")
+            return out
+
+        z = self.netE.encode(crop, prec)                                   # (B, 32 ngf) == (B, 16 ngf, 1, 2) NCHW
+        C = 16 * self.opt.ngf
+        H, W = self.sh, self.sw
+        x = torch.empty(B, H, W, C, dtype=torch.float32, device=dev)
+        _lib.check(lib.eml_resize_nearest(_lib.ptr(z), 0, 1, 2, _lib.ptr(x), C, H, W, C, B, 1, st), "eml_resize_nearest(latent)")
+        for name in ("head_0", "G_middle_0", "G_middle_1", "up_0", "up_1", "up_2", "up_3"):
+            blk = getattr(self, name)
+            x = blk.apply_nhwc(x, B, H, W, seg(H, W), prec)
+            C = blk.fout
+            if name not in ("G_middle_0", "up_3"):
+                x = upsample(x, H, W, C)
+                H, W = 2 * H, 2 * W
+        pc = self.sphere_conv1.packed(prec)
+        raw = _sphere_conv_raw(x, B, H, W, pc, 1, None, 2, prec)           # SphereConv(LeakyReLU(x))
+        out = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev)
+        _lib.check(lib.eml_tanh_to_nchw(_lib.ptr(raw), raw.shape[-1], _lib.ptr(self.sphere_conv1.bias), _lib.ptr(out), B, H * W, 3, 25.0, st),
+                   "eml_tanh_to_nchw")
+        return out

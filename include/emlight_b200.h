@@ -152,6 +152,46 @@ int eml_head_pool(const float *in, int in_pitch, const float *scale, const float
 int eml_linear_fp32(const float *a, const float *w, const float *bias, float *out, int M, int N, int K,
                     void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * G1-G4 -- GenProjector SPADE / SphereNet generator building blocks (all activations NHWC fp32).
+ *
+ * eml_im2col_lut: the resampling half of SphereConv2D (GenProjector/models/networks/spherenet/sphere_cnn.py:111-124,
+ * grid_sample on the tangent-plane pattern of :31-84) and of the ConvEncoder's stride-2 convolutions
+ * (models/networks/generator.py:100-104):
+ *     A[m, tap*Cp + c] = sum_{t<4} lut_w[p,tap,t] * act(x[b, lut_idx[p,tap,t], c] + bias[c])      m = b*out_pixels + p
+ * lut_idx (out_pixels,9,4) int32 source pixel (or -1 = zero padding), lut_w (out_pixels,9,4) fp32, shared by the batch.
+ * act: 0 none, 1 ReLU, 2 LeakyReLU(0.2).  Cp = C rounded up to 4 (padding columns are written as 0).
+ * The convolution itself is eml_conv_forward(EML_CONV_1x1) on A with weights laid out (O, 9*Cp).
+ */
+int eml_im2col_lut(const float *x, int x_pitch, int C, int Cp, const int *lut_idx, const float *lut_w, const float *bias,
+                   int act, float *A, int B, long out_pixels, long in_pixels, void *stream);
+
+/* SPADE.forward (models/networks/normalization.py:101-115) after the gamma/beta convolutions:
+ *   out = ((x - mean[c]) * inv_std[c]) * (1 + gamma + bias_gamma[c]) + (beta + bias_beta[c]), optional LeakyReLU(0.2);
+ * gamma_beta (M, gb_pitch) holds gamma in channels [0,C) and beta in [C,2C) (one GEMM with concatenated weights). */
+int eml_spade_modulate(const float *x, int x_pitch, const float *mean, const float *inv_std, const float *gamma_beta,
+                       int gb_pitch, const float *bias_gamma, const float *bias_beta, float *out, int out_pitch, long M,
+                       int C, int leaky_relu, void *stream);
+
+/* out = a + bias_a (+ r + bias_r): SPADEResnetBlock's x_s + dx (models/networks/architecture.py:51-58). r may be NULL. */
+int eml_bias_residual(const float *a, int a_pitch, const float *bias_a, const float *r, int r_pitch, const float *bias_r,
+                      float *out, int out_pitch, long M, int C, void *stream);
+
+/* F.interpolate(mode='nearest') to (Ho,Wo); source NHWC (pitch x_pitch) or NCHW (src_is_nchw=1); output NHWC
+ * (normalization.py:107 guide resize, generator.py:42,70 upsampling / latent expansion). */
+int eml_resize_nearest(const float *x, int x_pitch, int Hi, int Wi, float *out, int out_pitch, int Ho, int Wo, int C, int B,
+                       int src_is_nchw, void *stream);
+
+/* F.interpolate(mode='bilinear', align_corners=False): NCHW in, NHWC out (generator.py:116). */
+int eml_resize_bilinear_nchw(const float *x, int Hi, int Wi, float *out, int out_pitch, int Ho, int Wo, int C, int B, void *stream);
+
+/* nn.InstanceNorm2d(affine=False) + optional LeakyReLU(0.2) (normalization.py:45, generator.py:118-123). */
+int eml_instance_norm(const float *x, int x_pitch, float *out, int out_pitch, int B, int HW, int C, float eps, int leaky_relu,
+                      void *stream);
+
+/* out_nchw = (tanh(x + bias[c]) + 1) * scale (generator.py:85-86). */
+int eml_tanh_to_nchw(const float *x, int x_pitch, const float *bias, float *out, int B, int HW, int C, float scale, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

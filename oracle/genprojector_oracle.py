@@ -1,0 +1,175 @@
+"""CPU oracle for the GenProjector SPADE/SphereConv generator (test infrastructure, see oracle/__init__.py).
+
+Functional restatement (eval / inference mode, the path GenProjector/test.py:21-39 runs) of
+
+* SphereConv2D            GenProjector/models/networks/spherenet/sphere_cnn.py:11-124
+    tangent-plane 3x3 sampling pattern (get_xy :11-28, cal_index :31-58: gnomonic projection, centre forced to the pixel,
+    longitude wrapped mod W), laid out as a (1,3H/s,3W/s,2) grid (:75-84), then grid_sample (bilinear, zeros padding,
+    align_corners=False -- the torch>=1.3 default the in-container reference runs with) and conv2d(stride=3) (:122-123)
+* SPADE                   models/networks/normalization.py:68-115   BN(no affine, running stats) * (1+gamma) + beta,
+                          gamma/beta = SphereConv(ReLU(SphereConv(nearest-resized guide)))
+* SPADEResnetBlock        models/networks/architecture.py:22-69     learned shortcut when fin != fout, LeakyReLU(0.2)
+* spectral_norm (eval)    torch.nn.utils.spectral_norm: W = W_orig / (u^T W_mat v) with the stored u, v (no power iteration)
+* ConvEncoder             models/networks/generator.py:90-126       bilinear 128^2, 5 x [conv3x3 s2 + InstanceNorm] with LeakyReLU, fc
+* SPADEGenerator.forward  models/networks/generator.py:65-88        7 blocks / 5 nearest x2 upsamples, (tanh+1)*25
+
+over a state_dict with the reference's parameter names.
+"""
+import math
+from collections import OrderedDict
+from functools import lru_cache
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BLOCKS = (("head_0", 16, 16), ("G_middle_0", 16, 16), ("G_middle_1", 16, 16), ("up_0", 16, 8), ("up_1", 8, 4),
+          ("up_2", 4, 2), ("up_3", 2, 1))
+NHIDDEN = 128
+
+
+@lru_cache(None)
+def sphere_sample_coords(h, w, stride=1):
+    """(Ho, Wo, 3, 3, 2) float64 (row, col) sample positions in pixel units -- sphere_cnn.py:11-72 vectorised."""
+    pi = np.pi
+    dphi, dth = pi / h, 2 * pi / w
+    t, s = math.tan(dth), 1 / math.cos(dth) * math.tan(dphi)
+    xs = np.array([[-t, 0, t], [-t, 1, t], [-t, 0, t]], dtype=np.float64)
+    ys = np.array([[s, math.tan(dphi), s], [0, 1, 0], [-s, -math.tan(dphi), -s]], dtype=np.float64)
+    r = np.arange(0, h, stride, dtype=np.float64)[:, None, None, None]
+    c = np.arange(0, w, stride, dtype=np.float64)[None, :, None, None]
+    phi = -((r + 0.5) / h * pi - pi / 2)
+    theta = (c + 0.5) / w * 2 * pi - pi
+    x, y = xs[None, None], ys[None, None]
+    rho = np.sqrt(x ** 2 + y ** 2)
+    v = np.arctan(rho)
+    new_phi = np.arcsin(np.cos(v) * np.sin(phi) + y * np.sin(v) * np.cos(phi) / rho)
+    new_theta = theta + np.arctan(x * np.sin(v) / (rho * np.cos(phi) * np.cos(v) - y * np.sin(phi) * np.sin(v)))
+    new_r = (-new_phi + pi / 2) * h / pi - 0.5
+    new_c = ((new_theta + pi) * w / 2 / pi - 0.5 + w) % w
+    out = np.stack(np.broadcast_arrays(new_r, new_c), -1)
+    out[:, :, 1, 1, 0] = np.arange(0, h, stride)[:, None]
+    out[:, :, 1, 1, 1] = np.arange(0, w, stride)[None, :]
+    return out
+
+
+def sphere_grid(h, w, stride=1):
+    """The (1, 3Ho, 3Wo, 2) fp32 grid_sample grid of sphere_cnn.py:75-84 (x = col, y = row, normalised as 2p/size - 1)."""
+    co = sphere_sample_coords(h, w, stride)
+    gy = co[..., 0] * 2 / h - 1
+    gx = co[..., 1] * 2 / w - 1
+    g = np.stack((gx, gy), -1)                                    # (Ho, Wo, 3, 3, 2)
+    ho, wo = g.shape[:2]
+    g = g.transpose(0, 2, 1, 3, 4).reshape(1, ho * 3, wo * 3, 2)
+    return torch.from_numpy(g.astype(np.float32))
+
+
+def sphere_conv(x, weight, bias, stride=1):
+    grid = sphere_grid(x.shape[2], x.shape[3], stride).repeat(x.shape[0], 1, 1, 1)
+    s = F.grid_sample(x, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+    return F.conv2d(s, weight, bias, stride=3)
+
+
+def sn_weight(sd, prefix):
+    """Eval-mode spectral norm: W_orig / sigma, sigma = u . (W_mat v)."""
+    w = sd[prefix + ".weight_orig"]
+    u, v = sd[prefix + ".weight_u"], sd[prefix + ".weight_v"]
+    sigma = torch.dot(u, torch.mv(w.reshape(w.shape[0], -1), v))
+    return w / sigma
+
+
+def spade(sd, p, x, guide):
+    rm, rv = sd[p + ".param_free_norm.running_mean"], sd[p + ".param_free_norm.running_var"]
+    normalized = F.batch_norm(x, rm, rv, None, None, False, 0.0, 1e-5)
+    seg = F.interpolate(guide, size=x.shape[2:], mode="nearest")
+    actv = F.relu(sphere_conv(seg, sd[p + ".mlp_shared.0.weight"], sd[p + ".mlp_shared.0.bias"]))
+    gamma = sphere_conv(actv, sd[p + ".mlp_gamma.weight"], sd[p + ".mlp_gamma.bias"])
+    beta = sphere_conv(actv, sd[p + ".mlp_beta.weight"], sd[p + ".mlp_beta.bias"])
+    return normalized * (1 + gamma) + beta
+
+
+def spade_block(sd, p, x, guide, learned):
+    x_s = x
+    if learned:
+        x_s = sphere_conv(spade(sd, p + ".norm_s", x, guide), sn_weight(sd, p + ".conv_s"), sd[p + ".conv_s.bias"])
+    dx = sphere_conv(F.leaky_relu(spade(sd, p + ".norm_0", x, guide), 0.2), sn_weight(sd, p + ".conv_0"), sd[p + ".conv_0.bias"])
+    dx = sphere_conv(F.leaky_relu(spade(sd, p + ".norm_1", dx, guide), 0.2), sn_weight(sd, p + ".conv_1"), sd[p + ".conv_1.bias"])
+    return x_s + dx
+
+
+def encoder(sd, crop):
+    x = F.interpolate(crop, size=(128, 128), mode="bilinear")
+    for i in range(1, 6):
+        if i > 1:
+            x = F.leaky_relu(x, 0.2)
+        x = F.conv2d(x, sn_weight(sd, "netE.layer%d.0" % i), None, stride=2, padding=1)
+        x = F.instance_norm(x, eps=1e-5)
+    x = F.leaky_relu(x, 0.2)
+    return F.linear(x.reshape(x.shape[0], -1), sd["netE.fc.weight"], sd["netE.fc.bias"])
+
+
+def generator_forward(sd, guide, crop, ngf=64, taps=None):
+    """guide (B,3,128,256), crop (B,3,Hc,Wc) -> (B,3,128,256) in [0,50]."""
+    x = encoder(sd, crop).view(-1, 16 * ngf, 1, 2)
+    x = F.interpolate(x, size=(4, 8))
+    if taps is not None:
+        taps["latent"] = x
+    for i, (name, fi, fo) in enumerate(BLOCKS):
+        x = spade_block(sd, name, x, guide, fi != fo)
+        if taps is not None:
+            taps[name] = x
+        if name not in ("G_middle_0", "up_3"):
+            x = F.interpolate(x, scale_factor=2)
+    x = sphere_conv(F.leaky_relu(x, 0.2), sd["sphere_conv1.weight"], sd["sphere_conv1.bias"])
+    return (torch.tanh(x) + 1) * 25
+
+
+def init_generator_state_dict(seed=0, ngf=64):
+    """Deterministic parameters with the reference's names / shapes (253 entries, 118.4 M values at ngf=64)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+
+    def conv(name, o, i, k=3, gain=1.0, bias=True, spectral=False):
+        w = torch.randn(o, i, k, k, generator=g) * (gain / math.sqrt(i * k * k))
+        if bias:
+            sd[name + ".bias"] = 0.1 * torch.randn(o, generator=g)
+        if spectral:
+            sd[name + ".weight_orig"] = w
+            sd[name + ".weight_u"] = F.normalize(torch.randn(o, generator=g), dim=0)
+            sd[name + ".weight_v"] = F.normalize(torch.randn(i * k * k, generator=g), dim=0)
+        else:
+            sd[name + ".weight"] = w
+
+    def spade_p(name, c):
+        sd[name + ".param_free_norm.running_mean"] = 0.1 * torch.randn(c, generator=g)
+        sd[name + ".param_free_norm.running_var"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".param_free_norm.num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+        conv(name + ".mlp_shared.0", NHIDDEN, 3, gain=2.0)
+        conv(name + ".mlp_gamma", c, NHIDDEN, gain=0.5)
+        conv(name + ".mlp_beta", c, NHIDDEN, gain=0.5)
+
+    for name, fi, fo in BLOCKS:
+        fin, fout = fi * ngf, fo * ngf
+        fmid = min(fin, fout)
+        # spectral norm divides by u.Wv (|.| << the true sigma for random u, v): keep W_orig small enough that W/sigma is O(1)
+        conv(name + ".conv_0", fmid, fin, spectral=True)
+        conv(name + ".conv_1", fout, fmid, spectral=True)
+        if fin != fout:
+            conv(name + ".conv_s", fout, fin, spectral=True)
+        spade_p(name + ".norm_0", fin)
+        spade_p(name + ".norm_1", fmid)
+        if fin != fout:
+            spade_p(name + ".norm_s", fin)
+    conv("sphere_conv1", 3, ngf, gain=0.15)                     # keep the final tanh out of saturation so errors stay visible
+    chans = [3, ngf, 2 * ngf, 4 * ngf, 8 * ngf, 8 * ngf]
+    for i in range(1, 6):
+        conv("netE.layer%d.0" % i, chans[i], chans[i - 1], bias=False, spectral=True)
+    sd["netE.fc.weight"] = torch.randn(16 * ngf * 2, 8 * ngf * 16, generator=g) / math.sqrt(8 * ngf * 16)
+    sd["netE.fc.bias"] = 0.1 * torch.randn(16 * ngf * 2, generator=g)
+    # make the spectral-norm sigma well-conditioned: align u, v with one power iteration of each weight
+    for k in [k for k in sd if k.endswith(".weight_orig")]:
+        w = sd[k].reshape(sd[k].shape[0], -1)
+        v = F.normalize(torch.mv(w.t(), sd[k[:-5] + "_u"]), dim=0)
+        u = F.normalize(torch.mv(w, v), dim=0)
+        sd[k[:-5] + "_u"], sd[k[:-5] + "_v"] = u, v
+    return sd

@@ -106,6 +106,39 @@ def main():
         gold["gdirs_%d" % N] = dirs.grad.numpy(); gold["gsizes_%d" % N] = sizes.grad.numpy()
         gold["gcolors_%d" % N] = colors.grad.numpy()
     np.savez_compressed(os.path.join(OUT, "render.npz"), **gold)
+    # ---------------- GenProjector generator (generator.py / architecture.py / normalization.py / sphere_cnn.py imported unchanged) -----
+    import argparse
+    import types
+    for name in ("OpenEXR", "Imath", "imageio", "imageio.plugins", "imageio.plugins.freeimage", "vtk", "vtk.util", "vtk.util.numpy_support"):
+        sys.modules.setdefault(name, types.ModuleType(name))             # IO modules the hot path never calls (appendix C.3)
+    sys.modules["imageio.plugins.freeimage"].download = lambda: None
+    sys.modules["imageio"].plugins = sys.modules["imageio.plugins"]
+    sys.modules["imageio.plugins"].freeimage = sys.modules["imageio.plugins.freeimage"]
+    sys.modules["vtk"].util = sys.modules["vtk.util"]
+    sys.modules["vtk.util"].numpy_support = sys.modules["vtk.util.numpy_support"]
+    sys.path.insert(0, "/root/reference/GenProjector")
+    for k in [k for k in sys.modules if k == "util" or k.startswith("models")]:
+        del sys.modules[k]
+    from models.networks.generator import SPADEGenerator
+    from models.networks.spherenet import SphereConv2D
+    from oracle import genprojector_oracle as GO
+    ngf = 16
+    opt = argparse.Namespace(ngf=ngf, norm_G="spectralspadesyncbatch3x3", norm_E="spectralinstance", semantic_nc=3,
+                             num_upsampling_layers="normal", crop_size=256, aspect_ratio=2.0)
+    G = SPADEGenerator(opt).eval()
+    sdg = GO.init_generator_state_dict(seed=0, ngf=ngf)
+    G.load_state_dict(sdg)
+    gen = torch.Generator().manual_seed(3)
+    guide = torch.rand(1, 3, 128, 256, generator=gen) * 2
+    crop = torch.rand(1, 3, 160, 160, generator=gen)
+    with torch.no_grad():
+        out = G(guide, crop)
+        sc = SphereConv2D(5, 7, stride=2)
+        xs = torch.randn(2, 5, 16, 32, generator=gen)
+        ys = sc(xs)
+    np.savez_compressed(os.path.join(OUT, "generator.npz"), ngf=np.int64(ngf), sd_seed=np.int64(0), in_seed=np.int64(3),
+                        out=out.numpy()[:, :, ::2, ::2], out_mean=np.float64(out.double().mean()), out_std=np.float64(out.double().std()),
+                        sc_weight=sc.weight.detach().numpy(), sc_bias=sc.bias.detach().numpy(), sc_x=xs.numpy(), sc_y=ys.detach().numpy())
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
