@@ -220,6 +220,31 @@ def main():
                 "note": "achieved = algorithmic bytes (inputs read once + outputs written once, fp32) / CUDA-event time, summed over the family's launches in one step"}
     launches_per_step = 1 + sum(v["launches"] for v in fam.values()) + 1 + 2 + 1   # stem + convs + head_pool + 2 linear + render
 
+    # ---- secondary workloads (reported, not the headline): BASELINE configs[1] and configs[0]
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        Bt = 64
+        xt = torch.rand(Bt, 3, 192, 256, generator=gen).to(dev)
+        yt = torch.softmax(3 * torch.randn(Bt, N_ANCHORS, generator=gen), 1).view(Bt, N_ANCHORS, 1).to(dev)
+        loss_fn = E.SamplesLoss("sinkhorn", p=2, blur=.025, batchsize=Bt)
+        net.train()
+
+        def cfg1():                     # DenseNet fwd (batch-statistic BN, as train.py runs it) + Sinkhorn-EMD fwd + d/d(dist_pred)
+            with torch.no_grad():
+                o = net(xt)
+            d = o["distribution"].detach().view(Bt, N_ANCHORS, 1).requires_grad_()
+            loss_fn(d, yt).sum().backward()
+            return d.grad
+        for _ in range(3):
+            cfg1()
+        ms1 = timed(cfg1, 5) / 5
+        net.eval()
+        x1 = x[:1].contiguous()
+        for _ in range(3):
+            step(x1)
+        ms0 = timed(lambda: step(x1), 20) / 20
+        extra = {"config1_densenet_fwd_trainBN_plus_sinkhorn_fwd_bwd_b64": {"ms_per_step": round(ms1, 3), "maps_per_s": round(Bt / ms1 * 1e3, 1)},
+                 "config0_single_crop_latency_ms": round(ms0, 3)}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt, threads = time_cpu(args.cpu_sample, 3, 1)
@@ -234,7 +259,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "maps/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": pano_host.numel() * 4},
                 "gpu_launches": launches_per_step * args.steps, "clocks": sampler.summary(), "roofline": roofline,
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu, "other_workloads": extra}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
