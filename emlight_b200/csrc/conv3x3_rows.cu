@@ -129,34 +129,36 @@ __global__ void __launch_bounds__(ROWS_THREADS) conv3x3_rows_kernel(const RowsAr
     fence_proxy_async();
     __syncthreads();
 
-    // ---- 9 taps x 3 k-steps: shifted descriptor windows over the staging buffer
-    if (tid == 0) {
+    // ---- 9 taps x 3 k-steps: shifted descriptor windows over the staging buffer (warp-uniform, one elected lane issues)
+    if (warp == 0) {
         mbar_wait(bar_w, 0);
+        __syncwarp();
         tc_fence_after();
-        const uint32_t idesc = make_idesc_bf16(ROWS_TILE, a.N_pad);
-        const uint32_t wlbo = static_cast<uint32_t>(a.N_pad * 16);         // bytes between weight k-chunks
-        const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), w_s = smem_u32(w_sm);
-        uint32_t acc = 0;
-#pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap - dy * 3;
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(ROWS_TILE, a.N_pad);
+            const uint64_t dA_hi = make_nosw_desc(smem_u32(a_hi), PLANE, 128);
+            const uint64_t dA_lo = make_nosw_desc(smem_u32(a_lo), PLANE, 128);
+            const uint64_t dW_hi = make_nosw_desc(smem_u32(w_sm), static_cast<uint32_t>(a.N_pad * 16), 128);
+            const uint64_t dW_lo = dW_hi + static_cast<uint64_t>(w_img >> 4);
+            uint32_t acc = 0;
 #pragma unroll
-            for (int ks = 0; ks < KC / 2; ++ks) {
-                const uint32_t aoff = static_cast<uint32_t>(((dy * KC + 2 * ks) * ROWS_PP + dx) * 16);
-                const uint32_t woff = static_cast<uint32_t>((tap * KC + 2 * ks) * a.N_pad * 16);
-                const uint64_t dah = make_nosw_desc(a_hi_s + aoff, PLANE, 128);
-                const uint64_t dbh = make_nosw_desc(w_s + woff, wlbo, 128);
-                umma_bf16(tmem_base, dah, dbh, idesc, acc);
-                acc = 1;
-                if (SPLIT) {
-                    const uint64_t dal = make_nosw_desc(a_lo_s + aoff, PLANE, 128);
-                    const uint64_t dbl = make_nosw_desc(w_s + w_img + woff, wlbo, 128);
-                    umma_bf16(tmem_base, dal, dbh, idesc, 1u);
-                    umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+            for (int tap = 0; tap < 9; ++tap) {
+                const int dy = tap / 3, dx = tap - dy * 3;
+#pragma unroll
+                for (int ks = 0; ks < KC / 2; ++ks) {
+                    const uint64_t aoff = static_cast<uint32_t>((dy * KC + 2 * ks) * ROWS_PP + dx);
+                    const uint64_t woff = static_cast<uint32_t>((tap * KC + 2 * ks) * a.N_pad);
+                    umma_bf16(tmem_base, dA_hi + aoff, dW_hi + woff, idesc, acc);
+                    acc = 1;
+                    if (SPLIT) {
+                        umma_bf16(tmem_base, dA_lo + aoff, dW_hi + woff, idesc, 1u);
+                        umma_bf16(tmem_base, dA_hi + aoff, dW_lo + woff, idesc, 1u);
+                    }
                 }
             }
+            umma_commit(bar_acc);
         }
-        umma_commit(bar_acc);
+        __syncwarp();
     }
 
     // ---- epilogue: warps 0-3 own TMEM lanes [32w, 32w+32) = pixels x0 + 32w + lane

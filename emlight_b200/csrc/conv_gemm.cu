@@ -109,6 +109,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(const GemmArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
+    bool leader = false;                                    // one elected lane of warp 0 issues the MMAs (chosen while converged)
+    if (warp == 0) leader = elect_one();
 
     // ---- gather geometry: thread -> (channel quad `sub`, row group `rgrp` < 16); rows r = rgrp + 16*i, i < 8.
     const int sub = tid & 15, rgrp = tid >> 4;
@@ -227,23 +229,28 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(const GemmArgs a) {
         }
         fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
+            // warp-uniform issue: all lanes wait, one elected lane issues (inside `if (tid == 0)` ptxas emits an
+            // ELECT/R2UR loop in front of every UTCHMMA because the descriptors look thread-varying)
             mbar_wait(bar_full + 8 * s, static_cast<uint32_t>(it & 1));
             tc_fence_after();
-            const uint64_t da_hi = make_sw128_desc(smem_u32(a_hi));
-            const uint64_t db_hi = make_sw128_desc(smem_u32(b_hi));
-            const uint64_t da_lo = make_sw128_desc(smem_u32(a_lo));
-            const uint64_t db_lo = make_sw128_desc(smem_u32(b_hi + b_tile_bytes));
-            for (int k = 0; k < ksteps; ++k) {
-                const uint64_t adv = static_cast<uint64_t>(k * 2);      // +32 bytes per 16-wide k-step, >>4
-                umma_bf16(tmem_base, da_hi + adv, db_hi + adv, idesc, (c | k) != 0 ? 1u : 0u);
-                if (SPLIT) {
-                    umma_bf16(tmem_base, da_lo + adv, db_hi + adv, idesc, 1u);
-                    umma_bf16(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
+            if (leader) {
+                const uint64_t da_hi = make_sw128_desc(smem_u32(a_hi));
+                const uint64_t db_hi = make_sw128_desc(smem_u32(b_hi));
+                const uint64_t da_lo = da_hi + static_cast<uint64_t>(A_TILE_BYTES >> 4);
+                const uint64_t db_lo = db_hi + static_cast<uint64_t>(b_tile_bytes >> 4);
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint64_t adv = static_cast<uint64_t>(k * 2);      // +32 bytes per 16-wide k-step, >>4
+                    umma_bf16(tmem_base, da_hi + adv, db_hi + adv, idesc, (c | k) != 0 ? 1u : 0u);
+                    if (SPLIT) {
+                        umma_bf16(tmem_base, da_lo + adv, db_hi + adv, idesc, 1u);
+                        umma_bf16(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
+                    }
                 }
+                umma_commit(bar_done + 8 * s);                 // implies tcgen05.fence::before_thread_sync
+                if (c == a.nchunks - 1) umma_commit(bar_acc);
             }
-            umma_commit(bar_done + 8 * s);                 // implies tcgen05.fence::before_thread_sync
-            if (c == a.nchunks - 1) umma_commit(bar_acc);
+            __syncwarp();
         }
     }
 

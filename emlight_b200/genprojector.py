@@ -128,9 +128,11 @@ class _PackedConv:
         O, C = weight.shape[0], weight.shape[1]
         self.C, self.Cp, self.O = C, _up4(C), O
         K = 9 * self.Cp
-        wk = torch.zeros(O, 9, self.Cp, dtype=torch.float32, device=weight.device)
-        wk[:, :, :C] = weight.detach().float().permute(0, 2, 3, 1).reshape(O, 9, C)      # (O, tap, c)
-        self.wk = wk.reshape(O, K).contiguous()
+        if precision != "fp32":
+            K = (K + 63) & ~63                       # the TMA GEMM walks K in 64-wide chunks; pad columns are zero on both sides
+        wk = torch.zeros(O, K, dtype=torch.float32, device=weight.device)
+        wk[:, :9 * self.Cp].view(O, 9, self.Cp)[:, :, :C] = weight.detach().float().permute(0, 2, 3, 1).reshape(O, 9, C)   # (O, tap, c)
+        self.wk = wk
         self.K = K
         self.slices = []
         st = _lib.stream_ptr()
@@ -170,12 +172,31 @@ def _im2col(x, B, H, W, C, lut, bias, act):
     return A, ho, wo
 
 
-def _sphere_conv_raw(x, B, H, W, pc, stride, bias_in, act, precision):
-    """Bias-free SphereConv2D on an NHWC tensor: returns (B,Ho,Wo,up4(O)) holding W * S(act(x + bias_in))."""
-    A, ho, wo = _im2col(x, B, H, W, pc.C, _LUTS.get("sphere", H, W, stride, x.device), bias_in, act)
+def _conv_raw(x, B, H, W, pc, lut, bias_in, act, precision):
+    """Bias-free 3x3 (sphere or regular) convolution on an NHWC tensor: (B,Ho,Wo,up4(O)) = W * S(act(x + bias_in)).
+    fp32: fp32 im2col + the SIMT GEMM mode; bf16 / bf16x3: bf16 hi(/lo) im2col + the TMA-fed tcgen05 GEMM per <=256-channel slice."""
+    lib = _lib.load()
+    idx, wgt, ho, wo = lut
+    M = B * ho * wo
     out = torch.empty(B, ho, wo, _up4(pc.O), dtype=torch.float32, device=x.device)
-    _gemm(A, B * ho * wo, pc, out, out.shape[-1], 0, precision)
+    if precision == "fp32":
+        A, _, _ = _im2col(x, B, H, W, pc.C, lut, bias_in, act)
+        _gemm(A, M, pc, out, out.shape[-1], 0, precision)
+        return out
+    split = precision == "bf16x3"
+    a_hi = torch.empty(M, pc.K, dtype=torch.bfloat16, device=x.device)
+    a_lo = torch.empty(M, pc.K, dtype=torch.bfloat16, device=x.device) if split else None
+    st = _lib.stream_ptr()
+    _lib.check(lib.eml_im2col_lut_bf16(_lib.ptr(x), x.shape[-1], pc.C, pc.Cp, _lib.ptr(idx), _lib.ptr(wgt), _lib.ptr(bias_in), act,
+                                       _lib.ptr(a_hi), _lib.ptr(a_lo), pc.K, B, ho * wo, H * W, st), "eml_im2col_lut_bf16")
+    for n0, n, w_s, pack in pc.slices:
+        _lib.check(lib.eml_gemm_bf16(_lib.ptr(a_hi), _lib.ptr(a_lo), M, pc.K, _lib.ptr(pack), n, None, _lib.ptr(out), out.shape[-1], n0,
+                                     _lib.PRECISIONS[precision], st), "eml_gemm_bf16(%dx%dx%d)" % (M, n, pc.K))
     return out
+
+
+def _sphere_conv_raw(x, B, H, W, pc, stride, bias_in, act, precision):
+    return _conv_raw(x, B, H, W, pc, _LUTS.get("sphere", H, W, stride, x.device), bias_in, act, precision)
 
 
 # ----------------------------------------------------------------------------------------------------- modules
@@ -389,9 +410,8 @@ class ConvEncoder(nn.Module):
         for i in range(1, 6):
             conv = getattr(self, "layer%d" % i)[0]
             pc = conv.packed(precision)
-            A, ho, wo = _im2col(x, B, H, W, C, _LUTS.get("conv_s2", H, W, 2, dev), None, 0)    # LeakyReLU already applied by the norm below
-            raw = torch.empty(B, ho, wo, _up4(pc.O), dtype=torch.float32, device=dev)
-            _gemm(A, B * ho * wo, pc, raw, raw.shape[-1], 0, precision)
+            raw = _conv_raw(x, B, H, W, pc, _LUTS.get("conv_s2", H, W, 2, dev), None, 0, precision)   # LeakyReLU already applied by the norm below
+            ho, wo = raw.shape[1], raw.shape[2]
             x = torch.empty_like(raw)
             _lib.check(lib.eml_instance_norm(_lib.ptr(raw), raw.shape[-1], _lib.ptr(x), x.shape[-1], B, ho * wo, pc.O, 1e-5, 1, st),
                        "eml_instance_norm")

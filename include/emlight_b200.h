@@ -166,6 +166,17 @@ int eml_linear_fp32(const float *a, const float *w, const float *bias, float *ou
 int eml_im2col_lut(const float *x, int x_pitch, int C, int Cp, const int *lut_idx, const float *lut_w, const float *bias,
                    int act, float *A, int B, long out_pixels, long in_pixels, void *stream);
 
+/* Same gather emitting the operand split into bf16 hi / lo matrices (row length Kp = multiple of 64 >= 9*Cp, zero padded)
+ * for eml_gemm_bf16.  A_lo may be NULL (single-pass bf16). */
+int eml_im2col_lut_bf16(const float *x, int x_pitch, int C, int Cp, const int *lut_idx, const float *lut_w, const float *bias,
+                        int act, void *A_hi, void *A_lo, int Kp, int B, long out_pixels, long in_pixels, void *stream);
+
+/* TMA-fed tcgen05 GEMM (the convolution half of SphereConv2D, sphere_cnn.py:123, and of the ConvEncoder convs):
+ *   out[m, out_choff + n] = sum_k A[m,k] * W[n,k] (+ bias[n]),  A_hi/A_lo (M,Kp) bf16 row-major from eml_im2col_lut_bf16,
+ *   wpack = eml_conv_pack_weights(W as (N, Kp, 1, 1)), N <= 256 per call, precision EML_PREC_BF16 or EML_PREC_BF16X3. */
+int eml_gemm_bf16(const void *A_hi, const void *A_lo, long M, int Kp, const void *wpack, int N, const float *bias, float *out,
+                  int out_pitch, int out_choff, int precision, void *stream);
+
 /* SPADE.forward (models/networks/normalization.py:101-115) after the gamma/beta convolutions:
  *   out = ((x - mean[c]) * inv_std[c]) * (1 + gamma + bias_gamma[c]) + (beta + bias_beta[c]), optional LeakyReLU(0.2);
  * gamma_beta (M, gb_pitch) holds gamma in channels [0,C) and beta in [C,2C) (one GEMM with concatenated weights). */
