@@ -76,68 +76,76 @@ __global__ void __launch_bounds__(256) im2col_lut_kernel(const float *__restrict
 
 // Same gather, emitting the GEMM operand already split into bf16 hi / lo matrices of row length Kp (a multiple of 64;
 // columns >= 9*Cp are zero) -- the layout gemm_tma.cu's tensor maps describe.  A_lo may be NULL (single-pass bf16).
+// One warp per output pixel: the 9 LUT entries are warp-broadcast loads, lanes walk the channel quads, so the four source
+// reads are 512-byte coalesced segments and the hi/lo writes are 256-byte coalesced; no per-element integer division.
 __global__ void __launch_bounds__(256) im2col_lut_bf16_kernel(const float *__restrict__ x, int x_pitch, int C, int Cp,
                                                               const int *__restrict__ idx, const float *__restrict__ wgt,
                                                               const float *__restrict__ bias, int act,
                                                               __nv_bfloat16 *__restrict__ A_hi, __nv_bfloat16 *__restrict__ A_lo, int Kp,
-                                                              long Mo_img, long in_img_pixels, long total_quads) {
+                                                              int Mo_img, long in_img_pixels, long M) {
     const int cq = Cp >> 2, kq = Kp >> 2;
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total_quads;
-         i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int qk = static_cast<int>(i % kq);           // quad index along K
-        const long m = i / kq;
-        const int tap = qk / cq;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tap < 9) {
-            const int q = qk - tap * cq;
-            const long b = m / Mo_img;
-            const long mp = m - b * Mo_img;
-            const int c = q * 4;
-            const int4 id = *reinterpret_cast<const int4 *>(idx + (mp * 9 + tap) * 4);
-            const float4 w = *reinterpret_cast<const float4 *>(wgt + (mp * 9 + tap) * 4);
-            float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (bias != nullptr) {
-                bs.x = bias[c];
-                if (c + 1 < C) bs.y = bias[c + 1];
-                if (c + 2 < C) bs.z = bias[c + 2];
-                if (c + 3 < C) bs.w = bias[c + 3];
-            }
-            const float *xb = x + b * in_img_pixels * x_pitch + c;
+    const int lane = threadIdx.x & 31;
+    const bool vec = (x_pitch & 3) == 0;
+    for (long m = blockIdx.x * 8L + (threadIdx.x >> 5); m < M; m += gridDim.x * 8L) {
+        const long b = m / Mo_img;
+        const int mp = static_cast<int>(m - b * Mo_img);
+        const float *xb = x + b * in_img_pixels * x_pitch;
+        __nv_bfloat16 *row_hi = A_hi + m * Kp;
+        __nv_bfloat16 *row_lo = A_lo ? A_lo + m * Kp : nullptr;
+        for (int tap = 0; tap < 9; ++tap) {
+            const int4 id = __ldg(reinterpret_cast<const int4 *>(idx + (static_cast<long>(mp) * 9 + tap) * 4));
+            const float4 w = __ldg(reinterpret_cast<const float4 *>(wgt + (static_cast<long>(mp) * 9 + tap) * 4));
             const int ids[4] = {id.x, id.y, id.z, id.w};
             const float ws[4] = {w.x, w.y, w.z, w.w};
-            const bool full = c + 3 < C && (x_pitch & 3) == 0;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                if (ids[t] < 0) continue;
-                const float *p = xb + static_cast<long>(ids[t]) * x_pitch;
-                float4 v;
-                if (full) {
-                    v = __ldg(reinterpret_cast<const float4 *>(p));
-                } else {
-                    v.x = p[0];
-                    v.y = c + 1 < C ? p[1] : 0.f;
-                    v.z = c + 2 < C ? p[2] : 0.f;
-                    v.w = c + 3 < C ? p[3] : 0.f;
+            for (int q = lane; q < cq; q += 32) {
+                const int c = q * 4;
+                float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias != nullptr) {
+                    bs.x = bias[c];
+                    if (c + 1 < C) bs.y = bias[c + 1];
+                    if (c + 2 < C) bs.z = bias[c + 2];
+                    if (c + 3 < C) bs.w = bias[c + 3];
                 }
-                acc.x = fmaf(ws[t], apply_act(v.x + bs.x, act), acc.x);
-                acc.y = fmaf(ws[t], apply_act(v.y + bs.y, act), acc.y);
-                acc.z = fmaf(ws[t], apply_act(v.z + bs.z, act), acc.z);
-                acc.w = fmaf(ws[t], apply_act(v.w + bs.w, act), acc.w);
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool full = vec && c + 3 < C;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (ids[t] < 0) continue;
+                    const float *p = xb + static_cast<long>(ids[t]) * x_pitch + c;
+                    float4 v;
+                    if (full) {
+                        v = __ldg(reinterpret_cast<const float4 *>(p));
+                    } else {
+                        v.x = p[0];
+                        v.y = c + 1 < C ? p[1] : 0.f;
+                        v.z = c + 2 < C ? p[2] : 0.f;
+                        v.w = c + 3 < C ? p[3] : 0.f;
+                    }
+                    acc.x = fmaf(ws[t], apply_act(v.x + bs.x, act), acc.x);
+                    acc.y = fmaf(ws[t], apply_act(v.y + bs.y, act), acc.y);
+                    acc.z = fmaf(ws[t], apply_act(v.z + bs.z, act), acc.z);
+                    acc.w = fmaf(ws[t], apply_act(v.w + bs.w, act), acc.w);
+                }
+                if (c + 1 >= C) acc.y = 0.f;
+                if (c + 2 >= C) acc.z = 0.f;
+                if (c + 3 >= C) acc.w = 0.f;
+                __nv_bfloat162 h01 = __floats2bfloat162_rn(acc.x, acc.y), h23 = __floats2bfloat162_rn(acc.z, acc.w);
+                uint2 hv;
+                hv.x = *reinterpret_cast<uint32_t *>(&h01); hv.y = *reinterpret_cast<uint32_t *>(&h23);
+                const int ko = (tap * cq + q) * 4;
+                *reinterpret_cast<uint2 *>(row_hi + ko) = hv;
+                if (row_lo != nullptr) {
+                    __nv_bfloat162 l01 = __floats2bfloat162_rn(acc.x - __low2float(h01), acc.y - __high2float(h01));
+                    __nv_bfloat162 l23 = __floats2bfloat162_rn(acc.z - __low2float(h23), acc.w - __high2float(h23));
+                    uint2 lv;
+                    lv.x = *reinterpret_cast<uint32_t *>(&l01); lv.y = *reinterpret_cast<uint32_t *>(&l23);
+                    *reinterpret_cast<uint2 *>(row_lo + ko) = lv;
+                }
             }
-            if (c + 1 >= C) acc.y = 0.f;
-            if (c + 2 >= C) acc.z = 0.f;
-            if (c + 3 >= C) acc.w = 0.f;
         }
-        __nv_bfloat162 h01 = __floats2bfloat162_rn(acc.x, acc.y), h23 = __floats2bfloat162_rn(acc.z, acc.w);
-        uint2 hv;
-        hv.x = *reinterpret_cast<uint32_t *>(&h01); hv.y = *reinterpret_cast<uint32_t *>(&h23);
-        *reinterpret_cast<uint2 *>(A_hi + m * Kp + qk * 4) = hv;
-        if (A_lo != nullptr) {
-            __nv_bfloat162 l01 = __floats2bfloat162_rn(acc.x - __low2float(h01), acc.y - __high2float(h01));
-            __nv_bfloat162 l23 = __floats2bfloat162_rn(acc.z - __low2float(h23), acc.w - __high2float(h23));
-            uint2 lv;
-            lv.x = *reinterpret_cast<uint32_t *>(&l01); lv.y = *reinterpret_cast<uint32_t *>(&l23);
-            *reinterpret_cast<uint2 *>(A_lo + m * Kp + qk * 4) = lv;
+        for (int qk = 9 * cq + lane; qk < kq; qk += 32) {                 // zero the K padding
+            *reinterpret_cast<uint2 *>(row_hi + qk * 4) = make_uint2(0u, 0u);
+            if (row_lo != nullptr) *reinterpret_cast<uint2 *>(row_lo + qk * 4) = make_uint2(0u, 0u);
         }
     }
 }
@@ -306,10 +314,11 @@ extern "C" int eml_im2col_lut_bf16(const float *x, int x_pitch, int C, int Cp, c
     if (Kp < 9 * Cp || (Kp & 63)) return EML_E_SHAPE;
     if (act < 0 || act > 2) return EML_E_ARG;
     if ((x_pitch & 3) == 0) EML_CHECK_ALIGN16(x);
-    const long total = static_cast<long>(B) * out_pixels * (Kp / 4);
-    im2col_lut_bf16_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    if (out_pixels >= (1L << 31)) return EML_E_SHAPE;
+    const long M = static_cast<long>(B) * out_pixels;
+    im2col_lut_bf16_kernel<<<grid_for(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         x, x_pitch, C, Cp, lut_idx, lut_w, bias, act, static_cast<__nv_bfloat16 *>(A_hi), static_cast<__nv_bfloat16 *>(A_lo), Kp,
-        out_pixels, in_pixels, total);
+        static_cast<int>(out_pixels), in_pixels, M);
     return eml_launch_status();
 }
 

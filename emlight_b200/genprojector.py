@@ -439,6 +439,8 @@ class SPADEGenerator(nn.Module):
             raise ValueError("only num_upsampling_layers='normal' (the reference default) is implemented")
         self.opt = opt
         self.precision = precision
+        self.use_cuda_graph = False      # replay the whole forward (hundreds of launches) as one CUDA graph per input shape
+        self._graphs = {}
         nf = opt.ngf
         self.sw = opt.crop_size // 32
         self.sh = round(self.sw / opt.aspect_ratio)
@@ -459,7 +461,13 @@ class SPADEGenerator(nn.Module):
                                       "iteration) and backward are not implemented in this round; call .eval() for inference")
         _lib.require_cuda(input, crop)
         with torch.no_grad():
+            if self.use_cuda_graph:
+                from .graphs import graphed_call
+                return graphed_call(self._graphs, self._graph_key(), self._run, (input, crop))
             return self._run(input, crop)
+
+    def _graph_key(self):
+        return (self.precision,) + tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
 
     def _run(self, guide, crop):
         lib = _lib.load()

@@ -11,6 +11,8 @@ ap.add_argument("--batch", type=int, default=4)
 ap.add_argument("--ngf", type=int, default=64)
 ap.add_argument("--precision", default="bf16x3")
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--profile", action="store_true")
+ap.add_argument("--graph", action="store_true")
 args = ap.parse_args()
 opt = argparse.Namespace(ngf=args.ngf, norm_G="spectralspadesyncbatch3x3", norm_E="spectralinstance", semantic_nc=3,
                          num_upsampling_layers="normal", crop_size=256, aspect_ratio=2.0)
@@ -23,6 +25,32 @@ crop = torch.rand(args.batch, 3, 128, 128, generator=g).to(dev)
 for _ in range(2):
     out = G(guide, crop)
 torch.cuda.synchronize()
+if args.profile:
+    # per-entry-point device time of one forward, measured with CUDA events around every C-ABI call (no syncs inside)
+    from emlight_b200 import _lib
+    lib = _lib.load()
+    rec = []
+    import ctypes
+    class Wrap:
+        def __init__(self, name, fn): self.name, self.fn = name, fn
+        def __call__(self, *a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = self.fn(*a); e1.record(); rec.append((self.name, e0, e1)); return r
+    names = [n for n in _lib.SIGNATURES if n not in ("eml_version", "eml_error_string", "eml_device_ok", "eml_conv_wpack_bytes", "eml_sinkhorn_workspace_bytes")]
+    orig = {n: getattr(lib, n) for n in names}
+    for n in names: setattr(lib, n, Wrap(n, orig[n]))
+    t0 = time.perf_counter(); G(guide, crop); t_cpu = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    for n in names: setattr(lib, n, orig[n])
+    import collections
+    agg = collections.Counter(); cnt = collections.Counter()
+    for n, a, b in rec: agg[n] += a.elapsed_time(b); cnt[n] += 1
+    print("profile: host time to enqueue one forward %.2f ms, %d C-ABI calls" % (t_cpu * 1e3, len(rec)))
+    for n, v in agg.most_common(): print("  %-28s x%4d %8.3f ms" % (n, cnt[n], v))
+if args.graph:
+    G.use_cuda_graph = True
+    for _ in range(3): out = G(guide, crop)
+    torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(args.steps):
