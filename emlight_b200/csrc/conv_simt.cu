@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_simt_kernel(const SimtArgs 
 __global__ void __launch_bounds__(128) stem_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                    const float *__restrict__ scale, const float *__restrict__ shift,
                                                    float *__restrict__ out, int out_pitch, double *stats_raw,
-                                                   double *stats_out, long so_stride, int B, int H, int W, int C_out, int write_out) {
+                                                   double *stats_out, long so_stride, int B, int H, int W, int C_out, int write_out,
+                                                   int relu) {
     __shared__ float s_w[32 * 27];
     __shared__ float s_sc[32], s_sh[32];
     __shared__ double s_red[4][32][4];
@@ -140,7 +141,10 @@ __global__ void __launch_bounds__(128) stem_kernel(const float *__restrict__ x, 
     }
     float res[32];
 #pragma unroll
-    for (int o = 0; o < 32; ++o) res[o] = fmaxf(fmaf(acc[o], s_sc[o], s_sh[o]), 0.f);
+    for (int o = 0; o < 32; ++o) {
+        res[o] = fmaf(acc[o], s_sc[o], s_sh[o]);
+        if (relu) res[o] = fmaxf(res[o], 0.f);
+    }
     if (ok && write_out) {
         float *op = out + m * out_pitch;
         if ((out_pitch & 3) == 0 && (C_out & 3) == 0) {
@@ -288,14 +292,15 @@ int eml_conv_forward_simt(const eml_conv_params *p, cudaStream_t st) {
 
 extern "C" int eml_stem_forward(const float *x_nchw, const float *w_oihw, const float *scale, const float *shift,
                                 float *out, int out_pitch, double *stats_raw, double *stats_out,
-                                long stats_out_stride, int B, int H, int W, int C_out, int write_out, void *stream) {
+                                long stats_out_stride, int B, int H, int W, int C_out, int write_out, int relu,
+                                void *stream) {
     EML_CHECK_PTR(x_nchw); EML_CHECK_PTR(w_oihw);
     if (write_out) { EML_CHECK_PTR(out); EML_CHECK_ALIGN16(out); }
     if (B <= 0 || H <= 0 || W <= 0 || C_out <= 0 || C_out > 32 || out_pitch < C_out) return EML_E_SHAPE;
     const long P = static_cast<long>(B) * H * W;
     stem_kernel<<<static_cast<unsigned>((P + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
         x_nchw, w_oihw, scale, shift, out, out_pitch, stats_raw, stats_out,
-        stats_out_stride > 0 ? stats_out_stride : C_out, B, H, W, C_out, write_out);
+        stats_out_stride > 0 ? stats_out_stride : C_out, B, H, W, C_out, write_out, relu);
     return eml_launch_status();
 }
 

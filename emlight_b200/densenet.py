@@ -19,7 +19,9 @@ BatchNorm follows ``self.training`` like the reference: batch statistics (accumu
 epilogues, folded by eml_bn_fold) + running-stat update in train mode -- which is what the reference's test.py
 actually runs -- running statistics in eval mode.
 
-Backward through the network is not implemented in this round: outputs carry a grad_fn that raises.
+Backward (training-mode BatchNorm, the mode train.py runs) is `_backward`: both data-gradient convolutions are the same
+tcgen05 implicit-GEMM kernels with transposed / flipped weights, BatchNorm backward and the weight gradients are the kernels of
+csrc/bwd_ops.cu, the 48-channel bottleneck is recomputed instead of stored, the tiny fc / head GEMMs use torch.matmul (cuBLAS).
 """
 import math
 from collections import OrderedDict
@@ -69,19 +71,32 @@ class _DenseBlock(nn.Sequential):
             self.add_module("denselayer%d" % (i + 1), _DenseLayer(c_in + i * growth_rate, growth_rate, bn_size, drop_rate))
 
 
-class _ForwardOnly(torch.autograd.Function):
-    """Marks the outputs as differentiable-in-principle so that a training script fails loudly, not silently."""
+class _DenseNetFn(torch.autograd.Function):
+    """Whole-network autograd node: forward runs the kernel sequence, backward runs `DenseNet._backward` (training-mode BN only)."""
 
     @staticmethod
     def forward(ctx, module, x, *params):
         outs = module._run(x)
+        ctx.module = module
+        ctx.fwd_id = module._fwd_id
+        ctx.n_params = len(params)
+        ctx.save_for_backward(x)
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *grads):
-        raise NotImplementedError(
-            "emlight_b200.DenseNet: backward (dgrad/wgrad kernels) is not implemented in this round; "
-            "run inference under torch.no_grad() or use the reference module for training")
+        module = ctx.module
+        if not module._last_train:
+            raise NotImplementedError("emlight_b200.DenseNet.backward is implemented for training-mode BatchNorm (module.train()), "
+                                      "the mode RegressionNetwork/train.py runs; eval-mode backward is not implemented")
+        if ctx.fwd_id != module._fwd_id:
+            raise RuntimeError("emlight_b200.DenseNet: backward() must follow its own forward() (activations are kept in a single "
+                               "workspace and were overwritten by a later forward)")
+        (x,) = ctx.saved_tensors
+        named = module._backward(x, grads)
+        out = [named.get(n) for n, p in module.named_parameters() if p.requires_grad]
+        assert len(out) == ctx.n_params
+        return (None, None) + tuple(out)
 
 
 class DenseNet(nn.Module):
@@ -122,6 +137,8 @@ class DenseNet(nn.Module):
         self._cache = None                             # packed weights + folded eval-mode BN, keyed on param versions
         self._ws = {}                                  # activation workspaces keyed on (B,H,W,device)
         self.launch_log = None                         # set to a list to collect (kernel family, name, shape info, start, end events)
+        self._fwd_id = 0                               # bumped by every forward; backward checks it still owns the workspace
+        self._last_train = False
         self.use_cuda_graph = False                    # eval mode only: replay the 104-launch forward as one CUDA graph per input shape
         self._graphs = {}
 
@@ -132,7 +149,7 @@ class DenseNet(nn.Module):
             raise ValueError("expected input (B,3,H,W), got %s" % (tuple(x.shape),))
         params = [p for p in self.parameters() if p.requires_grad]
         if torch.is_grad_enabled() and (x.requires_grad or params):
-            d, i, r, a = _ForwardOnly.apply(self, x, *params)
+            d, i, r, a = _DenseNetFn.apply(self, x, *params)
         elif self.use_cuda_graph and not self.training and self.launch_log is None:
             from .graphs import graphed_call
             d, i, r, a = graphed_call(self._graphs, self._state_key(x.device), lambda t: tuple(self._run(t)), (x,))
@@ -324,6 +341,8 @@ class DenseNet(nn.Module):
         ws = self._workspace(B, H, W, dev)
         st = _lib.stream_ptr()
         train = self.training
+        self._fwd_id += 1
+        self._last_train = train
         f = self.features
         g = 4 * self.growth_rate
         so = ws["stats_offs"]
@@ -347,12 +366,12 @@ class DenseNet(nn.Module):
         if train:
             raw = stats[so["stem_raw"]:]
             _lib.check(lib.eml_stem_forward(_lib.ptr(x), _lib.ptr(c["w0"]), None, None, None, pitch, _lib.ptr(raw), None, 0,
-                                            B, H, W, f.conv0.out_channels, 0, st), "eml_stem_forward(stats)")
+                                            B, H, W, f.conv0.out_channels, 0, 1, st), "eml_stem_forward(stats)")
             self._fold(c, "norm0", f.norm0, stats=raw, stride=f.conv0.out_channels, count=B * H * W,
                        mean_var=mv(f.norm0, B * H * W))
         a0 = self._aff(c, "norm0")
         _lib.check(lib.eml_stem_forward(_lib.ptr(x), _lib.ptr(c["w0"]), _lib.ptr(a0[0]), _lib.ptr(a0[1]), _lib.ptr(slab), pitch,
-                                        None, _lib.ptr(s1) if train else None, pitch, B, H, W, f.conv0.out_channels, 1, st),
+                                        None, _lib.ptr(s1) if train else None, pitch, B, H, W, f.conv0.out_channels, 1, 1, st),
                    "eml_stem_forward")
         # ---- dense blocks + transitions
         pre = None
@@ -424,3 +443,170 @@ class DenseNet(nn.Module):
             m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
             bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
             bn.running_var.mul_(1 - m).add_(var, alpha=m * count / max(count - 1, 1))
+
+    # ------------------------------------------------------------------ backward (training-mode BN)
+    def _gemm_bwd(self, src_ptr, src_pitch, B, H, W, c_in, w_oihw, dst, mode):
+        """dst[..., :N] = conv(src, w) with no prologue affine, N sliced into <= 256 output channels (dgrad GEMMs)."""
+        lib = _lib.load()
+        st = _lib.stream_ptr()
+        N = w_oihw.shape[0]
+        taps = w_oihw.shape[2] * w_oihw.shape[3]
+        for n0 in range(0, N, 256):
+            n = min(256, N - n0)
+            w_s = w_oihw[n0:n0 + n].contiguous()
+            pack = None
+            if self.precision != "fp32":
+                pack = torch.empty(lib.eml_conv_wpack_bytes(n, c_in, taps), dtype=torch.uint8, device=dst.device)
+                _lib.check(lib.eml_conv_pack_weights(_lib.ptr(w_s), _lib.ptr(pack), n, c_in, taps, st), "eml_conv_pack_weights")
+            p = ConvParams()
+            p.in_ = src_ptr; p.scale = None; p.shift = None
+            p.w_oihw = w_s.data_ptr(); p.wpack = pack.data_ptr() if pack is not None else None
+            p.out = dst.data_ptr(); p.stats = None; p.stats_stride = 0
+            p.B, p.H, p.W = B, H, W
+            p.C_in, p.in_pitch = c_in, src_pitch
+            p.C_out, p.out_pitch, p.out_choff = n, dst.shape[-1], n0
+            p.mode, p.relu, p.precision = mode, 0, _lib.PRECISIONS[self.precision]
+            _lib.check(lib.eml_conv_forward(p, st), "eml_conv_forward(dgrad)")
+
+    @torch.no_grad()
+    def _backward(self, x, grads):
+        lib = _lib.load()
+        st = _lib.stream_ptr()
+        dev = x.device
+        B, _, H, W = x.shape
+        x = x.contiguous().float()
+        c = self._cache
+        ws = self._ws[(B, H, W, str(dev))]
+        f = self.features
+        g = 4 * self.growth_rate
+        gr = self.growth_rate
+        offs, o = {}, 0
+        for name, bn in self._bns():
+            offs[name] = (o, bn.num_features)
+            o += bn.num_features
+        mean_all = ws["bmean"]
+        inv_all = torch.rsqrt(ws["bvar"] + _EPS)
+        cmax = _up4(max(p[2] for p in self._plan))
+        sums = torch.zeros(2 * cmax, dtype=torch.float64, device=dev)
+        out = {}
+
+        def bn_bwd(name, bn, prefix, grad, g_pitch, xs, x_pitch, pre, relu, pool, h, w, M, C, dst, dst_pitch, accumulate):
+            """BatchNorm(+ReLU) backward: fills d gamma / d beta, writes or accumulates the input gradient."""
+            o0, _ = offs[name]
+            mean, inv = mean_all[o0:o0 + C], inv_all[o0:o0 + C]
+            pa, pb = (None, None) if pre is None else pre
+            sums.zero_()
+            _lib.check(lib.eml_bn_bwd_reduce(grad, g_pitch, xs, x_pitch, _lib.ptr(pa), _lib.ptr(pb), _lib.ptr(mean), _lib.ptr(inv),
+                                             _lib.ptr(bn.weight), _lib.ptr(bn.bias), relu, pool, h, w, M, C, _lib.ptr(sums), cmax, st),
+                       "eml_bn_bwd_reduce(%s)" % name)
+            _lib.check(lib.eml_bn_bwd_apply(grad, g_pitch, xs, x_pitch, _lib.ptr(pa), _lib.ptr(pb), _lib.ptr(mean), _lib.ptr(inv),
+                                            _lib.ptr(bn.weight), _lib.ptr(bn.bias), relu, pool, h, w, M, C, _lib.ptr(sums), cmax,
+                                            dst, dst_pitch, accumulate, 0, st), "eml_bn_bwd_apply(%s)" % name)
+            out[prefix + ".weight"] = sums[cmax:cmax + C].float()
+            out[prefix + ".bias"] = sums[:C].float()
+
+        # ---- heads and fc: plain small GEMMs (torch.matmul / cuBLAS)
+        heads = (("fc_dist", self.fc_dist), ("fc_intensity", self.fc_intensity), ("fc_rgb_ratio", self.fc_rgb_ratio), ("fc_ambient", self.fc_ambient))
+        dh = torch.cat([(gd if gd is not None else torch.zeros(B, m.out_features, device=dev)).float().reshape(B, -1)
+                        for gd, (_, m) in zip(grads, heads)], 1)
+        fc_out, pooled = ws["fc"], ws["pooled"]
+        dwh = dh.t() @ fc_out
+        o = 0
+        for n, m in heads:
+            out[n + ".weight"] = dwh[o:o + m.out_features].contiguous()
+            out[n + ".bias"] = dh[:, o:o + m.out_features].sum(0)
+            o += m.out_features
+        dfc = dh @ c["head_w"]
+        c_last = self._plan[-1][3]
+        P = self.fc.in_features // c_last
+        out["fc.weight"] = (dfc.t() @ pooled).view(-1, P, c_last).permute(0, 2, 1).reshape(self.fc.out_features, -1).contiguous()
+        out["fc.bias"] = dfc.sum(0)
+        dpool = dfc @ c["fc_w"]                                                  # (B, P*c_last) in (yo, xo, c) order
+        hl, wl = ws["t_last"].shape[1], ws["t_last"].shape[2]
+        k = self.avgpool_size
+        dz = (dpool.view(B, hl // k, wl // k, c_last).repeat_interleave(k, 1).repeat_interleave(k, 2) / float(k * k)).contiguous()
+        # relu + last_norm{last} backward -> gradient w.r.t. the stored raw transition output
+        nb = len(self._plan)
+        dt = torch.zeros(B, hl, wl, ws["t_last"].shape[3], dtype=torch.float32, device=dev)
+        ln = getattr(f, "last_norm%d" % self._plan[-1][0])
+        bn_bwd("ln%d" % self._plan[-1][0], ln, "features.last_norm%d" % self._plan[-1][0], _lib.ptr(dz), c_last, _lib.ptr(ws["t_last"]),
+               ws["t_last"].shape[3], None, 1, 0, hl, wl, B * hl * wl, c_last, _lib.ptr(dt), dt.shape[3], 0)
+        dbg = getattr(self, "_debug", None)
+        if dbg is not None:
+            dbg["dz"] = dz.clone(); dbg["dt_last"] = dt.clone(); dbg["t_last"] = ws["t_last"].clone()
+            o0, _ = offs["ln%d" % self._plan[-1][0]]
+            dbg["ln_mean"] = mean_all[o0:o0 + c_last].clone(); dbg["ln_inv"] = inv_all[o0:o0 + c_last].clone()
+
+        for bi in range(nb - 1, -1, -1):
+            b, c_in, c_out, c_tr = self._plan[bi]
+            slab = ws["slab"][bi]
+            pitch = slab.shape[3]
+            h, w = ws["geom"][bi]
+            M = B * h * w
+            Mp = B * (h // 2) * (w // 2)
+            pre = (c["pre"][bi, 0], c["pre"][bi, 1])
+            dS = torch.zeros(B, h, w, pitch, dtype=torch.float32, device=dev)
+            # ---- transition b: dp = dt . W_t ; dW_t ; BN(+ReLU, pooled gradient) backward into the slab gradient
+            tr = getattr(f, "transition%d" % b)
+            wt = tr.conv.weight.detach().float()                                  # (c_tr, c_out, 1, 1)
+            dp = torch.empty(B, h // 2, w // 2, _up4(c_out), dtype=torch.float32, device=dev)
+            self._gemm_bwd(dt.data_ptr(), dt.shape[3], B, h // 2, w // 2, c_tr, wt.permute(1, 0, 2, 3).contiguous(), dp, _lib.EML_CONV_1x1)
+            a_t = self._aff(c, "t%d.norm" % b)
+            dwt = torch.zeros(c_tr, c_out, dtype=torch.float32, device=dev)
+            _lib.check(lib.eml_wgrad_1x1(_lib.ptr(dt), dt.shape[3], c_tr, _lib.ptr(slab), pitch, c_out, _lib.ptr(a_t[0]), _lib.ptr(a_t[1]),
+                                         1, 1, h, w, _lib.ptr(dwt), Mp, st), "eml_wgrad_1x1(transition%d)" % b)
+            out["features.transition%d.conv.weight" % b] = dwt.view(c_tr, c_out, 1, 1)
+            bn_bwd("t%d.norm" % b, tr.norm, "features.transition%d.norm" % b, _lib.ptr(dp), dp.shape[3], _lib.ptr(slab), pitch, pre, 1, 1,
+                   h, w, M, c_out, _lib.ptr(dS), pitch, 1)
+            del dp
+            # ---- dense layers, last to first
+            blk = getattr(f, "denseblock%d" % b)
+            layers = list(blk.children())
+            dN = torch.empty(B, h, w, g, dtype=torch.float32, device=dev)
+            for l in range(len(layers) - 1, -1, -1):
+                layer = layers[l]
+                ci = c_in + l * gr
+                pfx = "features.denseblock%d.denselayer%d" % (b, l + 1)
+                n1, n2 = "b%d.l%d.norm1" % (b, l), "b%d.l%d.norm2" % (b, l)
+                a1, a2 = self._aff(c, n1), self._aff(c, n2)
+                # recompute the bottleneck (conv1 output) instead of having stored it
+                self._conv(c, "b%d.l%d.conv1" % (b, l), slab, pitch, h, w, B, ci, ws["bott"], g, 0, g, _lib.EML_CONV_1x1, 1, a1, None, g)
+                # gradient of this layer's 12 output channels; compacted because block 3's channel offsets (150 + 12 l) are not
+                # 16-byte aligned and the gather uses float4 loads
+                dy = dS[..., ci:ci + gr].contiguous()
+                w2 = layer.conv2.weight.detach().float()                          # (12, 48, 3, 3)
+                self._gemm_bwd(dy.data_ptr(), gr, B, h, w, gr, w2.permute(1, 0, 2, 3).flip(2, 3).contiguous(), dN, _lib.EML_CONV_3x3)
+                dw2 = torch.zeros(gr, g, 3, 3, dtype=torch.float32, device=dev)
+                _lib.check(lib.eml_wgrad_3x3(_lib.ptr(dy), gr, gr, _lib.ptr(ws["bott"]), g, g, _lib.ptr(a2[0]), _lib.ptr(a2[1]), _lib.ptr(dw2),
+                                             B, h, w, st), "eml_wgrad_3x3")
+                out[pfx + ".conv2.weight"] = dw2
+                bn_bwd(n2, layer.norm2, pfx + ".norm2", _lib.ptr(dN), g, _lib.ptr(ws["bott"]), g, None, 0, 0, h, w, M, g, _lib.ptr(dN), g, 0)
+                w1 = layer.conv1.weight.detach().float()                          # (48, ci, 1, 1)
+                dA = torch.empty(B, h, w, _up4(ci), dtype=torch.float32, device=dev)
+                self._gemm_bwd(dN.data_ptr(), g, B, h, w, g, w1.permute(1, 0, 2, 3).contiguous(), dA, _lib.EML_CONV_1x1)
+                dw1 = torch.zeros(g, ci, dtype=torch.float32, device=dev)
+                _lib.check(lib.eml_wgrad_1x1(_lib.ptr(dN), g, g, _lib.ptr(slab), pitch, ci, _lib.ptr(a1[0]), _lib.ptr(a1[1]), 1, 0, h, w,
+                                             _lib.ptr(dw1), M, st), "eml_wgrad_1x1(conv1)")
+                out[pfx + ".conv1.weight"] = dw1.view(g, ci, 1, 1)
+                bn_bwd(n1, layer.norm1, pfx + ".norm1", _lib.ptr(dA), dA.shape[3], _lib.ptr(slab), pitch, pre, 1, 0, h, w, M, ci,
+                       _lib.ptr(dS), pitch, 1)
+                del dA
+            # ---- block input
+            if bi > 0:
+                pb, _, _, ptr_c = self._plan[bi - 1]
+                ln = getattr(f, "last_norm%d" % pb)
+                dt = torch.zeros(B, h, w, pitch, dtype=torch.float32, device=dev)
+                bn_bwd("ln%d" % pb, ln, "features.last_norm%d" % pb, _lib.ptr(dS), pitch, _lib.ptr(slab), pitch, None, 0, 0, h, w, M, ptr_c,
+                       _lib.ptr(dt), pitch, 0)
+            else:
+                c0 = f.conv0.out_channels
+                z0 = torch.empty(B, h, w, c0, dtype=torch.float32, device=dev)
+                _lib.check(lib.eml_stem_forward(_lib.ptr(x), _lib.ptr(c["w0"]), None, None, _lib.ptr(z0), c0, None, None, 0, B, H, W, c0, 1, 0, st),
+                           "eml_stem_forward(recompute)")
+                dz0 = torch.empty_like(z0)
+                bn_bwd("norm0", f.norm0, "features.norm0", _lib.ptr(dS), pitch, _lib.ptr(z0), c0, None, 1, 0, h, w, M, c0, _lib.ptr(dz0), c0, 0)
+                dw0 = torch.zeros(c0, 3, 3, 3, dtype=torch.float32, device=dev)
+                _lib.check(lib.eml_wgrad_stem(_lib.ptr(dz0), c0, c0, _lib.ptr(x), _lib.ptr(dw0), B, H, W, st), "eml_wgrad_stem")
+                out["features.conv0.weight"] = dw0
+            del dS
+        return out

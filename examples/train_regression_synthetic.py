@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""The reference's regression training loop (RegressionNetwork/train.py:55-102) on synthetic data, running on the sm_100a
+drop-in modules: DenseNet forward/backward, SamplesLoss (Sinkhorn EMD) forward/backward, torch.optim.Adam.
+
+Single GPU:   python examples/train_regression_synthetic.py --steps 5
+Multi GPU :   torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 examples/train_regression_synthetic.py
+              (one process per GPU, the batch is sharded, ONE bucketed NCCL all-reduce of the gradients per step)
+
+The loss weights are train.py:92-98's: EMD x1000, L2(dist) x1000, intensity x0.1, rgb x100, ambient x1.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import torch.nn as nn
+
+import emlight_b200 as E
+from emlight_b200 import parallel
+
+
+def synthetic_batch(B, ln, gen, dev):
+    """Shapes / distributions of SURVEY.md section 8d."""
+    crop = torch.rand(B, 3, 192, 256, generator=gen)
+    dist = torch.softmax(3 * torch.randn(B, ln, generator=gen), 1)
+    inten = torch.rand(B, 1, generator=gen)
+    rgb = nn.functional.normalize(0.2 + 0.8 * torch.rand(B, 3, generator=gen), dim=1)
+    amb = 0.1 * torch.rand(B, 3, generator=gen)
+    return [t.to(dev) for t in (crop, dist, inten, rgb, amb)]
+
+
+def train_step(model, sam_loss, l2, optimizer, batch, ln, world):
+    crop, dist_gt, inten_gt, rgb_gt, amb_gt = batch
+    pred = model(crop)
+    dist_pred = pred["distribution"].view(-1, ln, 1)
+    dist_emloss = sam_loss(dist_pred, dist_gt.view(-1, ln, 1)).sum() * 1000.0
+    dist_l2loss = l2(dist_pred, dist_gt.view(-1, ln, 1)) * 1000.0
+    intensity_loss = l2(pred["intensity"], inten_gt) * 0.1
+    rgb_loss = l2(pred["rgb_ratio"], rgb_gt) * 100.0
+    ambient_loss = l2(pred["ambient"], amb_gt) * 1.0
+    loss = dist_emloss + dist_l2loss + intensity_loss + rgb_loss + ambient_loss
+    optimizer.zero_grad()
+    loss.backward()
+    if world > 1:
+        parallel.allreduce_mean_([p.grad for p in model.parameters() if p.grad is not None])
+    optimizer.step()
+    return loss.detach(), dist_emloss.detach()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=16, help="per GPU (train.py:25 uses 16)")
+    ap.add_argument("--anchors", type=int, default=96)
+    ap.add_argument("--precision", default="bf16x3")
+    args = ap.parse_args()
+    rank, world, local = parallel.env_rank_world()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    parallel.init("nccl", dev)
+    torch.manual_seed(0)
+    model = E.DenseNet(n_anchors=args.anchors, precision=args.precision).to(dev).train()
+    optimizer = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.999))           # train.py:55-57
+    l2 = nn.MSELoss().to(dev)
+    sam_loss = E.SamplesLoss("sinkhorn", p=2, blur=.025, batchsize=args.batch)               # train.py:61
+    gen = torch.Generator().manual_seed(1234 + rank)
+    batch = synthetic_batch(args.batch, args.anchors, gen, dev)                              # one fixed batch: the loss must go down
+    losses = []
+    for i in range(args.steps):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        loss, em = train_step(model, sam_loss, l2, optimizer, batch, args.anchors, world)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        losses.append(float(loss))
+        if rank == 0:
+            print(json.dumps({"step": i, "loss": float(loss), "dist_emloss": float(em), "ms": dt * 1e3,
+                              "maps_per_s": args.batch * world / dt}))
+    if rank == 0:
+        # NB: with Adam(1e-4) and the x1000 loss weights the first updates are noisy (the reference module shows the same
+        # 78 -> 470 -> 81 -> 123 pattern on such a batch); parity of the trajectory is checked in tests/test_training_gpu.py
+        print("losses:", " ".join("%.3f" % v for v in losses))
+
+
+if __name__ == "__main__":
+    main()

@@ -124,13 +124,13 @@ size_t eml_conv_wpack_bytes(int C_out, int C_in, int taps);
 int eml_conv_pack_weights(const float *w_oihw, void *wpack, int C_out, int C_in, int taps, void *stream);
 int eml_conv_forward(const eml_conv_params *p, void *stream);
 
-/* Stem: conv0 3x3 (3 -> C_out<=32) on the NCHW input image, fused affine+ReLU, NHWC output at channel 0.
+/* Stem: conv0 3x3 (3 -> C_out<=32) on the NCHW input image, fused affine (+ReLU when relu != 0), NHWC output at channel 0.
  * Replaces DenseNet.py:89-92 (conv0, norm0, relu0).  scale/shift NULL => raw convolution output.
  * stats_raw: NULL or (2,C_out) double accumulators of the pre-affine values; stats_out: NULL or accumulators of
  * the written values with the sum-of-squares row `stats_out_stride` doubles after the sum row (0 => C_out). */
 int eml_stem_forward(const float *x_nchw, const float *w_oihw, const float *scale, const float *shift,
                      float *out, int out_pitch, double *stats_raw, double *stats_out, long stats_out_stride,
-                     int B, int H, int W, int C_out, int write_out, void *stream);
+                     int B, int H, int W, int C_out, int write_out, int relu, void *stream);
 
 /* BatchNorm bookkeeping (DenseNet.py:17,30,41,91,122; eps 1e-5).
  * Given per-channel accumulators stats=(sum, sumsq) over `count` values of the STORED tensor t, an optional
@@ -202,6 +202,33 @@ int eml_instance_norm(const float *x, int x_pitch, float *out, int out_pitch, in
 
 /* out_nchw = (tanh(x + bias[c]) + 1) * scale (generator.py:85-86). */
 int eml_tanh_to_nchw(const float *x, int x_pitch, const float *bias, float *out, int B, int HW, int C, float scale, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * D1-D5 backward -- autograd of RegressionNetwork/DenseNet.py under training-mode BatchNorm (what train.py:82-102 runs).
+ * The data-gradient convolutions are eml_conv_forward with transposed / flipped weights; these entry points add the rest.
+ *
+ * BatchNorm backward in two passes over a BN whose input is the stored tensor x (u = pre_a*x + pre_b, xhat = (u-mean)*inv_std,
+ * z = gamma*xhat + beta, optional ReLU after it) and whose output gradient is `grad` (pool=1: grad is indexed by the 2x2-pooled
+ * pixel and scaled by 1/4 -- the transition's avg_pool2d):
+ *   reduce: sums[c] += sum g,  sums[sums_stride + c] += sum g*xhat      (g = grad masked by z > 0 when relu)   => d beta, d gamma
+ *   apply : du = gamma*inv_std*(g - sums0/M - xhat*sums1/M);  out (=|+=) du   (times pre_a when to_stored)
+ */
+int eml_bn_bwd_reduce(const float *grad, int g_pitch, const float *x, int x_pitch, const float *pre_a, const float *pre_b,
+                      const float *mean, const float *inv_std, const float *gamma, const float *beta, int relu, int pool, int H,
+                      int W, long M, int C, double *sums, long sums_stride, void *stream);
+int eml_bn_bwd_apply(const float *grad, int g_pitch, const float *x, int x_pitch, const float *pre_a, const float *pre_b,
+                     const float *mean, const float *inv_std, const float *gamma, const float *beta, int relu, int pool, int H,
+                     int W, long M, int C, const double *sums, long sums_stride, float *out, int out_pitch, int accumulate,
+                     int to_stored, void *stream);
+/* Weight gradients (accumulated into dW with atomics; zero dW first):
+ *   1x1 : dW[n,c]      += sum_m G[m,n] * act(scale[c]*x[m,c] + shift[c])       (pool=1: act, then 2x2 average; m over pooled pixels)
+ *   3x3 : dW[n,c,tap]  += sum_m dY[m,n] * (scale[c]*b[m+tap,c] + shift[c])      (zero outside the image; N <= 16, C <= 64)
+ *   stem: dW[o,ci,ky,kx] += sum_m dZ[m,o] * x_nchw[b,ci,y+ky-1,x+kx-1] */
+int eml_wgrad_1x1(const float *G, int g_pitch, int N, const float *x, int x_pitch, int C, const float *scale, const float *shift,
+                  int relu, int pool, int H, int W, float *dW, long M, void *stream);
+int eml_wgrad_3x3(const float *dY, int dy_pitch, int N, const float *b, int b_pitch, int C, const float *scale, const float *shift,
+                  float *dW, int B, int H, int W, void *stream);
+int eml_wgrad_stem(const float *dZ, int dz_pitch, int O, const float *x_nchw, float *dW, int B, int H, int W, void *stream);
 
 #ifdef __cplusplus
 }
