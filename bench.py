@@ -238,12 +238,22 @@ def main():
         for _ in range(3):
             cfg1()
         ms1 = timed(cfg1, 5) / 5
+        # BASELINE configs[1]/[3] as train.py runs it: forward + 5-term loss + full backward + Adam step
+        sys.path.insert(0, os.path.join(ROOT, "examples"))
+        from train_regression_synthetic import synthetic_batch, train_step
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.999))
+        tb = synthetic_batch(Bt, N_ANCHORS, gen, dev)
+        l2 = torch.nn.MSELoss()
+        for _ in range(2):
+            train_step(net, loss_fn, l2, opt, tb, N_ANCHORS, 1)
+        ms_tr = timed(lambda: train_step(net, loss_fn, l2, opt, tb, N_ANCHORS, 1), 3) / 3
         net.eval()
         x1 = x[:1].contiguous()
         for _ in range(3):
             step(x1)
         ms0 = timed(lambda: step(x1), 20) / 20
         extra = {"config1_densenet_fwd_trainBN_plus_sinkhorn_fwd_bwd_b64": {"ms_per_step": round(ms1, 3), "maps_per_s": round(Bt / ms1 * 1e3, 1)},
+                 "train_step_fwd_bwd_adam_b64": {"ms_per_step": round(ms_tr, 3), "maps_per_s": round(Bt / ms_tr * 1e3, 1)},
                  "config0_single_crop_latency_ms": round(ms0, 3)}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -82,6 +82,8 @@ def main():
         # NB: with Adam(1e-4) and the x1000 loss weights the first updates are noisy (the reference module shows the same
         # 78 -> 470 -> 81 -> 123 pattern on such a batch); parity of the trajectory is checked in tests/test_training_gpu.py
         print("losses:", " ".join("%.3f" % v for v in losses))
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
