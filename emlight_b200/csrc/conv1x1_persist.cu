@@ -26,7 +26,7 @@ constexpr int P_PWARPS = P_PRODUCERS / 32;
 constexpr int P_NROWS = P_TILE_M * 16 / P_PRODUCERS;   // rows per producer thread per chunk (4)
 constexpr int P_THREADS = P_PRODUCERS + 32 + 128;   // + MMA warp + 4 epilogue warps
 constexpr int P_A_TILE = P_TILE_M * P_CHUNK_K * 2;
-constexpr int P_ACC_COLS = 64;                  // TMEM columns per accumulator buffer (N_pad <= 64)
+constexpr int P_ACC_COLS = 128;                 // TMEM columns per accumulator buffer: [A_hi*B_hi | A_hi*B_lo] = 2 * N_pad <= 128
 
 struct PArgs {
     const float *in;
@@ -195,11 +195,16 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
             }
         }
         mbar_wait(bar_w, 0);
+        // bf16x3 with 2 MMAs per k-step: a chunk's packed weights [hi image | lo image] are 2*N_pad consecutive rows of ONE
+        // SWIZZLE_128B tile (N_pad % 8 == 0), so A_hi x [B_hi;B_lo] is a single N = 2*N_pad instruction filling columns
+        // [0,N_pad) with A_hi*B_hi and [N_pad,2*N_pad) with A_hi*B_lo; A_lo x B_hi (N = N_pad) adds into [0,N_pad);
+        // the epilogue sums the two halves.  A_hi is read from shared memory once instead of twice.
         const uint32_t idesc = make_idesc_bf16(P_TILE_M, a.N_pad);
+        const uint32_t idesc_cat = make_idesc_bf16(P_TILE_M, 2 * a.N_pad);
         const uint64_t dA0 = make_sw128_desc(smem_u32(smem));                 // stage 0, hi image
         const uint64_t dB0 = make_sw128_desc(smem_u32(w_sm));                 // chunk 0, hi image
         const uint32_t stage16 = STAGE_BYTES >> 4, alo16 = P_A_TILE >> 4;     // 16-byte units for the address field
-        const uint32_t wchunk16 = static_cast<uint32_t>(w_chunk_sm) >> 4, blo16 = static_cast<uint32_t>(b_tile_bytes) >> 4;
+        const uint32_t wchunk16 = static_cast<uint32_t>(w_chunk_sm) >> 4;
         uint32_t g = 0, j = 0;
         for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++j) {
             const uint32_t buf = j & 1, aph = (j >> 1) & 1;
@@ -214,14 +219,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
                     const int kvalid = min(P_CHUNK_K, a.C_in - c * P_CHUNK_K);
                     const int ksteps = (kvalid + 15) >> 4;
                     const uint64_t da_hi = dA0 + static_cast<uint64_t>(s * stage16), da_lo = da_hi + alo16;
-                    const uint64_t db_hi = dB0 + static_cast<uint64_t>(static_cast<uint32_t>(c) * wchunk16), db_lo = db_hi + blo16;
+                    const uint64_t db_hi = dB0 + static_cast<uint64_t>(static_cast<uint32_t>(c) * wchunk16);
                     for (int k = 0; k < ksteps; ++k) {
                         const uint64_t adv = static_cast<uint64_t>(k * 2);
-                        umma_bf16(d_tmem, da_hi + adv, db_hi + adv, idesc, (c | k) != 0 ? 1u : 0u);
-                        if (SPLIT) {
-                            umma_bf16(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
-                            umma_bf16(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
-                        }
+                        umma_bf16(d_tmem, da_hi + adv, db_hi + adv, SPLIT ? idesc_cat : idesc, (c | k) != 0 ? 1u : 0u);
+                        if (SPLIT) umma_bf16(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
                     }
                     umma_commit(bar_empty + 8 * s);
                     if (c == a.nchunks - 1) umma_commit(bar_accfull + 8 * buf);
@@ -253,6 +255,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
                 for (int g16 = 0; g16 < a.N_pad; g16 += 16) {
                     float v[16];
                     tmem_ld16(tmem_base + buf * P_ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g16), v);
+                    if (SPLIT) {
+                        float w2[16];
+                        tmem_ld16(tmem_base + buf * P_ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(a.N_pad + g16), w2);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] += w2[e];
+                    }
                     if (row_ok) {
 #pragma unroll
                         for (int e = 0; e < 16; ++e)
@@ -268,6 +276,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
             for (int g16 = 0; g16 < a.N_pad; g16 += 16) {
                 float v[16];
                 tmem_ld16(tmem_base + buf * P_ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g16), v);
+                if (SPLIT) {
+                    float w2[16];
+                    tmem_ld16(tmem_base + buf * P_ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(a.N_pad + g16), w2);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] += w2[e];
+                }
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq)
                     *reinterpret_cast<float4 *>(stage + ((g16 >> 2) + qq) * PLANE_F + row * 4) =
@@ -316,7 +330,7 @@ bool eml_persist_supported(const eml_conv_params *p) {
     if (p->precision != EML_PREC_BF16 && p->precision != EML_PREC_BF16X3) return false;
     const int N_pad = (p->C_out + 15) & ~15;
     const int nchunks = (p->C_in + P_CHUNK_K - 1) / P_CHUNK_K;
-    return N_pad <= P_ACC_COLS && persist_stages(nchunks, N_pad, p->precision == EML_PREC_BF16X3) >= 3;
+    return 2 * N_pad <= P_ACC_COLS && persist_stages(nchunks, N_pad, p->precision == EML_PREC_BF16X3) >= 3;
 }
 
 int eml_persist_forward(const eml_conv_params *p, cudaStream_t st) {
