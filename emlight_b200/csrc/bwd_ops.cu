@@ -63,19 +63,21 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnArgs a, doub
     }
 }
 
-// du = gamma*inv*(g - S1/M - xhat*S2/M); out (+)= du * (to_stored ? pre_a : 1)
+// du = gamma*inv*(g - S1/M - xhat*S2/M); out (+)= du * (to_stored ? pre_a : 1).  Block = 32 channels x 8 row lanes (coalesced
+// 128-byte channel segments, no per-element division).
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a, const double *sums, long stride, float *out, int o_pitch,
                                                            int accumulate, int to_stored) {
-    const long total = a.M * a.C;
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int rl = threadIdx.x >> 5;
+    if (c >= a.C) return;
     const double invM = 1.0 / static_cast<double>(a.M);
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(i % a.C);
-        const long m = i / a.C;
+    const float m1 = static_cast<float>(sums[c] * invM), m2 = static_cast<float>(sums[stride + c] * invM);
+    float k = a.gamma[c] * a.inv[c];
+    if (to_stored && a.pre_a) k *= a.pre_a[c];
+    for (long m = blockIdx.y * 8L + rl; m < a.M; m += gridDim.y * 8L) {
         float xhat;
         const float g = bn_masked_grad(a, m, c, xhat);
-        const float m1 = static_cast<float>(sums[c] * invM), m2 = static_cast<float>(sums[stride + c] * invM);
-        float du = a.gamma[c] * a.inv[c] * (g - m1 - xhat * m2);
-        if (to_stored && a.pre_a) du *= a.pre_a[c];
+        const float du = k * (g - m1 - xhat * m2);
         float *o = out + m * o_pitch + c;
         *o = accumulate ? *o + du : du;
     }
@@ -279,17 +281,24 @@ extern "C" int eml_bn_bwd_apply(const float *grad, int g_pitch, const float *x, 
     EML_CHECK_PTR(sums); EML_CHECK_PTR(out);
     if (M <= 0 || C <= 0 || x_pitch < C || g_pitch < C || out_pitch < C) return EML_E_SHAPE;
     const BnArgs a = make_bn(grad, g_pitch, x, x_pitch, pre_a, pre_b, mean, inv_std, gamma, beta, relu, pool, H, W, M, C);
-    long blocks = (M * C + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    bn_bwd_apply_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    long gy = (M + 8 * 32 - 1) / (8 * 32);
+    if (gy > 148 * 8) gy = 148 * 8;
+    dim3 grid((C + 31) / 32, static_cast<unsigned>(gy < 1 ? 1 : gy));
+    bn_bwd_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         a, sums, sums_stride > 0 ? sums_stride : C, out, out_pitch, accumulate, to_stored);
     return eml_launch_status();
 }
 
+bool eml_wgrad1x1_tc_supported(int N, int C, int pool, long M);                                         // wgrad1x1_tc.cu
+int eml_wgrad1x1_tc(const float *G, int g_pitch, int N, const float *x, int x_pitch, int C, const float *scale, const float *shift,
+                    int relu, float *dW, long M, int precision, cudaStream_t st);
+
 extern "C" int eml_wgrad_1x1(const float *G, int g_pitch, int N, const float *x, int x_pitch, int C, const float *scale,
-                             const float *shift, int relu, int pool, int H, int W, float *dW, long M, void *stream) {
+                             const float *shift, int relu, int pool, int H, int W, float *dW, long M, int precision, void *stream) {
     EML_CHECK_PTR(G); EML_CHECK_PTR(x); EML_CHECK_PTR(dW);
     if (M <= 0 || N <= 0 || C <= 0 || g_pitch < N || x_pitch < C) return EML_E_SHAPE;
+    if (precision != EML_PREC_FP32 && eml_wgrad1x1_tc_supported(N, C, pool, M))
+        return eml_wgrad1x1_tc(G, g_pitch, N, x, x_pitch, C, scale, shift, relu, dW, M, precision, static_cast<cudaStream_t>(stream));
     long gx = (M + 4095) / 4096;
     if (gx > 148 * 2) gx = 148 * 2;
     dim3 grid(static_cast<unsigned>(gx < 1 ? 1 : gx), (C + WG_TC - 1) / WG_TC, (N + WG_TN - 1) / WG_TN);

@@ -554,7 +554,7 @@ class DenseNet(nn.Module):
             a_t = self._aff(c, "t%d.norm" % b)
             dwt = torch.zeros(c_tr, c_out, dtype=torch.float32, device=dev)
             _lib.check(lib.eml_wgrad_1x1(_lib.ptr(dt), dt.shape[3], c_tr, _lib.ptr(slab), pitch, c_out, _lib.ptr(a_t[0]), _lib.ptr(a_t[1]),
-                                         1, 1, h, w, _lib.ptr(dwt), Mp, st), "eml_wgrad_1x1(transition%d)" % b)
+                                         1, 1, h, w, _lib.ptr(dwt), Mp, _lib.PRECISIONS[self.precision], st), "eml_wgrad_1x1(transition%d)" % b)
             out["features.transition%d.conv.weight" % b] = dwt.view(c_tr, c_out, 1, 1)
             bn_bwd("t%d.norm" % b, tr.norm, "features.transition%d.norm" % b, _lib.ptr(dp), dp.shape[3], _lib.ptr(slab), pitch, pre, 1, 1,
                    h, w, M, c_out, _lib.ptr(dS), pitch, 1)
@@ -586,7 +586,7 @@ class DenseNet(nn.Module):
                 self._gemm_bwd(dN.data_ptr(), g, B, h, w, g, w1.permute(1, 0, 2, 3).contiguous(), dA, _lib.EML_CONV_1x1)
                 dw1 = torch.zeros(g, ci, dtype=torch.float32, device=dev)
                 _lib.check(lib.eml_wgrad_1x1(_lib.ptr(dN), g, g, _lib.ptr(slab), pitch, ci, _lib.ptr(a1[0]), _lib.ptr(a1[1]), 1, 0, h, w,
-                                             _lib.ptr(dw1), M, st), "eml_wgrad_1x1(conv1)")
+                                             _lib.ptr(dw1), M, _lib.PRECISIONS[self.precision], st), "eml_wgrad_1x1(conv1)")
                 out[pfx + ".conv1.weight"] = dw1.view(g, ci, 1, 1)
                 bn_bwd(n1, layer.norm1, pfx + ".norm1", _lib.ptr(dA), dA.shape[3], _lib.ptr(slab), pitch, pre, 1, 0, h, w, M, ci,
                        _lib.ptr(dS), pitch, 1)
