@@ -83,6 +83,138 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a, const
     }
 }
 
+
+// ---- float4 variants (all pitches multiples of 4, 16-byte aligned bases): thread = 4 channels, 4 rows in flight ---------------
+__device__ __forceinline__ long bn_grad_row(const BnArgs &a, long m, float &gs) {
+    gs = 1.f;
+    if (!a.pool) return m;
+    const int xx = static_cast<int>(m % a.W);
+    const long t = m / a.W;
+    const int yy = static_cast<int>(t % a.H);
+    const long b = t / a.H;
+    gs = 0.25f;
+    return (b * (a.H >> 1) + (yy >> 1)) * (a.W >> 1) + (xx >> 1);
+}
+struct Bn4 { float pa[4], pb[4], mean[4], inv[4], gamma[4], beta[4]; };
+__device__ __forceinline__ void bn_load4(const BnArgs &a, int c, Bn4 &p) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const bool ok = c + e < a.C;
+        p.pa[e] = (ok && a.pre_a) ? a.pre_a[c + e] : 1.f;
+        p.pb[e] = (ok && a.pre_b) ? a.pre_b[c + e] : 0.f;
+        p.mean[e] = ok ? a.mean[c + e] : 0.f;
+        p.inv[e] = ok ? a.inv[c + e] : 0.f;
+        p.gamma[e] = ok ? a.gamma[c + e] : 0.f;
+        p.beta[e] = ok ? a.beta[c + e] : 0.f;
+    }
+}
+__device__ __forceinline__ void bn_eval4(const BnArgs &a, const Bn4 &p, const float4 xv, const float4 gv, float gs, float (&g)[4], float (&xh)[4]) {
+    const float x4[4] = {xv.x, xv.y, xv.z, xv.w}, g4[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        xh[e] = (fmaf(p.pa[e], x4[e], p.pb[e]) - p.mean[e]) * p.inv[e];
+        g[e] = g4[e] * gs;
+        if (a.relu && !(fmaf(p.gamma[e], xh[e], p.beta[e]) > 0.f)) g[e] = 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce4_kernel(const BnArgs a, double *sums, long stride) {
+    __shared__ double s1[8][128], s2[8][128];
+    const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + lane) * 4;
+    double a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+    if (c < a.C) {
+        Bn4 p; bn_load4(a, c, p);
+        for (long m0 = (blockIdx.y * 8L + rl) * 4; m0 < a.M; m0 += gridDim.y * 32L) {
+            float4 xv[4], gv[4]; float gs[4]; bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long m = m0 + u;
+                ok[u] = m < a.M;
+                if (!ok[u]) continue;
+                const long gm = bn_grad_row(a, m, gs[u]);
+                xv[u] = __ldg(reinterpret_cast<const float4 *>(a.x + m * a.x_pitch + c));
+                gv[u] = __ldg(reinterpret_cast<const float4 *>(a.grad + gm * a.g_pitch + c));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!ok[u]) continue;
+                float g[4], xh[4];
+                bn_eval4(a, p, xv[u], gv[u], gs[u], g, xh);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { a1[e] += g[e]; a2[e] += static_cast<double>(g[e]) * xh[e]; }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { s1[rl][lane * 4 + e] = a1[e]; s2[rl][lane * 4 + e] = a2[e]; }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int cc = blockIdx.x * 128 + threadIdx.x;
+        if (cc < a.C) {
+            double t1 = 0.0, t2 = 0.0;
+            for (int r = 0; r < 8; ++r) { t1 += s1[r][threadIdx.x]; t2 += s2[r][threadIdx.x]; }
+            atomicAdd(sums + cc, t1);
+            atomicAdd(sums + stride + cc, t2);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply4_kernel(const BnArgs a, const double *sums, long stride, float *out, int o_pitch,
+                                                            int accumulate, int to_stored) {
+    const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + lane) * 4;
+    if (c >= a.C) return;
+    Bn4 p; bn_load4(a, c, p);
+    const double invM = 1.0 / static_cast<double>(a.M);
+    float k[4], m1[4], m2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const bool okc = c + e < a.C;
+        m1[e] = okc ? static_cast<float>(sums[c + e] * invM) : 0.f;
+        m2[e] = okc ? static_cast<float>(sums[stride + c + e] * invM) : 0.f;
+        k[e] = p.gamma[e] * p.inv[e] * (to_stored ? p.pa[e] : 1.f);
+    }
+    const bool full = c + 3 < a.C;
+    for (long m0 = (blockIdx.y * 8L + rl) * 4; m0 < a.M; m0 += gridDim.y * 32L) {
+        float4 xv[4], gv[4], ov[4]; float gs[4]; bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long m = m0 + u;
+            ok[u] = m < a.M;
+            if (!ok[u]) continue;
+            const long gm = bn_grad_row(a, m, gs[u]);
+            xv[u] = __ldg(reinterpret_cast<const float4 *>(a.x + m * a.x_pitch + c));
+            gv[u] = *reinterpret_cast<const float4 *>(a.grad + gm * a.g_pitch + c);       // may alias `out` (in-place BN2 backward)
+            if (accumulate) ov[u] = *reinterpret_cast<const float4 *>(out + m * o_pitch + c);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!ok[u]) continue;
+            float g[4], xh[4], du[4];
+            bn_eval4(a, p, xv[u], gv[u], gs[u], g, xh);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) du[e] = k[e] * (g[e] - m1[e] - xh[e] * m2[e]);
+            float *o = out + (m0 + u) * o_pitch + c;
+            if (full) {
+                float4 r = make_float4(du[0], du[1], du[2], du[3]);
+                if (accumulate) { r.x += ov[u].x; r.y += ov[u].y; r.z += ov[u].z; r.w += ov[u].w; }
+                *reinterpret_cast<float4 *>(o) = r;
+            } else {                                           // tail quad: the neighbouring channels belong to other layers
+                const float o4[4] = {ov[u].x, ov[u].y, ov[u].z, ov[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (c + e < a.C) o[e] = accumulate ? o4[e] + du[e] : du[e];
+            }
+        }
+    }
+}
+
+inline bool bn_vec_ok(const BnArgs &a, const float *out, int o_pitch) {
+    auto al = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    return (a.g_pitch & 3) == 0 && (a.x_pitch & 3) == 0 && al(a.grad) && al(a.x) && (out == nullptr || ((o_pitch & 3) == 0 && al(out)));
+}
+
 // ---------------------------------------------------------------------------------------------- weight gradients
 // dW[n, c] += sum_m G[m, n] * A(m, c);  A = act(scale*x + shift) (optionally the average over the 2x2 pool window; then G / m index
 // pooled pixels).  Block tile 48 (n) x 64 (c); thread tile 3 x 4; rows in slabs of 32 staged in shared memory.
@@ -266,6 +398,15 @@ extern "C" int eml_bn_bwd_reduce(const float *grad, int g_pitch, const float *x,
     EML_CHECK_PTR(sums);
     if (M <= 0 || C <= 0 || x_pitch < C || g_pitch < C || (pool && (H <= 0 || W <= 0 || ((H | W) & 1)))) return EML_E_SHAPE;
     const BnArgs a = make_bn(grad, g_pitch, x, x_pitch, pre_a, pre_b, mean, inv_std, gamma, beta, relu, pool, H, W, M, C);
+    if (bn_vec_ok(a, nullptr, 0)) {
+        long gy = (M + 32 * 16 - 1) / (32 * 16);
+        const int gx = (C + 127) / 128;
+        const long cap = (148L * 8 + gx - 1) / gx;
+        if (gy > cap) gy = cap;
+        dim3 grid(gx, static_cast<unsigned>(gy < 1 ? 1 : gy));
+        bn_bwd_reduce4_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, sums, sums_stride > 0 ? sums_stride : C);
+        return eml_launch_status();
+    }
     long gy = (M + 8 * 64 - 1) / (8 * 64);
     if (gy > 148 * 4) gy = 148 * 4;
     dim3 grid((C + 31) / 32, static_cast<unsigned>(gy < 1 ? 1 : gy));
@@ -281,6 +422,16 @@ extern "C" int eml_bn_bwd_apply(const float *grad, int g_pitch, const float *x, 
     EML_CHECK_PTR(sums); EML_CHECK_PTR(out);
     if (M <= 0 || C <= 0 || x_pitch < C || g_pitch < C || out_pitch < C) return EML_E_SHAPE;
     const BnArgs a = make_bn(grad, g_pitch, x, x_pitch, pre_a, pre_b, mean, inv_std, gamma, beta, relu, pool, H, W, M, C);
+    if (bn_vec_ok(a, out, out_pitch)) {
+        long gy4 = (M + 32 * 4 - 1) / (32 * 4);
+        const int gx = (C + 127) / 128;
+        const long cap = (148L * 16 + gx - 1) / gx;
+        if (gy4 > cap) gy4 = cap;
+        dim3 grid4(gx, static_cast<unsigned>(gy4 < 1 ? 1 : gy4));
+        bn_bwd_apply4_kernel<<<grid4, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, sums, sums_stride > 0 ? sums_stride : C, out, out_pitch,
+                                                                                 accumulate, to_stored);
+        return eml_launch_status();
+    }
     long gy = (M + 8 * 32 - 1) / (8 * 32);
     if (gy > 148 * 8) gy = 148 * 8;
     dim3 grid((C + 31) / 32, static_cast<unsigned>(gy < 1 ? 1 : gy));

@@ -255,7 +255,8 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv3x3_roll_kernel(const RollA
     unsigned char *ring_hi = smem;
     unsigned char *ring_lo = smem + IMG_BYTES;             // only when SPLIT
     unsigned char *w_sm = smem + (SPLIT ? 2 : 1) * IMG_BYTES;
-    const int wn = SPLIT ? 32 : a.N_pad;                   // rows of the staged weight operand
+    const int wn = 2 * a.N_pad;                            // rows of the staged weight operand: always the [hi ; lo] image
+    const uint32_t acc_cols = (SPLIT ? 2 * a.N_pad : a.N_pad) <= 32 ? 32u : ((SPLIT ? 2 * a.N_pad : a.N_pad) <= 64 ? 64u : 128u);
     const int w_bytes = 9 * KC * wn * 16;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar_w = smem_u32(&s_bar[0]);
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv3x3_roll_kernel(const RollA
     }
     if (warp == 8) {
         __syncwarp();
-        tmem_alloc(smem_u32(&s_tmem), 64);
+        tmem_alloc(smem_u32(&s_tmem), 2 * acc_cols);
     }
     for (int i = tid; i < C_IN; i += RP_THREADS) {
         s_scale[i] = a.scale ? a.scale[i] : 1.f;
@@ -363,8 +364,8 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv3x3_roll_kernel(const RollA
             bulk_g2s(smem_u32(w_sm), ra.wcat, static_cast<uint32_t>(w_bytes), bar_w);
         }
         mbar_wait(bar_w, 0);
-        const uint32_t idesc_cat = make_idesc_bf16(ROWS_TILE, SPLIT ? 32 : a.N_pad);
-        const uint32_t idesc_16 = make_idesc_bf16(ROWS_TILE, 16);
+        const uint32_t idesc_cat = make_idesc_bf16(ROWS_TILE, SPLIT ? wn : a.N_pad);    // non-split reads only the hi rows
+        const uint32_t idesc_16 = make_idesc_bf16(ROWS_TILE, a.N_pad);
         // descriptor bases; per MMA only the 14-bit start-address field (16-byte units) moves
         const uint64_t dA_hi = make_nosw_desc(smem_u32(ring_hi), PLANE, 128);
         const uint64_t dA_lo = make_nosw_desc(smem_u32(ring_lo), PLANE, 128);
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv3x3_roll_kernel(const RollA
                 mbar_wait(bar_accempty + 8 * buf, aph ^ 1);
                 tc_fence_after();
                 if (leader) {
-                    const uint32_t d_tmem = tmem_base + buf * 32;
+                    const uint32_t d_tmem = tmem_base + buf * acc_cols;
                     uint32_t acc = 0;
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy) {
@@ -393,8 +394,8 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv3x3_roll_kernel(const RollA
                             for (int ks = 0; ks < KC / 2; ++ks) {
                                 const uint64_t aoff = slot16 + static_cast<uint32_t>(2 * ks * ROWS_PP + dx);
                                 const uint64_t woff = static_cast<uint32_t>(((dy * 3 + dx) * KC + 2 * ks) * wn);
-                                umma_bf16(d_tmem, dA_hi + aoff, dW + woff, idesc_cat, acc);       // hi*[hi|lo] -> cols 0..31
-                                if (SPLIT) umma_bf16(d_tmem, dA_lo + aoff, dW + woff, idesc_16, 1u);  // lo*hi -> cols 0..15
+                                umma_bf16(d_tmem, dA_hi + aoff, dW + woff, idesc_cat, acc);       // hi*[hi|lo] -> cols [0, 2*N_pad)
+                                if (SPLIT) umma_bf16(d_tmem, dA_lo + aoff, dW + woff, idesc_16, 1u);  // lo*hi -> cols [0, N_pad)
                                 acc = 1;
                             }
                         }
@@ -424,28 +425,32 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv3x3_roll_kernel(const RollA
                 __syncwarp();
                 tc_fence_after();
                 const int x = x0 + q4 * 32 + lane;
-                float v[16];
-                tmem_ld16(tmem_base + buf * 32 + (static_cast<uint32_t>(q4 * 32) << 16), v);
-                if (SPLIT) {
-                    float w2[16];
-                    tmem_ld16(tmem_base + buf * 32 + 16 + (static_cast<uint32_t>(q4 * 32) << 16), w2);
+                float *orow = a.out + ((b * a.H + (y0 + i)) * static_cast<long>(a.W) + (x < a.W ? x : 0)) * a.out_pitch + a.out_choff;
+                for (int g16 = 0; g16 < a.N_pad; g16 += 16) {
+                    float v[16];
+                    tmem_ld16(tmem_base + buf * acc_cols + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(g16), v);
+                    if (SPLIT) {
+                        float w2[16];
+                        tmem_ld16(tmem_base + buf * acc_cols + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(a.N_pad + g16), w2);
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) v[e] += w2[e];
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) rows_mbar_arrive(bar_accempty + 8 * buf);            // TMEM drained: release before the stores
-                if (x < a.W) {
-                    float *orow = a.out + ((b * a.H + (y0 + i)) * static_cast<long>(a.W) + x) * a.out_pitch + a.out_choff;
+                        for (int e = 0; e < 16; ++e) v[e] += w2[e];
+                    }
+                    if (g16 + 16 >= a.N_pad) {                                       // last column group read: release the accumulator
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) rows_mbar_arrive(bar_accempty + 8 * buf);
+                    }
+                    if (x < a.W) {
 #pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        const int n = qq * 4;
-                        if (vec_ok && n + 3 < a.C_out) {
-                            *reinterpret_cast<float4 *>(orow + n) = make_float4(v[n], v[n + 1], v[n + 2], v[n + 3]);
-                        } else {
+                        for (int qq = 0; qq < 4; ++qq) {
+                            const int n = g16 + qq * 4;
+                            if (vec_ok && n + 3 < a.C_out) {
+                                *reinterpret_cast<float4 *>(orow + n) = make_float4(v[qq * 4], v[qq * 4 + 1], v[qq * 4 + 2], v[qq * 4 + 3]);
+                            } else {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (n + e < a.C_out) orow[n + e] = v[n + e];
+                                for (int e = 0; e < 4; ++e)
+                                    if (n + e < a.C_out) orow[n + e] = v[qq * 4 + e];
+                            }
                         }
                     }
                 }
@@ -456,25 +461,26 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv3x3_roll_kernel(const RollA
     __syncthreads();
     if (warp == 8) {
         __syncwarp();
-        tmem_dealloc(tmem_base, 64);
+        tmem_dealloc(tmem_base, 2 * acc_cols);
     }
 }
 
-// OIHW fp32 -> [tap][kc][32 rows: n<16 hi(n), n>=16 lo(n-16)][8 bf16]  (the N=32 concatenated operand of the rolling kernel)
-__global__ void pack_cat_kernel(const float *__restrict__ w, unsigned char *__restrict__ out, int C_out, int C_in) {
-    const int KC = C_in / 8;
-    const int total = 9 * KC * 32 * 8;
+// OIHW fp32 -> [tap][kc][2*N_pad rows: n<N_pad hi(n), n>=N_pad lo(n-N_pad)][8 bf16]  (the concatenated operand of the rolling kernel)
+__global__ void pack_cat_kernel(const float *__restrict__ w, unsigned char *__restrict__ out, int C_out, int C_in, int C_in_pad, int N_pad) {
+    const int KC = C_in_pad / 8;
+    const int rows = 2 * N_pad;
+    const int total = 9 * KC * rows * 8;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int e = idx & 7;
-        const int n = (idx >> 3) & 31;
-        const int kc = (idx / 256) % KC;
-        const int tap = idx / (256 * KC);
-        const int c = kc * 8 + e, nn = n & 15;
+        const int n = (idx >> 3) % rows;
+        const int kc = (idx / (8 * rows)) % KC;
+        const int tap = idx / (8 * rows * KC);
+        const int c = kc * 8 + e, nn = n % N_pad;
         float v = 0.f;
-        if (nn < C_out) v = w[(static_cast<long>(nn) * C_in + c) * 9 + tap];
+        if (nn < C_out && c < C_in) v = w[(static_cast<long>(nn) * C_in + c) * 9 + tap];
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        *reinterpret_cast<__nv_bfloat16 *>(out + static_cast<size_t>(idx) * 2) = n < 16 ? hi : lo;
+        *reinterpret_cast<__nv_bfloat16 *>(out + static_cast<size_t>(idx) * 2) = n < N_pad ? hi : lo;
     }
 }
 
@@ -503,27 +509,35 @@ __global__ void pack_planar_kernel(const float *__restrict__ w, unsigned char *_
 }  // namespace
 
 // ---- entry points used by conv_gemm.cu's dispatcher
+static int rows_cin_pad(int C_in) { return C_in == 48 ? 48 : (C_in <= 16 ? 16 : 0); }      // channel counts the kernels are built for
+
 static size_t rows_planar_bytes(int C_out, int C_in) {
     const int N_pad = (C_out + 15) & ~15;
-    return static_cast<size_t>(2) * 9 * (C_in / 8) * N_pad * 16;
+    return static_cast<size_t>(2) * 9 * (rows_cin_pad(C_in) / 8) * N_pad * 16;
 }
 
 size_t eml_rows_wpack_bytes(int C_out, int C_in) {
-    if (C_in % 8) return 0;
-    // planar hi|lo image (non-persistent kernel) followed by the N=32 concatenated image (rolling kernel, C_out <= 16)
-    return rows_planar_bytes(C_out, C_in) + (C_out <= 16 ? static_cast<size_t>(9) * (C_in / 8) * 32 * 16 : 0);
+    if (rows_cin_pad(C_in) == 0 || C_out > 64) return 0;
+    // planar hi|lo image (non-persistent kernel) followed by the [hi;lo] concatenated image (rolling kernel)
+    const int N_pad = (C_out + 15) & ~15;
+    return rows_planar_bytes(C_out, C_in) + static_cast<size_t>(9) * (rows_cin_pad(C_in) / 8) * 2 * N_pad * 16;
 }
 
 int eml_rows_pack(const float *w_oihw, unsigned char *dst, int C_out, int C_in, cudaStream_t st) {
     const int N_pad = (C_out + 15) & ~15;
-    pack_planar_kernel<<<32, 256, 0, st>>>(w_oihw, dst, C_out, C_in, N_pad);
-    if (C_out <= 16) pack_cat_kernel<<<32, 256, 0, st>>>(w_oihw, dst + rows_planar_bytes(C_out, C_in), C_out, C_in);
+    if (C_in == 48) pack_planar_kernel<<<32, 256, 0, st>>>(w_oihw, dst, C_out, C_in, N_pad);     // image of the statistics-epilogue kernel
+    pack_cat_kernel<<<32, 256, 0, st>>>(w_oihw, dst + rows_planar_bytes(C_out, C_in), C_out, C_in, rows_cin_pad(C_in), N_pad);
     return eml_launch_status();
 }
 
 bool eml_rows_supported(const eml_conv_params *p) {
-    return p->mode == EML_CONV_3x3 && p->C_in == 48 && p->C_out <= 16 &&
-           ((p->W % ROWS_TILE) == 0 || (p->stats == nullptr && !eml_env_flag("EML_NO_PERSIST"))) &&
+    if (p->mode != EML_CONV_3x3) return false;
+    const bool persist_ok = p->stats == nullptr && !eml_env_flag("EML_NO_PERSIST");
+    // 12 -> 48 data gradient (conv2's dgrad): input pitch must give 16 readable, zero-padded channels
+    if (p->C_in <= 16 && p->in_pitch >= 16 && p->C_out <= 64 && persist_ok && p->scale == nullptr && p->shift == nullptr &&
+        (p->precision == EML_PREC_BF16 || p->precision == EML_PREC_BF16X3))
+        return true;
+    return p->C_in == 48 && p->C_out <= 16 && ((p->W % ROWS_TILE) == 0 || persist_ok) &&
            (p->precision == EML_PREC_BF16 || p->precision == EML_PREC_BF16X3);
 }
 
@@ -546,7 +560,7 @@ int eml_rows_forward(const eml_conv_params *p, const unsigned char *wplanar, cud
     if (a.stats == nullptr && !eml_env_flag("EML_NO_PERSIST")) {
         RollArgs ra{};
         ra.r = a;
-        ra.wcat = split ? wplanar + rows_planar_bytes(p->C_out, p->C_in) : wplanar;
+        ra.wcat = wplanar + rows_planar_bytes(p->C_out, p->C_in);
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -558,20 +572,20 @@ int eml_rows_forward(const eml_conv_params *p, const unsigned char *wplanar, cud
         ra.rb = rb;
         ra.bands_y = (p->H + rb - 1) / rb;
         ra.nunits = static_cast<long>(p->B) * tiles_x * ra.bands_y;
-        const size_t ring = static_cast<size_t>(RING) * KC * ROWS_PP * 16;
-        const size_t psm = (split ? 2 : 1) * ring + static_cast<size_t>(9) * KC * (split ? 32 : a.N_pad) * 16;
         const unsigned grid = static_cast<unsigned>(ra.nunits < sms ? ra.nunits : sms);
-        if (split) {
-            e = cudaFuncSetAttribute(conv3x3_roll_kernel<48, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psm));
-            if (e != cudaSuccess) return static_cast<int>(e);
-            conv3x3_roll_kernel<48, true><<<grid, RP_THREADS, psm, st>>>(ra);
-        } else {
-            e = cudaFuncSetAttribute(conv3x3_roll_kernel<48, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psm));
-            if (e != cudaSuccess) return static_cast<int>(e);
-            conv3x3_roll_kernel<48, false><<<grid, RP_THREADS, psm, st>>>(ra);
-        }
-        return eml_launch_status();
+        const int kc = rows_cin_pad(p->C_in) / 8;
+        const size_t ring = static_cast<size_t>(RING) * kc * ROWS_PP * 16;
+        const size_t psm = (split ? 2 : 1) * ring + static_cast<size_t>(9) * kc * 2 * a.N_pad * 16;
+        auto go = [&](auto kern) -> int {
+            cudaError_t ee = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psm));
+            if (ee != cudaSuccess) return static_cast<int>(ee);
+            kern<<<grid, RP_THREADS, psm, st>>>(ra);
+            return eml_launch_status();
+        };
+        if (p->C_in == 48) return split ? go(conv3x3_roll_kernel<48, true>) : go(conv3x3_roll_kernel<48, false>);
+        return split ? go(conv3x3_roll_kernel<16, true>) : go(conv3x3_roll_kernel<16, false>);
     }
+    if (p->C_in != 48) return EML_E_SHAPE;
     if (split) {
         e = cudaFuncSetAttribute(conv3x3_rows_kernel<48, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);

@@ -573,11 +573,12 @@ class DenseNet(nn.Module):
                 self._conv(c, "b%d.l%d.conv1" % (b, l), slab, pitch, h, w, B, ci, ws["bott"], g, 0, g, _lib.EML_CONV_1x1, 1, a1, None, g)
                 # gradient of this layer's 12 output channels; compacted because block 3's channel offsets (150 + 12 l) are not
                 # 16-byte aligned and the gather uses float4 loads
-                dy = dS[..., ci:ci + gr].contiguous()
+                dy = torch.zeros(B, h, w, 16, dtype=torch.float32, device=dev)        # 12 -> 16 channels: what the rolling 3x3 kernel stages
+                dy[..., :gr] = dS[..., ci:ci + gr]
                 w2 = layer.conv2.weight.detach().float()                          # (12, 48, 3, 3)
-                self._gemm_bwd(dy.data_ptr(), gr, B, h, w, gr, w2.permute(1, 0, 2, 3).flip(2, 3).contiguous(), dN, _lib.EML_CONV_3x3)
+                self._gemm_bwd(dy.data_ptr(), 16, B, h, w, gr, w2.permute(1, 0, 2, 3).flip(2, 3).contiguous(), dN, _lib.EML_CONV_3x3)
                 dw2 = torch.zeros(gr, g, 3, 3, dtype=torch.float32, device=dev)
-                _lib.check(lib.eml_wgrad_3x3(_lib.ptr(dy), gr, gr, _lib.ptr(ws["bott"]), g, g, _lib.ptr(a2[0]), _lib.ptr(a2[1]), _lib.ptr(dw2),
+                _lib.check(lib.eml_wgrad_3x3(_lib.ptr(dy), 16, gr, _lib.ptr(ws["bott"]), g, g, _lib.ptr(a2[0]), _lib.ptr(a2[1]), _lib.ptr(dw2),
                                              B, h, w, st), "eml_wgrad_3x3")
                 out[pfx + ".conv2.weight"] = dw2
                 bn_bwd(n2, layer.norm2, pfx + ".norm2", _lib.ptr(dN), g, _lib.ptr(ws["bott"]), g, None, 0, 0, h, w, M, g, _lib.ptr(dN), g, 0)

@@ -51,7 +51,7 @@ def test_argument_errors_need_no_gpu(lib):
     assert lib.eml_conv_forward(None, None) == -1
     p = ConvParams()
     assert lib.eml_conv_forward(p, None) == -1
-    assert lib.eml_conv_wpack_bytes(12, 48, 9) == 9 * 2 * 16 * 128 + 2 * 9 * 6 * 16 * 16 + 9 * 6 * 32 * 16    # generic chunks + planar hi|lo + N=32 concatenated image
+    assert lib.eml_conv_wpack_bytes(12, 48, 9) == 9 * 2 * 16 * 128 + 2 * 9 * 6 * 16 * 16 + 9 * 6 * 32 * 16    # generic chunks + planar hi|lo + [hi;lo] concatenated image
     assert lib.eml_conv_wpack_bytes(48, 150, 1) == 3 * 2 * 48 * 128
 
 
