@@ -457,10 +457,16 @@ extern "C" int eml_wgrad_1x1(const float *G, int g_pitch, int N, const float *x,
     return eml_launch_status();
 }
 
+bool eml_wgrad3x3_tc_supported(int N, int C);                                                            // wgrad3x3_tc.cu
+int eml_wgrad3x3_tc(const float *dY, int dy_pitch, int N, const float *b, int b_pitch, const float *scale, const float *shift,
+                    float *dW, int B, int H, int W, int precision, cudaStream_t st);
+
 extern "C" int eml_wgrad_3x3(const float *dY, int dy_pitch, int N, const float *b, int b_pitch, int C, const float *scale,
-                             const float *shift, float *dW, int B, int H, int W, void *stream) {
+                             const float *shift, float *dW, int B, int H, int W, int precision, void *stream) {
     EML_CHECK_PTR(dY); EML_CHECK_PTR(b); EML_CHECK_PTR(dW);
     if (B <= 0 || H <= 0 || W <= 0 || N <= 0 || N > 16 || C <= 0 || C > 64 || dy_pitch < N || b_pitch < C) return EML_E_SHAPE;
+    if (precision != EML_PREC_FP32 && eml_wgrad3x3_tc_supported(N, C) && (b_pitch & 3) == 0)
+        return eml_wgrad3x3_tc(dY, dy_pitch, N, b, b_pitch, scale, shift, dW, B, H, W, precision, static_cast<cudaStream_t>(stream));
     wgrad_3x3_kernel<<<148 * 2, 256, 0, static_cast<cudaStream_t>(stream)>>>(dY, dy_pitch, N, b, b_pitch, C, scale, shift, dW, B, H, W);
     return eml_launch_status();
 }

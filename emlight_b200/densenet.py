@@ -579,7 +579,7 @@ class DenseNet(nn.Module):
                 self._gemm_bwd(dy.data_ptr(), 16, B, h, w, gr, w2.permute(1, 0, 2, 3).flip(2, 3).contiguous(), dN, _lib.EML_CONV_3x3)
                 dw2 = torch.zeros(gr, g, 3, 3, dtype=torch.float32, device=dev)
                 _lib.check(lib.eml_wgrad_3x3(_lib.ptr(dy), 16, gr, _lib.ptr(ws["bott"]), g, g, _lib.ptr(a2[0]), _lib.ptr(a2[1]), _lib.ptr(dw2),
-                                             B, h, w, st), "eml_wgrad_3x3")
+                                             B, h, w, _lib.PRECISIONS[self.precision], st), "eml_wgrad_3x3")
                 out[pfx + ".conv2.weight"] = dw2
                 bn_bwd(n2, layer.norm2, pfx + ".norm2", _lib.ptr(dN), g, _lib.ptr(ws["bott"]), g, None, 0, 0, h, w, M, g, _lib.ptr(dN), g, 0)
                 w1 = layer.conv1.weight.detach().float()                          # (48, ci, 1, 1)

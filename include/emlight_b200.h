@@ -223,12 +223,13 @@ int eml_bn_bwd_apply(const float *grad, int g_pitch, const float *x, int x_pitch
 /* Weight gradients (accumulated into dW with atomics; zero dW first):
  *   1x1 : dW[n,c]      += sum_m G[m,n] * act(scale[c]*x[m,c] + shift[c])       (pool=1: act, then 2x2 average; m over pooled pixels)
  *         precision EML_PREC_FP32: fp32 FFMA; otherwise (N <= 64, C <= 256, no pool) a tcgen05 GEMM over K = pixels with MN-major operands
- *   3x3 : dW[n,c,tap]  += sum_m dY[m,n] * (scale[c]*b[m+tap,c] + shift[c])      (zero outside the image; N <= 16, C <= 64)
+ *   3x3 : dW[n,c,tap]  += sum_m dY[m,n] * (scale[c]*b[m+tap,c] + shift[c])      (zero outside the image; N <= 16, C <= 64;
+ *         precision other than EML_PREC_FP32 with C == 48: nine tcgen05 GEMMs over K = pixels on the rolling halo ring)
  *   stem: dW[o,ci,ky,kx] += sum_m dZ[m,o] * x_nchw[b,ci,y+ky-1,x+kx-1] */
 int eml_wgrad_1x1(const float *G, int g_pitch, int N, const float *x, int x_pitch, int C, const float *scale, const float *shift,
                   int relu, int pool, int H, int W, float *dW, long M, int precision, void *stream);
 int eml_wgrad_3x3(const float *dY, int dy_pitch, int N, const float *b, int b_pitch, int C, const float *scale, const float *shift,
-                  float *dW, int B, int H, int W, void *stream);
+                  float *dW, int B, int H, int W, int precision, void *stream);
 int eml_wgrad_stem(const float *dZ, int dz_pitch, int O, const float *x_nchw, float *dW, int B, int H, int W, void *stream);
 
 #ifdef __cplusplus
