@@ -252,9 +252,14 @@ def main():
         for _ in range(3):
             step(x1)
         ms0 = timed(lambda: step(x1), 20) / 20
+        net.use_cuda_graph = True                       # replay the 104-launch forward as one CUDA graph (emlight_b200/graphs.py)
+        for _ in range(3):
+            step(x1)
+        ms0g = timed(lambda: step(x1), 50) / 50
+        net.use_cuda_graph = False
         extra = {"config1_densenet_fwd_trainBN_plus_sinkhorn_fwd_bwd_b64": {"ms_per_step": round(ms1, 3), "maps_per_s": round(Bt / ms1 * 1e3, 1)},
                  "train_step_fwd_bwd_adam_b64": {"ms_per_step": round(ms_tr, 3), "maps_per_s": round(Bt / ms_tr * 1e3, 1)},
-                 "config0_single_crop_latency_ms": round(ms0, 3)}
+                 "config0_single_crop_latency_ms": round(ms0, 3), "config0_single_crop_latency_cuda_graph_ms": round(ms0g, 3)}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt, threads = time_cpu(args.cpu_sample, 3, 1)

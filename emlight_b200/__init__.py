@@ -6,6 +6,7 @@ Public surface mirrors the reference's:
     from emlight_b200 import SamplesLoss         # RegressionNetwork/geomloss: SamplesLoss  (gmloss: GMSamplesLoss)
     from emlight_b200 import sphere_points, convert_to_panorama     # RegressionNetwork/util.py
     from emlight_b200 import SphereConv2D, SPADE, SPADEResnetBlock, SPADEGenerator   # GenProjector/models/networks/*
+    from emlight_b200 import MultiscaleDiscriminator, GANLoss, VGGLoss, Pix2PixModel # discriminator.py, loss.py, pix2pix_model.py
 
 Module-name shims for unchanged reference scripts live in ``emlight_b200/dropin`` (put it on sys.path).
 All arithmetic runs in hand-written CUDA reached through the C ABI of include/emlight_b200.h.
@@ -13,7 +14,9 @@ All arithmetic runs in hand-written CUDA reached through the C ABI of include/em
 from .panorama import convert_to_panorama, render_from_params, sphere_points  # noqa: F401
 from .samples_loss import GMSamplesLoss, SamplesLoss  # noqa: F401
 from .densenet import DenseNet  # noqa: F401
-from .genprojector import SPADE, ConvEncoder, SPADEGenerator, SPADEResnetBlock, SphereConv2D  # noqa: F401
+from .genprojector import (SPADE, ConvEncoder, GANLoss, MultiscaleDiscriminator, NLayerDiscriminator, Pix2PixModel,  # noqa: F401
+                           SPADEGenerator, SPADEResnetBlock, SphereConv2D, VGG19, VGGLoss)
 
 __all__ = ["DenseNet", "SamplesLoss", "GMSamplesLoss", "sphere_points", "convert_to_panorama", "render_from_params",
-           "SphereConv2D", "SPADE", "SPADEResnetBlock", "ConvEncoder", "SPADEGenerator"]
+           "SphereConv2D", "SPADE", "SPADEResnetBlock", "ConvEncoder", "SPADEGenerator", "MultiscaleDiscriminator", "NLayerDiscriminator",
+           "GANLoss", "VGG19", "VGGLoss", "Pix2PixModel"]

@@ -282,6 +282,89 @@ __global__ void __launch_bounds__(256) tanh_out_kernel(const float *__restrict__
     }
 }
 
+
+// out = act(x + bias[c])   (discriminator model0: SphereConv + LeakyReLU, discriminator.py:91-92; VGG conv + ReLU)
+__global__ void __launch_bounds__(256) bias_act_kernel(const float *__restrict__ x, int x_pitch, const float *__restrict__ bias, int act,
+                                                       float *__restrict__ out, int out_pitch, long M, int C) {
+    const long total = M * C;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        const long m = i / C;
+        out[m * out_pitch + c] = apply_act(x[m * x_pitch + c] + (bias ? bias[c] : 0.f), act);
+    }
+}
+
+// mode 0: avg_pool2d(k=3, s=2, p=1, count_include_pad=False) (discriminator.py:48-51); mode 1: max_pool2d(k=2, s=2) (VGG19)
+__global__ void __launch_bounds__(256) pool_kernel(const float *__restrict__ x, int x_pitch, int Hi, int Wi, float *__restrict__ out,
+                                                   int out_pitch, int Ho, int Wo, int C, long B, int mode) {
+    const long total = B * Ho * Wo * C;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        long t = i / C;
+        const int xo = static_cast<int>(t % Wo); t /= Wo;
+        const int yo = static_cast<int>(t % Ho);
+        const long b = t / Ho;
+        float r;
+        if (mode == 0) {
+            float s = 0.f; int n = 0;
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int y = 2 * yo + dy, xx = 2 * xo + dx;
+                    if (y >= 0 && y < Hi && xx >= 0 && xx < Wi) { s += x[((b * Hi + y) * static_cast<long>(Wi) + xx) * x_pitch + c]; ++n; }
+                }
+            r = s / static_cast<float>(n);
+        } else {
+            r = -INFINITY;
+            for (int dy = 0; dy < 2; ++dy)
+                for (int dx = 0; dx < 2; ++dx) r = fmaxf(r, x[((b * Hi + 2 * yo + dy) * static_cast<long>(Wi) + 2 * xo + dx) * x_pitch + c]);
+        }
+        out[((b * Ho + yo) * static_cast<long>(Wo) + xo) * out_pitch + c] = r;
+    }
+}
+
+// Scalar loss reductions over NHWC tensors a (and b), accumulated in double (GenProjector/models/networks/loss.py:57-82,109-114;
+// pix2pix_model.py:101-122).  acc += sum over the M*C elements (mode 5: over the M pixels) of
+//   0: a                       (generator hinge: -mean(D(fake)))        1: min(a - 1, 0)   (D hinge, real)
+//   2: min(-a - 1, 0)          (D hinge, fake)                          3: |a - b|         (L1: VGG / feature matching)
+//   4: |a - b| * (m + (1-m)*50), m = mask[pixel]   (mask-weighted feature matching; the weight is >= 0 so it factors out of |.|)
+//   5: 1 - <a,b> / max(|a||b|, eps)                (cosine distance over the channel dimension)
+__global__ void __launch_bounds__(256) loss_reduce_kernel(const float *__restrict__ a, int a_pitch, const float *__restrict__ b, int b_pitch,
+                                                          const float *__restrict__ mask, long M, int C, int mode, double *acc) {
+    __shared__ double s_part[8];
+    double part = 0.0;
+    if (mode == 5) {
+        for (long m = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; m < M; m += static_cast<long>(gridDim.x) * blockDim.x) {
+            float ab = 0.f, aa = 0.f, bb = 0.f;
+            for (int c = 0; c < C; ++c) { const float u = a[m * a_pitch + c], v = b[m * b_pitch + c]; ab = fmaf(u, v, ab); aa = fmaf(u, u, aa); bb = fmaf(v, v, bb); }
+            part += 1.0 - static_cast<double>(ab / fmaxf(sqrtf(aa) * sqrtf(bb), 1e-20f));
+        }
+    } else {
+        const long total = M * C;
+        for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+            const int c = static_cast<int>(i % C);
+            const long m = i / C;
+            const float u = a[m * a_pitch + c];
+            float v;
+            if (mode == 0) v = u;
+            else if (mode == 1) v = fminf(u - 1.f, 0.f);
+            else if (mode == 2) v = fminf(-u - 1.f, 0.f);
+            else {
+                v = fabsf(u - b[m * b_pitch + c]);
+                if (mode == 4) { const float mk = mask[m]; v *= mk + (1.f - mk) * 50.f; }
+            }
+            part += v;
+        }
+    }
+    part = warp_sum_d(part);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_part[w];
+        atomicAdd(acc, t);
+    }
+}
+
 inline unsigned grid_for(long total, int per_block = 256) {
     long b = (total + per_block - 1) / per_block;
     const long cap = 148L * 16;
@@ -376,5 +459,35 @@ extern "C" int eml_tanh_to_nchw(const float *x, int x_pitch, const float *bias, 
     if (B <= 0 || C <= 0 || HW <= 0 || x_pitch < C) return EML_E_SHAPE;
     const long total = static_cast<long>(B) * C * HW;
     tanh_out_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_pitch, bias, out, B, HW, C, scale);
+    return eml_launch_status();
+}
+
+extern "C" int eml_bias_act(const float *x, int x_pitch, const float *bias, int act, float *out, int out_pitch, long M, int C, void *stream) {
+    EML_CHECK_PTR(x); EML_CHECK_PTR(out);
+    if (M <= 0 || C <= 0 || x_pitch < C || out_pitch < C) return EML_E_SHAPE;
+    if (act < 0 || act > 2) return EML_E_ARG;
+    bias_act_kernel<<<grid_for(M * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_pitch, bias, act, out, out_pitch, M, C);
+    return eml_launch_status();
+}
+
+extern "C" int eml_pool2d(const float *x, int x_pitch, int Hi, int Wi, float *out, int out_pitch, int C, int B, int mode, void *stream) {
+    EML_CHECK_PTR(x); EML_CHECK_PTR(out);
+    if (B <= 0 || C <= 0 || Hi <= 0 || Wi <= 0 || x_pitch < C || out_pitch < C) return EML_E_SHAPE;
+    if (mode != 0 && mode != 1) return EML_E_ARG;
+    if (mode == 1 && ((Hi | Wi) & 1)) return EML_E_SHAPE;
+    const int Ho = mode == 0 ? (Hi + 1) / 2 : Hi / 2, Wo = mode == 0 ? (Wi + 1) / 2 : Wi / 2;
+    const long total = static_cast<long>(B) * Ho * Wo * C;
+    pool_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_pitch, Hi, Wi, out, out_pitch, Ho, Wo, C, B, mode);
+    return eml_launch_status();
+}
+
+extern "C" int eml_loss_reduce(const float *a, int a_pitch, const float *b, int b_pitch, const float *mask, long M, int C, int mode,
+                               double *acc, void *stream) {
+    EML_CHECK_PTR(a); EML_CHECK_PTR(acc);
+    if (M <= 0 || C <= 0 || a_pitch < C) return EML_E_SHAPE;
+    if (mode < 0 || mode > 5) return EML_E_ARG;
+    if (mode >= 3) { EML_CHECK_PTR(b); if (b_pitch < C) return EML_E_SHAPE; }
+    if (mode == 4) EML_CHECK_PTR(mask);
+    loss_reduce_kernel<<<grid_for(mode == 5 ? M : M * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, a_pitch, b, b_pitch, mask, M, C, mode, acc);
     return eml_launch_status();
 }

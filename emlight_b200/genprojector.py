@@ -89,15 +89,15 @@ def _sphere_lut(h, w, stride):
 
 
 @lru_cache(maxsize=None)
-def _conv_s2_lut(h, w):
-    """Regular 3x3, stride 2, padding 1 convolution (ConvEncoder, generator.py:100-104) as a one-tap table."""
-    ho, wo = (h + 1) // 2, (w + 1) // 2
+def _conv_lut(h, w, stride=2):
+    """Regular 3x3, padding 1 convolution of stride 1 (VGG19) or 2 (ConvEncoder, generator.py:100-104) as a one-tap table."""
+    ho, wo = (h + stride - 1) // stride, (w + stride - 1) // stride
     yo, xo = np.meshgrid(np.arange(ho), np.arange(wo), indexing="ij")
     idx = np.full((ho, wo, 9, 4), -1, np.int32)
     wgt = np.zeros((ho, wo, 9, 4), np.float32)
     for ky in range(3):
         for kx in range(3):
-            yy, xx = 2 * yo + ky - 1, 2 * xo + kx - 1
+            yy, xx = stride * yo + ky - 1, stride * xo + kx - 1
             ok = (yy >= 0) & (yy < h) & (xx >= 0) & (xx < w)
             idx[:, :, ky * 3 + kx, 0] = np.where(ok, yy * w + xx, -1)
             wgt[:, :, ky * 3 + kx, 0] = ok
@@ -111,7 +111,7 @@ class _Luts:
     def get(self, kind, h, w, stride, device):
         key = (kind, h, w, stride, str(device))
         if key not in self.cache:
-            idx, wgt, ho, wo = _sphere_lut(h, w, stride) if kind == "sphere" else _conv_s2_lut(h, w)
+            idx, wgt, ho, wo = _sphere_lut(h, w, stride) if kind == "sphere" else _conv_lut(h, w, stride)
             self.cache[key] = (torch.from_numpy(idx).to(device), torch.from_numpy(wgt).to(device), ho, wo)
         return self.cache[key]
 
@@ -149,6 +149,15 @@ class _PackedConv:
 def _gemm(A, M, pc, out, out_pitch, choff, precision):
     """out[:, choff:choff+O] = A (M,K) @ W^T via eml_conv_forward (1x1 mode), sliced over the output channels."""
     lib = _lib.load()
+    if precision == "fp32" and pc.K * 16 * 4 > 200 * 1024:
+        # the SIMT conv kernel keeps a 16-channel weight panel in shared memory (K <= 3200); wider reductions (ngf=64 generator
+        # blocks, VGG conv4/5) take the tiled fp32 GEMM and are copied into the output slab
+        for n0, n, w_s, _ in pc.slices:
+            tmp = torch.empty(M, n, dtype=torch.float32, device=A.device)
+            _lib.check(lib.eml_linear_fp32(_lib.ptr(A), _lib.ptr(w_s), None, _lib.ptr(tmp), M, n, pc.K, _lib.stream_ptr()),
+                       "eml_linear_fp32(GEMM %dx%dx%d)" % (M, n, pc.K))
+            out.view(M, out_pitch)[:, choff + n0:choff + n0 + n] = tmp
+        return
     for n0, n, w_s, pack in pc.slices:
         p = ConvParams()
         p.in_ = A.data_ptr(); p.scale = None; p.shift = None
@@ -253,8 +262,8 @@ class SphereConv2D(nn.Module):
 class _SpectralSphereConv2D(SphereConv2D):
     """SphereConv2D under torch.nn.utils.spectral_norm naming: weight_orig (parameter), weight_u / weight_v (buffers)."""
 
-    def __init__(self, in_c, out_c):
-        super().__init__(in_c, out_c)
+    def __init__(self, in_c, out_c, stride=1, bias=True):
+        super().__init__(in_c, out_c, stride=stride, bias=bias)
         w = self.weight
         del self._parameters["weight"]
         self.register_parameter("weight_orig", Parameter(w.data))
@@ -410,7 +419,7 @@ class ConvEncoder(nn.Module):
         for i in range(1, 6):
             conv = getattr(self, "layer%d" % i)[0]
             pc = conv.packed(precision)
-            raw = _conv_raw(x, B, H, W, pc, _LUTS.get("conv_s2", H, W, 2, dev), None, 0, precision)   # LeakyReLU already applied by the norm below
+            raw = _conv_raw(x, B, H, W, pc, _LUTS.get("conv", H, W, 2, dev), None, 0, precision)   # LeakyReLU already applied by the norm below
             ho, wo = raw.shape[1], raw.shape[2]
             x = torch.empty_like(raw)
             _lib.check(lib.eml_instance_norm(_lib.ptr(raw), raw.shape[-1], _lib.ptr(x), x.shape[-1], B, ho * wo, pc.O, 1e-5, 1, st),
@@ -509,3 +518,355 @@ class SPADEGenerator(nn.Module):
         _lib.check(lib.eml_tanh_to_nchw(_lib.ptr(raw), raw.shape[-1], _lib.ptr(self.sphere_conv1.bias), _lib.ptr(out), B, H * W, 3, 25.0, st),
                    "eml_tanh_to_nchw")
         return out
+
+
+# ===================================================================================== discriminator, losses, model wrapper (G6-G8)
+def _nchw_to_nhwc(x, pitch):
+    """(B,C,H,W) -> zero-padded NHWC (B,H,W,pitch) through the nearest-resize kernel at identity scale."""
+    lib = _lib.load()
+    B, C, H, W = x.shape
+    out = torch.zeros(B, H, W, pitch, dtype=torch.float32, device=x.device)
+    _lib.check(lib.eml_resize_nearest(_lib.ptr(x.contiguous().float()), 0, H, W, _lib.ptr(out), pitch, H, W, C, B, 1, _lib.stream_ptr()),
+               "eml_resize_nearest(NCHW->NHWC)")
+    return out
+
+
+def _to_nchw(x, C):
+    return x[..., :C].permute(0, 3, 1, 2).contiguous()
+
+
+def _bias_act(raw, bias, act, M, C):
+    out = torch.empty_like(raw) if raw.shape[-1] == C else torch.zeros_like(raw)
+    _lib.check(_lib.load().eml_bias_act(_lib.ptr(raw), raw.shape[-1], _lib.ptr(bias), act, _lib.ptr(out), out.shape[-1], M, C, _lib.stream_ptr()),
+               "eml_bias_act")
+    return out
+
+
+def _pool(x, B, H, W, C, mode):
+    ho, wo = ((H + 1) // 2, (W + 1) // 2) if mode == 0 else (H // 2, W // 2)
+    out = torch.zeros(B, ho, wo, x.shape[-1], dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().eml_pool2d(_lib.ptr(x), x.shape[-1], H, W, _lib.ptr(out), out.shape[-1], C, B, mode, _lib.stream_ptr()), "eml_pool2d")
+    return out, ho, wo
+
+
+_RED_SUM, _RED_HINGE_REAL, _RED_HINGE_FAKE, _RED_L1, _RED_L1_MASKED, _RED_COS = range(6)
+
+
+def _reduce(acc, mode, a, M, C, a_pitch, b=None, b_pitch=0, mask=None):
+    _lib.check(_lib.load().eml_loss_reduce(_lib.ptr(a), a_pitch, _lib.ptr(b), b_pitch, _lib.ptr(mask), M, C, mode, _lib.ptr(acc), _lib.stream_ptr()),
+               "eml_loss_reduce(mode %d)" % mode)
+
+
+def _reduced_mean(mode, a, M, C, a_pitch, count, b=None, b_pitch=0, mask=None, sign=1.0):
+    acc = torch.zeros(1, dtype=torch.float64, device=a.device)
+    _reduce(acc, mode, a, M, C, a_pitch, b, b_pitch, mask)
+    return (acc * (sign / count)).float().reshape(())
+
+
+class NLayerDiscriminator(nn.Module):
+    """Drop-in for discriminator.NLayerDiscriminator (discriminator.py:69-125): SphereConv PatchGAN, ``model0..model{n}`` groups with
+    the reference's parameter names.  opt needs: ndf, n_layers_D, norm_D ('spectralinstance'), label_nc, output_nc, no_ganFeat_loss."""
+
+    def __init__(self, opt, precision="bf16x3"):
+        super().__init__()
+        if getattr(opt, "norm_D", "spectralinstance") != "spectralinstance":
+            raise ValueError("only norm_D='spectralinstance' (the reference default) is implemented")
+        self.opt = opt
+        self.precision = precision
+        nf = opt.ndf
+        self.input_nc = opt.label_nc + opt.output_nc
+        self.n_layers = opt.n_layers_D
+        self.model0 = nn.Sequential(SphereConv2D(self.input_nc, nf, stride=2), nn.LeakyReLU(0.2, False))
+        self.strides = [2]
+        for n in range(1, opt.n_layers_D):
+            nf_prev, nf = nf, min(nf * 2, 512)
+            stride = 1 if n == opt.n_layers_D - 1 else 2
+            self.strides.append(stride)
+            setattr(self, "model%d" % n, nn.Sequential(nn.Sequential(_SpectralSphereConv2D(nf_prev, nf, stride=stride, bias=False),
+                                                                     nn.InstanceNorm2d(nf, affine=False)), nn.LeakyReLU(0.2, False)))
+        setattr(self, "model%d" % opt.n_layers_D, nn.Sequential(SphereConv2D(nf, 3, stride=1)))
+
+    def features_nhwc(self, x, B, H, W):
+        """x NHWC (B,H,W,pitch>=up4(input_nc)) -> [(NHWC tensor, h, w, C)] * (n_layers+1)."""
+        lib = _lib.load()
+        prec = self.precision
+        st = _lib.stream_ptr()
+        outs = []
+        conv = self.model0[0]
+        raw = _sphere_conv_raw(x, B, H, W, conv.packed(prec), 2, None, 0, prec)
+        H, W = raw.shape[1], raw.shape[2]
+        x = _bias_act(raw, conv.bias, 2, B * H * W, conv.out_c)
+        outs.append((x, H, W, conv.out_c))
+        for n in range(1, self.n_layers):
+            conv = getattr(self, "model%d" % n)[0][0]
+            raw = _sphere_conv_raw(x, B, H, W, conv.packed(prec), conv.stride, None, 0, prec)
+            H, W = raw.shape[1], raw.shape[2]
+            x = torch.empty_like(raw)
+            _lib.check(lib.eml_instance_norm(_lib.ptr(raw), raw.shape[-1], _lib.ptr(x), x.shape[-1], B, H * W, conv.out_c, 1e-5, 1, st), "eml_instance_norm")
+            outs.append((x, H, W, conv.out_c))
+        conv = getattr(self, "model%d" % self.n_layers)[0]
+        raw = _sphere_conv_raw(x, B, H, W, conv.packed(prec), 1, None, 0, prec)
+        outs.append((_bias_act(raw, conv.bias, 0, B * H * W, 3), H, W, 3))
+        return outs
+
+    @torch.no_grad()
+    def forward(self, input):
+        _lib.require_cuda(input)
+        B, C, H, W = input.shape
+        outs = [_to_nchw(t, c) for t, _, _, c in self.features_nhwc(_nchw_to_nhwc(input, _up4(C)), B, H, W)]
+        return outs if not self.opt.no_ganFeat_loss else outs[-1]
+
+
+class MultiscaleDiscriminator(nn.Module):
+    """Drop-in for discriminator.MultiscaleDiscriminator (discriminator.py:16-65): ``discriminator_{i}`` on the input avg-pooled i times.
+    Forward only (stored spectral-norm vectors, as in eval mode); returns the reference's list of lists of NCHW tensors."""
+
+    def __init__(self, opt, precision="bf16x3"):
+        super().__init__()
+        if getattr(opt, "netD_subarch", "n_layer") != "n_layer":
+            raise ValueError("unrecognized discriminator subarchitecture %s" % opt.netD_subarch)
+        self.opt = opt
+        for i in range(opt.num_D):
+            self.add_module("discriminator_%d" % i, NLayerDiscriminator(opt, precision))
+
+    @property
+    def precision(self):
+        return self.discriminator_0.precision
+
+    @precision.setter
+    def precision(self, p):
+        for d in self.children():
+            d.precision = p
+
+    def features_nhwc(self, x, B, H, W):
+        result = []
+        C = self.discriminator_0.input_nc
+        for D in self.children():
+            result.append(D.features_nhwc(x, B, H, W))
+            x, H, W = _pool(x, B, H, W, C, 0)
+        return result
+
+    @torch.no_grad()
+    def forward(self, input):
+        _lib.require_cuda(input)
+        B, C, H, W = input.shape
+        feats = self.features_nhwc(_nchw_to_nhwc(input, _up4(C)), B, H, W)
+        result = [[_to_nchw(t, c) for t, _, _, c in fl] for fl in feats]
+        return result if not self.opt.no_ganFeat_loss else [[r[-1]] for r in result]
+
+
+class GANLoss(nn.Module):
+    """Drop-in for loss.GANLoss (loss.py:15-98), hinge mode (the reference default, train_options.py): scalar per call, the mean over
+    the multiscale list.  Values only -- there is no autograd graph behind the returned tensors."""
+
+    def __init__(self, gan_mode, target_real_label=1.0, target_fake_label=0.0, tensor=torch.FloatTensor, opt=None):
+        super().__init__()
+        if gan_mode not in ("ls", "original", "w", "hinge"):
+            raise ValueError("Unexpected gan_mode {}".format(gan_mode))
+        if gan_mode != "hinge":
+            raise NotImplementedError("emlight_b200.GANLoss: only gan_mode='hinge' (the reference default) is implemented")
+        self.gan_mode, self.opt = gan_mode, opt
+
+    @torch.no_grad()
+    def loss(self, input, target_is_real, for_discriminator=True):
+        _lib.require_cuda(input)
+        x = input.contiguous().float()
+        if for_discriminator:
+            mode = _RED_HINGE_REAL if target_is_real else _RED_HINGE_FAKE
+        else:
+            assert target_is_real, "The generator's hinge loss must be aiming for real"
+            mode = _RED_SUM
+        return _reduced_mean(mode, x, x.numel(), 1, 1, x.numel(), sign=-1.0)
+
+    def __call__(self, input, target_is_real, for_discriminator=True):
+        if isinstance(input, list):
+            loss = 0
+            for pred_i in input:
+                if isinstance(pred_i, list):
+                    pred_i = pred_i[-1]
+                loss = loss + self.loss(pred_i, target_is_real, for_discriminator)
+            return loss / len(input)
+        return self.loss(input, target_is_real, for_discriminator)
+
+
+_VGG_SLICES = ((0, "R"), (2, "R", "P", 5, "R"), (7, "R", "P", 10, "R"), (12, "R", 14, "R", 16, "R", "P", 19, "R"),
+               (21, "R", 23, "R", 25, "R", "P", 28, "R"))
+_VGG_CH = {0: (3, 64), 2: (64, 64), 5: (64, 128), 7: (128, 128), 10: (128, 256), 12: (256, 256), 14: (256, 256), 16: (256, 256),
+           19: (256, 512), 21: (512, 512), 23: (512, 512), 25: (512, 512), 28: (512, 512)}
+
+
+class VGG19(nn.Module):
+    """Drop-in for architecture.VGG19 (architecture.py:92-122): torchvision vgg19.features[0:30] cut into ``slice1..slice5`` with the
+    torchvision layer indices as module names, so a reference / torchvision state_dict loads.  There is no network here for the
+    ImageNet checkpoint: weights are whatever is loaded (He-initialised by default).  forward(X NCHW) -> 5 relu feature maps."""
+
+    def __init__(self, requires_grad=False, precision="bf16x3"):
+        super().__init__()
+        self.precision = precision
+        for s, ops in enumerate(_VGG_SLICES):
+            seq = nn.Sequential()
+            idx = None
+            for op in ops:
+                if op == "R":
+                    seq.add_module(str(idx + 1), nn.ReLU(inplace=True))
+                elif op == "P":
+                    seq.add_module(str(idx + 2), nn.MaxPool2d(2, 2))
+                    idx += 1
+                else:
+                    idx = op
+                    seq.add_module(str(idx), nn.Conv2d(*_VGG_CH[idx], kernel_size=3, padding=1))
+            setattr(self, "slice%d" % (s + 1), seq)
+        for prm in self.parameters():
+            prm.requires_grad = requires_grad
+        self._pc = {}
+
+    def _packed(self, conv, precision):
+        w = conv.weight
+        key = (w.data_ptr(), w._version, precision, str(w.device))
+        hit = self._pc.get(id(conv))
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = (key, _PackedConv(w, precision))
+            self._pc[id(conv)] = hit
+        return hit[1]
+
+    def features_nhwc(self, x, B, H, W):
+        """x NHWC (B,H,W,4) -> [(NHWC tensor, h, w, C)] * 5."""
+        prec = self.precision
+        outs = []
+        C = 3
+        for s in range(5):
+            for m in getattr(self, "slice%d" % (s + 1)):
+                if isinstance(m, nn.Conv2d):
+                    raw = _conv_raw(x, B, H, W, self._packed(m, prec), _LUTS.get("conv", H, W, 1, x.device), None, 0, prec)
+                    C = m.out_channels
+                    x = _bias_act(raw, m.bias, 1, B * H * W, C)           # conv bias + the ReLU that follows it
+                elif isinstance(m, nn.MaxPool2d):
+                    x, H, W = _pool(x, B, H, W, C, 1)
+            outs.append((x, H, W, C))
+        return outs
+
+    @torch.no_grad()
+    def forward(self, X):
+        _lib.require_cuda(X)
+        B, _, H, W = X.shape
+        return [_to_nchw(t, c) for t, _, _, c in self.features_nhwc(_nchw_to_nhwc(X, 4), B, H, W)]
+
+
+class VGGLoss(nn.Module):
+    """Drop-in for loss.VGGLoss (loss.py:102-114): sum_k w_k * L1(vgg_k(x), vgg_k(y)), w = 1/32, 1/16, 1/8, 1/4, 1.  x and y run as
+    one 2B batch.  Value only (no autograd)."""
+
+    def __init__(self, gpu_ids=None, precision="bf16x3"):
+        super().__init__()
+        self.vgg = VGG19(precision=precision).cuda()
+        self.weights = [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0]
+
+    @torch.no_grad()
+    def forward(self, x, y):
+        _lib.require_cuda(x, y)
+        B, _, H, W = x.shape
+        feats = self.vgg.features_nhwc(_nchw_to_nhwc(torch.cat([x, y], 0), 4), 2 * B, H, W)
+        loss = 0
+        for wk, (t, h, w, c) in zip(self.weights, feats):
+            M = B * h * w
+            loss = loss + wk * _reduced_mean(_RED_L1, t[:B], M, c, t.shape[-1], M * c, b=t[B:], b_pitch=t.shape[-1])
+        return loss
+
+
+@torch.no_grad()
+def feature_matching_loss(feats, B, mask):
+    """pix2pix_model.py:101-117 on the NHWC feature lists of a [fake; real] 2B batch: L1 between the mask-re-weighted fake and real
+    features (weight m + 50 (1-m)); the mask is nearest-resized from its previous size at every layer, like the reference (:111)."""
+    lib = _lib.load()
+    num_D = len(feats)
+    m = mask.contiguous().float()                                         # (B,1,H,W) == NHWC with one channel
+    mh, mw = m.shape[2], m.shape[3]
+    loss = 0
+    for fl in feats:
+        for t, h, w, c in fl[:-1]:
+            nm = torch.empty(B, h, w, 1, dtype=torch.float32, device=m.device)
+            _lib.check(lib.eml_resize_nearest(_lib.ptr(m), 1, mh, mw, _lib.ptr(nm), 1, h, w, 1, B, 0, _lib.stream_ptr()), "eml_resize_nearest(mask)")
+            m, mh, mw = nm, h, w
+            M = B * h * w
+            loss = loss + _reduced_mean(_RED_L1_MASKED, t[:B], M, c, t.shape[-1], M * c, b=t[B:], b_pitch=t.shape[-1], mask=m) / num_D
+    return loss.reshape(1)
+
+
+@torch.no_grad()
+def cosine_loss(fake, real):
+    """(1 - CosineSimilarity(dim=1, eps=1e-20)(fake, real)).mean()  (pix2pix_model.py:95,122)."""
+    B, C, H, W = fake.shape
+    a, b = _nchw_to_nhwc(fake, _up4(C)), _nchw_to_nhwc(real, _up4(C))
+    return _reduced_mean(_RED_COS, a, B * H * W, C, a.shape[-1], B * H * W, b=b, b_pitch=b.shape[-1])
+
+
+class Pix2PixModel(nn.Module):
+    """Drop-in for pix2pix_model.Pix2PixModel (pix2pix_model.py:12-186): mode dispatch 'inference' / 'generator' / 'discriminator'.
+    'inference' is the full product path.  'generator' and 'discriminator' EVALUATE the reference's loss dictionaries (same keys and
+    weights) on eval-mode networks; they carry no autograd graph -- GAN training (generator / discriminator backward, batch-statistic
+    SyncBN, spectral-norm power iteration) is not implemented in this round."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.netG = SPADEGenerator(opt).cuda().eval()
+        self.netD = MultiscaleDiscriminator(opt).cuda().eval() if opt.isTrain else None
+        if opt.isTrain:
+            self.criterionGAN = GANLoss(opt.gan_mode, opt=opt)
+            if not getattr(opt, "no_vgg_loss", False):
+                self.criterionVGG = VGGLoss(getattr(opt, "gpu_ids", None))
+
+    def forward(self, data, mode):
+        input, crop, real_image, map = data["input"].cuda(), data["crop"].cuda(), data["warped"].cuda(), data["map"].cuda()
+        if mode == "generator":
+            return self.compute_generator_loss(input, crop, real_image, map)
+        if mode == "discriminator":
+            return self.compute_discriminator_loss(input, crop, real_image)
+        if mode == "inference":
+            return self.generate_fake(input, crop)
+        raise ValueError("|mode| is invalid")
+
+    def create_optimizers(self, opt):
+        G_params = list(self.netG.parameters())
+        D_params = list(self.netD.parameters()) if opt.isTrain else []
+        G_lr, D_lr = (opt.lr, opt.lr) if opt.no_TTUR else (opt.lr / 2, opt.lr * 2)
+        return (torch.optim.Adam(G_params, lr=G_lr, betas=(opt.beta1, opt.beta2)),
+                torch.optim.Adam(D_params, lr=D_lr, betas=(opt.beta1, opt.beta2)))
+
+    def generate_fake(self, input, crop):
+        return self.netG(input, crop)
+
+    @torch.no_grad()
+    def _discriminate_nhwc(self, input, fake_image, real_image):
+        both = torch.cat([torch.cat([input, fake_image], 1), torch.cat([input, real_image], 1)], 0)
+        B2, C, H, W = both.shape
+        return self.netD.features_nhwc(_nchw_to_nhwc(both, _up4(C)), B2, H, W)
+
+    def discriminate(self, input, fake_image, real_image):
+        feats = self._discriminate_nhwc(input, fake_image, real_image)
+        B = input.shape[0]
+        return ([[_to_nchw(t[:B], c) for t, _, _, c in fl] for fl in feats], [[_to_nchw(t[B:], c) for t, _, _, c in fl] for fl in feats])
+
+    @torch.no_grad()
+    def compute_generator_loss(self, input, crop, real_image, map):
+        fake_image = self.generate_fake(input, crop)
+        B = input.shape[0]
+        feats = self._discriminate_nhwc(input, fake_image, real_image)
+        G_losses = {"GAN": self.criterionGAN([_to_nchw(fl[-1][0][:B], 3) for fl in feats], True, for_discriminator=False)}
+        if not self.opt.no_ganFeat_loss:
+            G_losses["GAN_Feat"] = feature_matching_loss(feats, B, map)
+        G_losses["VGG"] = self.criterionVGG(fake_image, real_image) * 5
+        G_losses["COS"] = cosine_loss(fake_image, real_image) * 5
+        return G_losses, fake_image
+
+    @torch.no_grad()
+    def compute_discriminator_loss(self, input, crop, real_image):
+        fake_image = self.generate_fake(input, crop)
+        B = input.shape[0]
+        feats = self._discriminate_nhwc(input, fake_image, real_image)
+        return {"D_Fake": self.criterionGAN([_to_nchw(fl[-1][0][:B], 3) for fl in feats], False, for_discriminator=True),
+                "D_real": self.criterionGAN([_to_nchw(fl[-1][0][B:], 3) for fl in feats], True, for_discriminator=True)}
+
+    def use_gpu(self):
+        return True

@@ -232,6 +232,16 @@ int eml_wgrad_3x3(const float *dY, int dy_pitch, int N, const float *b, int b_pi
                   float *dW, int B, int H, int W, int precision, void *stream);
 int eml_wgrad_stem(const float *dZ, int dz_pitch, int O, const float *x_nchw, float *dW, int B, int H, int W, void *stream);
 
+/* G6-G7 -- discriminator / loss building blocks (NHWC fp32).
+ * eml_bias_act: out = act(x + bias[c]) (act 0 none, 1 ReLU, 2 LeakyReLU(0.2)); discriminator.py:91-92, VGG conv+ReLU.
+ * eml_pool2d : mode 0 = avg_pool2d(3, stride 2, pad 1, count_include_pad=False) (discriminator.py:48-51), mode 1 = max_pool2d(2,2) (VGG19).
+ * eml_loss_reduce: *acc += sum of  0: a | 1: min(a-1,0) | 2: min(-a-1,0) | 3: |a-b| | 4: |a-b|*(m+(1-m)*50), m = mask[pixel] |
+ *                  5: per pixel 1 - cos(a,b) over channels   (loss.py:57-82,109-114; pix2pix_model.py:101-122); caller divides by the count. */
+int eml_bias_act(const float *x, int x_pitch, const float *bias, int act, float *out, int out_pitch, long M, int C, void *stream);
+int eml_pool2d(const float *x, int x_pitch, int Hi, int Wi, float *out, int out_pitch, int C, int B, int mode, void *stream);
+int eml_loss_reduce(const float *a, int a_pitch, const float *b, int b_pitch, const float *mask, long M, int C, int mode, double *acc,
+                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -173,3 +173,150 @@ def init_generator_state_dict(seed=0, ngf=64):
         u = F.normalize(torch.mv(w, v), dim=0)
         sd[k[:-5] + "_u"], sd[k[:-5] + "_v"] = u, v
     return sd
+
+
+# ===================================================================================== discriminator + losses (G6-G8)
+# * NLayerDiscriminator     models/networks/discriminator.py:69-125    SphereConv(6->ndf, s2)+LeakyReLU; 3 x [spectral SphereConv
+#                           (s2, s2, s1) + InstanceNorm2d(affine=False) + LeakyReLU]; SphereConv(->3); all 5 outputs returned
+# * MultiscaleDiscriminator models/networks/discriminator.py:16-65     D_i on the input avg-pooled i times (3x3 s2 p1, pad not counted)
+# * GANLoss (hinge)         models/networks/loss.py:57-98              mean over the multiscale list of the per-scale scalar
+# * VGG19 / VGGLoss         models/networks/architecture.py:92-122, loss.py:102-114   torchvision vgg19.features[0:30], 5 relu taps
+# * generator / discriminator loss composition   models/pix2pix_model.py:92-141
+VGG_CFG = ((0, 3, 64), (2, 64, 64), (5, 64, 128), (7, 128, 128), (10, 128, 256), (12, 256, 256), (14, 256, 256), (16, 256, 256),
+           (19, 256, 512), (21, 512, 512), (23, 512, 512), (25, 512, 512), (28, 512, 512))
+VGG_SLICES = ((0,), (2, "P", 5), (7, "P", 10), (12, 14, 16, "P", 19), (21, 23, 25, "P", 28))
+VGG_WEIGHTS = (1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0)
+
+
+def d_channels(ndf=64, n_layers=4):
+    ch = [ndf]
+    for _ in range(1, n_layers):
+        ch.append(min(ch[-1] * 2, 512))
+    return ch
+
+
+def nlayer_discriminator(sd, p, x, n_layers=4):
+    """One PatchGAN: returns the n_layers+1 intermediate outputs (discriminator.py:113-123)."""
+    outs = []
+    x = F.leaky_relu(sphere_conv(x, sd[p + "model0.0.weight"], sd[p + "model0.0.bias"], stride=2), 0.2)
+    outs.append(x)
+    for n in range(1, n_layers):
+        stride = 1 if n == n_layers - 1 else 2
+        x = sphere_conv(x, sn_weight(sd, p + "model%d.0.0" % n), None, stride=stride)       # bias removed by the instance-norm wrapper
+        x = F.leaky_relu(F.instance_norm(x, eps=1e-5), 0.2)
+        outs.append(x)
+    outs.append(sphere_conv(x, sd[p + "model%d.0.weight" % n_layers], sd[p + "model%d.0.bias" % n_layers], stride=1))
+    return outs
+
+
+def multiscale_discriminator(sd, x, num_D=2, n_layers=4):
+    result = []
+    for i in range(num_D):
+        result.append(nlayer_discriminator(sd, "discriminator_%d." % i, x, n_layers))
+        x = F.avg_pool2d(x, kernel_size=3, stride=2, padding=[1, 1], count_include_pad=False)
+    return result
+
+
+def hinge_loss(preds, target_is_real, for_discriminator=True):
+    """GANLoss('hinge').__call__ on a multiscale list (loss.py:65-98)."""
+    total = 0.0
+    for p in preds:
+        p = p[-1] if isinstance(p, (list, tuple)) else p
+        if not for_discriminator:
+            l = -p.mean()
+        elif target_is_real:
+            l = -torch.clamp(p - 1, max=0).mean()
+        else:
+            l = -torch.clamp(-p - 1, max=0).mean()
+        total = total + l
+    return total / len(preds)
+
+
+def feature_matching_loss(pred_fake, pred_real, mask):
+    """pix2pix_model.py:101-117 -- note the mask is re-interpolated from its PREVIOUS size at every layer (:111)."""
+    num_D = len(pred_fake)
+    loss = 0.0
+    for i in range(num_D):
+        for j in range(len(pred_fake[i]) - 1):
+            h, w = pred_fake[i][j].shape[2:]
+            mask = F.interpolate(mask, size=(h, w))
+            fw = pred_fake[i][j] * mask + pred_fake[i][j] * (1 - mask) * 50
+            rw = pred_real[i][j] * mask + pred_real[i][j] * (1 - mask) * 50
+            loss = loss + F.l1_loss(fw, rw) / num_D
+    return loss
+
+
+def vgg_features(sd, x, p="vgg."):
+    outs = []
+    for s, ops in enumerate(VGG_SLICES):
+        for op in ops:
+            if op == "P":
+                x = F.max_pool2d(x, 2, 2)
+            else:
+                x = F.relu(F.conv2d(x, sd["%sslice%d.%d.weight" % (p, s + 1, op)], sd["%sslice%d.%d.bias" % (p, s + 1, op)], padding=1))
+        outs.append(x)
+    return outs
+
+
+def vgg_loss(sd, x, y, p="vgg."):
+    fx, fy = vgg_features(sd, x, p), vgg_features(sd, y, p)
+    return sum(w * F.l1_loss(a, b) for w, a, b in zip(VGG_WEIGHTS, fx, fy))
+
+
+def cosine_loss(fake, real):
+    return (1 - F.cosine_similarity(fake, real, dim=1, eps=1e-20)).mean()
+
+
+def split_pred(pred):
+    """Pix2PixModel.divide_pred (pix2pix_model.py:164-178)."""
+    return ([[t[:t.size(0) // 2] for t in p] for p in pred], [[t[t.size(0) // 2:] for t in p] for p in pred])
+
+
+def generator_losses(sd_d, sd_vgg, guide, fake, real, mask, num_D=2, n_layers=4):
+    """compute_generator_loss (pix2pix_model.py:92-128) given the generated image: {'GAN','GAN_Feat','VGG','COS'}."""
+    pred = multiscale_discriminator(sd_d, torch.cat([torch.cat([guide, fake], 1), torch.cat([guide, real], 1)], 0), num_D, n_layers)
+    pf, pr = split_pred(pred)
+    return {"GAN": hinge_loss(pf, True, False), "GAN_Feat": feature_matching_loss(pf, pr, mask),
+            "VGG": vgg_loss(sd_vgg, fake, real) * 5, "COS": cosine_loss(fake, real) * 5}
+
+
+def discriminator_losses(sd_d, guide, fake, real, num_D=2, n_layers=4):
+    """compute_discriminator_loss (pix2pix_model.py:130-141): {'D_Fake','D_real'}."""
+    pred = multiscale_discriminator(sd_d, torch.cat([torch.cat([guide, fake], 1), torch.cat([guide, real], 1)], 0), num_D, n_layers)
+    pf, pr = split_pred(pred)
+    return {"D_Fake": hinge_loss(pf, False, True), "D_real": hinge_loss(pr, True, True)}
+
+
+def init_discriminator_state_dict(seed=0, ndf=64, num_D=2, n_layers=4, input_nc=6):
+    """Deterministic parameters with the reference's names (spectral layers: weight_orig/_u/_v, bias deleted by the norm wrapper)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    ch = d_channels(ndf, n_layers)
+    for d in range(num_D):
+        p = "discriminator_%d." % d
+        sd[p + "model0.0.weight"] = torch.randn(ch[0], input_nc, 3, 3, generator=g) / math.sqrt(input_nc * 9)
+        sd[p + "model0.0.bias"] = 0.1 * torch.randn(ch[0], generator=g)
+        for n in range(1, n_layers):
+            w = torch.randn(ch[n], ch[n - 1], 3, 3, generator=g) / math.sqrt(ch[n - 1] * 9)
+            u = F.normalize(torch.randn(ch[n], generator=g), dim=0)
+            wm = w.reshape(ch[n], -1)
+            v = F.normalize(torch.mv(wm.t(), u), dim=0)
+            u = F.normalize(torch.mv(wm, v), dim=0)
+            sd[p + "model%d.0.0.weight_orig" % n] = w
+            sd[p + "model%d.0.0.weight_u" % n] = u
+            sd[p + "model%d.0.0.weight_v" % n] = v
+        sd[p + "model%d.0.weight" % n_layers] = torch.randn(3, ch[-1], 3, 3, generator=g) / math.sqrt(ch[-1] * 9)
+        sd[p + "model%d.0.bias" % n_layers] = 0.1 * torch.randn(3, generator=g)
+    return sd
+
+
+def init_vgg_state_dict(seed=0, p="vgg."):
+    """He-initialised VGG19 feature weights under the reference's slice names (there is no network for the ImageNet checkpoint;
+    parity is about the arithmetic, the production weights load through the same keys)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    slice_of = {op: s + 1 for s, ops in enumerate(VGG_SLICES) for op in ops if op != "P"}
+    for idx, ci, co in VGG_CFG:
+        sd["%sslice%d.%d.weight" % (p, slice_of[idx], idx)] = torch.randn(co, ci, 3, 3, generator=g) * math.sqrt(2.0 / (ci * 9))
+        sd["%sslice%d.%d.bias" % (p, slice_of[idx], idx)] = 0.05 * torch.randn(co, generator=g)
+    return sd

@@ -139,6 +139,51 @@ def main():
     np.savez_compressed(os.path.join(OUT, "generator.npz"), ngf=np.int64(ngf), sd_seed=np.int64(0), in_seed=np.int64(3),
                         out=out.numpy()[:, :, ::2, ::2], out_mean=np.float64(out.double().mean()), out_std=np.float64(out.double().std()),
                         sc_weight=sc.weight.detach().numpy(), sc_bias=sc.bias.detach().numpy(), sc_x=xs.numpy(), sc_y=ys.detach().numpy())
+    # ---------------- GenProjector discriminator + losses (discriminator.py / loss.py / architecture.py VGG19 / pix2pix_model.py unchanged) ----
+    # Pix2PixModel.forward needs .cuda(); its loss-composition methods are called unbound on a stand-in ``self`` that carries the
+    # reference's own netD / GANLoss / VGGLoss objects.  VGG19 weights: torchvision's ImageNet checkpoint is not reachable (no
+    # network) -> vgg19(weights=None) loaded with GO.init_vgg_state_dict(0) under the reference's slice names.
+    import torchvision
+    _vgg19 = torchvision.models.vgg19
+    torchvision.models.vgg19 = lambda pretrained=False, **kw: _vgg19(weights=None)
+    from models.pix2pix_model import Pix2PixModel
+    from models.networks.discriminator import MultiscaleDiscriminator
+    from models.networks.loss import GANLoss, VGGLoss
+    from models.networks.architecture import VGG19
+    ndf = 16
+    optd = argparse.Namespace(ndf=ndf, norm_D="spectralinstance", label_nc=3, output_nc=3, num_D=2, n_layers_D=4, netD_subarch="n_layer",
+                              no_ganFeat_loss=False, no_vgg_loss=False, gpu_ids=[])
+    D = MultiscaleDiscriminator(optd).eval()
+    D.load_state_dict(GO.init_discriminator_state_dict(0, ndf))
+    vgg = VGG19().eval()
+    vgg.load_state_dict(GO.init_vgg_state_dict(0, p=""))
+    vl = VGGLoss.__new__(VGGLoss)                                         # VGGLoss.__init__ hard-codes .cuda(); forward is the reference's
+    torch.nn.Module.__init__(vl)
+    vl.vgg, vl.criterion, vl.weights = vgg, torch.nn.L1Loss(), [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0]
+    gen = torch.Generator().manual_seed(5)
+    guide = torch.rand(1, 3, 128, 256, generator=gen) * 2
+    fake = torch.rand(1, 3, 128, 256, generator=gen) * 50 * torch.rand(1, 1, 128, 256, generator=gen) ** 4
+    real = torch.rand(1, 3, 128, 256, generator=gen) * 50 * torch.rand(1, 1, 128, 256, generator=gen) ** 4
+    mask = (torch.rand(1, 1, 128, 256, generator=gen) > 0.3).float()
+    m = types.SimpleNamespace(opt=optd, FloatTensor=torch.FloatTensor, netD=D, criterionVGG=vl, criterionFeat=torch.nn.L1Loss(),
+                              criterionGAN=GANLoss("hinge", tensor=torch.FloatTensor, opt=optd), generate_fake=lambda i, c: fake)
+    for n in ("discriminate", "divide_pred"):
+        setattr(m, n, types.MethodType(getattr(Pix2PixModel, n), m))
+    with torch.no_grad():
+        gl, _ = Pix2PixModel.compute_generator_loss(m, guide, None, real, mask)
+        dl = Pix2PixModel.compute_discriminator_loss(m, guide, None, real)
+        feats = D(torch.cat([torch.cat([guide, fake], 1), torch.cat([guide, real], 1)], 0))
+        vf = vgg(fake)
+    gold = {"ndf": np.int64(ndf), "sd_seed": np.int64(0), "vgg_seed": np.int64(0), "in_seed": np.int64(5)}
+    for k, v in list(gl.items()) + list(dl.items()):
+        gold["loss_" + k] = np.float64(float(v))
+    for i, fl in enumerate(feats):
+        for j, f in enumerate(fl):
+            gold["d%d_%d" % (i, j)] = f.numpy()[:, ::max(1, f.shape[1] // 8), ::2, ::2].astype(np.float32) if j < 4 else f.numpy()
+    for j, f in enumerate(vf):
+        gold["vgg_%d_absmean" % j] = np.float64(f.double().abs().mean())
+        gold["vgg_%d" % j] = f.numpy()[:, ::max(1, f.shape[1] // 8), ::4, ::4].astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "discriminator.npz"), **gold)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -33,7 +33,7 @@ def test_generator_oracle_matches_reference_golden():
 
 def test_sampling_tables_reproduce_grid_sample():
     """The product's 4-tap tables (emlight_b200.genprojector._sphere_lut) applied on the host == grid_sample on the reference grid."""
-    from emlight_b200.genprojector import _conv_s2_lut, _sphere_lut
+    from emlight_b200.genprojector import _conv_lut, _sphere_lut
     for (h, w, s) in ((4, 8, 1), (16, 32, 1), (16, 32, 2), (128, 256, 1)):
         idx, wgt, ho, wo = _sphere_lut(h, w, s)
         x = torch.randn(1, 2, h, w, generator=torch.Generator().manual_seed(h))
@@ -42,7 +42,7 @@ def test_sampling_tables_reproduce_grid_sample():
         flat = torch.cat([x.view(2, h * w), torch.zeros(2, 1)], 1)                                                     # slot -1 -> 0
         got = (flat[:, torch.from_numpy(idx).long()] * torch.from_numpy(wgt)).sum(-1)
         assert (got - ref).abs().max() < 2e-5, (h, w, s)
-    idx, wgt, ho, wo = _conv_s2_lut(9, 12)
+    idx, wgt, ho, wo = _conv_lut(9, 12, 2)
     x = torch.randn(1, 1, 9, 12)
     cols = F.unfold(x, 3, padding=1, stride=2).view(9, ho * wo).t()                                                    # (pixels, taps)
     flat = torch.cat([x.view(-1), torch.zeros(1)])
