@@ -212,7 +212,8 @@ def main():
     roofs = {k: {"ms_per_step": round(v["ms"], 3), "launches": v["launches"], "share_of_step": round(v["ms"] / step_ms, 3),
                  "GBps": round(v["bytes"] / v["ms"] / 1e6, 1), "TFLOPs": round(v["flops"] / v["ms"] / 1e9, 2)} for k, v in fam.items()}
     achieved = fam[top]["bytes"] / fam[top]["ms"] / 1e6
-    roofline = {"kernel": {"conv1x1": "conv_gemm_kernel<0,SPLIT>", "conv3x3": "conv_gemm_kernel<1,SPLIT>",
+    roofline = {"kernel": {"dense_layer": "dense_layer_kernel<SPLIT> (csrc/dense_layer.cu)",
+                           "conv1x1": "conv1x1_persist_kernel<SPLIT,RELU>", "conv3x3": "conv3x3_roll_kernel<48,SPLIT>",
                            "pool1x1": "conv_gemm_kernel<2,SPLIT>"}[top],
                 "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
                 "frac": round(achieved / hbm_peak, 4), "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",

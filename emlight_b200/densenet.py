@@ -30,7 +30,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import ConvParams
+from ._lib import ConvParams, DenseLayerParams
 
 _EPS = 1e-5
 
@@ -141,6 +141,7 @@ class DenseNet(nn.Module):
         self._last_train = False
         self.use_cuda_graph = False                    # eval mode only: replay the 104-launch forward as one CUDA graph per input shape
         self._graphs = {}
+        self.fuse_dense_layers = True                  # eval mode: one composite-filter kernel per dense layer (csrc/dense_layer.cu)
 
     # ------------------------------------------------------------------ reference-facing API
     def forward(self, x):
@@ -183,7 +184,7 @@ class DenseNet(nn.Module):
     def _state_key(self, device):
         vs = tuple((p.data_ptr(), p._version) for p in self.parameters())
         bs = tuple((b.data_ptr(), b._version) for b in self.buffers())
-        return (str(device), self.precision, vs, bs if not self.training else None)
+        return (str(device), self.precision, self.fuse_dense_layers, vs, bs if not self.training else None)
 
     @torch.no_grad()
     def _pack(self, device):
@@ -264,6 +265,55 @@ class DenseNet(nn.Module):
                 c["pre"][bi + 1, 0, :c_tr] = a[:c_tr]
                 c["pre"][bi + 1, 1, :c_tr] = s[:c_tr]
                 pre = (c["pre"][bi + 1, 0], c["pre"][bi + 1, 1])
+        if self.fuse_dense_layers and self.precision != "fp32":
+            self._compose_layers(c)
+
+    def _compose_layers(self, c):
+        """Eval mode: conv2 o norm2 o conv1 is linear (no ReLU between them, DenseNet.py:41-43) -> one 3x3 filter per layer,
+        Weff[(dy,dx,o), ci] = sum_b W2[o,b,dy,dx] * scale2[b] * W1[b,ci], plus the bias table of the norm2 shift seen through
+        the taps that fall inside the image (include/emlight_b200.h: eml_dense_layer_forward).  fp64 on the device, once per
+        parameter version."""
+        lib = _lib.load()
+        st = _lib.stream_ptr()
+        g = self.growth_rate
+        c["fused"] = {}
+        valid = ((1, 2), (0, 1, 2), (0, 1))             # taps inside the image for the first / interior / last row or column
+        for b, c_in, _, _ in self._plan:
+            blk = getattr(self.features, "denseblock%d" % b)
+            for l, layer in enumerate(blk.children()):
+                ci = c_in + l * g
+                s2, t2 = self._aff(c, "b%d.l%d.norm2" % (b, l))
+                nb = layer.conv1.out_channels
+                w1 = layer.conv1.weight.detach().double().view(nb, ci)
+                w2 = layer.conv2.weight.detach().double()                                  # (g, nb, 3, 3)
+                weff = torch.einsum("obyx,b,bc->yxoc", w2, s2[:nb].double(), w1).reshape(9 * g, ci).float().contiguous()
+                beta = torch.einsum("obyx,b->yxo", w2, t2[:nb].double())                   # (3, 3, g)
+                bias9 = torch.stack([torch.stack([beta[list(valid[rc])][:, list(valid[cc])].sum((0, 1)) for cc in range(3)])
+                                     for rc in range(3)]).float().contiguous()
+                buf = torch.empty(lib.eml_conv_wpack_bytes(9 * g, ci, 1), dtype=torch.uint8, device=weff.device)
+                _lib.check(lib.eml_conv_pack_weights(_lib.ptr(weff), _lib.ptr(buf), 9 * g, ci, 1, st), "eml_conv_pack_weights(composite)")
+                c["fused"][(b, l)] = (buf, bias9)
+
+    def _dense_layer(self, c, key, slab, pitch, h, w, B, ci):
+        lib = _lib.load()
+        buf, bias9 = c["fused"][key]
+        sc, sh = self._aff(c, "b%d.l%d.norm1" % key)
+        p = DenseLayerParams()
+        p.in_ = slab.data_ptr(); p.scale = sc.data_ptr(); p.shift = sh.data_ptr()
+        p.wpack = buf.data_ptr(); p.bias9 = bias9.data_ptr(); p.out = slab.data_ptr()
+        p.B, p.H, p.W, p.C_in, p.in_pitch = B, h, w, ci, pitch
+        p.growth, p.out_pitch, p.out_choff = self.growth_rate, pitch, ci
+        p.precision = _lib.PRECISIONS[self.precision]
+        if self.launch_log is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        _lib.check(lib.eml_dense_layer_forward(p, _lib.stream_ptr()), "eml_dense_layer_forward(b%d.l%d)" % key)
+        if self.launch_log is not None:
+            e1.record()
+            g, nb = self.growth_rate, 4 * self.growth_rate
+            M = B * h * w
+            # algorithmic bytes: the slab channels read once + the 12 new channels written once; flops of the reference layer
+            self.launch_log.append(("dense_layer", "b%d.l%d" % key, 4 * M * (ci + g), 2 * M * (ci * nb + 9 * nb * g), e0, e1))
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, B, H, W, device):
@@ -386,6 +436,10 @@ class DenseNet(nn.Module):
                 ci = c_in + l * self.growth_rate
                 n1, n2 = "b%d.l%d.norm1" % (b, l), "b%d.l%d.norm2" % (b, l)
                 mid = stats[so["b%d.l%d.mid" % (b, l)]:]
+                if (not train and "fused" in c and
+                        lib.eml_dense_layer_supported(h, w, ci, self.growth_rate, _lib.PRECISIONS[self.precision])):
+                    self._dense_layer(c, (b, l), slab, pitch, h, w, B, ci)
+                    continue
                 if train:
                     self._fold(c, n1, layer.norm1, stats=sstat, stride=pitch, count=count, pre=pre, mean_var=mv(layer.norm1, count))
                 self._conv(c, "b%d.l%d.conv1" % (b, l), slab, pitch, h, w, B, ci, ws["bott"], g, 0, g, _lib.EML_CONV_1x1, 1,

@@ -124,6 +124,34 @@ size_t eml_conv_wpack_bytes(int C_out, int C_in, int taps);
 int eml_conv_pack_weights(const float *w_oihw, void *wpack, int C_out, int C_in, int taps, void *stream);
 int eml_conv_forward(const eml_conv_params *p, void *stream);
 
+/* D2 in ONE kernel for inference-mode BatchNorm -- norm1, relu1, conv1, norm2, conv2 of RegressionNetwork/DenseNet.py:26-55.
+ * There is no nonlinearity between conv1 and conv2 (DenseNet.py:30-43), so with running statistics the layer is a single 3x3
+ * convolution of a = relu(scale*x + shift) with the composite filter
+ *     Weff[(dy,dx,o), c] = sum_b W2[o,b,dy,dx] * scale2[b] * W1[b,c]        (9*growth rows ordered dy, dx, o)
+ * plus the position-dependent bias  sum_{(dy,dx) inside the image} sum_b W2[o,b,dy,dx] * shift2[b]  (zero padding is applied
+ * to the norm2 OUTPUT).  The 4*growth-channel bottleneck is never written to memory.
+ *   in     (B,H,W,in_pitch) fp32 NHWC slab, channels [0,C_in) read
+ *   scale, shift  (C_in) folded norm1 (eml_bn_fold)
+ *   wpack  eml_conv_pack_weights(Weff viewed as a (9*growth, C_in, 1, 1) filter, taps = 1)
+ *   bias9  (3,3,growth) fp32: bias for [row class][column class], classes 0 = first row/column, 1 = interior, 2 = last
+ *   out    (B,H,W,out_pitch); channels [out_choff, out_choff+growth) written (normally the same slab at out_choff = C_in)
+ * Supported (eml_dense_layer_supported != 0): growth == 12, W in {128, 256}, C_in % 4 == 0, C_in <= 320,
+ * precision EML_PREC_BF16 / EML_PREC_BF16X3.  Other shapes: eml_conv_forward twice (conv1 then conv2). */
+typedef struct eml_dense_layer_params {
+    const float *in;
+    const float *scale;
+    const float *shift;
+    const void *wpack;
+    const float *bias9;
+    float *out;
+    int B, H, W;
+    int C_in, in_pitch;
+    int growth, out_pitch, out_choff;
+    int precision;
+} eml_dense_layer_params;
+int eml_dense_layer_supported(int H, int W, int C_in, int growth, int precision);
+int eml_dense_layer_forward(const eml_dense_layer_params *p, void *stream);
+
 /* Stem: conv0 3x3 (3 -> C_out<=32) on the NCHW input image, fused affine (+ReLU when relu != 0), NHWC output at channel 0.
  * Replaces DenseNet.py:89-92 (conv0, norm0, relu0).  scale/shift NULL => raw convolution output.
  * stats_raw: NULL or (2,C_out) double accumulators of the pre-affine values; stats_out: NULL or accumulators of

@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Summarise `ncu --set full` reports (.ncu-rep) as a markdown table for profiles/.
+usage: python tools/ncu_summary.py out.md "title" rep1.ncu-rep [rep2.ncu-rep ...]"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+        "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio"]
+
+
+def load(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    h = rows[0]
+    return [(dict(zip(h, r)), dict(zip(h, rows[1]))) for r in rows[2:]]
+
+
+def main():
+    out_md, title, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
+    cols = []
+    for rep in reps:
+        cols.extend(load(rep))
+    lines = ["# " + title, "", "| metric | " + " | ".join("`%s`" % c[0]["Kernel Name"].split("::")[-1].split("(")[0] for c in cols) + " | unit |",
+             "|---|" + "---|" * (len(cols) + 1)]
+    for k in KEYS:
+        if all(k not in c[0] for c in cols):
+            continue
+        lines.append("| %s | " % k + " | ".join(c[0].get(k, "") for c in cols) + " | %s |" % cols[0][1].get(k, ""))
+    open(out_md, "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines))
+
+
+if __name__ == "__main__":
+    main()
