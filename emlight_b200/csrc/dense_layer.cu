@@ -19,9 +19,19 @@
 //     accumulators (tcgen05.st / tcgen05.ld, lane-private, no shared-memory traffic);
 //   * the completed row U[x, (dx,o)] goes through one shared-memory row buffer, where y[x,o] = U[x-1,0,o] + U[x,1,o] + U[x+1,2,o]
 //     + bias is formed and written with coalesced float4 stores into the slab at channel offset C_in.
-// Roles (800 threads, 1 CTA/SM, persistent over bands): warps 0-15 producers (NHWC gather, norm1 affine, ReLU folded into
-// cvt.rz.relu.bf16x2, bf16 hi/lo split, SWIZZLE_128B K-major ring; register double-buffered loads), warp 16 MMA issuer
-// (resident composite weights, 3 tcgen05.mma per k-step in bf16x3), warps 17-24 epilogue (one warpgroup per half row).
+//
+// Operand pipeline (measured on B200 with tools/micro/*: register-staged LDG loads from one CTA per SM top out near 4.2 TB/s
+// whatever the depth, TMA boxes of 128-byte rows reach 5.5-6.4 TB/s from a 4-8 stage ring, 64-byte rows only 3.7 TB/s):
+//   warp 16     TMA     one cp.async.bulk.tensor.2d per stage: box = 32 channels x 128 pixels of RAW fp32 slab (128-byte rows,
+//                       SWIZZLE_128B, channels past C_in zero-filled by the tensor map), ring of 16 KB stages
+//   warps 0-15  CONVERT four warpgroups take stages round-robin and convert IN PLACE: a raw 128-byte row (32 fp32) becomes
+//                       [32 bf16 hi | 32 bf16 lo] = the same 128 bytes, i.e. the stage turns into a K-major SWIZZLE_128B tile whose
+//                       K columns 0-31 are the hi parts and 32-63 the lo parts (norm1 affine, ReLU folded into
+//                       cvt.rz.relu.bf16x2).  The 8 lanes that own one row read before any of them writes (__syncwarp).
+//   warp 17     MMA     per 16-channel k-step three tcgen05.mma (hi*Bhi, lo*Bhi, hi*Blo): A descriptors are the stage base
+//                       + 32k bytes (hi) / + 64 + 32k bytes (lo); composite weights resident in shared memory
+//   warps 20-27 EPILOGUE one warpgroup per half row (stencil above)
+#include <cuda.h>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -29,61 +39,72 @@ namespace {
 using namespace eml;
 
 constexpr int F_TILE_M = 128;
-constexpr int F_CHUNK_K = 64;
-constexpr int F_MAX_STAGES = 4;
-constexpr int F_PRODUCERS = 512;
-constexpr int F_PWARPS = F_PRODUCERS / 32;
-constexpr int F_EPI = 256;                              // 2 warpgroups
-constexpr int F_THREADS = F_PRODUCERS + 32 + F_EPI;     // 800
-constexpr int F_A_TILE = F_TILE_M * F_CHUNK_K * 2;      // 16 KB (one bf16 image)
+constexpr int F_STAGE_C = 32;                           // channels per ring stage
+constexpr int F_STAGE_BYTES = F_TILE_M * F_STAGE_C * 4; // 16 KB: raw fp32 in, [hi | lo] bf16 out
+constexpr int F_MAX_STAGES = 12;
+constexpr int F_CWARPS = 16;                            // converter warps (4 warpgroups)
+constexpr int F_TMA_WARP = 16, F_MMA_WARP = 17;         // warps 18, 19 idle (keeps the epilogue warpgroups 4-aligned)
+constexpr int F_EPI_WARP0 = 20;
+constexpr int F_THREADS = (F_EPI_WARP0 + 8) * 32;       // 896
 constexpr int F_G = 12;                                 // growth rate (output channels)
 constexpr int F_GRP = 3 * F_G;                          // 36 columns per dy group, ordered (dx, o)
 constexpr int F_NPAD = 112;
 constexpr int F_ZSTRIDE = 128;                          // TMEM columns between the two Z buffers
 constexpr int F_UBASE = 256;                            // TMEM column of the partial-row slots
 constexpr int F_USTRIDE = 48;                           // [slot(2)][half(2)] x 48 columns (36 used)
-constexpr int F_MAX_C = 320;                            // 5 K-chunks
-constexpr int F_WCHUNK = 2 * F_NPAD * 128;              // bytes of one packed weight chunk [hi | lo]
+constexpr int F_MAX_C = 320;                            // 5 weight chunks of 64 channels
+constexpr int F_WCHUNK = 2 * F_NPAD * 128;              // bytes of one packed weight chunk [hi | lo] (64 channels)
 constexpr int F_SROW = F_GRP;                           // floats per pixel in the row buffer
 
 struct FArgs {
-    const float *in;
     const float *scale;
     const float *shift;
     const unsigned char *wpack;
     const float *bias9;          // (3 row classes, 3 column classes, 12)
     float *out;
     int B, H, W, R;              // R = output rows per band (H % R == 0)
-    int C_in, in_pitch, out_pitch, out_choff;
-    int nchunks, stages;
+    int C_in, out_pitch, out_choff;
+    int nwchunks, nstg, stages;  // 64-channel weight chunks, 32-channel stages per tile, ring depth
     long nbands;
 };
 
 __device__ __forceinline__ void f_mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void f_tmem_ld4(uint32_t taddr, float (&v)[4]) {
-    uint32_t r[4];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void f_tmem_st16(uint32_t taddr, const float (&v)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
-        : "memory");
-}
-__device__ __forceinline__ void f_tmem_st4(uint32_t taddr, const float (&v)[4]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
-                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+__device__ __forceinline__ void f_tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
                  : "memory");
 }
+// TMEM <-> registers, 32 lanes x N columns.  Loads are issued WITHOUT waiting so that several can be in flight; the values are
+// valid after f_tmem_wait_ld(v) on the same array (which also ties the registers to the wait for the compiler).
+template <int N> __device__ __forceinline__ void f_tmem_ld(uint32_t taddr, float (&v)[N]);
+template <> __device__ __forceinline__ void f_tmem_ld<8>(uint32_t taddr, float (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(taddr) : "memory");
+}
+template <> __device__ __forceinline__ void f_tmem_ld<4>(uint32_t taddr, float (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(taddr) : "memory");
+}
+template <int N> __device__ __forceinline__ void f_tmem_wait_ld(float (&v)[N]);
+template <> __device__ __forceinline__ void f_tmem_wait_ld<8>(float (&v)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]) :: "memory");
+}
+template <> __device__ __forceinline__ void f_tmem_wait_ld<4>(float (&v)[4]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) :: "memory");
+}
+template <int N> __device__ __forceinline__ void f_tmem_st(uint32_t taddr, const float (&v)[N]);
+template <> __device__ __forceinline__ void f_tmem_st<8>(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+template <> __device__ __forceinline__ void f_tmem_st<4>(uint32_t taddr, const float (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+
 __device__ __forceinline__ void f_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // relu + truncation to bf16 in one instruction: d = {bf16(max(hi_in,0)), bf16(max(lo_in,0))}, round toward zero, so that for
@@ -99,36 +120,62 @@ __device__ __forceinline__ uint32_t cvt_rn_relu_bf16x2(float lo_in, float hi_in)
     return d;
 }
 
-// norm1 affine + ReLU + bf16 hi/lo split of 4 consecutive channels -> two 8-byte shared-memory stores.
+// norm1 affine + ReLU + bf16 hi/lo split of 4 consecutive channels.
 template <bool SPLIT>
-__device__ __forceinline__ void f_store_quad(unsigned char *a_hi, unsigned char *a_lo, uint32_t off, float4 v, float4 sc, float4 sh) {
+__device__ __forceinline__ void f_convert_quad(float4 v, float4 sc, float4 sh, uint2 &hv, uint2 &lv) {
     const float o0 = fmaf(v.x, sc.x, sh.x), o1 = fmaf(v.y, sc.y, sh.y), o2 = fmaf(v.z, sc.z, sh.z), o3 = fmaf(v.w, sc.w, sh.w);
-    uint2 hv;
     if (SPLIT) {
         hv.x = cvt_rz_relu_bf16x2(o0, o1);
         hv.y = cvt_rz_relu_bf16x2(o2, o3);
-        uint2 lv;
         lv.x = cvt_rn_relu_bf16x2(o0 - __uint_as_float(hv.x << 16), o1 - __uint_as_float(hv.x & 0xffff0000u));
         lv.y = cvt_rn_relu_bf16x2(o2 - __uint_as_float(hv.y << 16), o3 - __uint_as_float(hv.y & 0xffff0000u));
-        *reinterpret_cast<uint2 *>(a_lo + off) = lv;
     } else {
         hv.x = cvt_rn_relu_bf16x2(o0, o1);
         hv.y = cvt_rn_relu_bf16x2(o2, o3);
+        lv = make_uint2(0u, 0u);
     }
-    *reinterpret_cast<uint2 *>(a_hi + off) = hv;
 }
 
-// Walks the CTA's bands -> row tiles -> K chunks in the order every role agrees on.
+// One slice of N accumulator columns of the row stencil (see the file header): five TMEM loads in flight, one wait.
+//   emit:      srow[off..]  = Z[dy=2] + U[rho-1]           (output row rho-1 complete)
+//   init_next: U[rho+1]     = Z[dy=0]                       (overwrites the slot U[rho-1] was read from)
+//   upd:       U[rho]       = Z[dy=1] (+ U[rho] when upd_add)
+template <int N>
+__device__ __forceinline__ void f_stencil_piece(uint32_t zc, uint32_t us0, uint32_t us1, uint32_t off, float *srow, bool emit,
+                                                bool init_next, bool upd, bool upd_add) {
+    float z2[N], u0[N], z0[N], z1[N], u1[N];
+    if (emit) { f_tmem_ld<N>(zc + 2 * F_GRP + off, z2); f_tmem_ld<N>(us0 + off, u0); }
+    if (init_next) f_tmem_ld<N>(zc + off, z0);
+    if (upd) { f_tmem_ld<N>(zc + F_GRP + off, z1); if (upd_add) f_tmem_ld<N>(us1 + off, u1); }
+    if (emit) {
+        f_tmem_wait_ld<N>(z2); f_tmem_wait_ld<N>(u0);
+#pragma unroll
+        for (int e = 0; e < N; e += 4)
+            *reinterpret_cast<float4 *>(srow + off + e) = make_float4(z2[e] + u0[e], z2[e + 1] + u0[e + 1], z2[e + 2] + u0[e + 2], z2[e + 3] + u0[e + 3]);
+    }
+    if (init_next) { f_tmem_wait_ld<N>(z0); f_tmem_st<N>(us0 + off, z0); }
+    if (upd) {
+        f_tmem_wait_ld<N>(z1);
+        if (upd_add) {
+            f_tmem_wait_ld<N>(u1);
+#pragma unroll
+            for (int e = 0; e < N; ++e) z1[e] += u1[e];
+        }
+        f_tmem_st<N>(us1 + off, z1);
+    }
+}
+
+// Walks the CTA's bands -> row tiles in the order every role agrees on.
 struct BandIter {
     long band;
     long m0;         // first pixel (b*H*W + r*W + x) of the current tile
-    int nt, t, c;    // tiles in the band, current tile, current chunk
+    int nt, t;       // tiles in the band, current tile
     bool valid;
 };
 __device__ __forceinline__ void band_init(BandIter &it, const FArgs &a, long band) {
     it.band = band;
     it.valid = band < a.nbands;
-    it.t = 0; it.c = 0; it.nt = 0; it.m0 = 0;
+    it.t = 0; it.nt = 0; it.m0 = 0;
     if (!it.valid) return;
     const int bpi = a.H / a.R;
     const long img = band / bpi;
@@ -137,48 +184,41 @@ __device__ __forceinline__ void band_init(BandIter &it, const FArgs &a, long ban
     it.nt = (hi - lo + 1) * (a.W / F_TILE_M);
     it.m0 = (img * a.H + lo) * a.W;
 }
-__device__ __forceinline__ void band_next_chunk(BandIter &it, const FArgs &a, int grid) {
-    if (++it.c < a.nchunks) return;
-    it.c = 0;
-    it.m0 += F_TILE_M;
-    if (++it.t < it.nt) return;
-    band_init(it, a, it.band + grid);
-}
 
 template <bool SPLIT>
-__global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const FArgs a) {
+__global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_constant__ CUtensorMap tmap, const FArgs a) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long s_bar[2 * F_MAX_STAGES + 1 + 4];
+    __shared__ __align__(8) unsigned long long s_bar[3 * F_MAX_STAGES + 1 + 4];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_scale[F_MAX_C], s_shift[F_MAX_C], s_bias[9 * F_G + 4];
 
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * F_A_TILE;
     const int NST = a.stages;
-    unsigned char *w_sm = smem + NST * STAGE_BYTES;
-    float *s_row = reinterpret_cast<float *>(w_sm + static_cast<size_t>(a.nchunks) * F_WCHUNK);   // [(W + 2) pixels][36]
+    unsigned char *w_sm = smem + NST * F_STAGE_BYTES;
+    float *s_row = reinterpret_cast<float *>(w_sm + static_cast<size_t>(a.nwchunks) * F_WCHUNK);   // [(W + 2) pixels][36]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int TPR = a.W / F_TILE_M;                        // tiles per image row (1 or 2)
 
-    const uint32_t bar_full = smem_u32(&s_bar[0]);
-    const uint32_t bar_empty = smem_u32(&s_bar[F_MAX_STAGES]);
-    const uint32_t bar_w = smem_u32(&s_bar[2 * F_MAX_STAGES]);
-    const uint32_t bar_zfull = smem_u32(&s_bar[2 * F_MAX_STAGES + 1]);     // [2]
-    const uint32_t bar_zempty = smem_u32(&s_bar[2 * F_MAX_STAGES + 3]);    // [2]
+    const uint32_t bar_full = smem_u32(&s_bar[0]);                          // TMA landed (raw fp32)
+    const uint32_t bar_ready = smem_u32(&s_bar[F_MAX_STAGES]);              // converted to bf16 hi/lo
+    const uint32_t bar_empty = smem_u32(&s_bar[2 * F_MAX_STAGES]);          // consumed by the MMAs
+    const uint32_t bar_w = smem_u32(&s_bar[3 * F_MAX_STAGES]);
+    const uint32_t bar_zfull = smem_u32(&s_bar[3 * F_MAX_STAGES + 1]);      // [2]
+    const uint32_t bar_zempty = smem_u32(&s_bar[3 * F_MAX_STAGES + 3]);     // [2]
 
     if (tid == 0) {
-        for (int s = 0; s < F_MAX_STAGES; ++s) { mbar_init(bar_full + 8 * s, F_PWARPS); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < F_MAX_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_ready + 8 * s, 4); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_w, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(bar_zfull + 8 * i, 1); mbar_init(bar_zempty + 8 * i, 4); }
         fence_mbar_init();
     }
     for (int i = tid; i < F_MAX_C; i += F_THREADS) {
-        s_scale[i] = i < a.C_in ? a.scale[i] : 0.f;        // channels past C_in convert to exact zeros (their weights are 0 too)
+        s_scale[i] = i < a.C_in ? a.scale[i] : 0.f;        // channels past C_in arrive as zeros (TMA fill) and stay exact zeros
         s_shift[i] = i < a.C_in ? a.shift[i] : 0.f;
     }
     for (int i = tid; i < 9 * F_G; i += F_THREADS) s_bias[i] = a.bias9[i];
     if (tid < F_SROW) { s_row[tid] = 0.f; s_row[(a.W + 1) * F_SROW + tid] = 0.f; }   // zero pixels left and right of the row
-    if (warp == F_PWARPS) {
+    if (warp == F_MMA_WARP) {
         __syncwarp();
         tmem_alloc(smem_u32(&s_tmem), 512);
     }
@@ -188,59 +228,83 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const FArgs a
     const uint32_t tmem_base = s_tmem;
     const int grid = static_cast<int>(gridDim.x);
 
-    if (warp < F_PWARPS) {
-        // =========================================================== PRODUCERS: thread = (pixel row, 4 channels of each k-step)
-        const int row = tid >> 2, sub = tid & 3, r7 = row & 7;
-        const uint32_t st_base = static_cast<uint32_t>((row >> 3) * 1024 + r7 * 128 + (sub & 1) * 8);
-        const int jsub = sub >> 1;
-        auto issue = [&](const BandIter &it, float4 (&v)[4]) {
-            const int c0 = it.c * F_CHUNK_K + sub * 4;
-            const float *p = a.in + (it.m0 + row) * a.in_pitch + c0;
+    if (warp < F_CWARPS) {
+        // =========================================================== CONVERTERS (in place, raw fp32 -> [bf16 hi | bf16 lo])
+        // warpgroup cg owns ring slots s with s % 4 == cg; lane = (16-byte chunk c of the row, row sub-index);
+        // a warp covers 4 rows per step, 8 steps per stage; the 8 lanes of a row finish reading before any of them writes.
+        const int cg = warp >> 2, w4 = warp & 3;
+        const int c = lane & 7, rsub = lane >> 3;
+        // step i of a warp covers rows 32 w4 + 8 (i >> 1) + (i & 1) + {0, 2, 4, 6}: the four rows differ in bit 2 of (row & 7), so
+        // their hi (chunks 0-3 ^ row) and lo (chunks 4-7 ^ row) stores spread over all 32 banks
+        const uint32_t row0 = static_cast<uint32_t>(32 * w4 + 2 * rsub);
+        uint32_t rd_off[2], hi_off[2], lo_off[2];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c0 + k * 16 < a.C_in) v[k] = __ldg(reinterpret_cast<const float4 *>(p + k * 16));
-            }
-        };
-        auto process = [&](int c, const float4 (&v)[4], int s) {
-            unsigned char *a_hi = smem + static_cast<size_t>(s) * STAGE_BYTES;
-            unsigned char *a_lo = a_hi + F_A_TILE;
-            const int ks = min(4, (a.C_in - c * F_CHUNK_K + 15) >> 4);
-            const int q0 = (c * F_CHUNK_K >> 2) + sub;
+        for (int par = 0; par < 2; ++par) {
+            const uint32_t r7 = static_cast<uint32_t>(2 * rsub + par);
+            rd_off[par] = ((static_cast<uint32_t>(c) ^ r7) << 4);
+            hi_off[par] = ((static_cast<uint32_t>(c >> 1) ^ r7) << 4) + static_cast<uint32_t>(c & 1) * 8;
+            lo_off[par] = ((static_cast<uint32_t>(4 + (c >> 1)) ^ r7) << 4) + static_cast<uint32_t>(c & 1) * 8;
+        }
+        long total = 0;                                     // stages this CTA processes
+        for (long band = blockIdx.x; band < a.nbands; band += grid) {
+            BandIter it;
+            band_init(it, a, band);
+            total += static_cast<long>(it.nt) * a.nstg;
+        }
+        // A ring slot always belongs to the same warpgroup (slot % 4): every phase of its mbarriers is then observed in order by
+        // one waiter.  (Round-robin over the global stage number would let a warpgroup skip phases of a slot when the ring depth
+        // is not a multiple of 4, and a parity wait cannot tell phase n from phase n + 2.)
+        for (long g = 0; g < total; ++g) {
+            const int s = static_cast<int>(g % NST);
+            if ((s & 3) != cg) continue;
+            const uint32_t ph = static_cast<uint32_t>(g / NST) & 1;
+            const int j = static_cast<int>(g % a.nstg);                           // stage index inside the tile
+            const float4 sc = *reinterpret_cast<const float4 *>(&s_scale[j * F_STAGE_C + 4 * c]);
+            const float4 sh = *reinterpret_cast<const float4 *>(&s_shift[j * F_STAGE_C + 4 * c]);
+            unsigned char *st = smem + static_cast<size_t>(s) * F_STAGE_BYTES + row0 * 128;
+            mbar_wait(bar_full + 8 * s, ph);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (k < ks) {
-                    const float4 sc = *reinterpret_cast<const float4 *>(&s_scale[(q0 + k * 4) << 2]);
-                    const float4 sh = *reinterpret_cast<const float4 *>(&s_shift[(q0 + k * 4) << 2]);
-                    f_store_quad<SPLIT>(a_hi, a_lo, st_base + ((((k << 1) + jsub) ^ r7) << 4), v[k], sc, sh);
-                }
+            for (int i = 0; i < 8; i += 2) {
+                unsigned char *r0p = st + (i >> 1) * 1024, *r1p = r0p + 128;    // rows row0 + 8 (i/2) and the next one
+                const float4 v0 = *reinterpret_cast<const float4 *>(r0p + rd_off[0]);
+                const float4 v1 = *reinterpret_cast<const float4 *>(r1p + rd_off[1]);
+                uint2 h0, l0, h1, l1;
+                f_convert_quad<SPLIT>(v0, sc, sh, h0, l0);
+                f_convert_quad<SPLIT>(v1, sc, sh, h1, l1);
+                __syncwarp();                                                    // every lane of these rows has read its chunk
+                *reinterpret_cast<uint2 *>(r0p + hi_off[0]) = h0;
+                *reinterpret_cast<uint2 *>(r0p + lo_off[0]) = l0;
+                *reinterpret_cast<uint2 *>(r1p + hi_off[1]) = h1;
+                *reinterpret_cast<uint2 *>(r1p + lo_off[1]) = l1;
             }
-        };
-        float4 cur[4], nxt[4];
-        BandIter it, nx;
-        band_init(it, a, blockIdx.x);
-        if (it.valid) issue(it, cur);
-        uint32_t g = 0;
-        while (it.valid) {
-            nx = it;
-            band_next_chunk(nx, a, grid);
-            if (nx.valid) issue(nx, nxt);
-            const int s = g % NST;
-            const uint32_t ph = (g / NST) & 1;
-            mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            process(it.c, cur, s);
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) f_mbar_arrive(bar_full + 8 * s);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
-            it = nx; ++g;
+            if (lane == 0) f_mbar_arrive(bar_ready + 8 * s);
         }
-    } else if (warp == F_PWARPS) {
+    } else if (warp == F_TMA_WARP) {
+        // =========================================================== TMA ISSUER
+        if (lane == 0) {
+            long g = 0;
+            for (long band = blockIdx.x; band < a.nbands; band += grid) {
+                BandIter it;
+                band_init(it, a, band);
+                for (int t = 0; t < it.nt; ++t) {
+                    const int m0 = static_cast<int>(it.m0 + static_cast<long>(t) * F_TILE_M);
+                    for (int j = 0; j < a.nstg; ++j, ++g) {
+                        const int s = static_cast<int>(g % NST);
+                        const uint32_t ph = static_cast<uint32_t>(g / NST) & 1;
+                        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                        mbar_expect_tx(bar_full + 8 * s, F_STAGE_BYTES);
+                        f_tma_load_2d(smem_u32(smem + static_cast<size_t>(s) * F_STAGE_BYTES), &tmap, j * F_STAGE_C, m0, bar_full + 8 * s);
+                    }
+                }
+            }
+        }
+    } else if (warp == F_MMA_WARP) {
         // =========================================================== MMA ISSUER
         const bool leader = elect_one();
         if (leader) {
-            const uint32_t bytes = static_cast<uint32_t>(a.nchunks) * F_WCHUNK;
+            const uint32_t bytes = static_cast<uint32_t>(a.nwchunks) * F_WCHUNK;
             mbar_expect_tx(bar_w, bytes);
             bulk_g2s(smem_u32(w_sm), a.wpack, bytes, bar_w);
         }
@@ -248,45 +312,48 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const FArgs a
         const uint32_t idesc = make_idesc_bf16(F_TILE_M, F_NPAD);
         const uint64_t dA0 = make_sw128_desc(smem_u32(smem));
         const uint64_t dB0 = make_sw128_desc(smem_u32(w_sm));
-        const uint32_t stage16 = STAGE_BYTES >> 4, alo16 = F_A_TILE >> 4, wchunk16 = F_WCHUNK >> 4, blo16 = (F_NPAD * 128) >> 4;
-        uint32_t g = 0, j = 0;
+        const uint32_t stage16 = F_STAGE_BYTES >> 4, wchunk16 = F_WCHUNK >> 4, blo16 = (F_NPAD * 128) >> 4;
+        const int ksteps_total = (a.C_in + 15) >> 4;
+        long g = 0;
+        uint32_t jt = 0;
         for (long band = blockIdx.x; band < a.nbands; band += grid) {
             BandIter it;
             band_init(it, a, band);
-            for (int t = 0; t < it.nt; ++t, ++j) {
-                const uint32_t zb = j & 1, zph = (j >> 1) & 1;
+            for (int t = 0; t < it.nt; ++t, ++jt) {
+                const uint32_t zb = jt & 1, zph = (jt >> 1) & 1;
                 mbar_wait(bar_zempty + 8 * zb, zph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + zb * F_ZSTRIDE;
-                for (int c = 0; c < a.nchunks; ++c, ++g) {
-                    const uint32_t s = g % NST;
-                    const uint32_t ph = (g / NST) & 1;
-                    mbar_wait(bar_full + 8 * s, ph);
+                for (int j = 0; j < a.nstg; ++j, ++g) {
+                    const uint32_t s = static_cast<uint32_t>(g % NST);
+                    const uint32_t ph = static_cast<uint32_t>(g / NST) & 1;
+                    mbar_wait(bar_ready + 8 * s, ph);
                     tc_fence_after();
                     if (leader) {
-                        const int ks = min(4, (a.C_in - c * F_CHUNK_K + 15) >> 4);
-                        const uint64_t da_hi = dA0 + static_cast<uint64_t>(s * stage16), da_lo = da_hi + alo16;
-                        const uint64_t db_hi = dB0 + static_cast<uint64_t>(static_cast<uint32_t>(c) * wchunk16), db_lo = db_hi + blo16;
+                        const int ks = min(2, ksteps_total - 2 * j);
+                        const uint64_t da = dA0 + static_cast<uint64_t>(s * stage16);
+                        const uint64_t db_hi = dB0 + static_cast<uint64_t>(static_cast<uint32_t>(j >> 1) * wchunk16 + static_cast<uint32_t>(j & 1) * 4);
+                        const uint64_t db_lo = db_hi + blo16;
                         for (int k = 0; k < ks; ++k) {
-                            const uint64_t adv = static_cast<uint64_t>(k * 2);
-                            umma_bf16(d_tmem, da_hi + adv, db_hi + adv, idesc, (c | k) != 0 ? 1u : 0u);
+                            const uint64_t adv = static_cast<uint64_t>(k * 2);       // 32 bytes per k-step, in 16-byte units
+                            umma_bf16(d_tmem, da + adv, db_hi + adv, idesc, (j | k) != 0 ? 1u : 0u);
                             if (SPLIT) {
-                                umma_bf16(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
-                                umma_bf16(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
+                                umma_bf16(d_tmem, da + 4 + adv, db_hi + adv, idesc, 1u);   // lo half of the row: + 64 bytes
+                                umma_bf16(d_tmem, da + adv, db_lo + adv, idesc, 1u);
                             }
                         }
                         umma_commit(bar_empty + 8 * s);
-                        if (c == a.nchunks - 1) umma_commit(bar_zfull + 8 * zb);
+                        if (j == a.nstg - 1) umma_commit(bar_zfull + 8 * zb);
                     }
                     __syncwarp();
                 }
             }
         }
-    } else {
+    } else if (warp >= F_EPI_WARP0) {
         // =========================================================== EPILOGUE: warpgroup wg owns half-row wg; thread = pixel
-        const int ew = warp - (F_PWARPS + 1);                 // 0..7
+        const int ew = warp - F_EPI_WARP0;                   // 0..7
         const int wg = ew >> 2, q = warp & 3;                 // TMEM lane quarter = warp % 4
-        const int et = tid - (F_PRODUCERS + 32);              // 0..255
+        const int et = tid - F_EPI_WARP0 * 32;                // 0..255
         const int nE = F_TILE_M * TPR;                        // epilogue threads that take part (128 or 256)
         const bool active = wg < TPR;
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -316,52 +383,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const FArgs a
                     __syncwarp();
                     tc_fence_after();
 #pragma unroll
-                    for (int piece = 0; piece < 2; ++piece) {
-                        const uint32_t off = piece * 16;
-                        float z[16], u[16];
-                        if (emit) {
-                            tmem_ld16(zc + 2 * F_GRP + off, z);
-                            tmem_ld16(us0 + off, u);
-#pragma unroll
-                            for (int e = 0; e < 16; e += 4)
-                                *reinterpret_cast<float4 *>(srow + off + e) = make_float4(z[e] + u[e], z[e + 1] + u[e + 1], z[e + 2] + u[e + 2], z[e + 3] + u[e + 3]);
-                        }
-                        if (init_next) {
-                            tmem_ld16(zc + off, z);
-                            f_tmem_st16(us0 + off, z);
-                        }
-                        if (upd) {
-                            tmem_ld16(zc + F_GRP + off, z);
-                            if (upd_add) {
-                                tmem_ld16(us1 + off, u);
-#pragma unroll
-                                for (int e = 0; e < 16; ++e) z[e] += u[e];
-                            }
-                            f_tmem_st16(us1 + off, z);
-                        }
-                    }
-                    {
-                        const uint32_t off = 32;
-                        float z[4], u[4];
-                        if (emit) {
-                            f_tmem_ld4(zc + 2 * F_GRP + off, z);
-                            f_tmem_ld4(us0 + off, u);
-                            *reinterpret_cast<float4 *>(srow + off) = make_float4(z[0] + u[0], z[1] + u[1], z[2] + u[2], z[3] + u[3]);
-                        }
-                        if (init_next) {
-                            f_tmem_ld4(zc + off, z);
-                            f_tmem_st4(us0 + off, z);
-                        }
-                        if (upd) {
-                            f_tmem_ld4(zc + F_GRP + off, z);
-                            if (upd_add) {
-                                f_tmem_ld4(us1 + off, u);
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) z[e] += u[e];
-                            }
-                            f_tmem_st4(us1 + off, z);
-                        }
-                    }
+                    for (int piece = 0; piece < 9; ++piece)            // 4 columns x 5 arrays = 20 registers in flight per slice
+                        f_stencil_piece<4>(zc, us0, us1, piece * 4, srow, emit, init_next, upd, upd_add);
                     f_tmem_wait_st();
                     tc_fence_before();
                     __syncwarp();
@@ -373,16 +396,17 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const FArgs a
                         else {
                             if (!flush) continue;
                             orow = rho;
-                            float z[16];
-#pragma unroll
-                            for (int piece = 0; piece < 2; ++piece) {
-                                tmem_ld16(us1 + piece * 16, z);
-#pragma unroll
-                                for (int e = 0; e < 16; e += 4)
-                                    *reinterpret_cast<float4 *>(srow + piece * 16 + e) = make_float4(z[e], z[e + 1], z[e + 2], z[e + 3]);
-                            }
                             float z4[4];
-                            f_tmem_ld4(us1 + 32, z4);
+#pragma unroll
+                            for (int piece = 0; piece < 4; ++piece) {            // rare (once per image): no need to batch
+                                float z[8];
+                                f_tmem_ld<8>(us1 + piece * 8, z);
+                                f_tmem_wait_ld<8>(z);
+                                *reinterpret_cast<float4 *>(srow + piece * 8) = make_float4(z[0], z[1], z[2], z[3]);
+                                *reinterpret_cast<float4 *>(srow + piece * 8 + 4) = make_float4(z[4], z[5], z[6], z[7]);
+                            }
+                            f_tmem_ld<4>(us1 + 32, z4);
+                            f_tmem_wait_ld<4>(z4);
                             *reinterpret_cast<float4 *>(srow + 32) = make_float4(z4[0], z4[1], z4[2], z4[3]);
                         }
                         asm volatile("bar.sync 1, %0;" ::"r"(nE) : "memory");     // the whole row is staged
@@ -409,20 +433,33 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const FArgs a
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == F_PWARPS) {
+    if (warp == F_MMA_WARP) {
         __syncwarp();
         tmem_dealloc(tmem_base, 512);
     }
 }
 
-size_t fused_smem(int nchunks, int W, bool split, int stages) {
-    return static_cast<size_t>(stages) * (split ? 2 : 1) * F_A_TILE + static_cast<size_t>(nchunks) * F_WCHUNK +
-           static_cast<size_t>(W + 2) * F_SROW * 4 + 1024;
+size_t fused_smem(int nwchunks, int W, int stages) {
+    return static_cast<size_t>(stages) * F_STAGE_BYTES + static_cast<size_t>(nwchunks) * F_WCHUNK + static_cast<size_t>(W + 2) * F_SROW * 4 + 1024;
 }
-int fused_stages(int nchunks, int W, bool split) {
-    for (int st = F_MAX_STAGES; st >= 2; --st)
-        if (fused_smem(nchunks, W, split, st) <= 227 * 1024) return st;
+int fused_stages(int nwchunks, int W) {
+    for (int st = F_MAX_STAGES; st >= 4; --st)
+        if (fused_smem(nwchunks, W, st) <= 227 * 1024 - 3400) return st;   // static shared memory (barriers, affine tables: 3344 B) counts too
     return 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn f_get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
 }
 
 }  // namespace
@@ -430,7 +467,7 @@ int fused_stages(int nchunks, int W, bool split) {
 extern "C" int eml_dense_layer_supported(int H, int W, int C_in, int growth, int precision) {
     if (growth != F_G || (W != 128 && W != 256) || H < 2 || C_in <= 0 || C_in > F_MAX_C || (C_in & 3)) return 0;
     if (precision != EML_PREC_BF16 && precision != EML_PREC_BF16X3) return 0;
-    return fused_stages((C_in + F_CHUNK_K - 1) / F_CHUNK_K, W, precision == EML_PREC_BF16X3) >= 2 ? 1 : 0;
+    return fused_stages((C_in + 63) / 64, W) >= 4 ? 1 : 0;
 }
 
 extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *stream) {
@@ -441,7 +478,8 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
     if ((p->in_pitch & 3) || p->in_pitch < p->C_in || (p->out_pitch & 3) || (p->out_choff & 3) || p->out_choff < 0 ||
         p->out_pitch < p->out_choff + F_G)
         return EML_E_ALIGN;
-    if (static_cast<long>(p->B) * p->H * p->W >= (1L << 31)) return EML_E_SHAPE;
+    const long npix = static_cast<long>(p->B) * p->H * p->W;
+    if (npix >= (1L << 31)) return EML_E_SHAPE;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -458,27 +496,41 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
         const int r = atoi(env);
         if (r > 0 && p->H % r == 0) R = r;
     }
+    // the slab as a 2-D fp32 tensor (channels [0, C_in) x pixels, pixel stride in_pitch): boxes of 32 channels x 128 pixels
+    EncodeTiledFn enc = f_get_encode();
+    if (enc == nullptr) return EML_E_ARG;
+    CUtensorMap tmap;
+    {
+        const cuuint64_t dims[2] = {static_cast<cuuint64_t>(p->C_in), static_cast<cuuint64_t>(npix)};
+        const cuuint64_t strides[1] = {static_cast<cuuint64_t>(p->in_pitch) * 4};
+        const cuuint32_t box[2] = {F_STAGE_C, F_TILE_M};
+        const cuuint32_t estr[2] = {1, 1};
+        if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p->in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return EML_E_ARG;
+    }
     FArgs a{};
-    a.in = p->in; a.scale = p->scale; a.shift = p->shift; a.wpack = static_cast<const unsigned char *>(p->wpack);
+    a.scale = p->scale; a.shift = p->shift; a.wpack = static_cast<const unsigned char *>(p->wpack);
     a.bias9 = p->bias9; a.out = p->out;
     a.B = p->B; a.H = p->H; a.W = p->W; a.R = R;
-    a.C_in = p->C_in; a.in_pitch = p->in_pitch; a.out_pitch = p->out_pitch; a.out_choff = p->out_choff;
-    a.nchunks = (p->C_in + F_CHUNK_K - 1) / F_CHUNK_K;
-    const bool split = p->precision == EML_PREC_BF16X3;
-    a.stages = fused_stages(a.nchunks, p->W, split);
+    a.C_in = p->C_in; a.out_pitch = p->out_pitch; a.out_choff = p->out_choff;
+    a.nwchunks = (p->C_in + 63) / 64;
+    a.nstg = (p->C_in + F_STAGE_C - 1) / F_STAGE_C;
+    a.stages = fused_stages(a.nwchunks, p->W);
     a.nbands = static_cast<long>(p->B) * (p->H / R);
-    const size_t smem = fused_smem(a.nchunks, p->W, split, a.stages);
+    const bool split = p->precision == EML_PREC_BF16X3;
+    const size_t smem = fused_smem(a.nwchunks, p->W, a.stages);
     const unsigned grid = static_cast<unsigned>(a.nbands < sms ? a.nbands : sms);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
     if (split) {
         e = cudaFuncSetAttribute(dense_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);
-        dense_layer_kernel<true><<<grid, F_THREADS, smem, st>>>(a);
+        dense_layer_kernel<true><<<grid, F_THREADS, smem, st>>>(tmap, a);
     } else {
         e = cudaFuncSetAttribute(dense_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);
-        dense_layer_kernel<false><<<grid, F_THREADS, smem, st>>>(a);
+        dense_layer_kernel<false><<<grid, F_THREADS, smem, st>>>(tmap, a);
     }
     return eml_launch_status();
 }
