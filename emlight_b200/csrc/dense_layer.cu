@@ -230,21 +230,17 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
 
     if (warp < F_CWARPS) {
         // =========================================================== CONVERTERS (in place, raw fp32 -> [bf16 hi | bf16 lo])
-        // warpgroup cg owns ring slots s with s % 4 == cg; lane = (16-byte chunk c of the row, row sub-index);
-        // a warp covers 4 rows per step, 8 steps per stage; the 8 lanes of a row finish reading before any of them writes.
+        // warpgroup cg owns ring slots s with s % 4 == cg.  lane = (channel octet cp, row sub-index rs): per step a warp converts
+        // 8 rows x 32 channels, 4 steps per stage; the 4 lanes of a row finish reading before any of them writes (__syncwarp).
+        // Rows are dealt so that the two rows of every quarter-warp differ in bits 0 and 2 of (row & 7): the 16-byte loads
+        // (chunks {2cp, 2cp+1} ^ row) and the 16-byte hi / lo stores (chunks cp ^ row, (4+cp) ^ row) are then bank-conflict free.
         const int cg = warp >> 2, w4 = warp & 3;
-        const int c = lane & 7, rsub = lane >> 3;
-        // step i of a warp covers rows 32 w4 + 8 (i >> 1) + (i & 1) + {0, 2, 4, 6}: the four rows differ in bit 2 of (row & 7), so
-        // their hi (chunks 0-3 ^ row) and lo (chunks 4-7 ^ row) stores spread over all 32 banks
-        const uint32_t row0 = static_cast<uint32_t>(32 * w4 + 2 * rsub);
-        uint32_t rd_off[2], hi_off[2], lo_off[2];
-#pragma unroll
-        for (int par = 0; par < 2; ++par) {
-            const uint32_t r7 = static_cast<uint32_t>(2 * rsub + par);
-            rd_off[par] = ((static_cast<uint32_t>(c) ^ r7) << 4);
-            hi_off[par] = ((static_cast<uint32_t>(c >> 1) ^ r7) << 4) + static_cast<uint32_t>(c & 1) * 8;
-            lo_off[par] = ((static_cast<uint32_t>(4 + (c >> 1)) ^ r7) << 4) + static_cast<uint32_t>(c & 1) * 8;
-        }
+        const int cp = lane & 3, rs = lane >> 2;
+        const uint32_t r7 = static_cast<uint32_t>((0x63724150u >> (4 * rs)) & 7u);     // rs -> 0,5,1,4,2,7,3,6 : pairs (x, x^5)
+        const uint32_t lane_row = static_cast<uint32_t>(w4) * 4096u + r7 * 128u;
+        const uint32_t rd0 = lane_row + (((2u * cp) ^ r7) << 4), rd1 = lane_row + (((2u * cp + 1u) ^ r7) << 4);
+        const uint32_t hi_o = lane_row + ((static_cast<uint32_t>(cp) ^ r7) << 4), lo_o = lane_row + (((4u + cp) ^ r7) << 4);
+        const uint32_t ring = smem_u32(smem);
         long total = 0;                                     // stages this CTA processes
         for (long band = blockIdx.x; band < a.nbands; band += grid) {
             BandIter it;
@@ -259,23 +255,24 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
             if ((s & 3) != cg) continue;
             const uint32_t ph = static_cast<uint32_t>(g / NST) & 1;
             const int j = static_cast<int>(g % a.nstg);                           // stage index inside the tile
-            const float4 sc = *reinterpret_cast<const float4 *>(&s_scale[j * F_STAGE_C + 4 * c]);
-            const float4 sh = *reinterpret_cast<const float4 *>(&s_shift[j * F_STAGE_C + 4 * c]);
-            unsigned char *st = smem + static_cast<size_t>(s) * F_STAGE_BYTES + row0 * 128;
+            const float4 sc0 = *reinterpret_cast<const float4 *>(&s_scale[j * F_STAGE_C + 8 * cp]);
+            const float4 sc1 = *reinterpret_cast<const float4 *>(&s_scale[j * F_STAGE_C + 8 * cp + 4]);
+            const float4 sh0 = *reinterpret_cast<const float4 *>(&s_shift[j * F_STAGE_C + 8 * cp]);
+            const float4 sh1 = *reinterpret_cast<const float4 *>(&s_shift[j * F_STAGE_C + 8 * cp + 4]);
+            const uint32_t st = ring + static_cast<uint32_t>(s) * F_STAGE_BYTES;
             mbar_wait(bar_full + 8 * s, ph);
 #pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-                unsigned char *r0p = st + (i >> 1) * 1024, *r1p = r0p + 128;    // rows row0 + 8 (i/2) and the next one
-                const float4 v0 = *reinterpret_cast<const float4 *>(r0p + rd_off[0]);
-                const float4 v1 = *reinterpret_cast<const float4 *>(r1p + rd_off[1]);
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t o = st + static_cast<uint32_t>(i) * 1024u;
+                float4 v0, v1;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "r"(o + rd0) : "memory");
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w) : "r"(o + rd1) : "memory");
                 uint2 h0, l0, h1, l1;
-                f_convert_quad<SPLIT>(v0, sc, sh, h0, l0);
-                f_convert_quad<SPLIT>(v1, sc, sh, h1, l1);
-                __syncwarp();                                                    // every lane of these rows has read its chunk
-                *reinterpret_cast<uint2 *>(r0p + hi_off[0]) = h0;
-                *reinterpret_cast<uint2 *>(r0p + lo_off[0]) = l0;
-                *reinterpret_cast<uint2 *>(r1p + hi_off[1]) = h1;
-                *reinterpret_cast<uint2 *>(r1p + lo_off[1]) = l1;
+                f_convert_quad<SPLIT>(v0, sc0, sh0, h0, l0);
+                f_convert_quad<SPLIT>(v1, sc1, sh1, h1, l1);
+                __syncwarp();                                                    // every lane of these rows has read its chunks
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + hi_o), "r"(h0.x), "r"(h0.y), "r"(h1.x), "r"(h1.y) : "memory");
+                if (SPLIT) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + lo_o), "r"(l0.x), "r"(l0.y), "r"(l1.x), "r"(l1.y) : "memory");
             }
             fence_proxy_async();
             __syncwarp();
