@@ -212,12 +212,21 @@ def main():
     roofs = {k: {"ms_per_step": round(v["ms"], 3), "launches": v["launches"], "share_of_step": round(v["ms"] / step_ms, 3),
                  "GBps": round(v["bytes"] / v["ms"] / 1e6, 1), "TFLOPs": round(v["flops"] / v["ms"] / 1e9, 2)} for k, v in fam.items()}
     achieved = fam[top]["bytes"] / fam[top]["ms"] / 1e6
+    # DRAM traffic of the dominant family per launch, from the committed ncu launch list of this same command (profiles/)
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp) and B == 256:
+        tj = json.load(open(tp))
+        if top in tj["families"]:
+            traffic = tj["families"][top]["traffic_bytes_per_launch"]
+            traffic_src = "profiles/r01_traffic.json (ncu dram__bytes_read+write, avg per launch); algorithmic bytes per launch = %d" % (
+                fam[top]["bytes"] // fam[top]["launches"])
     roofline = {"kernel": {"dense_layer": "dense_layer_kernel<SPLIT> (csrc/dense_layer.cu)",
                            "conv1x1": "conv1x1_persist_kernel<SPLIT,RELU>", "conv3x3": "conv3x3_roll_kernel<48,SPLIT>",
                            "pool1x1": "conv_gemm_kernel<2,SPLIT>"}[top],
-                "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s", "launches": fam[top]["launches"],
                 "frac": round(achieved / hbm_peak, 4), "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
-                "traffic": None, "families": roofs,
+                "traffic": traffic, "traffic_source": traffic_src, "families": roofs,
                 "note": "achieved = algorithmic bytes (inputs read once + outputs written once, fp32) / CUDA-event time, summed over the family's launches in one step"}
     launches_per_step = 1 + sum(v["launches"] for v in fam.values()) + 1 + 2 + 1   # stem + convs + head_pool + 2 linear + render
 

@@ -270,6 +270,23 @@ int eml_pool2d(const float *x, int x_pitch, int Hi, int Wi, float *out, int out_
 int eml_loss_reduce(const float *a, int a_pitch, const float *b, int b_pitch, const float *mask, long M, int C, int mode, double *acc,
                     void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * N1-N2 -- spherical needlets (Needlets/sphere_needlets.py, mat_gen2.py, gt_gen_j3.py).
+ *
+ * eml_needlet_basis: SN_matrix of sphere_needlets.py:196-238 `SNvertex` ([Y_00 | psi_0 | ... | psi_jmax], float64) through the
+ * addition theorem,  psi_jk(x) = sum_l coef[j][l] P_l(x . xi_jk),  coef[j][l] = sqrt(lambda_j) b(l/B^j) (2l+1)/(4 pi)  (zero outside
+ * the level's band; the host builds it from sphere_needlets.py:10-29,39-50,73-74).
+ *   xyz (P,3) unit vectors of the evaluation grid, centres (K,3) HEALPix cubature points of all levels concatenated
+ *   (sphere_needlets.py:109-116), level (K) int32 level index of each centre, coef (nlev, lmax+1), out (P, out_pitch >= K+1).
+ * eml_split_bf16: x (rows, cols) fp32, row stride ld -> bf16 hi / lo (rows, Kp >= cols, zero padded) = operands of eml_gemm_bf16,
+ * which computes the projection coef = (SN*omega)^T pano (gt_gen_j3.py:39-43) and the reconstruction rec = SN coef (mat_gen2.py:55).
+ * eml_needlet_sparsify: coef (B,n,ch) in place; for every range [ranges[2i], ranges[2i+1]) of rows, per image, zero the entries
+ * with |v| <= frac * max|v| over the range (mat_gen2.py:43-51: the j=3 and j=2 blocks, frac 0.1). */
+int eml_needlet_basis(const double *xyz, long P, const double *centres, const int *level, int K, const double *coef, int nlev,
+                      int lmax, double *out, long out_pitch, void *stream);
+int eml_split_bf16(const float *x, long rows, int cols, long ld, void *hi, void *lo, int Kp, void *stream);
+int eml_needlet_sparsify(float *coef, int B, int n, int ch, const int *ranges, int nranges, float frac, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,75 @@
+"""CPU: the needlets oracle (parity unpinned -- healpy / SN_Matrix3.npy are not available) is checked against itself
+(line-by-line transcription of sphere_needlets.py vs the addition-theorem closed form) and against analytic properties; the
+product's host-side tables (emlight_b200.needlets) are checked against the oracle's independent implementations."""
+import numpy as np
+import pytest
+
+from oracle import needlets_oracle as NO
+
+
+def test_transcription_equals_closed_form():
+    rng = np.random.default_rng(0)
+    theta = np.concatenate(([0.0, np.pi, np.pi / 2], rng.uniform(0, np.pi, 4)))
+    phi = np.concatenate(([0.0, 2 * np.pi, 0.3], rng.uniform(0, 2 * np.pi, 4)))
+    direct = NO.SNvertex_direct(theta, phi, 2)                 # sphere_needlets.py:34-104,182-238 step by step
+    closed = NO.needlet_matrix(theta, phi, 2)
+    assert direct.shape == closed.shape == (7, 1 + 12 + 48 + 192)
+    assert np.abs(direct - closed).max() < 1e-13
+
+
+@pytest.mark.parametrize("nside", [1, 2, 4, 8])
+def test_healpix_ring_scheme(nside):
+    v = NO.pix2vec(nside)
+    th, ph = NO.pix2ang(nside)
+    assert v.shape == (3, 12 * nside * nside)
+    assert np.abs((v ** 2).sum(0) - 1).max() < 1e-14
+    assert np.abs(v.sum(1)).max() < 1e-12                       # centres of an equal-area, symmetric pixelisation
+    assert np.all(np.diff(th) >= -1e-15)                        # RING order: colatitude never decreases
+    # every pixel has its antipode in the set (what spneedlet_pair relies on)
+    corr = v.T @ v
+    assert np.all((corr + 1 < 1e-10).sum(1) == 1)
+    if nside == 1:                                              # published values: rings at z = 2/3, 0, -2/3; first pixel at phi = pi/4
+        assert np.allclose(np.cos(th), np.repeat([2 / 3, 0, -2 / 3], 4))
+        assert np.allclose(ph[:4], np.pi / 4 + np.arange(4) * np.pi / 2)
+        assert np.allclose(ph[4:8], np.arange(4) * np.pi / 2)
+
+
+def test_window_is_a_partition_of_unity():
+    # sum_j b(l / B^j)^2 = 1 for 1 <= l <= B^jmax (needlet frame condition); b vanishes outside (1/B, B)
+    bv = NO.b_vector(4, 16)
+    assert np.allclose((bv ** 2).sum(0)[:16], 1.0, atol=1e-8)
+    assert NO.fun_b(0.5) == 0.0 and NO.fun_b(2.0) < 1e-12 and abs(NO.fun_b(1.0) - 1.0) < 1e-12
+
+
+def test_level_sizes_and_pairs():
+    assert [NO.level_nside(j) for j in range(4)] == [1, 2, 4, 8]
+    assert [NO.level_range(j, 16) for j in range(4)] == [(1, 2), (1, 4), (2, 8), (4, 16)]
+    pair, use = NO.spneedlet_pair(1)
+    assert len(pair) == 60 and len(use) == 30 and all(pair[pair[i]] == i for i in range(60))
+
+
+def test_projection_reconstruction_of_a_band_limited_map():
+    # the constant function is Y_00 * sqrt(4 pi): projecting it on [Y_00 | needlets] gives ~sqrt(4 pi) on column 0 and ~0 elsewhere
+    theta, phi = NO.pano_grid(16, 32)
+    SN = NO.needlet_matrix(theta, phi, 1)
+    omega = NO.solid_angle_map(32).reshape(-1)
+    assert abs(omega.sum() - 4 * np.pi) < 1e-10
+    coef = NO.project(np.ones((16 * 32, 3)), SN, omega)
+    # (approximately: the reference evaluates the basis on an endpoint-inclusive grid but integrates with half-pixel solid angles)
+    assert abs(coef[0, 0] - np.sqrt(4 * np.pi)) < 0.05 and np.abs(coef[1:]).max() < 0.15
+    sp = NO.sparsify(np.arange(30.0).reshape(10, 3) - 14, level_slices=((6, None), (2, 6)), frac=0.5)
+    assert sp[:2].tolist() == [[-14, -13, -12], [-11, -10, -9]] and (sp[6:] != 0).sum() == 8
+
+
+def test_product_host_tables_match_oracle():
+    from emlight_b200 import needlets as PN
+    for nside in (1, 2, 4, 8):
+        assert np.abs(PN.healpix_centres(nside) - NO.pix2vec(nside).T).max() < 1e-14
+    assert np.abs(PN.level_coefficients(3) - NO.level_coefficients(3)).max() < 1e-15
+    assert PN.spneedlet_pair(1) == tuple(list(map(int, x)) for x in NO.spneedlet_pair(1))
+    assert np.array_equal(PN.getSolidAngleMap(256), NO.solid_angle_map(256))
+    pts, lev = PN.cubature_points(3)
+    assert pts.shape == (1020, 3) and np.bincount(lev).tolist() == [12, 48, 192, 768]
+    th, ph = PN.pano_grid()
+    tho, pho = NO.pano_grid()
+    assert np.array_equal(th, tho) and np.array_equal(ph, pho)

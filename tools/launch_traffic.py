@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Per-family DRAM traffic from an ncu launch list (gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum per launch).
+usage: python tools/launch_traffic.py gpurun_out/launches.csv profiles/r01_traffic.json"""
+import csv
+import json
+import sys
+
+FAMILIES = (("dense_layer", "dense_layer"), ("conv1x1_persist", "conv1x1"), ("conv3x3_roll", "conv3x3"), ("conv3x3_rows", "conv3x3"),
+            ("conv_gemm", "pool1x1"), ("stem", "stem"), ("linear", "linear"), ("sg_render", "render"), ("head_pool", "head_pool"))
+
+
+def main():
+    src, dst = sys.argv[1], sys.argv[2]
+    launches = {}
+    for r in csv.reader(open(src)):
+        if len(r) > 10 and r[0].isdigit():
+            launches.setdefault(int(r[0]), {"name": r[4]})[r[-3]] = float(r[-1])
+    fam = {}
+    for i in sorted(launches):
+        l = launches[i]
+        name = next((f for key, f in FAMILIES if key in l["name"]), "other")
+        f = fam.setdefault(name, {"launches": 0, "time_ms": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0})
+        f["launches"] += 1
+        f["time_ms"] += l.get("gpu__time_duration.sum", 0.0) / 1e6
+        f["dram_read_bytes"] += l.get("dram__bytes_read.sum", 0.0)
+        f["dram_write_bytes"] += l.get("dram__bytes_write.sum", 0.0)
+    total = sum(f["time_ms"] for f in fam.values())
+    for f in fam.values():
+        f["share_of_step"] = round(f["time_ms"] / total, 4)
+        f["traffic_bytes_per_launch"] = round((f["dram_read_bytes"] + f["dram_write_bytes"]) / f["launches"])
+        f["time_ms"] = round(f["time_ms"], 3)
+    out = {"source": src, "how": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one bench step (B=256)",
+           "step_ms_under_ncu": round(total, 3), "families": fam}
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
