@@ -7,6 +7,7 @@ Public surface mirrors the reference's:
     from emlight_b200 import sphere_points, convert_to_panorama     # RegressionNetwork/util.py
     from emlight_b200 import SphereConv2D, SPADE, SPADEResnetBlock, SPADEGenerator   # GenProjector/models/networks/*
     from emlight_b200 import MultiscaleDiscriminator, GANLoss, VGGLoss, Pix2PixModel # discriminator.py, loss.py, pix2pix_model.py
+    from emlight_b200.needlets import SNvertex, NeedletTransform                     # Needlets/sphere_needlets.py, mat_gen2.py (needs scipy)
 
 Module-name shims for unchanged reference scripts live in ``emlight_b200/dropin`` (put it on sys.path).
 All arithmetic runs in hand-written CUDA reached through the C ABI of include/emlight_b200.h.
