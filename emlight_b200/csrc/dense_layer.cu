@@ -16,7 +16,7 @@
 //   * a CTA walks DOWN a band of R image rows (full width, R+2 rows of Z); per row tile the epilogue thread that owns pixel x
 //     adds the tile's dy=2 columns to the partial sum of output row r-1 (-> complete, emitted), its dy=1 columns to row r and
 //     stores its dy=0 columns as the start of row r+1.  The two in-flight partial rows live in TENSOR MEMORY next to the
-//     accumulators (tcgen05.st / tcgen05.ld, lane-private, no shared-memory traffic);
+//     three Z accumulators (tcgen05.st / tcgen05.ld, lane-private, no shared-memory traffic);
 //   * the completed row U[x, (dx,o)] goes through one shared-memory row buffer, where y[x,o] = U[x-1,0,o] + U[x,1,o] + U[x+1,2,o]
 //     + bias is formed and written with coalesced float4 stores into the slab at channel offset C_in.
 //
@@ -49,9 +49,10 @@ constexpr int F_THREADS = (F_EPI_WARP0 + 8) * 32;       // 896
 constexpr int F_G = 12;                                 // growth rate (output channels)
 constexpr int F_GRP = 3 * F_G;                          // 36 columns per dy group, ordered (dx, o)
 constexpr int F_NPAD = 112;
-constexpr int F_ZSTRIDE = 128;                          // TMEM columns between the two Z buffers
-constexpr int F_UBASE = 256;                            // TMEM column of the partial-row slots
-constexpr int F_USTRIDE = 48;                           // [slot(2)][half(2)] x 48 columns (36 used)
+constexpr int F_NZ = 3;                                 // Z accumulator buffers (tile j uses buffer j % 3)
+constexpr int F_ZSTRIDE = 112;                          // TMEM columns per Z buffer
+constexpr int F_UBASE = F_NZ * F_ZSTRIDE;               // 336: TMEM column of the partial-row slots
+constexpr int F_USTRIDE = 36;                           // [slot(2)][half(2)] x 36 columns -> 336 + 144 = 480 of 512 columns
 constexpr int F_MAX_C = 320;                            // 5 weight chunks of 64 channels
 constexpr int F_WCHUNK = 2 * F_NPAD * 128;              // bytes of one packed weight chunk [hi | lo] (64 channels)
 constexpr int F_SROW = F_GRP;                           // floats per pixel in the row buffer
@@ -188,7 +189,7 @@ __device__ __forceinline__ void band_init(BandIter &it, const FArgs &a, long ban
 template <bool SPLIT>
 __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_constant__ CUtensorMap tmap, const FArgs a) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long s_bar[3 * F_MAX_STAGES + 1 + 4];
+    __shared__ __align__(8) unsigned long long s_bar[3 * F_MAX_STAGES + 1 + 2 * F_NZ];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_scale[F_MAX_C], s_shift[F_MAX_C], s_bias[9 * F_G + 4];
 
@@ -203,13 +204,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
     const uint32_t bar_ready = smem_u32(&s_bar[F_MAX_STAGES]);              // converted to bf16 hi/lo
     const uint32_t bar_empty = smem_u32(&s_bar[2 * F_MAX_STAGES]);          // consumed by the MMAs
     const uint32_t bar_w = smem_u32(&s_bar[3 * F_MAX_STAGES]);
-    const uint32_t bar_zfull = smem_u32(&s_bar[3 * F_MAX_STAGES + 1]);      // [2]
-    const uint32_t bar_zempty = smem_u32(&s_bar[3 * F_MAX_STAGES + 3]);     // [2]
+    const uint32_t bar_zfull = smem_u32(&s_bar[3 * F_MAX_STAGES + 1]);      // [F_NZ]
+    const uint32_t bar_zempty = smem_u32(&s_bar[3 * F_MAX_STAGES + 1 + F_NZ]);   // [F_NZ]
 
     if (tid == 0) {
         for (int s = 0; s < F_MAX_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_ready + 8 * s, 4); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_w, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_zfull + 8 * i, 1); mbar_init(bar_zempty + 8 * i, 4); }
+        for (int i = 0; i < F_NZ; ++i) { mbar_init(bar_zfull + 8 * i, 1); mbar_init(bar_zempty + 8 * i, 4); }
         fence_mbar_init();
     }
     for (int i = tid; i < F_MAX_C; i += F_THREADS) {
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
             BandIter it;
             band_init(it, a, band);
             for (int t = 0; t < it.nt; ++t, ++jt) {
-                const uint32_t zb = jt & 1, zph = (jt >> 1) & 1;
+                const uint32_t zb = jt % F_NZ, zph = (jt / F_NZ) & 1;
                 mbar_wait(bar_zempty + 8 * zb, zph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + zb * F_ZSTRIDE;
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
                     // ---- this warpgroup's tile of Z row rho
                     const uint32_t jt = j + static_cast<uint32_t>(wg);
                     j += static_cast<uint32_t>(TPR);
-                    const uint32_t zb = jt & 1, zph = (jt >> 1) & 1;
+                    const uint32_t zb = jt % F_NZ, zph = (jt / F_NZ) & 1;
                     const bool emit = rho - 1 >= r0;                          // output row rho-1 completes now
                     const bool upd = rho >= r0 && rho <= rend;                // output row rho receives its dy=1 part
                     const bool upd_add = rho > rlo;                           // ... on top of the dy=0 part stored by row rho-1
