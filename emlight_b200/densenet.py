@@ -39,6 +39,12 @@ def _up4(n):
     return (n + 3) & ~3
 
 
+def _up8(n):
+    """Slab pixel pitch in floats: records that are a multiple of 32 bytes keep every pixel's channels on the same sector grid,
+    which lets the dense-layer kernel write its 12 new channels as two FULL 32-byte sectors (csrc/dense_layer.cu, wide store)."""
+    return (n + 7) & ~7
+
+
 class _Transition(nn.Sequential):
     def __init__(self, c_in, c_out):
         super().__init__()
@@ -330,7 +336,7 @@ class DenseNet(nn.Module):
         ws = {"slab": [], "geom": []}
         h, w = H, W
         for b, c_in, c_out, c_tr in self._plan:
-            ws["slab"].append(torch.empty(B, h, w, _up4(c_out), dtype=torch.float32, device=device))
+            ws["slab"].append(torch.empty(B, h, w, _up8(c_out), dtype=torch.float32, device=device))
             ws["geom"].append((h, w))
             h, w = h // 2, w // 2
         ws["bott"] = torch.empty(B, H, W, 4 * self.growth_rate, dtype=torch.float32, device=device)
@@ -341,7 +347,7 @@ class DenseNet(nn.Module):
         n = 2 * 32
         so = {"stem_raw": 0}
         for bi, (b, c_in, c_out, c_tr) in enumerate(self._plan):
-            so["slab%d" % b] = n; n += 2 * _up4(c_out)
+            so["slab%d" % b] = n; n += 2 * _up8(c_out)
             for l in range(self.block_config[bi]):
                 so["b%d.l%d.mid" % (b, l)] = n; n += 2 * 4 * self.growth_rate
         so["t_last"] = n; n += 2 * _up4(c_last)

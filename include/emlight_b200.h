@@ -135,6 +135,9 @@ int eml_conv_forward(const eml_conv_params *p, void *stream);
  *   wpack  eml_conv_pack_weights(Weff viewed as a (9*growth, C_in, 1, 1) filter, taps = 1)
  *   bias9  (3,3,growth) fp32: bias for [row class][column class], classes 0 = first row/column, 1 = interior, 2 = last
  *   out    (B,H,W,out_pitch); channels [out_choff, out_choff+growth) written (normally the same slab at out_choff = C_in)
+ * Full-sector stores: when `out` is 32-byte aligned, out_pitch % 8 == 0, out_choff % 8 == 0 and out_choff + 16 <= out_pitch the
+ * kernel writes 64 bytes per pixel instead of 48 -- it ZEROES channels [out_choff+12, out_choff+16) (in a dense block these belong
+ * to the next layer, which writes them later) so that no 32-byte DRAM sector is left half-written.
  * Supported (eml_dense_layer_supported != 0): growth == 12, W in {128, 256}, C_in % 4 == 0, C_in <= 320,
  * precision EML_PREC_BF16 / EML_PREC_BF16X3.  Other shapes: eml_conv_forward twice (conv1 then conv2). */
 typedef struct eml_dense_layer_params {

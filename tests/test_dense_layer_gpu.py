@@ -61,9 +61,9 @@ CASES = [
     (2, 6, 256, 24, 216, None),        # block-1 geometry, first layer (one k-chunk, two tiles per row)
     (2, 6, 256, 60, 216, 3),           # bands of 3 rows: halo rows recomputed, top/bottom of image in different bands
     (1, 8, 256, 204, 216, 4),          # block-1 last layer: 4 K-chunks (2-stage ring), partial last chunk (12 channels)
-    (3, 8, 128, 108, 300, 8),          # block-2 geometry: one tile per row, whole image per band
-    (2, 4, 128, 288, 300, 2),          # block-2 last layer: 5 K-chunks
-    (40, 16, 128, 132, 300, None),     # 640 rows -> several bands per CTA (persistent loop, U slots reused across bands)
+    (3, 8, 128, 108, 304, 8),          # block-2 geometry: one tile per row, whole image per band
+    (2, 4, 128, 288, 304, 2),          # block-2 last layer: 5 K-chunks; the 4 filler channels end exactly at the pitch
+    (40, 16, 128, 132, 300, None),     # 640 rows -> several bands per CTA; pitch not a multiple of 8 -> plain 48-byte stores
     (5, 12, 256, 96, 216, 6),          # odd image count
 ]
 
@@ -88,9 +88,14 @@ def test_dense_layer_matches_reference(lib, cuda, case, precision):
     got = out[..., c_in:c_in + G].double()
     err = (got - ref).abs().max().item() / ref.abs().max().item()
     assert err < TOL[precision], err
-    # only the 12 new channels were written
+    # only the 12 new channels were written -- plus, with full-sector stores (pitch % 8 == 0 and c_in % 8 == 0), the 4 channels
+    # behind them zeroed (include/emlight_b200.h)
     assert torch.equal(out[..., :c_in], x[..., :c_in])
-    assert torch.isnan(out[..., c_in + G:]).all()
+    tail = c_in + G
+    if pitch % 8 == 0 and c_in % 8 == 0 and c_in + G + 4 <= pitch:
+        assert (out[..., tail:tail + 4] == 0).all()
+        tail += 4
+    assert torch.isnan(out[..., tail:]).all()
 
 
 def test_dense_layer_rejects_unsupported(lib, cuda):
