@@ -5,8 +5,8 @@ timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit $?"; tail -2 gpurun_out/bench_n1.err
 tail -c 3200 gpurun_out/bench_n1.json
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref exit $?"; tail -c 600 gpurun_out/bench_ref.json
-KF='regex:dense_layer|conv|stem_kernel|head_pool|linear_kernel|sg_render'
-timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$KF" -s 216 -c 72 --csv --log-file gpurun_out/launches.csv \
+KF='regex:dense_layer|conv|stem_kernel|head_pool|linear_kernel|sg_render|gemm_tma|split_bf16'
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$KF" -s 160 -c 170 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:dense_layer -s 106 -c 1 -o gpurun_out/prof_dense_c144 -f \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?"

@@ -6,7 +6,7 @@ import json
 import sys
 
 FAMILIES = (("dense_layer", "dense_layer"), ("conv1x1_persist", "conv1x1"), ("conv3x3_roll", "conv3x3"), ("conv3x3_rows", "conv3x3"),
-            ("conv_gemm", "pool1x1"), ("stem", "stem"), ("linear", "linear"), ("sg_render", "render"), ("head_pool", "head_pool"))
+            ("conv_gemm", "pool1x1"), ("stem", "stem"), ("linear", "linear"), ("gemm_tma", "fc_gemm"), ("split_bf16", "fc_gemm"), ("sg_render", "render"), ("head_pool", "head_pool"))
 
 
 def main():
@@ -15,8 +15,19 @@ def main():
     for r in csv.reader(open(src)):
         if len(r) > 10 and r[0].isdigit():
             launches.setdefault(int(r[0]), {"name": r[4]})[r[-3]] = float(r[-1])
+    # keep exactly one step: from the first stem launch up to (not including) the next one
+    order = sorted(launches)
+    stems = [i for i in order if "stem" in launches[i]["name"]]
+    if len(stems) >= 2:
+        order = [i for i in order if stems[0] <= i < stems[1]]
+    elif len(stems) == 1:
+        # the window straddles a step boundary: find the period L of the kernel-name sequence and unroll one step from the stem
+        names = [launches[i]["name"] for i in order]
+        n, k = len(names), order.index(stems[0])
+        L = next((L for L in range(n // 2 + 1, n + 1) if all(names[i] == names[i + L] for i in range(n - L))), n)
+        order = [order[k + t] if k + t < n else order[k + t - L] for t in range(L)]
     fam = {}
-    for i in sorted(launches):
+    for i in order:
         l = launches[i]
         name = next((f for key, f in FAMILIES if key in l["name"]), "other")
         f = fam.setdefault(name, {"launches": 0, "time_ms": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0})
