@@ -20,12 +20,6 @@ def main():
     stems = [i for i in order if "stem" in launches[i]["name"]]
     if len(stems) >= 2:
         order = [i for i in order if stems[0] <= i < stems[1]]
-    elif len(stems) == 1:
-        # the window straddles a step boundary: find the period L of the kernel-name sequence and unroll one step from the stem
-        names = [launches[i]["name"] for i in order]
-        n, k = len(names), order.index(stems[0])
-        L = next((L for L in range(n // 2 + 1, n + 1) if all(names[i] == names[i + L] for i in range(n - L))), n)
-        order = [order[k + t] if k + t < n else order[k + t - L] for t in range(L)]
     fam = {}
     for i in order:
         l = launches[i]
