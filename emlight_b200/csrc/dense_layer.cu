@@ -68,6 +68,7 @@ struct FArgs {
     int nwchunks, nstg, stages;  // 64-channel weight chunks, 32-channel stages per tile, ring depth
     int wide;                    // 0: store the 12 new channels (48 B per pixel); 1: also zero the 4 channels after them (64 B)
     long nbands;
+    int pair;                    // W == 64: a tile is row r of image 2k (pixels 0-63) next to row r of image 2k+1 (pixels 64-127)
 };
 
 __device__ __forceinline__ void f_mbar_arrive(uint32_t bar) {
@@ -180,10 +181,10 @@ __device__ __forceinline__ void band_init(BandIter &it, const FArgs &a, long ban
     it.t = 0; it.nt = 0; it.m0 = 0;
     if (!it.valid) return;
     const int bpi = a.H / a.R;
-    const long img = band / bpi;
+    const long img = (band / bpi) * (a.pair ? 2 : 1);     // first image of the band
     const int r0 = static_cast<int>(band % bpi) * a.R;
     const int lo = max(r0 - 1, 0), hi = min(r0 + a.R, a.H - 1);
-    it.nt = (hi - lo + 1) * (a.W / F_TILE_M);
+    it.nt = (hi - lo + 1) * (a.pair ? 1 : a.W / F_TILE_M);
     it.m0 = (img * a.H + lo) * a.W;
 }
 
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
     unsigned char *w_sm = smem + NST * F_STAGE_BYTES;
     float *s_row = reinterpret_cast<float *>(w_sm + static_cast<size_t>(a.nwchunks) * F_WCHUNK);   // [(W + 2) pixels][36]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int TPR = a.W / F_TILE_M;                        // tiles per image row (1 or 2)
+    const int TPR = a.pair ? 1 : a.W / F_TILE_M;           // tiles per image row (1 or 2)
 
     const uint32_t bar_full = smem_u32(&s_bar[0]);                          // TMA landed (raw fp32)
     const uint32_t bar_ready = smem_u32(&s_bar[F_MAX_STAGES]);              // converted to bf16 hi/lo
@@ -219,7 +220,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
         s_shift[i] = i < a.C_in ? a.shift[i] : 0.f;
     }
     for (int i = tid; i < 9 * F_G; i += F_THREADS) s_bias[i] = a.bias9[i];
-    if (tid < F_SROW) { s_row[tid] = 0.f; s_row[(a.W + 1) * F_SROW + tid] = 0.f; }   // zero pixels left and right of the row
+    if (tid < F_SROW) {                                    // zero pixels left and right of the row (of both rows in pair mode)
+        s_row[tid] = 0.f; s_row[(a.W + 1) * F_SROW + tid] = 0.f;
+        if (a.pair) { s_row[(a.W + 2) * F_SROW + tid] = 0.f; s_row[(2 * a.W + 3) * F_SROW + tid] = 0.f; }
+    }
     if (warp == F_MMA_WARP) {
         __syncwarp();
         tmem_alloc(smem_u32(&s_tmem), 512);
@@ -288,13 +292,19 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
                 BandIter it;
                 band_init(it, a, band);
                 for (int t = 0; t < it.nt; ++t) {
-                    const int m0 = static_cast<int>(it.m0 + static_cast<long>(t) * F_TILE_M);
+                    const int m0 = static_cast<int>(it.m0 + static_cast<long>(t) * (a.pair ? a.W : F_TILE_M));
                     for (int j = 0; j < a.nstg; ++j, ++g) {
                         const int s = static_cast<int>(g % NST);
                         const uint32_t ph = static_cast<uint32_t>(g / NST) & 1;
+                        const uint32_t dst = smem_u32(smem + static_cast<size_t>(s) * F_STAGE_BYTES);
                         mbar_wait(bar_empty + 8 * s, ph ^ 1);
                         mbar_expect_tx(bar_full + 8 * s, F_STAGE_BYTES);
-                        f_tma_load_2d(smem_u32(smem + static_cast<size_t>(s) * F_STAGE_BYTES), &tmap, j * F_STAGE_C, m0, bar_full + 8 * s);
+                        if (a.pair) {                 // two boxes of 64 pixels: the same row of two consecutive images
+                            f_tma_load_2d(dst, &tmap, j * F_STAGE_C, m0, bar_full + 8 * s);
+                            f_tma_load_2d(dst + F_STAGE_BYTES / 2, &tmap, j * F_STAGE_C, m0 + a.H * a.W, bar_full + 8 * s);
+                        } else {
+                            f_tma_load_2d(dst, &tmap, j * F_STAGE_C, m0, bar_full + 8 * s);
+                        }
                     }
                 }
             }
@@ -361,7 +371,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
             uint32_t j = 0;                                   // tile counter (all tiles of this CTA, both halves)
             for (long band = blockIdx.x; band < a.nbands; band += grid) {
                 const int bpi = a.H / a.R;
-                const long img = band / bpi;
+                const long img = (band / bpi) * (a.pair ? 2 : 1);
                 const int r0 = static_cast<int>(band % bpi) * a.R;
                 const int rlo = max(r0 - 1, 0), rhi = min(r0 + a.R, a.H - 1), rend = r0 + a.R - 1;    // rend = last output row
                 for (int rho = rlo; rho <= rhi; ++rho) {
@@ -377,7 +387,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
                     const uint32_t zc = lane_addr + zb * F_ZSTRIDE;
                     const uint32_t us0 = lane_addr + F_UBASE + ((((rho + 1) & 1) * 2 + wg) * F_USTRIDE);   // U[rho-1] in, U[rho+1] out
                     const uint32_t us1 = lane_addr + F_UBASE + (((rho & 1) * 2 + wg) * F_USTRIDE);         // U[rho]
-                    float *srow = s_row + (wg * F_TILE_M + px + 1) * F_SROW;
+                    float *srow = s_row + (wg * F_TILE_M + px + 1 + (a.pair ? 2 * (px >> 6) : 0)) * F_SROW;
                     mbar_wait(bar_zfull + 8 * zb, zph);
                     __syncwarp();
                     tc_fence_after();
@@ -412,9 +422,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
                         const int rc = orow == 0 ? 0 : (orow == a.H - 1 ? 2 : 1);
                         float *obase = a.out + ((img * a.H + orow) * a.W) * a.out_pitch + a.out_choff;
                         if (a.wide == 0) {
-                            for (int f = et; f < a.W * 3; f += nE) {
-                                const int x = f / 3, qd = f - x * 3;
-                                const float *s0 = s_row + x * F_SROW + qd * 4;         // pixel x-1 (buffer index x), dx = 0
+                            const int npx = a.pair ? 2 * a.W : a.W;                    // pixels staged per row (pair mode: two images)
+                            const bool al16 = (a.out_choff & 3) == 0;                  // block 3 starts its channels on an 8-byte boundary only
+                            for (int f = et; f < npx * 3; f += nE) {
+                                const int p = f / 3, qd = f - p * 3;
+                                const int half = a.pair ? p >> 6 : 0, x = a.pair ? p & 63 : p;
+                                const float *s0 = s_row + (p + 2 * half) * F_SROW + qd * 4;   // pixel x-1 (buffer index of x, minus one), dx = 0
                                 const float4 v0 = *reinterpret_cast<const float4 *>(s0);
                                 const float4 v1 = *reinterpret_cast<const float4 *>(s0 + F_SROW + F_G);
                                 const float4 v2 = *reinterpret_cast<const float4 *>(s0 + 2 * F_SROW + 2 * F_G);
@@ -423,7 +436,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
                                 float4 o;
                                 o.x = v0.x + v1.x + v2.x + bb.x; o.y = v0.y + v1.y + v2.y + bb.y;
                                 o.z = v0.z + v1.z + v2.z + bb.z; o.w = v0.w + v1.w + v2.w + bb.w;
-                                *reinterpret_cast<float4 *>(obase + static_cast<long>(x) * a.out_pitch + qd * 4) = o;
+                                float *dst = obase + (static_cast<long>(half) * a.H * a.W + x) * a.out_pitch + qd * 4;
+                                if (al16) {
+                                    *reinterpret_cast<float4 *>(dst) = o;
+                                } else {
+                                    *reinterpret_cast<float2 *>(dst) = make_float2(o.x, o.y);
+                                    *reinterpret_cast<float2 *>(dst + 2) = make_float2(o.z, o.w);
+                                }
                             }
                         } else {
                             // 64 bytes per pixel = two FULL 32-byte sectors when the new channels start on a sector boundary: the fourth
@@ -465,7 +484,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
 }
 
 size_t fused_smem(int nwchunks, int W, int stages) {
-    return static_cast<size_t>(stages) * F_STAGE_BYTES + static_cast<size_t>(nwchunks) * F_WCHUNK + static_cast<size_t>(W + 2) * F_SROW * 4 + 1024;
+    return static_cast<size_t>(stages) * F_STAGE_BYTES + static_cast<size_t>(nwchunks) * F_WCHUNK + static_cast<size_t>(W == 64 ? 2 * (W + 2) : W + 2) * F_SROW * 4 + 1024;
 }
 int fused_stages(int nwchunks, int W) {
     for (int st = F_MAX_STAGES; st >= 4; --st)
@@ -490,7 +509,8 @@ EncodeTiledFn f_get_encode() {
 }  // namespace
 
 extern "C" int eml_dense_layer_supported(int H, int W, int C_in, int growth, int precision) {
-    if (growth != F_G || (W != 128 && W != 256) || H < 2 || C_in <= 0 || C_in > F_MAX_C || (C_in & 3)) return 0;
+    if (growth != F_G || (W != 64 && W != 128 && W != 256) || H < 2 || C_in <= 0 || C_in > F_MAX_C) return 0;
+    if (W == 64 ? (C_in & 1) : (C_in & 3)) return 0;          // output channel offset: 8-byte (W = 64, float2 stores) or 16-byte aligned
     if (precision != EML_PREC_BF16 && precision != EML_PREC_BF16X3) return 0;
     return fused_stages((C_in + 63) / 64, W) >= 4 ? 1 : 0;
 }
@@ -500,7 +520,9 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
     EML_CHECK_PTR(p->wpack); EML_CHECK_PTR(p->bias9);
     EML_CHECK_ALIGN16(p->in); EML_CHECK_ALIGN16(p->out); EML_CHECK_ALIGN16(p->wpack);
     if (p->B <= 0 || !eml_dense_layer_supported(p->H, p->W, p->C_in, p->growth, p->precision)) return EML_E_SHAPE;
-    if ((p->in_pitch & 3) || p->in_pitch < p->C_in || (p->out_pitch & 3) || (p->out_choff & 3) || p->out_choff < 0 ||
+    const bool pair = p->W == 64;                            // two images side by side in one 128-pixel tile
+    if (pair && (p->B & 1)) return EML_E_SHAPE;
+    if ((p->in_pitch & 3) || p->in_pitch < p->C_in || (p->out_pitch & 3) || (p->out_choff & (pair ? 1 : 3)) || p->out_choff < 0 ||
         p->out_pitch < p->out_choff + F_G)
         return EML_E_ALIGN;
     const long npix = static_cast<long>(p->B) * p->H * p->W;
@@ -513,7 +535,7 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
     long best = -1;
     for (int r = 1; r <= p->H; ++r) {
         if (p->H % r) continue;
-        const long nb = static_cast<long>(p->B) * (p->H / r);
+        const long nb = static_cast<long>(pair ? p->B / 2 : p->B) * (p->H / r);
         const long cost = ((nb + sms - 1) / sms) * (r + 2);
         if (best < 0 || cost < best || (cost == best && r > R)) { best = cost; R = r; }
     }
@@ -528,7 +550,7 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
     {
         const cuuint64_t dims[2] = {static_cast<cuuint64_t>(p->C_in), static_cast<cuuint64_t>(npix)};
         const cuuint64_t strides[1] = {static_cast<cuuint64_t>(p->in_pitch) * 4};
-        const cuuint32_t box[2] = {F_STAGE_C, F_TILE_M};
+        const cuuint32_t box[2] = {F_STAGE_C, static_cast<cuuint32_t>(pair ? 64 : F_TILE_M)};
         const cuuint32_t estr[2] = {1, 1};
         if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p->in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -541,11 +563,12 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
     a.C_in = p->C_in; a.out_pitch = p->out_pitch; a.out_choff = p->out_choff;
     a.nwchunks = (p->C_in + 63) / 64;
     a.nstg = (p->C_in + F_STAGE_C - 1) / F_STAGE_C;
-    a.nbands = static_cast<long>(p->B) * (p->H / R);
+    a.pair = pair ? 1 : 0;
+    a.nbands = static_cast<long>(pair ? p->B / 2 : p->B) * (p->H / R);
     // full-sector stores (see the output pass): possible when every pixel record starts on a 32-byte boundary
     a.wide = 0;
     if ((reinterpret_cast<uintptr_t>(p->out) & 31u) == 0 && (p->out_pitch & 7) == 0 && !eml_env_flag("EML_DENSE_NARROW_STORE")) {
-        if ((p->out_choff & 7) == 0 && p->out_choff + F_G + 4 <= p->out_pitch) a.wide = 1;
+        if (!pair && (p->out_choff & 7) == 0 && p->out_choff + F_G + 4 <= p->out_pitch) a.wide = 1;
     }
     const bool split = p->precision == EML_PREC_BF16X3;
     a.stages = fused_stages(a.nwchunks, p->W);

@@ -451,7 +451,7 @@ class DenseNet(nn.Module):
                 ci = c_in + l * self.growth_rate
                 n1, n2 = "b%d.l%d.norm1" % (b, l), "b%d.l%d.norm2" % (b, l)
                 mid = stats[so["b%d.l%d.mid" % (b, l)]:]
-                if (not train and "fused" in c and
+                if (not train and "fused" in c and (w != 64 or B % 2 == 0) and    # W = 64 tiles hold a row of two images
                         lib.eml_dense_layer_supported(h, w, ci, self.growth_rate, _lib.PRECISIONS[self.precision])):
                     self._dense_layer(c, (b, l), slab, pitch, h, w, B, ci)
                     continue

@@ -138,7 +138,8 @@ int eml_conv_forward(const eml_conv_params *p, void *stream);
  * Full-sector stores: when `out` is 32-byte aligned, out_pitch % 8 == 0, out_choff % 8 == 0 and out_choff + 16 <= out_pitch the
  * kernel writes 64 bytes per pixel instead of 48 -- it ZEROES channels [out_choff+12, out_choff+16) (in a dense block these belong
  * to the next layer, which writes them later) so that no 32-byte DRAM sector is left half-written.
- * Supported (eml_dense_layer_supported != 0): growth == 12, W in {128, 256}, C_in % 4 == 0, C_in <= 320,
+ * Supported (eml_dense_layer_supported != 0): growth == 12, C_in <= 320, and W in {128, 256} with C_in % 4 == 0, or W == 64 with
+ * C_in % 2 == 0 and an even B (a 128-pixel tile is then the same row of two consecutive images; float2 stores),
  * precision EML_PREC_BF16 / EML_PREC_BF16X3.  Other shapes: eml_conv_forward twice (conv1 then conv2). */
 typedef struct eml_dense_layer_params {
     const float *in;

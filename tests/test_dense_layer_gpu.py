@@ -65,6 +65,9 @@ CASES = [
     (2, 4, 128, 288, 304, 2),          # block-2 last layer: 5 K-chunks; the 4 filler channels end exactly at the pitch
     (40, 16, 128, 132, 300, None),     # 640 rows -> several bands per CTA; pitch not a multiple of 8 -> plain 48-byte stores
     (5, 12, 256, 96, 216, 6),          # odd image count
+    (2, 6, 64, 150, 344, None),        # block-3 geometry: a tile = the same row of two images; channel offset only 8-byte aligned
+    (6, 8, 64, 318, 344, 4),           # block-3 second-to-last layer: 5 K-chunks, three image pairs, bands of 4 rows
+    (4, 48, 64, 174, 344, None),       # full block-3 image height
 ]
 
 
@@ -99,7 +102,8 @@ def test_dense_layer_matches_reference(lib, cuda, case, precision):
 
 
 def test_dense_layer_rejects_unsupported(lib, cuda):
-    assert lib.eml_dense_layer_supported(48, 64, 150, G, 1) == 0        # block-3 geometry (W = 64): two-kernel path
+    assert lib.eml_dense_layer_supported(48, 64, 330, G, 1) == 0        # block-3 last layer: 6 weight chunks do not fit
+    assert lib.eml_dense_layer_supported(24, 32, 150, G, 1) == 0        # W = 32: two-kernel path
     assert lib.eml_dense_layer_supported(96, 128, 108, 16, 1) == 0      # other growth rates
     assert lib.eml_dense_layer_supported(96, 128, 108, G, 2) == 0       # fp32 SIMT mode has no fused kernel
 
@@ -114,7 +118,7 @@ def test_densenet_fused_equals_two_kernel_path(cuda):
             if isinstance(m, torch.nn.BatchNorm2d):
                 m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
                 m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.1)
-    x = torch.rand(3, 3, 192, 256, generator=torch.Generator().manual_seed(9)).to(cuda)
+    x = torch.rand(4, 3, 192, 256, generator=torch.Generator().manual_seed(9)).to(cuda)     # even batch: block 3 fuses too (pairs)
     with torch.no_grad():
         net.fuse_dense_layers = True
         a = {k: v.clone() for k, v in net(x).items()}
