@@ -360,6 +360,9 @@ bool eml_rows_supported(const eml_conv_params *p);
 bool eml_persist_supported(const eml_conv_params *p);
 int eml_persist_forward(const eml_conv_params *p, cudaStream_t st);
 int eml_rows_forward(const eml_conv_params *p, const unsigned char *wplanar, cudaStream_t st);
+// dense_layer.cu: TMA-fed pipeline with a pooling epilogue (transition with C_out <= 112)
+bool eml_dense_pool_supported(const eml_conv_params *p);
+int eml_dense_pool_forward(const eml_conv_params *p, cudaStream_t st);
 
 static size_t generic_wpack_bytes(int C_out, int C_in, int taps) {
     const int cpt = (C_in + CHUNK_K - 1) / CHUNK_K;
@@ -403,6 +406,7 @@ extern "C" int eml_conv_forward(const eml_conv_params *p, void *stream) {
     EML_CHECK_PTR(p->wpack);
     EML_CHECK_ALIGN16(p->wpack);
     if (static_cast<long>(p->B) * p->H * p->W >= (1L << 31)) return EML_E_SHAPE;
+    if (eml_dense_pool_supported(p)) return eml_dense_pool_forward(p, st);
     if (eml_persist_supported(p) && !eml_env_flag("EML_NO_PERSIST")) return eml_persist_forward(p, st);
     if (eml_rows_supported(p))
         return eml_rows_forward(p, static_cast<const unsigned char *>(p->wpack) + generic_wpack_bytes(p->C_out, p->C_in, 9), st);

@@ -68,6 +68,9 @@ struct FArgs {
     int nwchunks, nstg, stages;  // 64-channel weight chunks, 32-channel stages per tile, ring depth
     int wide;                    // 0: store the 12 new channels (48 B per pixel); 1: also zero the 4 channels after them (64 B)
     long nbands;
+    int pool;                    // transition mode (eml_transition_forward): tile = a PAIR of image rows accumulated into one Z buffer by
+                                 // the tensor core (vertical half of the 2x2 average), epilogue = horizontal pair sum, x 0.25, N channels out
+    int n_out;                   // pool mode: output channels
     int pair;                    // W == 64: a tile is row r of image 2k (pixels 0-63) next to row r of image 2k+1 (pixels 64-127)
 };
 
@@ -108,6 +111,7 @@ template <> __device__ __forceinline__ void f_tmem_st<4>(uint32_t taddr, const f
                  ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
 }
 
+__device__ __forceinline__ void f_tmem_ld16(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
 __device__ __forceinline__ void f_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // relu + truncation to bf16 in one instruction: d = {bf16(max(hi_in,0)), bf16(max(lo_in,0))}, round toward zero, so that for
@@ -175,6 +179,7 @@ struct BandIter {
     int nt, t;       // tiles in the band, current tile
     bool valid;
 };
+template <bool POOL>
 __device__ __forceinline__ void band_init(BandIter &it, const FArgs &a, long band) {
     it.band = band;
     it.valid = band < a.nbands;
@@ -183,12 +188,12 @@ __device__ __forceinline__ void band_init(BandIter &it, const FArgs &a, long ban
     const int bpi = a.H / a.R;
     const long img = (band / bpi) * (a.pair ? 2 : 1);     // first image of the band
     const int r0 = static_cast<int>(band % bpi) * a.R;
-    const int lo = max(r0 - 1, 0), hi = min(r0 + a.R, a.H - 1);
-    it.nt = (hi - lo + 1) * (a.pair ? 1 : a.W / F_TILE_M);
+    const int lo = POOL ? r0 : max(r0 - 1, 0), hi = POOL ? r0 + a.R - 1 : min(r0 + a.R, a.H - 1);
+    it.nt = (POOL ? (hi - lo + 1) / 2 : hi - lo + 1) * (a.pair ? 1 : a.W / F_TILE_M);
     it.m0 = (img * a.H + lo) * a.W;
 }
 
-template <bool SPLIT>
+template <bool SPLIT, bool POOL>
 __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_constant__ CUtensorMap tmap, const FArgs a) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_bar[3 * F_MAX_STAGES + 1 + 2 * F_NZ];
@@ -219,7 +224,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
         s_scale[i] = i < a.C_in ? a.scale[i] : 0.f;        // channels past C_in arrive as zeros (TMA fill) and stay exact zeros
         s_shift[i] = i < a.C_in ? a.shift[i] : 0.f;
     }
-    for (int i = tid; i < 9 * F_G; i += F_THREADS) s_bias[i] = a.bias9[i];
+    if (a.bias9 != nullptr)
+        for (int i = tid; i < 9 * F_G; i += F_THREADS) s_bias[i] = a.bias9[i];
     if (tid < F_SROW) {                                    // zero pixels left and right of the row (of both rows in pair mode)
         s_row[tid] = 0.f; s_row[(a.W + 1) * F_SROW + tid] = 0.f;
         if (a.pair) { s_row[(a.W + 2) * F_SROW + tid] = 0.f; s_row[(2 * a.W + 3) * F_SROW + tid] = 0.f; }
@@ -247,20 +253,21 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
         const uint32_t rd0 = lane_row + (((2u * cp) ^ r7) << 4), rd1 = lane_row + (((2u * cp + 1u) ^ r7) << 4);
         const uint32_t hi_o = lane_row + ((static_cast<uint32_t>(cp) ^ r7) << 4), lo_o = lane_row + (((4u + cp) ^ r7) << 4);
         const uint32_t ring = smem_u32(smem);
-        long total = 0;                                     // stages this CTA processes
+        uint32_t total = 0;                                 // stages this CTA processes (32-bit: the modulo arithmetic below is per stage)
         for (long band = blockIdx.x; band < a.nbands; band += grid) {
             BandIter it;
-            band_init(it, a, band);
-            total += static_cast<long>(it.nt) * a.nstg;
+            band_init<POOL>(it, a, band);
+            total += static_cast<uint32_t>(it.nt) * static_cast<uint32_t>(POOL ? 2 * a.nstg : a.nstg);
         }
         // A ring slot always belongs to the same warpgroup (slot % 4): every phase of its mbarriers is then observed in order by
         // one waiter.  (Round-robin over the global stage number would let a warpgroup skip phases of a slot when the ring depth
         // is not a multiple of 4, and a parity wait cannot tell phase n from phase n + 2.)
-        for (long g = 0; g < total; ++g) {
-            const int s = static_cast<int>(g % NST);
+        const uint32_t nst_u = static_cast<uint32_t>(NST), nstg_u = static_cast<uint32_t>(a.nstg);
+        for (uint32_t g = 0; g < total; ++g) {
+            const int s = static_cast<int>(g % nst_u);
             if ((s & 3) != cg) continue;
-            const uint32_t ph = static_cast<uint32_t>(g / NST) & 1;
-            const int j = static_cast<int>(g % a.nstg);                           // stage index inside the tile
+            const uint32_t ph = (g / nst_u) & 1;
+            const int j = static_cast<int>(g % nstg_u);                              // (pool mode: 2 nstg stages per tile, same slices twice)                 // channel slice of this stage (pool mode: two rows per tile)
             const float4 sc0 = *reinterpret_cast<const float4 *>(&s_scale[j * F_STAGE_C + 8 * cp]);
             const float4 sc1 = *reinterpret_cast<const float4 *>(&s_scale[j * F_STAGE_C + 8 * cp + 4]);
             const float4 sh0 = *reinterpret_cast<const float4 *>(&s_shift[j * F_STAGE_C + 8 * cp]);
@@ -287,23 +294,30 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
     } else if (warp == F_TMA_WARP) {
         // =========================================================== TMA ISSUER
         if (lane == 0) {
-            long g = 0;
+            uint32_t g = 0;
+            const uint32_t nst_u = static_cast<uint32_t>(NST);
             for (long band = blockIdx.x; band < a.nbands; band += grid) {
                 BandIter it;
-                band_init(it, a, band);
+                band_init<POOL>(it, a, band);
                 for (int t = 0; t < it.nt; ++t) {
-                    const int m0 = static_cast<int>(it.m0 + static_cast<long>(t) * (a.pair ? a.W : F_TILE_M));
-                    for (int j = 0; j < a.nstg; ++j, ++g) {
-                        const int s = static_cast<int>(g % NST);
-                        const uint32_t ph = static_cast<uint32_t>(g / NST) & 1;
+                    const int TPRt = a.W / F_TILE_M;
+                    // pool mode: tile t = (row pair t / TPR, half t % TPR); its first nstg stages are the upper row, the rest the lower one
+                    const int m0 = POOL ? static_cast<int>(it.m0 + static_cast<long>(t / TPRt) * 2 * a.W + (t % TPRt) * F_TILE_M)
+                                          : static_cast<int>(it.m0 + static_cast<long>(t) * (a.pair ? a.W : F_TILE_M));
+                    const int tpt = POOL ? 2 * a.nstg : a.nstg;
+                    for (int jj = 0; jj < tpt; ++jj, ++g) {
+                        const int j = POOL && jj >= a.nstg ? jj - a.nstg : jj;
+                        const int mrow = POOL && jj >= a.nstg ? m0 + a.W : m0;
+                        const int s = static_cast<int>(g % nst_u);
+                        const uint32_t ph = (g / nst_u) & 1;
                         const uint32_t dst = smem_u32(smem + static_cast<size_t>(s) * F_STAGE_BYTES);
                         mbar_wait(bar_empty + 8 * s, ph ^ 1);
                         mbar_expect_tx(bar_full + 8 * s, F_STAGE_BYTES);
                         if (a.pair) {                 // two boxes of 64 pixels: the same row of two consecutive images
-                            f_tma_load_2d(dst, &tmap, j * F_STAGE_C, m0, bar_full + 8 * s);
-                            f_tma_load_2d(dst + F_STAGE_BYTES / 2, &tmap, j * F_STAGE_C, m0 + a.H * a.W, bar_full + 8 * s);
+                            f_tma_load_2d(dst, &tmap, j * F_STAGE_C, mrow, bar_full + 8 * s);
+                            f_tma_load_2d(dst + F_STAGE_BYTES / 2, &tmap, j * F_STAGE_C, mrow + a.H * a.W, bar_full + 8 * s);
                         } else {
-                            f_tma_load_2d(dst, &tmap, j * F_STAGE_C, m0, bar_full + 8 * s);
+                            f_tma_load_2d(dst, &tmap, j * F_STAGE_C, mrow, bar_full + 8 * s);
                         }
                     }
                 }
@@ -323,19 +337,21 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
         const uint64_t dB0 = make_sw128_desc(smem_u32(w_sm));
         const uint32_t stage16 = F_STAGE_BYTES >> 4, wchunk16 = F_WCHUNK >> 4, blo16 = (F_NPAD * 128) >> 4;
         const int ksteps_total = (a.C_in + 15) >> 4;
-        long g = 0;
-        uint32_t jt = 0;
+        uint32_t g = 0, jt = 0;
+        const uint32_t nst_u = static_cast<uint32_t>(NST);
         for (long band = blockIdx.x; band < a.nbands; band += grid) {
             BandIter it;
-            band_init(it, a, band);
+            band_init<POOL>(it, a, band);
             for (int t = 0; t < it.nt; ++t, ++jt) {
                 const uint32_t zb = jt % F_NZ, zph = (jt / F_NZ) & 1;
                 mbar_wait(bar_zempty + 8 * zb, zph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + zb * F_ZSTRIDE;
-                for (int j = 0; j < a.nstg; ++j, ++g) {
-                    const uint32_t s = static_cast<uint32_t>(g % NST);
-                    const uint32_t ph = static_cast<uint32_t>(g / NST) & 1;
+                const int tpt = POOL ? 2 * a.nstg : a.nstg;
+                for (int jj = 0; jj < tpt; ++jj, ++g) {
+                    const int j = POOL && jj >= a.nstg ? jj - a.nstg : jj;
+                    const uint32_t s = g % nst_u;
+                    const uint32_t ph = (g / nst_u) & 1;
                     mbar_wait(bar_ready + 8 * s, ph);
                     tc_fence_after();
                     if (leader) {
@@ -345,14 +361,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
                         const uint64_t db_lo = db_hi + blo16;
                         for (int k = 0; k < ks; ++k) {
                             const uint64_t adv = static_cast<uint64_t>(k * 2);       // 32 bytes per k-step, in 16-byte units
-                            umma_bf16(d_tmem, da + adv, db_hi + adv, idesc, (j | k) != 0 ? 1u : 0u);
+                            umma_bf16(d_tmem, da + adv, db_hi + adv, idesc, (jj | k) != 0 ? 1u : 0u);
                             if (SPLIT) {
                                 umma_bf16(d_tmem, da + 4 + adv, db_hi + adv, idesc, 1u);   // lo half of the row: + 64 bytes
                                 umma_bf16(d_tmem, da + adv, db_lo + adv, idesc, 1u);
                             }
                         }
                         umma_commit(bar_empty + 8 * s);
-                        if (j == a.nstg - 1) umma_commit(bar_zfull + 8 * zb);
+                        if (jj == tpt - 1) umma_commit(bar_zfull + 8 * zb);
                     }
                     __syncwarp();
                 }
@@ -367,7 +383,49 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
         const bool active = wg < TPR;
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const int px = q * 32 + lane;                         // pixel inside the tile
-        if (active) {
+        if (POOL && active) {
+            // ---------------- transition: Z = sum over the two image rows (accumulated by the MMAs); horizontal pair sum by shuffle,
+            // x 0.25, the lane pair of a pooled pixel splits the channel quads between its two lanes and stores straight to the output
+            uint32_t j = 0;
+            const int nquad = (a.n_out + 3) >> 2;
+            const int Wp = a.W >> 1, Hp = a.H >> 1;
+            for (long band = blockIdx.x; band < a.nbands; band += grid) {
+                const int bpi = a.H / a.R;
+                const long img = band / bpi;
+                const int r0 = static_cast<int>(band % bpi) * a.R;
+                for (int rp = 0; rp < a.R / 2; ++rp) {
+                    const uint32_t jt = j + static_cast<uint32_t>(wg);
+                    j += static_cast<uint32_t>(TPR);
+                    const uint32_t zb = jt % F_NZ, zph = (jt / F_NZ) & 1;
+                    const uint32_t zc = lane_addr + zb * F_ZSTRIDE;
+                    float *op = a.out + ((img * Hp + (r0 >> 1) + rp) * Wp + wg * (F_TILE_M / 2) + (px >> 1)) * a.out_pitch + a.out_choff;
+                    mbar_wait(bar_zfull + 8 * zb, zph);
+                    __syncwarp();
+                    tc_fence_after();
+                    for (int q0 = 0; q0 < nquad; q0 += 4) {                  // 16 accumulator columns per round trip
+                        float z[16];
+                        f_tmem_ld16(zc + q0 * 4, z);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) z[e] = 0.25f * (z[e] + __shfl_xor_sync(0xffffffffu, z[e], 1));
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            const int qd = q0 + qq;
+                            if (qd < nquad && ((qd & 1) == (lane & 1))) {        // even quads from the even lane, odd quads from the odd lane
+                                const int n = qd * 4;
+                                if (n + 3 < a.n_out) {
+                                    *reinterpret_cast<float4 *>(op + n) = make_float4(z[qq * 4], z[qq * 4 + 1], z[qq * 4 + 2], z[qq * 4 + 3]);
+                                } else {
+                                    for (int e = 0; e < 4; ++e) if (n + e < a.n_out) op[n + e] = z[qq * 4 + e];
+                                }
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) f_mbar_arrive(bar_zempty + 8 * zb);
+                }
+            }
+        } else if (!POOL && active) {
             uint32_t j = 0;                                   // tile counter (all tiles of this CTA, both halves)
             for (long band = blockIdx.x; band < a.nbands; band += grid) {
                 const int bpi = a.H / a.R;
@@ -577,13 +635,78 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
     if (split) {
-        e = cudaFuncSetAttribute(dense_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        e = cudaFuncSetAttribute(dense_layer_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);
-        dense_layer_kernel<true><<<grid, F_THREADS, smem, st>>>(tmap, a);
+        dense_layer_kernel<true, false><<<grid, F_THREADS, smem, st>>>(tmap, a);
     } else {
-        e = cudaFuncSetAttribute(dense_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        e = cudaFuncSetAttribute(dense_layer_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);
-        dense_layer_kernel<false><<<grid, F_THREADS, smem, st>>>(tmap, a);
+        dense_layer_kernel<false, false><<<grid, F_THREADS, smem, st>>>(tmap, a);
+    }
+    return eml_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------ transition (POOL2) on the same pipeline
+// norm + relu + conv1x1 + avg_pool2d(2) of RegressionNetwork/DenseNet.py:14-21 for C_out <= 112 (transition1: 216 -> 108): the TMA ring,
+// the in-place conversion and the MMA loop are the dense layer's; the 2x2 average is split between the tensor core (the two image rows
+// of a pooled row accumulate into ONE accumulator) and the epilogue (adjacent pixels = adjacent lanes, one shuffle).  Reached through
+// eml_conv_forward(EML_CONV_POOL2); every other shape keeps conv_gemm_kernel<2>.
+bool eml_dense_pool_supported(const eml_conv_params *p) {
+    if (p->mode != EML_CONV_POOL2 || p->stats != nullptr || !p->relu) return false;
+    if (p->precision != EML_PREC_BF16 && p->precision != EML_PREC_BF16X3) return false;
+    if ((p->W != 128 && p->W != 256) || (p->H & 1) || p->C_in > F_MAX_C || (p->C_in & 3) || ((p->C_out + 15) & ~15) != F_NPAD) return false;
+    if ((p->out_pitch & 3) || (p->out_choff & 3) || p->scale == nullptr || p->shift == nullptr) return false;
+    if (eml_env_flag("EML_NO_TMA_TRANSITION")) return false;
+    return fused_stages((p->C_in + 63) / 64, p->W) >= 4;
+}
+
+int eml_dense_pool_forward(const eml_conv_params *p, cudaStream_t st) {
+    const long npix = static_cast<long>(p->B) * p->H * p->W;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int R = p->H;
+    long best = -1;
+    for (int r = 2; r <= p->H; r += 2) {                       // bands of whole row pairs, no halo
+        if (p->H % r) continue;
+        const long nb = static_cast<long>(p->B) * (p->H / r);
+        const long cost = ((nb + sms - 1) / sms) * r;
+        if (best < 0 || cost < best || (cost == best && r > R)) { best = cost; R = r; }
+    }
+    EncodeTiledFn enc = f_get_encode();
+    if (enc == nullptr) return EML_E_ARG;
+    CUtensorMap tmap;
+    {
+        const cuuint64_t dims[2] = {static_cast<cuuint64_t>(p->C_in), static_cast<cuuint64_t>(npix)};
+        const cuuint64_t strides[1] = {static_cast<cuuint64_t>(p->in_pitch) * 4};
+        const cuuint32_t box[2] = {F_STAGE_C, F_TILE_M};
+        const cuuint32_t estr[2] = {1, 1};
+        if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p->in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return EML_E_ARG;
+    }
+    FArgs a{};
+    a.scale = p->scale; a.shift = p->shift; a.wpack = static_cast<const unsigned char *>(p->wpack);
+    a.bias9 = nullptr; a.out = p->out;
+    a.B = p->B; a.H = p->H; a.W = p->W; a.R = R;
+    a.C_in = p->C_in; a.out_pitch = p->out_pitch; a.out_choff = p->out_choff;
+    a.nwchunks = (p->C_in + 63) / 64;
+    a.nstg = (p->C_in + F_STAGE_C - 1) / F_STAGE_C;
+    a.pool = 1; a.n_out = p->C_out;
+    a.stages = fused_stages(a.nwchunks, p->W);
+    a.nbands = static_cast<long>(p->B) * (p->H / R);
+    const bool split = p->precision == EML_PREC_BF16X3;
+    const size_t smem = fused_smem(a.nwchunks, p->W, a.stages);
+    const unsigned grid = static_cast<unsigned>(a.nbands < sms ? a.nbands : sms);
+    cudaError_t e;
+    if (split) {
+        e = cudaFuncSetAttribute(dense_layer_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return static_cast<int>(e);
+        dense_layer_kernel<true, true><<<grid, F_THREADS, smem, st>>>(tmap, a);
+    } else {
+        e = cudaFuncSetAttribute(dense_layer_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return static_cast<int>(e);
+        dense_layer_kernel<false, true><<<grid, F_THREADS, smem, st>>>(tmap, a);
     }
     return eml_launch_status();
 }

@@ -94,7 +94,11 @@ def test_conv_matches_reference(lib, cuda, case, precision):
 
 
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
-@pytest.mark.parametrize("case", [c for c in CASES if c[0] != "pool"] + [("1x1", 40, 48, 64, 132, 216, 48, 48, 0, True)],
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] != "pool"] + [("1x1", 40, 48, 64, 132, 216, 48, 48, 0, True),
+                                  # transition1 geometry without statistics -> the TMA-fed pipeline of dense_layer.cu with a pooling
+                                  # epilogue (row pairs accumulate in TMEM, column pairs by shuffle): two tiles per row / one tile per row
+                                  ("pool", 2, 8, 256, 216, 216, 108, 304, 0, True), ("pool", 3, 4, 128, 204, 216, 100, 112, 4, True),
+                                  ("pool", 37, 12, 128, 216, 216, 108, 108, 0, True)],
                          ids=lambda c: "%s-B%d-%dx%d-c%d" % (c[0], c[1], c[2], c[3], c[4]))
 def test_conv_persistent_kernels(lib, cuda, case, precision):
     """Without a statistics epilogue the dispatcher picks the persistent warp-specialised kernels (one CTA per SM walking
