@@ -24,6 +24,8 @@ def main():
     for i in order:
         l = launches[i]
         name = next((f for key, f in FAMILIES if key in l["name"]), "other")
+        if name == "dense_layer" and "dense_layer_kernel<1, 1>" in l["name"].replace("(bool)", ""):
+            name = "pool1x1"                                  # dense_layer_kernel<SPLIT, POOL = true> is transition1 (eml_conv_forward POOL2)
         f = fam.setdefault(name, {"launches": 0, "time_ms": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0})
         f["launches"] += 1
         f["time_ms"] += l.get("gpu__time_duration.sum", 0.0) / 1e6
