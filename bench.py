@@ -295,6 +295,24 @@ def main():
         extra = {"config1_densenet_fwd_trainBN_plus_sinkhorn_fwd_bwd_b64": {"ms_per_step": round(ms1, 3), "maps_per_s": round(Bt / ms1 * 1e3, 1)},
                  "train_step_fwd_bwd_adam_b64": {"ms_per_step": round(ms_tr, 3), "maps_per_s": round(Bt / ms_tr * 1e3, 1)},
                  "config0_single_crop_latency_ms": round(ms0, 3), "config0_single_crop_latency_cuda_graph_ms": round(ms0g, 3)}
+        # BASELINE configs[4] (per GPU share of B=512 over 8 GPUs = 64; here the whole 512 on one GPU): needlet j=3 projection + reconstruction
+        try:
+            from emlight_b200.needlets import NeedletTransform
+            del xt, yt, tb
+            torch.cuda.empty_cache()
+            nt = NeedletTransform(jmax=3, device=dev)
+            pn = torch.exp(torch.randn(512, 3, 128, 256, device=dev))
+            for _ in range(2):
+                nt.reconstruct(nt.project(pn))
+            ms_p = timed(lambda: nt.project(pn), 3) / 3
+            cf = nt.project(pn)
+            ms_r = timed(lambda: nt.reconstruct(cf), 3) / 3
+            extra["config4_needlets_j3_b512"] = {"project_ms": round(ms_p, 3), "reconstruct_ms": round(ms_r, 3),
+                                                 "maps_per_s_project_plus_reconstruct": round(512 / (ms_p + ms_r) * 1e3, 1),
+                                                 "coefficients": nt.n}
+            del nt, pn, cf
+        except Exception as e:                                  # noqa: BLE001  (secondary workload: never fail the headline line)
+            extra["config4_needlets_j3_b512"] = {"error": "%s: %s" % (type(e).__name__, e)}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt, threads = time_cpu(args.cpu_sample, 3, 1)
