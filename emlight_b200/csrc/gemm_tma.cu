@@ -33,6 +33,7 @@ struct GArgs {
     int N, N_pad, out_pitch, out_choff;
     int nchunks, stages;
     long mtiles;
+    int ksplit, cps;                // split-K: work item = (m-tile, K range of cps chunks); partial sums are added with red.global
 };
 
 __device__ __forceinline__ void g_mbar_arrive(uint32_t bar) {
@@ -76,9 +77,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tma_kernel(const __grid_con
         // ================================================================ LOADER
         const bool leader = elect_one();
         uint32_t g = 0;
-        for (long t = blockIdx.x; t < a.mtiles; t += gridDim.x) {
-            const int m0 = static_cast<int>(t * G_TILE_M);
-            for (int c = 0; c < a.nchunks; ++c, ++g) {
+        for (long t = blockIdx.x; t < a.mtiles * a.ksplit; t += gridDim.x) {
+            const int m0 = static_cast<int>((t % a.mtiles) * G_TILE_M);
+            const int c_lo = static_cast<int>(t / a.mtiles) * a.cps, c_hi = min(a.nchunks, c_lo + a.cps);
+            for (int c = c_lo; c < c_hi; ++c, ++g) {
                 const uint32_t s = g % a.stages, ph = (g / a.stages) & 1;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
                 if (leader) {
@@ -101,11 +103,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tma_kernel(const __grid_con
         const uint32_t stage16 = static_cast<uint32_t>(stage_bytes) >> 4, alo16 = G_A_TILE >> 4;
         const uint32_t bhi16 = static_cast<uint32_t>((SPLIT ? 2 : 1) * G_A_TILE) >> 4, blo16 = static_cast<uint32_t>(b_tile) >> 4;
         uint32_t g = 0, j = 0;
-        for (long t = blockIdx.x; t < a.mtiles; t += gridDim.x, ++j) {
+        for (long t = blockIdx.x; t < a.mtiles * a.ksplit; t += gridDim.x, ++j) {
             const uint32_t buf = j & 1, aph = (j >> 1) & 1;
             mbar_wait(bar_accempty + 8 * buf, aph ^ 1);
             const uint32_t d_tmem = tmem_base + buf * acc_cols;
-            for (int c = 0; c < a.nchunks; ++c, ++g) {
+            const int c_lo = static_cast<int>(t / a.mtiles) * a.cps, c_hi = min(a.nchunks, c_lo + a.cps);
+            for (int c = c_lo; c < c_hi; ++c, ++g) {
                 const uint32_t s = g % a.stages, ph = (g / a.stages) & 1;
                 mbar_wait(bar_full + 8 * s, ph);
                 tc_fence_after();
@@ -115,14 +118,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tma_kernel(const __grid_con
 #pragma unroll
                     for (int k = 0; k < G_CHUNK_K / 16; ++k) {
                         const uint64_t adv = static_cast<uint64_t>(k * 2);
-                        umma_bf16(d_tmem, da_hi + adv, db_hi + adv, idesc, (c | k) != 0 ? 1u : 0u);
+                        umma_bf16(d_tmem, da_hi + adv, db_hi + adv, idesc, (c != c_lo || k != 0) ? 1u : 0u);
                         if (SPLIT) {
                             umma_bf16(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
                             umma_bf16(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
                         }
                     }
                     umma_commit(bar_empty + 8 * s);
-                    if (c == a.nchunks - 1) umma_commit(bar_accfull + 8 * buf);
+                    if (c == c_hi - 1) umma_commit(bar_accfull + 8 * buf);
                 }
                 __syncwarp();
             }
@@ -132,12 +135,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tma_kernel(const __grid_con
         const int q = warp & 3;
         const bool vec_ok = ((a.out_pitch | a.out_choff) & 3) == 0;
         uint32_t j = 0;
-        for (long t = blockIdx.x; t < a.mtiles; t += gridDim.x, ++j) {
+        for (long t = blockIdx.x; t < a.mtiles * a.ksplit; t += gridDim.x, ++j) {
             const uint32_t buf = j & 1, aph = (j >> 1) & 1;
             mbar_wait(bar_accfull + 8 * buf, aph);
             __syncwarp();
             tc_fence_after();
-            const long m = t * G_TILE_M + q * 32 + lane;
+            const bool first_k = t < a.mtiles;                  // the K range that also adds the bias
+            const long m = (t % a.mtiles) * G_TILE_M + q * 32 + lane;
             const bool row_ok = m < a.M;
             float *orow = a.out + (row_ok ? m : 0) * a.out_pitch + a.out_choff;
             for (int g16 = 0; g16 < a.N_pad; g16 += 16) {
@@ -148,13 +152,18 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tma_kernel(const __grid_con
                     for (int qq = 0; qq < 4; ++qq) {
                         const int n = g16 + qq * 4;
                         float4 o = make_float4(v[qq * 4], v[qq * 4 + 1], v[qq * 4 + 2], v[qq * 4 + 3]);
-                        if (a.bias != nullptr) {
+                        if (a.bias != nullptr && first_k) {
                             if (n < a.N) o.x += a.bias[n];
                             if (n + 1 < a.N) o.y += a.bias[n + 1];
                             if (n + 2 < a.N) o.z += a.bias[n + 2];
                             if (n + 3 < a.N) o.w += a.bias[n + 3];
                         }
-                        if (vec_ok && n + 3 < a.N) {
+                        if (a.ksplit > 1) {                     // partial sum of one K range: accumulate (out zeroed by the caller)
+                            if (n < a.N) atomicAdd(orow + n, o.x);
+                            if (n + 1 < a.N) atomicAdd(orow + n + 1, o.y);
+                            if (n + 2 < a.N) atomicAdd(orow + n + 2, o.z);
+                            if (n + 3 < a.N) atomicAdd(orow + n + 3, o.w);
+                        } else if (vec_ok && n + 3 < a.N) {
                             *reinterpret_cast<float4 *>(orow + n) = o;
                         } else {
                             if (n < a.N) orow[n] = o.x;
@@ -208,8 +217,8 @@ int make_map(CUtensorMap *map, const void *base, long M, int Kp) {
 
 }  // namespace
 
-extern "C" int eml_gemm_bf16(const void *A_hi, const void *A_lo, long M, int Kp, const void *wpack, int N, const float *bias,
-                             float *out, int out_pitch, int out_choff, int precision, void *stream) {
+static int gemm_impl(const void *A_hi, const void *A_lo, long M, int Kp, const void *wpack, int N, const float *bias,
+                     float *out, int out_pitch, int out_choff, int precision, int ksplit, void *stream) {
     EML_CHECK_PTR(A_hi); EML_CHECK_PTR(wpack); EML_CHECK_PTR(out);
     EML_CHECK_ALIGN16(A_hi); EML_CHECK_ALIGN16(wpack);
     if (M <= 0 || Kp <= 0 || (Kp % G_CHUNK_K) || N <= 0 || N > 256 || out_pitch < out_choff + N || out_choff < 0) return EML_E_SHAPE;
@@ -226,6 +235,9 @@ extern "C" int eml_gemm_bf16(const void *A_hi, const void *A_lo, long M, int Kp,
     a.N = N; a.N_pad = (N + 15) & ~15; a.out_pitch = out_pitch; a.out_choff = out_choff;
     a.nchunks = Kp / G_CHUNK_K;
     a.mtiles = (M + G_TILE_M - 1) / G_TILE_M;
+    if (ksplit < 1 || ksplit > a.nchunks) return EML_E_ARG;
+    a.cps = (a.nchunks + ksplit - 1) / ksplit;
+    a.ksplit = (a.nchunks + a.cps - 1) / a.cps;            // no empty K ranges
     const int stage_bytes = (split ? 2 : 1) * (G_A_TILE + a.N_pad * 128);
     int stages = (225 * 1024) / stage_bytes;
     if (stages > 6) stages = 6;
@@ -235,7 +247,8 @@ extern "C" int eml_gemm_bf16(const void *A_hi, const void *A_lo, long M, int Kp,
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned grid = static_cast<unsigned>(a.mtiles < sms ? a.mtiles : sms);
+    const long items = a.mtiles * a.ksplit;
+    const unsigned grid = static_cast<unsigned>(items < sms ? items : sms);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
     if (split) {
@@ -248,4 +261,17 @@ extern "C" int eml_gemm_bf16(const void *A_hi, const void *A_lo, long M, int Kp,
         gemm_tma_kernel<false><<<grid, G_THREADS, smem, st>>>(tm_hi, tm_lo, a);
     }
     return eml_launch_status();
+}
+
+extern "C" int eml_gemm_bf16(const void *A_hi, const void *A_lo, long M, int Kp, const void *wpack, int N, const float *bias,
+                             float *out, int out_pitch, int out_choff, int precision, void *stream) {
+    return gemm_impl(A_hi, A_lo, M, Kp, wpack, N, bias, out, out_pitch, out_choff, precision, 1, stream);
+}
+
+// Split-K variant for short-and-deep products (needlet projection: M = 3 B rows, K = 32768 pixels): the K chunks are dealt to
+// `ksplit` work items per m-tile and the partial sums are accumulated with float atomics, so `out` must be ZERO on entry and the
+// result is reproducible only to fp32 summation order.
+extern "C" int eml_gemm_bf16_splitk(const void *A_hi, const void *A_lo, long M, int Kp, const void *wpack, int N, const float *bias,
+                                    float *out, int out_pitch, int out_choff, int precision, int ksplit, void *stream) {
+    return gemm_impl(A_hi, A_lo, M, Kp, wpack, N, bias, out, out_pitch, out_choff, precision, ksplit, stream);
 }

@@ -228,10 +228,13 @@ class NeedletTransform:
         _lib.check(lib.eml_split_bf16(_lib.ptr(planes), M, self.P, self.P, _lib.ptr(a_hi), _lib.ptr(a_lo), self._Kp_pix, st),
                    "eml_split_bf16(pano)")
         pitch = (self.n + 3) // 4 * 4
-        out = torch.empty(M, pitch, dtype=torch.float32, device=self.device)
+        # short and deep (M = 3B rows, K = 32768 pixels): split K so that every SM gets a piece (partial sums by float atomics)
+        out = torch.zeros(M, pitch, dtype=torch.float32, device=self.device)
+        mtiles = (M + 127) // 128
+        ksplit = max(1, min(self._Kp_pix // 64, 148 // mtiles))
         for n0, rows, buf in self._proj_packs:
-            _lib.check(lib.eml_gemm_bf16(_lib.ptr(a_hi), _lib.ptr(a_lo), M, self._Kp_pix, _lib.ptr(buf), rows, None, _lib.ptr(out),
-                                         pitch, n0, self.precision, st), "eml_gemm_bf16(needlet projection)")
+            _lib.check(lib.eml_gemm_bf16_splitk(_lib.ptr(a_hi), _lib.ptr(a_lo), M, self._Kp_pix, _lib.ptr(buf), rows, None, _lib.ptr(out),
+                                                pitch, n0, self.precision, ksplit, st), "eml_gemm_bf16_splitk(needlet projection)")
         return out[:, :self.n].reshape(-1, 3, self.n).permute(0, 2, 1).contiguous()    # (B, n, 3)
 
     @torch.no_grad()

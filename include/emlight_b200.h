@@ -208,6 +208,10 @@ int eml_im2col_lut_bf16(const float *x, int x_pitch, int C, int Cp, const int *l
  *   wpack = eml_conv_pack_weights(W as (N, Kp, 1, 1)), N <= 256 per call, precision EML_PREC_BF16 or EML_PREC_BF16X3. */
 int eml_gemm_bf16(const void *A_hi, const void *A_lo, long M, int Kp, const void *wpack, int N, const float *bias, float *out,
                   int out_pitch, int out_choff, int precision, void *stream);
+/* Split-K form for short-and-deep products (needlet projection, gt_gen_j3.py:39-43: M = 3 B rows, K = 32768 pixels): the K chunks are
+ * dealt to `ksplit` work items per 128-row tile and accumulated with float atomics -- `out` must be ZERO on entry (1 <= ksplit <= Kp/64). */
+int eml_gemm_bf16_splitk(const void *A_hi, const void *A_lo, long M, int Kp, const void *wpack, int N, const float *bias, float *out,
+                         int out_pitch, int out_choff, int precision, int ksplit, void *stream);
 
 /* SPADE.forward (models/networks/normalization.py:101-115) after the gamma/beta convolutions:
  *   out = ((x - mean[c]) * inv_std[c]) * (1 + gamma + bias_gamma[c]) + (beta + bias_beta[c]), optional LeakyReLU(0.2);

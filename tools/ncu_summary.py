@@ -16,7 +16,10 @@ KEYS = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "sm__inst_executed.sum.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed"]
 
 
 def load(rep):
