@@ -5,7 +5,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_lon
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libemlight_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 EML_CONV_1x1, EML_CONV_3x3, EML_CONV_POOL2 = 0, 1, 2
 EML_PREC_BF16, EML_PREC_BF16X3, EML_PREC_FP32 = 0, 1, 2
@@ -65,6 +65,7 @@ SIGNATURES = {
     "eml_gemm_bf16_splitk": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "eml_spade_modulate": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_long,
                                    c_int, c_int, c_void_p]),
+    "eml_channel_stats": (c_int, [c_void_p, c_int, c_long, c_int, c_void_p, c_void_p]),
     "eml_bias_residual": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_long, c_int, c_void_p]),
     "eml_resize_nearest": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "eml_resize_bilinear_nchw": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -491,3 +491,45 @@ extern "C" int eml_loss_reduce(const float *a, int a_pitch, const float *b, int 
     loss_reduce_kernel<<<grid_for(mode == 5 ? M : M * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, a_pitch, b, b_pitch, mask, M, C, mode, acc);
     return eml_launch_status();
 }
+
+// Per-channel sum / sum of squares of an NHWC tensor (SPADE's parameter-free BatchNorm in training mode, normalization.py:80:
+// batch statistics over (B, H, W)).  blockDim = (channel lanes, row lanes); float partials over <= 64 rows, double beyond.
+__global__ void __launch_bounds__(256) channel_stats_kernel(const float *__restrict__ x, int x_pitch, long M, int C, double *__restrict__ sums) {
+    __shared__ double s_acc[2][256];
+    const int cl = threadIdx.x, rl = threadIdx.y, nrl = blockDim.y;
+    for (int c0 = 0; c0 < C; c0 += blockDim.x) {
+        const int c = c0 + cl;
+        double a1 = 0.0, a2 = 0.0;
+        if (c < C) {
+            for (long m0 = static_cast<long>(blockIdx.x) * nrl * 64; m0 < M; m0 += static_cast<long>(gridDim.x) * nrl * 64) {
+                float p1 = 0.f, p2 = 0.f;
+                for (int i = 0; i < 64; ++i) {
+                    const long m = m0 + static_cast<long>(i) * nrl + rl;
+                    if (m < M) { const float v = x[m * x_pitch + c]; p1 += v; p2 = fmaf(v, v, p2); }
+                }
+                a1 += p1; a2 += p2;
+            }
+        }
+        const int t = rl * blockDim.x + cl;
+        s_acc[0][t] = a1; s_acc[1][t] = a2;
+        __syncthreads();
+        if (rl == 0 && c < C) {
+            for (int r = 1; r < nrl; ++r) { a1 += s_acc[0][r * blockDim.x + cl]; a2 += s_acc[1][r * blockDim.x + cl]; }
+            atomicAdd(sums + c, a1);
+            atomicAdd(sums + C + c, a2);
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int eml_channel_stats(const float *x, int x_pitch, long M, int C, double *sums, void *stream) {
+    EML_CHECK_PTR(x); EML_CHECK_PTR(sums);
+    if (M <= 0 || C <= 0 || x_pitch < C) return EML_E_SHAPE;
+    int bx = 32;
+    while (bx < C && bx < 256) bx <<= 1;
+    const dim3 block(bx, 256 / bx);
+    const long chunks = (M + block.y * 64 - 1) / (block.y * 64);
+    const unsigned grid = static_cast<unsigned>(chunks < 148 * 4 ? chunks : 148 * 4);
+    channel_stats_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(x, x_pitch, M, C, sums);
+    return eml_launch_status();
+}

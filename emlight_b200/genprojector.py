@@ -13,8 +13,9 @@ reference checkpoints load; in eval mode the weight is ``weight_orig / (u . W v)
 packed bf16 hi/lo weight images at pack time.  Every convolution is LUT gather (``eml_im2col_lut``) + tcgen05 GEMM
 (``eml_conv_forward``); normalisation / modulation / resize / tanh are the small kernels of ``csrc/spade_ops.cu``.
 
-This round implements the eval-mode forward (what ``GenProjector/test.py:21-39`` runs: running-statistics BatchNorm inside
-SPADE, stored spectral-norm vectors).  Training-mode forward (batch-statistic SyncBN, power iteration) and backward raise.
+Forward values in both modes: eval (what ``GenProjector/test.py:21-39`` runs: running-statistics BatchNorm inside SPADE, stored
+spectral-norm vectors) and train (batch-statistic (Sync)BatchNorm with running-stat update, one power iteration per spectral
+convolution per forward).  Backward is not built: outputs carry no autograd graph.
 """
 import math
 import re
@@ -259,6 +260,18 @@ class SphereConv2D(nn.Module):
         return out[..., :self.out_c].permute(0, 3, 1, 2).contiguous()
 
 
+def _spectral_sigma(module, w):
+    """sigma of torch.nn.utils.spectral_norm: in training mode ONE power iteration first (u, v updated in place, eps 1e-12), in eval
+    mode the stored vectors (GenProjector/models/networks/architecture.py:37-40, normalization.py:29 wrap their convs with it)."""
+    wm = w.reshape(w.shape[0], -1)
+    if module.training:
+        v = nn.functional.normalize(torch.mv(wm.t(), module.weight_u), dim=0, eps=1e-12)
+        u = nn.functional.normalize(torch.mv(wm, v), dim=0, eps=1e-12)
+        module.weight_v.copy_(v)
+        module.weight_u.copy_(u)
+    return torch.dot(module.weight_u, torch.mv(wm, module.weight_v))
+
+
 class _SpectralSphereConv2D(SphereConv2D):
     """SphereConv2D under torch.nn.utils.spectral_norm naming: weight_orig (parameter), weight_u / weight_v (buffers)."""
 
@@ -272,11 +285,16 @@ class _SpectralSphereConv2D(SphereConv2D):
 
     def effective_weight(self):
         w = self.weight_orig
-        sigma = torch.dot(self.weight_u, torch.mv(w.reshape(w.shape[0], -1), self.weight_v))
-        return w / sigma
+        return w / _spectral_sigma(self, w)
 
     def _tracked(self):
         return (self.weight_orig, self.weight_u, self.weight_v)
+
+    def packed(self, precision):
+        if self.training:                          # the power iteration changes u, v every forward: nothing to cache
+            with torch.no_grad():
+                return _PackedConv(self.effective_weight(), precision)
+        return super().packed(precision)
 
 
 class _SpectralConv2d(nn.Module):
@@ -295,11 +313,13 @@ class _SpectralConv2d(nn.Module):
 
     def packed(self, precision):
         w = self.weight_orig
+        if self.training:
+            with torch.no_grad():
+                return _PackedConv(w / _spectral_sigma(self, w), precision)
         key = (w.data_ptr(), w._version, self.weight_u._version, self.weight_v._version, precision, str(w.device))
         if self._pc is None or self._pc[0] != key:
             with torch.no_grad():
-                sigma = torch.dot(self.weight_u, torch.mv(w.reshape(w.shape[0], -1), self.weight_v))
-                self._pc = (key, _PackedConv(w / sigma, precision))
+                self._pc = (key, _PackedConv(w / _spectral_sigma(self, w), precision))
         return self._pc[1]
 
 
@@ -341,8 +361,27 @@ class SPADE(nn.Module):
         lib = _lib.load()
         C = self.norm_nc
         bn = self.param_free_norm
-        mean = bn.running_mean if x_bias is None else bn.running_mean - x_bias            # (x + b - m) = x - (m - b)
-        inv = torch.rsqrt(bn.running_var + bn.eps)
+        if self.training:
+            # batch statistics over (B, H, W) of x + x_bias (normalization.py:80,104; SynchronizedBatchNorm2d = one all-reduce of the
+            # 2C sums when several processes share the batch), then the running-statistics update of nn.BatchNorm (momentum 0.1)
+            M = B * H * W
+            sums = torch.zeros(2, C, dtype=torch.float64, device=x.device)
+            _lib.check(lib.eml_channel_stats(_lib.ptr(x), x.shape[-1], M, C, _lib.ptr(sums), _lib.stream_ptr()), "eml_channel_stats")
+            n = float(M)
+            if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+                torch.distributed.all_reduce(sums)
+                n *= torch.distributed.get_world_size()
+            m_raw = sums[0] / n
+            var = (sums[1] / n - m_raw * m_raw).clamp_min(0.0)
+            mean = m_raw.float()                                                           # the bias shifts the mean and cancels
+            inv = torch.rsqrt(var.float() + bn.eps)
+            m_full = mean if x_bias is None else mean + x_bias
+            bn.running_mean.mul_(1 - bn.momentum).add_(bn.momentum * m_full)
+            bn.running_var.mul_(1 - bn.momentum).add_(bn.momentum * (var * (n / max(n - 1.0, 1.0))).float())
+            # (num_batches_tracked stays untouched: the reference's SynchronizedBatchNorm2d never increments it)
+        else:
+            mean = bn.running_mean if x_bias is None else bn.running_mean - x_bias        # (x + b - m) = x - (m - b)
+            inv = torch.rsqrt(bn.running_var + bn.eps)
         shared = self.mlp_shared[0]
         actv = _sphere_conv_raw(seg, B, H, W, shared.packed(precision), 1, None, 0, precision)
         gb = _sphere_conv_raw(actv, B, H, W, self._packed_gb(precision), 1, shared.bias, 1, precision)      # relu(actv + bias)
@@ -465,12 +504,11 @@ class SPADEGenerator(nn.Module):
         self.netE = ConvEncoder(opt)
 
     def forward(self, input, crop):
-        if self.training:
-            raise NotImplementedError("emlight_b200.SPADEGenerator: training-mode forward (batch-statistic SyncBN, spectral-norm power "
-                                      "iteration) and backward are not implemented in this round; call .eval() for inference")
+        # training mode = the reference's train-mode FORWARD (batch-statistic BatchNorm inside SPADE with running-stat update,
+        # one spectral-norm power iteration per wrapped convolution); the output carries no autograd graph -- backward is not built
         _lib.require_cuda(input, crop)
         with torch.no_grad():
-            if self.use_cuda_graph:
+            if self.use_cuda_graph and not self.training:
                 from .graphs import graphed_call
                 return graphed_call(self._graphs, self._graph_key(), self._run, (input, crop))
             return self._run(input, crop)

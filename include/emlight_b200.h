@@ -220,6 +220,11 @@ int eml_spade_modulate(const float *x, int x_pitch, const float *mean, const flo
                        int gb_pitch, const float *bias_gamma, const float *bias_beta, float *out, int out_pitch, long M,
                        int C, int leaky_relu, void *stream);
 
+/* Training-mode statistics of SPADE's parameter-free (Sync)BatchNorm (normalization.py:80,104): sums[c] += sum_m x[m,c],
+ * sums[C + c] += sum_m x[m,c]^2 over the M = B*H*W rows of an NHWC tensor (the caller zeroes `sums`; with several processes the
+ * 2C doubles are all-reduced before the mean / variance are formed, which is what SynchronizedBatchNorm2d's master does). */
+int eml_channel_stats(const float *x, int x_pitch, long M, int C, double *sums, void *stream);
+
 /* out = a + bias_a (+ r + bias_r): SPADEResnetBlock's x_s + dx (models/networks/architecture.py:51-58). r may be NULL. */
 int eml_bias_residual(const float *a, int a_pitch, const float *bias_a, const float *r, int r_pitch, const float *bias_r,
                       float *out, int out_pitch, long M, int C, void *stream);

@@ -70,17 +70,28 @@ def sphere_conv(x, weight, bias, stride=1):
     return F.conv2d(s, weight, bias, stride=3)
 
 
-def sn_weight(sd, prefix):
-    """Eval-mode spectral norm: W_orig / sigma, sigma = u . (W_mat v)."""
+def sn_weight(sd, prefix, upd=None):
+    """Spectral norm: W_orig / sigma, sigma = u . (W_mat v).  Eval mode (upd is None): the stored u, v.  Training mode (upd = dict that
+    receives the new buffers): torch.nn.utils.spectral_norm's single power iteration first, v = normalize(W^T u), u = normalize(W v)."""
     w = sd[prefix + ".weight_orig"]
     u, v = sd[prefix + ".weight_u"], sd[prefix + ".weight_v"]
-    sigma = torch.dot(u, torch.mv(w.reshape(w.shape[0], -1), v))
+    wm = w.reshape(w.shape[0], -1)
+    if upd is not None:
+        v = F.normalize(torch.mv(wm.t(), u), dim=0, eps=1e-12)
+        u = F.normalize(torch.mv(wm, v), dim=0, eps=1e-12)
+        upd[prefix + ".weight_u"], upd[prefix + ".weight_v"] = u, v
+    sigma = torch.dot(u, torch.mv(wm, v))
     return w / sigma
 
 
-def spade(sd, p, x, guide):
+def spade(sd, p, x, guide, upd=None):
     rm, rv = sd[p + ".param_free_norm.running_mean"], sd[p + ".param_free_norm.running_var"]
-    normalized = F.batch_norm(x, rm, rv, None, None, False, 0.0, 1e-5)
+    if upd is None:
+        normalized = F.batch_norm(x, rm, rv, None, None, False, 0.0, 1e-5)
+    else:                                  # training: batch statistics + running-stat update (normalization.py:80, momentum 0.1)
+        rm, rv = rm.clone(), rv.clone()
+        normalized = F.batch_norm(x, rm, rv, None, None, True, 0.1, 1e-5)
+        upd[p + ".param_free_norm.running_mean"], upd[p + ".param_free_norm.running_var"] = rm, rv
     seg = F.interpolate(guide, size=x.shape[2:], mode="nearest")
     actv = F.relu(sphere_conv(seg, sd[p + ".mlp_shared.0.weight"], sd[p + ".mlp_shared.0.bias"]))
     gamma = sphere_conv(actv, sd[p + ".mlp_gamma.weight"], sd[p + ".mlp_gamma.bias"])
@@ -88,34 +99,35 @@ def spade(sd, p, x, guide):
     return normalized * (1 + gamma) + beta
 
 
-def spade_block(sd, p, x, guide, learned):
+def spade_block(sd, p, x, guide, learned, upd=None):
     x_s = x
     if learned:
-        x_s = sphere_conv(spade(sd, p + ".norm_s", x, guide), sn_weight(sd, p + ".conv_s"), sd[p + ".conv_s.bias"])
-    dx = sphere_conv(F.leaky_relu(spade(sd, p + ".norm_0", x, guide), 0.2), sn_weight(sd, p + ".conv_0"), sd[p + ".conv_0.bias"])
-    dx = sphere_conv(F.leaky_relu(spade(sd, p + ".norm_1", dx, guide), 0.2), sn_weight(sd, p + ".conv_1"), sd[p + ".conv_1.bias"])
+        x_s = sphere_conv(spade(sd, p + ".norm_s", x, guide, upd), sn_weight(sd, p + ".conv_s", upd), sd[p + ".conv_s.bias"])
+    dx = sphere_conv(F.leaky_relu(spade(sd, p + ".norm_0", x, guide, upd), 0.2), sn_weight(sd, p + ".conv_0", upd), sd[p + ".conv_0.bias"])
+    dx = sphere_conv(F.leaky_relu(spade(sd, p + ".norm_1", dx, guide, upd), 0.2), sn_weight(sd, p + ".conv_1", upd), sd[p + ".conv_1.bias"])
     return x_s + dx
 
 
-def encoder(sd, crop):
+def encoder(sd, crop, upd=None):
     x = F.interpolate(crop, size=(128, 128), mode="bilinear")
     for i in range(1, 6):
         if i > 1:
             x = F.leaky_relu(x, 0.2)
-        x = F.conv2d(x, sn_weight(sd, "netE.layer%d.0" % i), None, stride=2, padding=1)
+        x = F.conv2d(x, sn_weight(sd, "netE.layer%d.0" % i, upd), None, stride=2, padding=1)
         x = F.instance_norm(x, eps=1e-5)
     x = F.leaky_relu(x, 0.2)
     return F.linear(x.reshape(x.shape[0], -1), sd["netE.fc.weight"], sd["netE.fc.bias"])
 
 
-def generator_forward(sd, guide, crop, ngf=64, taps=None):
-    """guide (B,3,128,256), crop (B,3,Hc,Wc) -> (B,3,128,256) in [0,50]."""
-    x = encoder(sd, crop).view(-1, 16 * ngf, 1, 2)
+def generator_forward(sd, guide, crop, ngf=64, taps=None, upd=None):
+    """guide (B,3,128,256), crop (B,3,Hc,Wc) -> (B,3,128,256) in [0,50].  upd = None: eval mode; upd = {}: the train-mode forward
+    (batch-statistic BatchNorm in SPADE, one spectral-norm power iteration per wrapped conv), upd receives every updated buffer."""
+    x = encoder(sd, crop, upd).view(-1, 16 * ngf, 1, 2)
     x = F.interpolate(x, size=(4, 8))
     if taps is not None:
         taps["latent"] = x
     for i, (name, fi, fo) in enumerate(BLOCKS):
-        x = spade_block(sd, name, x, guide, fi != fo)
+        x = spade_block(sd, name, x, guide, fi != fo, upd)
         if taps is not None:
             taps[name] = x
         if name not in ("G_middle_0", "up_3"):

@@ -31,6 +31,30 @@ def test_generator_oracle_matches_reference_golden():
     assert np.abs(y.numpy() - g["sc_y"]).max() <= 1e-5
 
 
+def test_generator_train_mode_oracle_matches_reference_golden():
+    """Train-mode forward (batch-statistic BatchNorm in SPADE, spectral-norm power iteration): two consecutive steps of the reference
+    module in .train() (oracle/make_golden_gen_train.py) vs the oracle threading the updated buffers through."""
+    g = np.load(os.path.join(GOLDEN, "generator_train.npz"))
+    ngf = int(g["ngf"])
+    sd = GO.init_generator_state_dict(seed=int(g["sd_seed"]), ngf=ngf)
+    gen = torch.Generator().manual_seed(int(g["in_seed"]))
+    guide = torch.rand(2, 3, 128, 256, generator=gen) * 2
+    crop = torch.rand(2, 3, 128, 128, generator=gen)
+    with torch.no_grad():
+        upd = {}
+        out1 = GO.generator_forward(sd, guide, crop, ngf, upd=upd)
+        sd.update(upd)
+        upd = {}
+        out2 = GO.generator_forward(sd, guide * 0.5, crop, ngf, upd=upd)
+        sd.update(upd)
+    assert np.abs(out1.numpy()[:, :, ::2, ::2] - g["out1"]).max() <= 1e-3
+    assert np.abs(out2.numpy()[:, :, ::2, ::2] - g["out2"]).max() <= 1e-3
+    for k in g.files:
+        if k.startswith("buf_") and not k.endswith("num_batches_tracked"):
+            want = g[k]
+            assert np.abs(sd[k[4:]].numpy() - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), k
+
+
 def test_sampling_tables_reproduce_grid_sample():
     """The product's 4-tap tables (emlight_b200.genprojector._sphere_lut) applied on the host == grid_sample on the reference grid."""
     from emlight_b200.genprojector import _conv_lut, _sphere_lut

@@ -76,5 +76,30 @@ def test_generator_batch_and_errors(cuda):
     assert torch.equal(again, out[1:2])                                              # per-sample independence, run-to-run identical
     with pytest.raises(RuntimeError, match="CUDA"):
         G(guide, crop)
-    with pytest.raises(NotImplementedError):
-        G.train()(guide.to(cuda), crop.to(cuda))
+
+
+def test_generator_train_mode_forward_matches_reference_golden(cuda):
+    """.train() forward: batch-statistic BatchNorm inside SPADE (eml_channel_stats) with running-stat update and one spectral-norm
+    power iteration per wrapped convolution, two consecutive steps vs the reference module (tests/golden/generator_train.npz)."""
+    import emlight_b200 as E
+    g = np.load(os.path.join(GOLDEN, "generator_train.npz"))
+    ngf = int(g["ngf"])
+    G = E.SPADEGenerator(_opt(ngf)).to(cuda).train()
+    G.load_state_dict(GO.init_generator_state_dict(seed=int(g["sd_seed"]), ngf=ngf))
+    gen = torch.Generator().manual_seed(int(g["in_seed"]))
+    guide = torch.rand(2, 3, 128, 256, generator=gen) * 2
+    crop = torch.rand(2, 3, 128, 128, generator=gen)
+    out1 = G(guide.to(cuda), crop.to(cuda)).cpu()
+    out2 = G((guide * 0.5).to(cuda), crop.to(cuda)).cpu()
+    assert not out1.requires_grad                                                     # forward values only: no autograd graph
+    assert np.abs(out1.numpy()[:, :, ::2, ::2] - g["out1"]).max() / 50.0 <= 1e-3
+    assert np.abs(out2.numpy()[:, :, ::2, ::2] - g["out2"]).max() / 50.0 <= 1e-3
+    sd = G.state_dict()
+    for k in g.files:
+        if k.startswith("buf_"):
+            want, got = g[k], sd[k[4:]].cpu().numpy()
+            assert np.abs(got - want).max() <= 1e-3 * max(1.0, np.abs(want).max()), k
+    # eval afterwards uses the updated running statistics / vectors and is deterministic
+    G.eval()
+    a = G(guide.to(cuda), crop.to(cuda))
+    assert torch.equal(a, G(guide.to(cuda), crop.to(cuda)))
