@@ -300,6 +300,16 @@ int eml_needlet_basis(const double *xyz, long P, const double *centres, const in
 int eml_split_bf16(const float *x, long rows, int cols, long ld, void *hi, void *lo, int Kp, void *stream);
 int eml_needlet_sparsify(float *coef, int B, int n, int ch, const int *ranges, int nranges, float frac, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * SURVEY 8(f) rank 1 -- ground-truth light parameters from an HDR panorama, the inverse of the SG render.
+ * Replaces RegressionNetwork/representation/distribution_representation.py:89-119 `extract_mesh.compute` for a batch:
+ *   hdr (B,H,W,3) fp32; idx (H*W) int32 nearest-anchor LUT (host, :77-86); ster (H) float64 row weights sin((r+.5)/H*pi) (:69-74);
+ *   lit = weighted intensity > 5 % of the image's maximum; anchors[k] = sum of lit weighted pixels with idx == k; ambient = the rest;
+ *   dist (B,ln) = anchor energy / total, intensity (B) = |sum_k anchors[k]|, rgb_ratio (B,3), ambient (B,3), map (B,H,W) u8 or NULL.
+ * Accumulation in float64 like the reference's numpy; ln <= 512. */
+int eml_extract_params(const float *hdr, const int *idx, const double *ster, int B, int H, int W, int ln, float *dist,
+                       float *intensity, float *rgb_ratio, float *ambient, unsigned char *map, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
