@@ -310,6 +310,13 @@ int eml_needlet_sparsify(float *coef, int B, int n, int ch, const int *ranges, i
 int eml_extract_params(const float *hdr, const int *idx, const double *ster, int B, int H, int W, int ln, float *dist,
                        float *intensity, float *rgb_ratio, float *ambient, unsigned char *map, void *stream);
 
+/* SURVEY 8(f) rank 2 -- `TonemapHDR.__call__` (RegressionNetwork/util.py:36-66; applied to every crop by data.py:62-73):
+ *   p = x^(1/gamma) (use_gamma) ; r = percentile_q of the strictly positive p, numpy's linear interpolation (exact radix selection per
+ *   image, no sort) ; alpha[b] = max_mapping / (r + 1e-10) unless alpha_given ; out = alpha[b] * p, clipped to [0,1] when clip.
+ * x, out (B, per_image) fp32 (out may alias x); alpha (B) fp32 in (alpha_given) or out. */
+int eml_tonemap_hdr(const float *x, float *out, float *alpha, int B, long per_image, float gamma, float percentile, float max_mapping,
+                    int use_gamma, int clip, int alpha_given, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
