@@ -12,12 +12,12 @@ Public surface mirrors the reference's:
 Module-name shims for unchanged reference scripts live in ``emlight_b200/dropin`` (put it on sys.path).
 All arithmetic runs in hand-written CUDA reached through the C ABI of include/emlight_b200.h.
 """
-from .panorama import convert_to_panorama, render_from_params, sphere_points  # noqa: F401
+from .panorama import convert_to_panorama, genprojector_guide, render_from_params, sphere_points  # noqa: F401
 from .samples_loss import GMSamplesLoss, SamplesLoss  # noqa: F401
 from .densenet import DenseNet  # noqa: F401
 from .genprojector import (SPADE, ConvEncoder, GANLoss, MultiscaleDiscriminator, NLayerDiscriminator, Pix2PixModel,  # noqa: F401
                            SPADEGenerator, SPADEResnetBlock, SphereConv2D, VGG19, VGGLoss)
 
-__all__ = ["DenseNet", "SamplesLoss", "GMSamplesLoss", "sphere_points", "convert_to_panorama", "render_from_params",
+__all__ = ["DenseNet", "SamplesLoss", "GMSamplesLoss", "sphere_points", "convert_to_panorama", "render_from_params", "genprojector_guide",
            "SphereConv2D", "SPADE", "SPADEResnetBlock", "ConvEncoder", "SPADEGenerator", "MultiscaleDiscriminator", "NLayerDiscriminator",
            "GANLoss", "VGG19", "VGGLoss", "Pix2PixModel"]

@@ -77,3 +77,25 @@ def test_render_linearity_and_edge_cases(cuda):
     z = RO.pixel_dirs()[2]
     assert np.abs(one.cpu().numpy()[0, 1] - 2 * np.exp((z - 1) / 0.5)).max() < 1e-4
     assert E.convert_to_panorama(dirs[:0], sizes[:0], c1[:0]).shape == (0, 3, 128, 256)
+
+
+def test_genprojector_guide_matches_data_py(cuda):
+    """GenProjector/data.py:86-102 restated with the oracle render: env = (pano(dist * intensity * 0.01 * rgb) + ambient / 32768) * alpha."""
+    import emlight_b200 as E
+    from oracle import render_oracle as RO
+    B, N = 3, 128
+    g = torch.Generator().manual_seed(8)
+    dist = torch.softmax(3 * torch.randn(B, N, generator=g), 1)
+    inten = torch.rand(B, generator=g) * 400 + 50
+    rgb = torch.nn.functional.normalize(torch.rand(B, 3, generator=g) + 0.2, dim=1)
+    amb = torch.rand(B, 3, generator=g) * 2000
+    alpha = torch.rand(B, generator=g) + 0.2
+    out = E.genprojector_guide(dist.to(cuda), inten.to(cuda), rgb.to(cuda), amb.to(cuda), alpha.to(cuda)).cpu().numpy()
+    dirs = np.tile(RO.sphere_points(N).astype(np.float32).reshape(1, -1), (B, 1))
+    cols = RO.compose_colors(dist.numpy(), inten.numpy().reshape(B, 1), rgb.numpy(), gain=0.01)
+    ref = RO.convert_to_panorama(dirs, np.full((B, N), 0.0025, np.float32), cols)
+    ref = (ref + (amb.numpy() / (128 * 256))[:, :, None, None]) * alpha.numpy()[:, None, None, None]
+    assert out.shape == ref.shape
+    assert np.abs(out - ref).max() <= 2e-3 * np.abs(ref).max()
+    one = E.genprojector_guide(dist[:1].to(cuda), inten[:1].to(cuda), rgb[:1].to(cuda), amb[:1].to(cuda), float(alpha[0])).cpu().numpy()
+    assert np.abs(one - out[:1]).max() <= 1e-6 * np.abs(out).max()
