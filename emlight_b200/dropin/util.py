@@ -1,2 +1,4 @@
-"""`import util; util.sphere_points(n); util.convert_to_panorama(dirs, sizes, colors)` (RegressionNetwork/train.py:67,111,122)."""
+"""`import util; util.sphere_points(n); util.convert_to_panorama(dirs, sizes, colors)` (RegressionNetwork/train.py:67,111,122),
+`util.TonemapHDR(gamma, percentile, max_mapping)` (RegressionNetwork/data.py:62-73 / util.py:36-66; CUDA tensors in, CUDA tensors out)."""
 from emlight_b200.panorama import convert_to_panorama, sphere_points  # noqa: F401
+from emlight_b200.tonemap import TonemapHDR  # noqa: F401
