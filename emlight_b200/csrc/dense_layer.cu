@@ -55,7 +55,8 @@ constexpr int F_UBASE = F_NZ * F_ZSTRIDE;               // 336: TMEM column of t
 constexpr int F_USTRIDE = 36;                           // [slot(2)][half(2)] x 36 columns -> 336 + 144 = 480 of 512 columns
 constexpr int F_MAX_C = 320;                            // 5 weight chunks of 64 channels
 constexpr int F_WCHUNK = 2 * F_NPAD * 128;              // bytes of one packed weight chunk [hi | lo] (64 channels)
-constexpr int F_SROW = F_GRP;                           // floats per pixel in the row buffer
+// floats per pixel in the row buffer: template parameter SROW = 36 (packed) or 44 (176 B = 48 B mod 128: the (pixel, quad) stream of the
+// output pass and the per-pixel stores become bank-conflict free; chosen by the host whenever it does not cost a ring stage)
 
 struct FArgs {
     const float *scale;
@@ -193,7 +194,7 @@ __device__ __forceinline__ void band_init(BandIter &it, const FArgs &a, long ban
     it.m0 = (img * a.H + lo) * a.W;
 }
 
-template <bool SPLIT, bool POOL>
+template <bool SPLIT, bool POOL, int F_SROW>
 __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_constant__ CUtensorMap tmap, const FArgs a) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_bar[3 * F_MAX_STAGES + 1 + 2 * F_NZ];
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
     }
     if (a.bias9 != nullptr)
         for (int i = tid; i < 9 * F_G; i += F_THREADS) s_bias[i] = a.bias9[i];
-    if (tid < F_SROW) {                                    // zero pixels left and right of the row (of both rows in pair mode)
+    if (tid < F_GRP) {                                     // zero pixels left and right of the row (of both rows in pair mode)
         s_row[tid] = 0.f; s_row[(a.W + 1) * F_SROW + tid] = 0.f;
         if (a.pair) { s_row[(a.W + 2) * F_SROW + tid] = 0.f; s_row[(2 * a.W + 3) * F_SROW + tid] = 0.f; }
     }
@@ -541,12 +542,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
     }
 }
 
-size_t fused_smem(int nwchunks, int W, int stages) {
-    return static_cast<size_t>(stages) * F_STAGE_BYTES + static_cast<size_t>(nwchunks) * F_WCHUNK + static_cast<size_t>(W == 64 ? 2 * (W + 2) : W + 2) * F_SROW * 4 + 1024;
+size_t fused_smem(int nwchunks, int W, int stages, int srow = F_GRP) {
+    return static_cast<size_t>(stages) * F_STAGE_BYTES + static_cast<size_t>(nwchunks) * F_WCHUNK + static_cast<size_t>(W == 64 ? 2 * (W + 2) : W + 2) * srow * 4 + 1024;
 }
-int fused_stages(int nwchunks, int W) {
+int fused_stages(int nwchunks, int W, int srow = F_GRP) {
     for (int st = F_MAX_STAGES; st >= 4; --st)
-        if (fused_smem(nwchunks, W, st) <= 227 * 1024 - 3400) return st;   // static shared memory (barriers, affine tables: 3344 B) counts too
+        if (fused_smem(nwchunks, W, st, srow) <= 227 * 1024 - 3400) return st;   // static shared memory (barriers, affine tables: 3344 B) counts too
     return 0;
 }
 
@@ -628,21 +629,22 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
     if ((reinterpret_cast<uintptr_t>(p->out) & 31u) == 0 && (p->out_pitch & 7) == 0 && !eml_env_flag("EML_DENSE_NARROW_STORE")) {
         if (!pair && (p->out_choff & 7) == 0 && p->out_choff + F_G + 4 <= p->out_pitch) a.wide = 1;
     }
-    const bool split = p->precision == EML_PREC_BF16X3;
     a.stages = fused_stages(a.nwchunks, p->W);
-    const size_t smem = fused_smem(a.nwchunks, p->W, a.stages);
+    const bool wide_rows = fused_stages(a.nwchunks, p->W, 44) == a.stages && !eml_env_flag("EML_DENSE_PACKED_ROWS");
+    const bool split = p->precision == EML_PREC_BF16X3;
+    const size_t smem = fused_smem(a.nwchunks, p->W, a.stages, wide_rows ? 44 : F_GRP);
     const unsigned grid = static_cast<unsigned>(a.nbands < sms ? a.nbands : sms);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e;
-    if (split) {
-        e = cudaFuncSetAttribute(dense_layer_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    auto go = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);
-        dense_layer_kernel<true, false><<<grid, F_THREADS, smem, st>>>(tmap, a);
-    } else {
-        e = cudaFuncSetAttribute(dense_layer_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return static_cast<int>(e);
-        dense_layer_kernel<false, false><<<grid, F_THREADS, smem, st>>>(tmap, a);
-    }
+        kern<<<grid, F_THREADS, smem, st>>>(tmap, a);
+        return EML_OK;
+    };
+    int rc;
+    if (split) rc = wide_rows ? go(dense_layer_kernel<true, false, 44>) : go(dense_layer_kernel<true, false, F_GRP>);
+    else rc = wide_rows ? go(dense_layer_kernel<false, false, 44>) : go(dense_layer_kernel<false, false, F_GRP>);
+    if (rc != EML_OK) return rc;
     return eml_launch_status();
 }
 
@@ -700,13 +702,13 @@ int eml_dense_pool_forward(const eml_conv_params *p, cudaStream_t st) {
     const unsigned grid = static_cast<unsigned>(a.nbands < sms ? a.nbands : sms);
     cudaError_t e;
     if (split) {
-        e = cudaFuncSetAttribute(dense_layer_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        e = cudaFuncSetAttribute(dense_layer_kernel<true, true, F_GRP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);
-        dense_layer_kernel<true, true><<<grid, F_THREADS, smem, st>>>(tmap, a);
+        dense_layer_kernel<true, true, F_GRP><<<grid, F_THREADS, smem, st>>>(tmap, a);
     } else {
-        e = cudaFuncSetAttribute(dense_layer_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        e = cudaFuncSetAttribute(dense_layer_kernel<false, true, F_GRP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);
-        dense_layer_kernel<false, true><<<grid, F_THREADS, smem, st>>>(tmap, a);
+        dense_layer_kernel<false, true, F_GRP><<<grid, F_THREADS, smem, st>>>(tmap, a);
     }
     return eml_launch_status();
 }
