@@ -55,6 +55,27 @@ def test_argument_errors_need_no_gpu(lib):
     assert lib.eml_conv_wpack_bytes(48, 150, 1) == 3 * 2 * 48 * 128
 
 
+def test_new_entry_points_validate_arguments_without_a_gpu(lib):
+    """Host-side logic of the round-1 additions: shape predicates and NULL / range checks return before any launch."""
+    from emlight_b200._lib import DenseLayerParams
+    G = 12
+    # the one-kernel dense layer: blocks 1-2 (W 256 / 128, C_in % 4 == 0), block 3 as image pairs (W 64, C_in % 2 == 0), <= 5 weight chunks
+    assert [lib.eml_dense_layer_supported(192, 256, 24 + 12 * l, G, 1) for l in range(16)] == [1] * 16
+    assert [lib.eml_dense_layer_supported(96, 128, 108 + 12 * l, G, 1) for l in range(16)] == [1] * 16
+    assert [lib.eml_dense_layer_supported(48, 64, 150 + 12 * l, G, 1) for l in range(16)] == [1] * 15 + [0]
+    assert lib.eml_dense_layer_supported(192, 256, 26, G, 1) == 0 and lib.eml_dense_layer_supported(48, 64, 151, G, 1) == 0
+    assert lib.eml_dense_layer_supported(192, 256, 24, G, 2) == 0            # fp32 SIMT mode: two-kernel path
+    assert lib.eml_dense_layer_forward(None, None) == -1
+    assert lib.eml_dense_layer_forward(DenseLayerParams(), None) == -1
+    assert lib.eml_needlet_basis(None, 1, None, None, 1, None, 1, 1, None, 2, None) == -1
+    assert lib.eml_split_bf16(None, 1, 1, 1, None, None, 64, None) == -1
+    assert lib.eml_needlet_sparsify(None, 1, 1, 1, None, 1, 0.1, None) == -1
+    assert lib.eml_gemm_bf16_splitk(None, None, 1, 64, None, 1, None, None, 4, 0, 1, 1, None) == -1
+    assert lib.eml_channel_stats(None, 4, 1, 4, None, None) == -1
+    assert lib.eml_extract_params(None, None, None, 1, 128, 256, 64, None, None, None, None, None, None) == -1
+    assert lib.eml_tonemap_hdr(None, None, None, 1, 1, 2.4, 50.0, 0.5, 1, 1, 0, None) == -1
+
+
 def test_state_dict_contract_matches_reference_names():
     import emlight_b200 as E
     from oracle.densenet_oracle import init_state_dict
