@@ -1,0 +1,142 @@
+"""Wire formats: the OpenEXR reader / writer against an independent implementation of the format — OpenCV's
+bundled OpenEXR library — through committed fixtures (`oracle/make_golden_exr.py`) and, when cv2 is importable, live in both
+directions; the parameter pickle of `RegressionNetwork/test.py:79-85` as `GenProjector/data.py:64-94` reads it.  Bit-exact."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from emlight_b200 import wire
+
+EXR_DIR = os.path.join(os.path.dirname(__file__), "golden", "exr")
+CODECS = ["none", "rle", "zips", "zip", "piz"]
+
+
+def _cv2():
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    return pytest.importorskip("cv2")
+
+
+@pytest.mark.parametrize("ptype", ["float", "half"])
+@pytest.mark.parametrize("codec", CODECS)
+def test_load_exr_matches_openexr_fixture(codec, ptype):
+    expected = np.load(os.path.join(EXR_DIR, "expected.npz"))[f"{codec}_{ptype}"]
+    got = wire.load_exr(os.path.join(EXR_DIR, f"{codec}_{ptype}.exr"))
+    assert got.dtype == np.float32 and got.shape == expected.shape == (37, 53, 3)
+    assert np.array_equal(got, expected)
+
+
+def test_read_exr_channels_keeps_stored_type():
+    ch = wire.read_exr_channels(os.path.join(EXR_DIR, "piz_half.exr"))
+    assert sorted(ch) == ["B", "G", "R"] and all(v.dtype == np.float16 for v in ch.values())
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 100), (16, 32), (17, 5), (128, 256)])
+def test_write_exr_round_trip_and_layout(tmp_path, shape):
+    rng = np.random.default_rng(sum(shape))
+    img = rng.lognormal(0.0, 1.5, shape + (3,)).astype(np.float32)
+    if shape[0] > 2:
+        img[1] = 0.0  # a compressible line next to incompressible ones
+    path = str(tmp_path / "out.exr")
+    wire.write_exr(path, img)
+    assert np.array_equal(wire.load_exr(path), img)
+    raw = open(path, "rb").read()
+    # what OpenEXR.Header(W, H) + writePixels produce (util.py:301-306): FLOAT B, G, R; ZIP; increasing Y
+    assert raw[:8] == bytes([0x76, 0x2F, 0x31, 0x01, 2, 0, 0, 0])
+    i = raw.index(b"compression\0compression\0")
+    assert raw[i + 24:i + 29] == b"\x01\0\0\0\x03"
+    ch = wire.read_exr_channels(path)
+    assert list(ch) == ["B", "G", "R"] and all(v.dtype == np.float32 for v in ch.values())
+
+
+def test_write_exr_accepts_float64_and_rejects_bad_shapes(tmp_path):
+    img = np.linspace(0, 5, 4 * 6 * 3).reshape(4, 6, 3)
+    wire.write_exr(str(tmp_path / "d.exr"), img)
+    assert np.array_equal(wire.load_exr(str(tmp_path / "d.exr")), img.astype(np.float32))
+    with pytest.raises(ValueError):
+        wire.write_exr(str(tmp_path / "bad.exr"), np.zeros((4, 6)))
+    with pytest.raises(ValueError):
+        wire.write_exr(str(tmp_path / "bad.exr"), np.zeros((0, 6, 3)))
+
+
+def test_load_exr_rejects_garbage_and_unsupported(tmp_path):
+    p = tmp_path / "x.exr"
+    p.write_bytes(b"not an exr file at all")
+    with pytest.raises(ValueError, match="magic"):
+        wire.load_exr(str(p))
+    good = open(os.path.join(EXR_DIR, "zip_float.exr"), "rb").read()
+    tiled = bytearray(good)
+    tiled[5] |= 0x02  # version flag 0x200: tiled
+    p.write_bytes(bytes(tiled))
+    with pytest.raises(ValueError, match="tiled"):
+        wire.load_exr(str(p))
+    lossy = bytearray(good)
+    i = good.index(b"compression\0compression\0")
+    lossy[i + 28] = 8  # DWAA
+    p.write_bytes(bytes(lossy))
+    with pytest.raises(ValueError, match="DWAA"):
+        wire.load_exr(str(p))
+    trunc = good[:len(good) - 40]
+    p.write_bytes(trunc)
+    with pytest.raises(Exception):
+        wire.load_exr(str(p))
+
+
+def test_openexr_library_reads_what_we_write(tmp_path):
+    cv2 = _cv2()
+    rng = np.random.default_rng(3)
+    for shape in [(128, 256), (33, 7)]:
+        img = rng.lognormal(0.0, 1.0, shape + (3,)).astype(np.float32)
+        img[::3] = np.round(img[::3])
+        path = str(tmp_path / "ours.exr")
+        wire.write_exr(path, img)
+        back = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+        assert back is not None and np.array_equal(back[:, :, ::-1], img)
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_we_read_what_the_openexr_library_writes(tmp_path, codec):
+    cv2 = _cv2()
+    flag = {"none": cv2.IMWRITE_EXR_COMPRESSION_NO, "rle": cv2.IMWRITE_EXR_COMPRESSION_RLE, "zips": cv2.IMWRITE_EXR_COMPRESSION_ZIPS,
+            "zip": cv2.IMWRITE_EXR_COMPRESSION_ZIP, "piz": cv2.IMWRITE_EXR_COMPRESSION_PIZ}[codec]
+    y, x = np.mgrid[0:128, 0:256]
+    pano = np.stack([np.exp(4 * np.cos(x / 40.0) * np.sin(y / 20.0)), (x + 2 * y) / 64.0, np.full(x.shape, 0.25)], -1).astype(np.float32)
+    for ptype in (cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_TYPE_HALF):
+        path = str(tmp_path / "theirs.exr")
+        assert cv2.imwrite(path, pano[:, :, ::-1], [cv2.IMWRITE_EXR_TYPE, ptype, cv2.IMWRITE_EXR_COMPRESSION, flag])
+        expected = cv2.imread(path, cv2.IMREAD_UNCHANGED)[:, :, ::-1]
+        assert np.array_equal(wire.load_exr(path), expected)
+
+
+def test_parametric_lights_pickle_contract(tmp_path):
+    torch = pytest.importorskip("torch")
+    N = 128
+    dist = torch.softmax(torch.randn(2, N), 1)
+    rgb = torch.rand(2, 3)
+    inten = torch.rand(2, 1)
+    path = str(tmp_path / "im.pickle")
+    # test.py:79-82 passes sample 0's heads
+    wire.save_parametric_lights(path, dist[0].view(N), rgb[0].view(3), inten[0])
+    with open(path, "rb") as handle:  # GenProjector/data.py:64-66 reads it with plain pickle.load
+        pkl = pickle.load(handle)
+    assert set(pkl) == {"distribution", "rgb_ratio", "intensity"}
+    assert pkl["distribution"].shape == (N,) and pkl["rgb_ratio"].shape == (3,) and pkl["intensity"].shape == ()
+    assert all(isinstance(v, np.ndarray) and v.dtype == np.float32 for v in pkl.values())
+    rec = wire.load_parametric_lights(path)
+    assert np.array_equal(rec["distribution"], dist[0].numpy()) and float(rec["intensity"]) == float(inten[0])
+    with pytest.raises(ValueError):
+        wire.save_parametric_lights(path, dist, rgb[0], inten[0])  # a whole batch is not one record
+    with open(path, "wb") as handle:
+        pickle.dump({"distribution": 1}, handle)
+    with pytest.raises(KeyError):
+        wire.load_parametric_lights(path)
+
+
+def test_dropin_util_exposes_exr_io():
+    import importlib.util
+    here = os.path.join(os.path.dirname(__file__), "..", "emlight_b200", "dropin", "util.py")
+    spec = importlib.util.spec_from_file_location("_dropin_util_wire", here)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.load_exr is wire.load_exr and mod.write_exr is wire.write_exr
