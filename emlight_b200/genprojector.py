@@ -488,6 +488,7 @@ class SPADEGenerator(nn.Module):
         self.opt = opt
         self.precision = precision
         self.use_cuda_graph = False      # replay the whole forward (hundreds of launches) as one CUDA graph per input shape
+        self.autograd = False            # opt-in: train-mode forward recorded on a tape so that .backward() works (gp_train.py)
         self._graphs = {}
         nf = opt.ngf
         self.sw = opt.crop_size // 32
@@ -507,6 +508,9 @@ class SPADEGenerator(nn.Module):
         # training mode = the reference's train-mode FORWARD (batch-statistic BatchNorm inside SPADE with running-stat update,
         # one spectral-norm power iteration per wrapped convolution); the output carries no autograd graph -- backward is not built
         _lib.require_cuda(input, crop)
+        if self.autograd and self.training and torch.is_grad_enabled():
+            from . import gp_train
+            return gp_train.run_with_tape(lambda tape: (gp_train.generator(tape, self, input, crop, True),), list(self.parameters()))[0]
         with torch.no_grad():
             if self.use_cuda_graph and not self.training:
                 from .graphs import graphed_call
@@ -848,6 +852,7 @@ class Pix2PixModel(nn.Module):
     def __init__(self, opt):
         super().__init__()
         self.opt = opt
+        self.autograd = False            # opt-in: loss dictionaries carry an autograd node (gp_train.py) so the trainer's .backward() works
         self.netG = SPADEGenerator(opt).cuda().eval()
         self.netD = MultiscaleDiscriminator(opt).cuda().eval() if opt.isTrain else None
         if opt.isTrain:
@@ -886,8 +891,21 @@ class Pix2PixModel(nn.Module):
         B = input.shape[0]
         return ([[_to_nchw(t[:B], c) for t, _, _, c in fl] for fl in feats], [[_to_nchw(t[B:], c) for t, _, _, c in fl] for fl in feats])
 
-    @torch.no_grad()
     def compute_generator_loss(self, input, crop, real_image, map):
+        if self.autograd and torch.is_grad_enabled():
+            from . import gp_train
+
+            def runner(tape):
+                fake = gp_train.generator(tape, self.netG, input, crop, self.netG.training)
+                return tuple(gp_train.generator_losses(tape, self, fake, input, real_image, map)) + (fake,)
+
+            outs = gp_train.run_with_tape(runner, list(self.netG.parameters()))
+            keys = ["GAN"] + ([] if self.opt.no_ganFeat_loss else ["GAN_Feat"]) + ["VGG", "COS"]
+            return dict(zip(keys, outs[:-1])), outs[-1]
+        with torch.no_grad():
+            return self._generator_loss_values(input, crop, real_image, map)
+
+    def _generator_loss_values(self, input, crop, real_image, map):
         fake_image = self.generate_fake(input, crop)
         B = input.shape[0]
         feats = self._discriminate_nhwc(input, fake_image, real_image)
@@ -898,8 +916,18 @@ class Pix2PixModel(nn.Module):
         G_losses["COS"] = cosine_loss(fake_image, real_image) * 5
         return G_losses, fake_image
 
-    @torch.no_grad()
     def compute_discriminator_loss(self, input, crop, real_image):
+        if self.autograd and torch.is_grad_enabled():
+            from . import gp_train
+            with torch.no_grad():
+                fake = self.generate_fake(input, crop).detach()
+            outs = gp_train.run_with_tape(lambda tape: tuple(gp_train.discriminator_losses(tape, self, fake, input, real_image)),
+                                          list(self.netD.parameters()))
+            return {"D_Fake": outs[0], "D_real": outs[1]}
+        with torch.no_grad():
+            return self._discriminator_loss_values(input, crop, real_image)
+
+    def _discriminator_loss_values(self, input, crop, real_image):
         fake_image = self.generate_fake(input, crop)
         B = input.shape[0]
         feats = self._discriminate_nhwc(input, fake_image, real_image)

@@ -1,0 +1,152 @@
+"""Device primitives of the GenProjector TRAINING path (`gp_train.py`), one function per kernel entry point of include/emlight_b200.h.
+
+Every function here launches hand-written CUDA through the C ABI on NHWC fp32 tensors `(B, H, W, pitch)` with `pitch = up4(C)`;
+nothing runs on the CPU.  They are kept in one namespace so that `tests/test_gp_train_cpu.py` can swap them for torch stand-ins and
+check the tape / backward algebra of `gp_train.py` against autograd of the oracle on a box without a GPU -- the product never does.
+The forward-only inference path (`genprojector.py`) does not go through this module.
+"""
+import torch
+
+from . import _lib
+from .genprojector import (_LUTS, _PackedConv, _bias_act, _conv_raw, _im2col, _nchw_to_nhwc, _pool, _reduce, _up4)  # noqa: F401
+
+PackedConv = _PackedConv
+
+
+def lut(kind, h, w, stride, device):
+    """(idx (P,9,4) int32, wgt (P,9,4) fp32, ho, wo): 'sphere' = SphereConv2D's tangent-plane bilinear taps, 'conv' = regular 3x3 pad 1."""
+    return _LUTS.get(kind, h, w, stride, device)
+
+
+def conv_raw(x, B, H, W, pc, lut_, bias_in, act, precision):
+    """(B,ho,wo,up4(O)) = Wk * S(act(x + bias_in)): LUT gather + tcgen05 GEMM (genprojector._conv_raw)."""
+    return _conv_raw(x, B, H, W, pc, lut_, bias_in, act, precision)
+
+
+def im2col(x, B, H, W, C, lut_, bias_in, act):
+    """fp32 operand A (B*ho*wo, 9*up4(C)) of the convolution above (recomputed in the backward for the weight gradient)."""
+    return _im2col(x, B, H, W, C, lut_, bias_in, act)[0]
+
+
+def bias_act(raw, bias, act, M, C):
+    return _bias_act(raw, bias, act, M, C)
+
+
+def pool(x, B, H, W, C, mode):
+    return _pool(x, B, H, W, C, mode)
+
+
+def nchw_to_nhwc(x, pitch):
+    return _nchw_to_nhwc(x, pitch)
+
+
+def loss_sum(mode, a, M, C, a_pitch, b=None, b_pitch=0, mask=None):
+    """float64 scalar tensor: eml_loss_reduce(mode) over M rows x C channels."""
+    acc = torch.zeros(1, dtype=torch.float64, device=a.device)
+    _reduce(acc, mode, a, M, C, a_pitch, b, b_pitch, mask)
+    return acc
+
+
+def instance_norm(raw, B, HW, C, lrelu):
+    out = torch.empty_like(raw)
+    _lib.check(_lib.load().eml_instance_norm(_lib.ptr(raw), raw.shape[-1], _lib.ptr(out), out.shape[-1], B, HW, C, 1e-5, int(lrelu),
+                                             _lib.stream_ptr()), "eml_instance_norm")
+    return out
+
+
+def channel_sums(x, M, C):
+    """(2, C) float64: per-channel sum and sum of squares over the M rows."""
+    sums = torch.zeros(2, C, dtype=torch.float64, device=x.device)
+    _lib.check(_lib.load().eml_channel_stats(_lib.ptr(x), x.shape[-1], M, C, _lib.ptr(sums), _lib.stream_ptr()), "eml_channel_stats")
+    return sums
+
+
+def spade_modulate(x, mean, inv, gb, bias_gamma, bias_beta, M, C, lrelu):
+    shape = x.shape[:-1] + (_up4(C),)
+    out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().eml_spade_modulate(_lib.ptr(x), x.shape[-1], _lib.ptr(mean.contiguous()), _lib.ptr(inv.contiguous()), _lib.ptr(gb),
+                                              gb.shape[-1], _lib.ptr(bias_gamma), _lib.ptr(bias_beta), _lib.ptr(out), out.shape[-1], M, C,
+                                              int(lrelu), _lib.stream_ptr()), "eml_spade_modulate")
+    return out
+
+
+def bias_residual(a, bias_a, r, bias_r, M, C):
+    shape = a.shape[:-1] + (_up4(C),)
+    out = torch.empty(shape, dtype=torch.float32, device=a.device)
+    _lib.check(_lib.load().eml_bias_residual(_lib.ptr(a), a.shape[-1], _lib.ptr(bias_a), _lib.ptr(r), r.shape[-1] if r is not None else 0,
+                                             _lib.ptr(bias_r), _lib.ptr(out), out.shape[-1], M, C, _lib.stream_ptr()), "eml_bias_residual")
+    return out
+
+
+def resize_nearest(x, x_pitch, Hi, Wi, Ho, Wo, C, B, src_is_nchw, out_pitch):
+    out = torch.zeros(B, Ho, Wo, out_pitch, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().eml_resize_nearest(_lib.ptr(x), x_pitch, Hi, Wi, _lib.ptr(out), out_pitch, Ho, Wo, C, B, int(src_is_nchw),
+                                              _lib.stream_ptr()), "eml_resize_nearest")
+    return out
+
+
+def resize_bilinear_nchw(x, Ho, Wo):
+    """(B,3,Hi,Wi) NCHW -> (B,Ho,Wo,4) NHWC, F.interpolate(mode='bilinear', align_corners=False)."""
+    B, C, Hi, Wi = x.shape
+    out = torch.zeros(B, Ho, Wo, _up4(C), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().eml_resize_bilinear_nchw(_lib.ptr(x.contiguous().float()), Hi, Wi, _lib.ptr(out), out.shape[-1], Ho, Wo, C, B,
+                                                    _lib.stream_ptr()), "eml_resize_bilinear_nchw")
+    return out
+
+
+def tanh_to_nchw(raw, bias, B, H, W, C, scale):
+    out = torch.empty(B, C, H, W, dtype=torch.float32, device=raw.device)
+    _lib.check(_lib.load().eml_tanh_to_nchw(_lib.ptr(raw), raw.shape[-1], _lib.ptr(bias), _lib.ptr(out), B, H * W, C, float(scale),
+                                            _lib.stream_ptr()), "eml_tanh_to_nchw")
+    return out
+
+
+def linear(a, w, bias):
+    """(M,N) = a (M,K) @ w (N,K)^T + bias: fp32 FFMA kernel (the encoder's fc)."""
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    _lib.check(_lib.load().eml_linear_fp32(_lib.ptr(a.contiguous()), _lib.ptr(w.contiguous()), _lib.ptr(bias), _lib.ptr(out), M, N, K,
+                                           _lib.stream_ptr()), "eml_linear_fp32")
+    return out
+
+
+def mm_nt(a, b, precision="bf16x3"):
+    """(M,N) fp32 = a (M,K) @ b (N,K)^T on the TMA-fed tcgen05 GEMM: `a` is split into bf16 hi/lo rows (eml_split_bf16), `b` is packed
+    as the resident operand in slices of <= 256 rows (eml_conv_pack_weights); short-and-deep products (few row tiles, long K -- the
+    weight gradients, K = pixels) take the split-K kernel so that every SM gets a piece."""
+    lib = _lib.load()
+    _lib.require_cuda(a, b)
+    a = a.contiguous().float()
+    b = b.contiguous().float()
+    M, K = a.shape
+    N = b.shape[0]
+    if b.shape[1] != K:
+        raise ValueError("mm_nt: inner dimensions differ (%d vs %d)" % (K, b.shape[1]))
+    st = _lib.stream_ptr()
+    if precision == "fp32":
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+        _lib.check(lib.eml_linear_fp32(_lib.ptr(a), _lib.ptr(b), None, _lib.ptr(out), M, N, K, st), "eml_linear_fp32(mm_nt %dx%dx%d)" % (M, N, K))
+        return out
+    Kp = (K + 63) // 64 * 64
+    split = precision == "bf16x3"
+    a_hi = torch.empty(M, Kp, dtype=torch.bfloat16, device=a.device)
+    a_lo = torch.empty_like(a_hi) if split else None
+    _lib.check(lib.eml_split_bf16(_lib.ptr(a), M, K, K, _lib.ptr(a_hi), _lib.ptr(a_lo), Kp, st), "eml_split_bf16")
+    pitch = _up4(N)
+    mtiles = (M + 127) // 128
+    ksplit = max(1, min(Kp // 64, 148 // mtiles))
+    deep = ksplit > 1 and Kp >= 2048
+    out = (torch.zeros if deep else torch.empty)(M, pitch, dtype=torch.float32, device=a.device)
+    prec = _lib.PRECISIONS[precision]
+    for n0 in range(0, N, 256):
+        rows = min(256, N - n0)
+        buf = torch.empty(lib.eml_conv_wpack_bytes(rows, K, 1), dtype=torch.uint8, device=a.device)
+        _lib.check(lib.eml_conv_pack_weights(_lib.ptr(b[n0:n0 + rows]), _lib.ptr(buf), rows, K, 1, st), "eml_conv_pack_weights(mm_nt)")
+        if deep:
+            _lib.check(lib.eml_gemm_bf16_splitk(_lib.ptr(a_hi), _lib.ptr(a_lo), M, Kp, _lib.ptr(buf), rows, None, _lib.ptr(out), pitch, n0,
+                                                prec, ksplit, st), "eml_gemm_bf16_splitk(%dx%dx%d)" % (M, rows, K))
+        else:
+            _lib.check(lib.eml_gemm_bf16(_lib.ptr(a_hi), _lib.ptr(a_lo), M, Kp, _lib.ptr(buf), rows, None, _lib.ptr(out), pitch, n0, prec, st),
+                       "eml_gemm_bf16(%dx%dx%d)" % (M, rows, K))
+    return out[:, :N] if pitch != N else out

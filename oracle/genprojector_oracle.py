@@ -77,8 +77,9 @@ def sn_weight(sd, prefix, upd=None):
     u, v = sd[prefix + ".weight_u"], sd[prefix + ".weight_v"]
     wm = w.reshape(w.shape[0], -1)
     if upd is not None:
-        v = F.normalize(torch.mv(wm.t(), u), dim=0, eps=1e-12)
-        u = F.normalize(torch.mv(wm, v), dim=0, eps=1e-12)
+        with torch.no_grad():              # like torch's SpectralNorm.compute_weight: u, v are constants of the autograd graph
+            v = F.normalize(torch.mv(wm.t(), u), dim=0, eps=1e-12)
+            u = F.normalize(torch.mv(wm, v), dim=0, eps=1e-12)
         upd[prefix + ".weight_u"], upd[prefix + ".weight_v"] = u, v
     sigma = torch.dot(u, torch.mv(wm, v))
     return w / sigma
