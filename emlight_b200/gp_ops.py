@@ -2,7 +2,8 @@
 
 Every function here launches hand-written CUDA through the C ABI on NHWC fp32 tensors `(B, H, W, pitch)` with `pitch = up4(C)`;
 nothing runs on the CPU.  They are kept in one namespace so that `tests/test_gp_train_cpu.py` can swap them for torch stand-ins and
-check the tape / backward algebra of `gp_train.py` against autograd of the oracle on a box without a GPU -- the product never does.
+check the tape / backward algebra of `gp_train.py` against torch autograd of the CPU restatement on a box without a GPU -- the product
+never does.
 The forward-only inference path (`genprojector.py`) does not go through this module.
 """
 import torch
@@ -150,3 +151,74 @@ def mm_nt(a, b, precision="bf16x3"):
             _lib.check(lib.eml_gemm_bf16(_lib.ptr(a_hi), _lib.ptr(a_lo), M, Kp, _lib.ptr(buf), rows, None, _lib.ptr(out), pitch, n0, prec, st),
                        "eml_gemm_bf16(%dx%dx%d)" % (M, rows, K))
     return out[:, :N] if pitch != N else out
+
+
+# ------------------------------------------------------------------------------------------------- adjoint kernels (csrc/gp_bwd.cu)
+def _fn(name):
+    return getattr(_lib.load(), name)
+
+
+def _st():
+    return _lib.stream_ptr()
+
+
+def col2im(dA, Cp, lut_, B, in_pixels):
+    """dx (B, in_pixels, Cp) = adjoint of the 4-tap gather applied to dA (B*out_pixels, 9*Cp)."""
+    idx, wgt, ho, wo = lut_
+    dA = dA.contiguous()
+    dx = torch.zeros(B, in_pixels, Cp, dtype=torch.float32, device=dA.device)
+    _lib.check(_fn("eml_col2im_lut")(_lib.ptr(dA), Cp, _lib.ptr(idx), _lib.ptr(wgt), _lib.ptr(dx), Cp, B, ho * wo, in_pixels, _st()),
+               "eml_col2im_lut")
+    return dx
+
+
+def act_bwd(dx, x, bias, act, M, C, want_sums):
+    """dx[..., :C] *= act'(x[..., :C] + bias) in place; returns the per-channel sums of the result (float64) when asked."""
+    sums = torch.zeros(C, dtype=torch.float64, device=dx.device) if want_sums else None
+    if act or want_sums:
+        _lib.check(_fn("eml_act_bwd")(_lib.ptr(dx), dx.shape[-1], _lib.ptr(x), x.shape[-1] if x is not None else 0, _lib.ptr(bias), int(act), M,
+                                      C, _lib.ptr(sums), _st()), "eml_act_bwd")
+    return sums
+
+
+def bias_act_bwd(g, out, act, M, C, want_sums):
+    g = g.contiguous()
+    dx = torch.zeros_like(out)
+    sums = torch.zeros(C, dtype=torch.float64, device=out.device) if want_sums else None
+    _lib.check(_fn("eml_bias_act_bwd")(_lib.ptr(g), g.shape[-1], _lib.ptr(out), out.shape[-1], int(act), _lib.ptr(dx), dx.shape[-1], M, C,
+                                       _lib.ptr(sums), _st()), "eml_bias_act_bwd")
+    return dx, sums
+
+
+def spade_bwd(g, out, x, mean, inv, gb, bias_gamma, M, C, lrelu):
+    """(d_gb like gb, d_xhat like x, sums (4,C) float64 = [d bias_gamma, d bias_beta, sum d_xhat, sum d_xhat*xhat])."""
+    g = g.contiguous()
+    d_gb = torch.zeros_like(gb)
+    d_xhat = torch.zeros_like(x)
+    sums = torch.zeros(4, C, dtype=torch.float64, device=x.device)
+    _lib.check(_fn("eml_spade_bwd")(_lib.ptr(g), g.shape[-1], _lib.ptr(out), out.shape[-1], _lib.ptr(x), x.shape[-1], _lib.ptr(mean.contiguous()),
+                                    _lib.ptr(inv.contiguous()), _lib.ptr(gb), gb.shape[-1], _lib.ptr(bias_gamma), _lib.ptr(d_gb), _lib.ptr(d_xhat),
+                                    d_xhat.shape[-1], M, C, int(lrelu), _lib.ptr(sums), _st()), "eml_spade_bwd")
+    return d_gb, d_xhat, sums
+
+
+def bn_free_bwd(d_xhat, x, mean, inv, sums2, count, M, C):
+    """dx like d_xhat: batch-statistic mode with sums2 (2,C) float64, running-statistic mode with sums2 None."""
+    dx = torch.zeros_like(d_xhat)
+    if sums2 is not None:
+        sums2 = sums2.contiguous()
+        mean = mean.contiguous()
+    _lib.check(_fn("eml_bn_free_bwd")(_lib.ptr(d_xhat), d_xhat.shape[-1], _lib.ptr(x) if sums2 is not None else None,
+                                      x.shape[-1] if sums2 is not None else 0, _lib.ptr(mean) if sums2 is not None else None,
+                                      _lib.ptr(inv.contiguous()), _lib.ptr(sums2), float(count), _lib.ptr(dx), dx.shape[-1], M, C, _st()),
+               "eml_bn_free_bwd")
+    return dx
+
+
+def instance_norm_bwd(g, out, raw, B, HW, C, lrelu, eps=1e-5):
+    g = g.contiguous()
+    sums = torch.zeros(B, 4, C, dtype=torch.float64, device=out.device)
+    dx = torch.zeros_like(raw)
+    _lib.check(_fn("eml_instance_norm_bwd")(_lib.ptr(g), g.shape[-1], _lib.ptr(out), out.shape[-1], _lib.ptr(raw), raw.shape[-1], B, HW, C,
+                                            float(eps), int(lrelu), _lib.ptr(sums), _lib.ptr(dx), dx.shape[-1], _st()), "eml_instance_norm_bwd")
+    return dx

@@ -10,15 +10,17 @@ Split of work in this first version:
 * all contractions -- forward convolutions, data gradients `dA = dY Wk`, weight gradients `dWk^T = A^T dY` (K = pixels, split-K) --
   run on the TMA-fed tcgen05 GEMM through `gp_ops.mm_nt` / `gp_ops.conv_raw`; the im2col operand of the weight gradient is
   recomputed with the forward's gather kernel instead of being stored;
-* the gather's adjoint (col2im through the sampling table), the element-wise adjoints and the per-channel reductions are written with
-  device-agnostic torch tensor ops on the same NHWC buffers (ATen kernels on the GPU) -- they are the next thing to move into
-  `csrc/spade_ops.cu`.
+* the gather's adjoint (col2im through the sampling table), activation / bias, SPADE modulation, parameter-free BatchNorm and
+  InstanceNorm adjoints are the kernels of `csrc/gp_bwd.cu` (`gp_ops.col2im`, `act_bwd`, `bias_act_bwd`, `spade_bwd`, `bn_free_bwd`,
+  `instance_norm_bwd`);
+* the remaining glue -- nearest-upsample / latent / tanh adjoints, the two pooling adjoints (through ATen's own pooling backward),
+  loss seeds, batch slicing and layout permutes -- is device-agnostic torch tensor code on the same NHWC buffers.
 Semantics follow the reference's modules in `.train()`: batch-statistic (Sync)BatchNorm inside SPADE with the running-stat update and
 one all-reduce of the per-channel sums when several processes share the batch (forward AND backward), one spectral-norm power
 iteration per wrapped convolution per forward with `u`, `v` treated as constants in the backward (torch.nn.utils.spectral_norm).
 
-STATUS: the algebra is checked on CPU against autograd of the oracle (`tests/test_gp_train_cpu.py`, torch stand-ins for the
-primitives); the B200 run of `tests/test_gp_train_gpu.py` is pending (round-1 GPU budget was spent before this landed), so the path is
+STATUS: the algebra is checked on CPU against torch autograd of the reference restatement (`tests/test_gp_train_cpu.py`: torch
+stand-ins for the forward primitives, the adjoint kernels through their host-emulation build); the B200 run of `tests/test_gp_train_gpu.py` is pending (round-1 GPU budget was spent before this landed), so the path is
 opt-in: `SPADEGenerator.autograd = True` / `Pix2PixModel.autograd = True`.
 """
 import torch
@@ -159,23 +161,13 @@ def conv(tape, x, B, H, W, C, w_eff, lut, bias_in, bias_in_param, act, precision
             return
         wk_t = pc.wk[:, :9 * Cp].t().contiguous()                                             # (9 Cp, O)
         dA = ops.mm_nt(g2, wk_t, precision)                                                   # (M, 9 Cp)
-        dxa = torch.zeros(B, H * W, Cp, dtype=torch.float32, device=x.device)
-        dA3 = dA.reshape(B, ho * wo * 9, Cp)
-        for t in range(4):                                                                    # adjoint of the 4-tap gather
-            w_t = wgt[:, :, t].reshape(-1)
-            if not bool((w_t != 0).any()):
-                continue
-            dxa.index_add_(1, idx[:, :, t].reshape(-1).clamp_min(0).long(), dA3 * w_t.view(1, -1, 1))
-        dx = dxa[..., :C].reshape(B, H, W, C)
-        if act or bias_in is not None:
-            u = x[..., :C] if bias_in is None else x[..., :C] + bias_in
-            m = _act_grad(u, act)
-            if m is not None:
-                dx = dx * m
+        dx = ops.col2im(dA, Cp, lut, B, H * W).reshape(B, H, W, Cp)                          # adjoint of the 4-tap gather
+        del dA
+        sums = ops.act_bwd(dx, x, bias_in, act, B * H * W, C, need_b)                         # dx *= act'(x + bias_in), sum per channel
         if need_b:
-            tape.add_param(bias_in_param, dx.sum((0, 1, 2)))
+            tape.add_param(bias_in_param, sums.float())
         if need_dx:
-            tape.add(x, _pad_c(dx, x.shape[-1]))
+            tape.add(x, dx if x.shape[-1] == Cp else _pad_c(dx[..., :C], x.shape[-1]))
 
     tape.record(bwd)
     return raw, ho, wo
@@ -188,13 +180,11 @@ def bias_act(tape, raw, bias, act, B, H, W, C):
         g = tape.take(out)
         if g is None:
             return
-        g = g[..., :C]
-        if act == 1:
-            g = g * (out[..., :C] > 0)
-        elif act == 2:
-            g = g * torch.where(out[..., :C] > 0, 1.0, _LRELU)
-        tape.add_param(bias, g.sum((0, 1, 2)))
-        tape.add(raw, _pad_c(g, raw.shape[-1]))
+        need_b = bias is not None and bias.requires_grad
+        dx, sums = ops.bias_act_bwd(g, out, act, B * H * W, C, need_b)
+        if need_b:
+            tape.add_param(bias, sums.float())
+        tape.add(raw, dx)
 
     tape.record(bwd)
     return out
@@ -207,17 +197,7 @@ def instance_norm(tape, raw, B, H, W, C, lrelu=True, eps=1e-5):
         g = tape.take(out)
         if g is None:
             return
-        g = g[..., :C]
-        o = out[..., :C]
-        if lrelu:
-            g = g * torch.where(o > 0, 1.0, _LRELU)
-            xhat = torch.where(o > 0, o, o / _LRELU)
-        else:
-            xhat = o
-        var = raw[..., :C].var((1, 2), unbiased=False, keepdim=True)
-        inv = torch.rsqrt(var + eps)
-        dx = inv * (g - g.mean((1, 2), keepdim=True) - xhat * (g * xhat).mean((1, 2), keepdim=True))
-        tape.add(raw, _pad_c(dx, raw.shape[-1]))
+        tape.add(raw, ops.instance_norm_bwd(g, out, raw, B, H * W, C, lrelu, eps))
 
     tape.record(bwd)
     return out
@@ -270,28 +250,22 @@ def spade(tape, mod, x, B, H, W, seg, x_bias, lrelu, precision, training):
         g = tape.take(out)
         if g is None:
             return
-        g = g[..., :C]
-        if lrelu:
-            g = g * torch.where(out[..., :C] > 0, 1.0, _LRELU)
-        xhat = (x[..., :C] - mean) * inv
-        gxh = g * xhat
-        d_gb = torch.zeros_like(gb)
-        d_gb[..., :C] = gxh
-        d_gb[..., C:2 * C] = g
+        d_gb, d_xhat, sums = ops.spade_bwd(g, out, x, mean, inv, gb, gamma.bias.detach(), M, C, lrelu)
         tape.add(gb, d_gb)
-        tape.add_param(gamma.bias, gxh.sum((0, 1, 2)))
-        tape.add_param(beta.bias, g.sum((0, 1, 2)))
-        d_xhat = g * (1.0 + gb[..., :C] + gamma.bias.detach())
+        tape.add_param(gamma.bias, sums[0].float())
+        tape.add_param(beta.bias, sums[1].float())
         if training:
-            s = torch.stack([d_xhat.sum((0, 1, 2), dtype=torch.float64), (d_xhat * xhat).sum((0, 1, 2), dtype=torch.float64)])
+            s2 = sums[2:4].clone()
             if _world() > 1:
-                torch.distributed.all_reduce(s)
-            dx = inv * (d_xhat - (s[0] / n).float() - xhat * (s[1] / n).float())
+                torch.distributed.all_reduce(s2)
+            dx = ops.bn_free_bwd(d_xhat, x, mean, inv, s2, n, M, C)
+            if x_bias is not None:                                  # a shift in front of a batch-statistic BatchNorm cancels exactly
+                tape.add_param(x_bias, torch.zeros_like(x_bias))
         else:
-            dx = inv * d_xhat
-        if x_bias is not None:
-            tape.add_param(x_bias, dx.sum((0, 1, 2)))
-        tape.add(x, _pad_c(dx, x.shape[-1]))
+            dx = ops.bn_free_bwd(d_xhat, None, None, inv, None, 0.0, M, C)
+            if x_bias is not None:
+                tape.add_param(x_bias, (inv.double() * sums[2]).float())
+        tape.add(x, dx)
 
     tape.record(bwd)
     return out
@@ -306,7 +280,7 @@ def bias_residual(tape, a, bias_a, r, bias_r, B, H, W, C):
         if g is None:
             return
         gc = g[..., :C]
-        s = gc.sum((0, 1, 2))
+        s = ops.channel_sums(g.contiguous(), B * H * W, C)[0].float() if (bias_a is not None or bias_r is not None) else None
         if bias_a is not None:
             tape.add_param(bias_a, s)
         if bias_r is not None:

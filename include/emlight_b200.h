@@ -273,6 +273,39 @@ int eml_wgrad_3x3(const float *dY, int dy_pitch, int N, const float *b, int b_pi
                   float *dW, int B, int H, int W, int precision, void *stream);
 int eml_wgrad_stem(const float *dZ, int dz_pitch, int O, const float *x_nchw, float *dW, int B, int H, int W, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * G1-G6 backward -- adjoints used by the GenProjector training steps (pix2pix_model.py:92-141 -> trainers' loss.backward()).
+ * The contractions (data gradient dA = dY Wk, weight gradient dWk^T = A^T dY) are eml_gemm_bf16[_splitk] on operands prepared with
+ * eml_split_bf16 / eml_conv_pack_weights / eml_im2col_lut; these entry points are the HBM-bound passes around them.  Per-channel
+ * sums are accumulated in double into caller-zeroed buffers.
+ *
+ * eml_col2im_lut: adjoint of the eml_im2col_lut gather (sphere_cnn.py:111-124 grid_sample backward):
+ *     dx[b, lut_idx[p,tap,t], c] += lut_w[p,tap,t] * dA[b*out_pixels + p, tap*Cp + c]      (float atomics; dx ZERO on entry)
+ * eml_act_bwd: dx *= act'(x + bias) in place (the activation eml_im2col_lut applies before gathering), bias_sums[c] += sum_m dx
+ *     (act 0 with bias_sums != NULL: only the sums).
+ * eml_bias_act_bwd: adjoint of eml_bias_act from its OUTPUT: dx = g * act'(out), bias_sums[c] += sum_m dx.
+ * eml_spade_bwd: adjoint of eml_spade_modulate (normalization.py:101-115): with g' = g * lrelu'(out), xhat = (x - mean) * inv_std
+ *     d_gb[:, c] = g' * xhat, d_gb[:, C + c] = g' (same pitch as gamma_beta), d_xhat = g' * (1 + gamma + bias_gamma),
+ *     sums (4, C) += [sum g' xhat (d bias_gamma), sum g' (d bias_beta), sum d_xhat, sum d_xhat * xhat].
+ * eml_bn_free_bwd: parameter-free BatchNorm backward (normalization.py:80,104): dx = inv_std * (d_xhat - s0/count - xhat * s1/count)
+ *     with sums = (2, C) [sum d_xhat, sum d_xhat * xhat] (all-reduced by the caller when several processes share the batch);
+ *     sums == NULL: running-statistics mode, dx = inv_std * d_xhat.
+ * eml_instance_norm_bwd: adjoint of eml_instance_norm (InstanceNorm2d(affine=False) + optional LeakyReLU) from its output and raw
+ *     input; `sums` is a caller-zeroed (B, 4, C) double scratch. */
+int eml_col2im_lut(const float *dA, int Cp, const int *lut_idx, const float *lut_w, float *dx, int dx_pitch, int B, long out_pixels,
+                   long in_pixels, void *stream);
+int eml_act_bwd(float *dx, int dx_pitch, const float *x, int x_pitch, const float *bias, int act, long M, int C, double *bias_sums,
+                void *stream);
+int eml_bias_act_bwd(const float *g, int g_pitch, const float *out, int out_pitch, int act, float *dx, int dx_pitch, long M, int C,
+                     double *bias_sums, void *stream);
+int eml_spade_bwd(const float *g, int g_pitch, const float *out, int out_pitch, const float *x, int x_pitch, const float *mean,
+                  const float *inv_std, const float *gamma_beta, int gb_pitch, const float *bias_gamma, float *d_gb, float *d_xhat,
+                  int dxh_pitch, long M, int C, int leaky_relu, double *sums, void *stream);
+int eml_bn_free_bwd(const float *d_xhat, int dxh_pitch, const float *x, int x_pitch, const float *mean, const float *inv_std,
+                    const double *sums, double count, float *dx, int dx_pitch, long M, int C, void *stream);
+int eml_instance_norm_bwd(const float *g, int g_pitch, const float *out, int out_pitch, const float *raw, int raw_pitch, int B, long HW,
+                          int C, float eps, int leaky_relu, double *sums, float *dx, int dx_pitch, void *stream);
+
 /* G6-G7 -- discriminator / loss building blocks (NHWC fp32).
  * eml_bias_act: out = act(x + bias[c]) (act 0 none, 1 ReLU, 2 LeakyReLU(0.2)); discriminator.py:91-92, VGG conv+ReLU.
  * eml_pool2d : mode 0 = avg_pool2d(3, stride 2, pad 1, count_include_pad=False) (discriminator.py:48-51), mode 1 = max_pool2d(2,2) (VGG19).

@@ -1,5 +1,6 @@
-"""CPU check of the GenProjector training tape (`emlight_b200/gp_train.py`): every device primitive of `gp_ops` is replaced by a torch
-stand-in that restates the kernel's contract from include/emlight_b200.h, and the gradients the tape produces are compared with
+"""CPU check of the GenProjector training tape (`emlight_b200/gp_train.py`): every FORWARD device primitive of `gp_ops` is replaced by a
+torch stand-in that restates the kernel's contract from include/emlight_b200.h, the ADJOINT kernels of csrc/gp_bwd.cu run as
+themselves through their host emulation build (see tests/test_gp_bwd_emulated.py), and the gradients the tape produces are compared with
 torch autograd through the oracle (`oracle/genprojector_oracle.py`, the reference's modules restated functionally).  This pins the
 backward ALGEBRA (adjoint of the sampling-table gather, SPADE / batch-statistic BatchNorm / InstanceNorm / spectral-norm adjoints,
 loss seeds, gradient routing through the [fake; real] batches); the same tape on the real kernels is `tests/test_gp_train_gpu.py`."""
@@ -130,9 +131,30 @@ def sim_tanh_to_nchw(raw, bias, B, H, W, C, scale):
     return ((torch.tanh(raw[..., :C] + bias) + 1) * scale).permute(0, 3, 1, 2).contiguous()
 
 
+@pytest.fixture(scope="module")
+def emu_lib(tmp_path_factory):
+    """csrc/gp_bwd.cu compiled for the host (EML_EMULATE): the adjoint KERNELS themselves run inside these tests."""
+    import ctypes
+    import os
+    import subprocess
+    from emlight_b200 import _lib
+    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "emlight_b200", "csrc", "gp_bwd.cu")
+    out = str(tmp_path_factory.mktemp("emu") / "libgp_bwd_emu.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DEML_EMULATE", "-x", "c++", src, "-o", out])
+    lib = ctypes.CDLL(out)
+    fns = {}
+    for name in ("eml_col2im_lut", "eml_act_bwd", "eml_bias_act_bwd", "eml_spade_bwd", "eml_bn_free_bwd", "eml_instance_norm_bwd"):
+        fn = getattr(lib, name + "_emu")
+        fn.restype, fn.argtypes = _lib.SIGNATURES[name]
+        fns[name] = fn
+    return fns
+
+
 @pytest.fixture()
-def sim(monkeypatch):
+def sim(monkeypatch, emu_lib):
     from emlight_b200 import gp_ops
+    monkeypatch.setattr(gp_ops, "_fn", lambda name: emu_lib[name])
+    monkeypatch.setattr(gp_ops, "_st", lambda: None)
     for name, fn in dict(PackedConv=SimPackedConv, conv_raw=sim_conv_raw, im2col=sim_im2col, bias_act=sim_bias_act, pool=sim_pool,
                          nchw_to_nhwc=sim_nchw_to_nhwc, loss_sum=sim_loss_sum, instance_norm=sim_instance_norm,
                          channel_sums=sim_channel_sums, spade_modulate=sim_spade_modulate, bias_residual=sim_bias_residual,
