@@ -143,3 +143,57 @@ def test_pix2pix_trainer_steps(cuda):
         sum(v.sum() for v in d_losses.values()).backward()
         assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.netD.parameters())
         od.step()
+
+
+def test_adjoint_kernels_match_their_host_emulation(cuda, lib, tmp_path):
+    """csrc/gp_bwd.cu on the GPU against the SAME source compiled for the host (g++ -DEML_EMULATE, tests/test_gp_bwd_emulated.py pins
+    that build against autograd): col2im with real atomics, column-worker reductions at a size that fills the machine."""
+    import ctypes
+    import subprocess
+    from ctypes import c_void_p
+    from emlight_b200 import _lib
+    from emlight_b200.genprojector import _sphere_lut
+    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "emlight_b200", "csrc", "gp_bwd.cu")
+    so = str(tmp_path / "libgp_bwd_emu.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DEML_EMULATE", "-x", "c++", src, "-o", so])
+    emu = ctypes.CDLL(so)
+
+    def both(name, args_cpu):
+        fe = getattr(emu, name + "_emu")
+        fe.restype, fe.argtypes = _lib.SIGNATURES[name]
+        cpu = [a.clone() if torch.is_tensor(a) else a for a in args_cpu]
+        gpu = [a.to(cuda) if torch.is_tensor(a) else a for a in args_cpu]
+        P = lambda a: (c_void_p(a.data_ptr()) if torch.is_tensor(a) else a)
+        assert fe(*[P(a) for a in cpu], None) == 0
+        _lib.check(getattr(lib, name)(*[P(a) for a in gpu], _lib.stream_ptr()), name)
+        torch.cuda.synchronize()
+        return cpu, [a.cpu() if torch.is_tensor(a) else a for a in gpu]
+
+    gen = torch.Generator().manual_seed(0)
+    h, w, C, B = 32, 64, 12, 3
+    idx, wgt, ho, wo = _sphere_lut(h, w, 1)
+    idx, wgt = torch.from_numpy(idx).contiguous(), torch.from_numpy(wgt).contiguous()
+    dA = torch.randn(B * ho * wo, 9 * C, generator=gen)
+    c, g = both("eml_col2im_lut", [dA, C, idx, wgt, torch.zeros(B, h * w, C), C, B, ho * wo, h * w])
+    assert float((c[4] - g[4]).abs().max()) <= 1e-4 * float(c[4].abs().max())
+    M, C = 70000, 36
+    x, gr = torch.randn(M, C, generator=gen), torch.randn(M, C, generator=gen)
+    bias = torch.randn(C, generator=gen)
+    c, g = both("eml_act_bwd", [gr, C, x, C, bias, 2, M, C, torch.zeros(C, dtype=torch.float64)])
+    assert torch.equal(c[0], g[0]) and torch.allclose(c[8], g[8], rtol=1e-9, atol=1e-9)
+    c, g = both("eml_bias_act_bwd", [gr, C, x, C, 1, torch.zeros(M, C), C, M, C, torch.zeros(C, dtype=torch.float64)])
+    assert torch.equal(c[5], g[5]) and torch.allclose(c[9], g[9], rtol=1e-9, atol=1e-9)
+    mean, inv = x.mean(0).contiguous(), torch.rsqrt(x.var(0, unbiased=False) + 1e-5).contiguous()
+    gb = torch.randn(M, 2 * C, generator=gen) * 0.3
+    out = torch.randn(M, C, generator=gen)
+    c, g = both("eml_spade_bwd", [gr, C, out, C, x, C, mean, inv, gb, 2 * C, bias, torch.zeros(M, 2 * C), torch.zeros(M, C), C, M, C, 1,
+                                  torch.zeros(4, C, dtype=torch.float64)])
+    assert torch.allclose(c[11], g[11], atol=1e-6) and torch.allclose(c[12], g[12], atol=1e-6) and torch.allclose(c[17], g[17], rtol=1e-9, atol=1e-7)
+    sums2 = c[17][2:].contiguous()
+    c2, g2 = both("eml_bn_free_bwd", [c[12], C, x, C, mean, inv, sums2, float(M), torch.zeros(M, C), C, M, C])
+    assert torch.allclose(c2[8], g2[8], atol=1e-6)
+    Bn, HW, C = 4, 4096, 20
+    raw, gi = torch.randn(Bn, HW, C, generator=gen) * 2, torch.randn(Bn, HW, C, generator=gen)
+    o = torch.nn.functional.leaky_relu((raw - raw.mean(1, keepdim=True)) * torch.rsqrt(raw.var(1, unbiased=False, keepdim=True) + 1e-5), 0.2).contiguous()
+    c, g = both("eml_instance_norm_bwd", [gi, C, o, C, raw, C, Bn, HW, C, 1e-5, 1, torch.zeros(Bn, 4, C, dtype=torch.float64), torch.zeros(Bn, HW, C), C])
+    assert torch.allclose(c[12], g[12], atol=1e-5)
