@@ -5,3 +5,5 @@ OpenEXR bindings)."""
 from emlight_b200.panorama import convert_to_panorama, sphere_points  # noqa: F401
 from emlight_b200.tonemap import TonemapHDR  # noqa: F401
 from emlight_b200.wire import load_exr, write_exr  # noqa: F401
+from emlight_b200.handlers import (PanoramaHandler, cartesian_to_polar, polar_to_cartesian, print_model_parm_nums,  # noqa: F401
+                                   tonemapping)
