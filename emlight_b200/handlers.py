@@ -4,7 +4,7 @@
 These are the callers' data-preparation utilities (numpy on the host, as in the reference), restated so that the module-name shim
 `dropin/util.py` satisfies every name those scripts import; file reading goes through `emlight_b200.wire` (no OpenEXR / Imath), and
 `tonemapping` -- the same arithmetic as `TonemapHDR(2.4, 99, 0.8)` -- runs on the tonemap kernel.  Pinned against the reference's own
-code (exec'd from util.py:69-220) by `oracle/make_golden_handlers.py` -> `tests/golden/handlers.npz`.
+code (exec'd from util.py:69-220) through `tests/golden/handlers.npz` (`tests/test_handlers_cpu.py`).
 """
 import numpy as np
 
