@@ -131,15 +131,14 @@ def sim_tanh_to_nchw(raw, bias, B, H, W, C, scale):
     return ((torch.tanh(raw[..., :C] + bias) + 1) * scale).permute(0, 3, 1, 2).contiguous()
 
 
-@pytest.fixture(scope="module")
-def emu_lib(tmp_path_factory):
+def build_emu(outdir):
     """csrc/gp_bwd.cu compiled for the host (EML_EMULATE): the adjoint KERNELS themselves run inside these tests."""
     import ctypes
     import os
     import subprocess
     from emlight_b200 import _lib
     src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "emlight_b200", "csrc", "gp_bwd.cu")
-    out = str(tmp_path_factory.mktemp("emu") / "libgp_bwd_emu.so")
+    out = os.path.join(str(outdir), "libgp_bwd_emu.so")
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DEML_EMULATE", "-x", "c++", src, "-o", out])
     lib = ctypes.CDLL(out)
     fns = {}
@@ -150,18 +149,27 @@ def emu_lib(tmp_path_factory):
     return fns
 
 
-@pytest.fixture()
-def sim(monkeypatch, emu_lib):
-    from emlight_b200 import gp_ops
-    monkeypatch.setattr(gp_ops, "_fn", lambda name: emu_lib[name])
-    monkeypatch.setattr(gp_ops, "_st", lambda: None)
+def install_sims(gp_ops, emu_fns, setter=setattr):
+    setter(gp_ops, "_fn", lambda name: emu_fns[name])
+    setter(gp_ops, "_st", lambda: None)
     for name, fn in dict(PackedConv=SimPackedConv, conv_raw=sim_conv_raw, im2col=sim_im2col, bias_act=sim_bias_act, pool=sim_pool,
                          nchw_to_nhwc=sim_nchw_to_nhwc, loss_sum=sim_loss_sum, instance_norm=sim_instance_norm,
                          channel_sums=sim_channel_sums, spade_modulate=sim_spade_modulate, bias_residual=sim_bias_residual,
                          resize_nearest=sim_resize_nearest, resize_bilinear_nchw=sim_resize_bilinear_nchw,
                          tanh_to_nchw=sim_tanh_to_nchw, linear=lambda a, w, b: a @ w.t() + b,
                          mm_nt=lambda a, b, precision="bf16x3": a @ b.t()).items():
-        monkeypatch.setattr(gp_ops, name, fn)
+        setter(gp_ops, name, fn)
+
+
+@pytest.fixture(scope="module")
+def emu_lib(tmp_path_factory):
+    return build_emu(tmp_path_factory.mktemp("emu"))
+
+
+@pytest.fixture()
+def sim(monkeypatch, emu_lib):
+    from emlight_b200 import gp_ops
+    install_sims(gp_ops, emu_lib, monkeypatch.setattr)
     from emlight_b200 import gp_train
     return gp_train
 
