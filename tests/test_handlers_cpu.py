@@ -80,3 +80,39 @@ def test_dataset_discovers_pairs_like_the_reference(tmp_path):
         wire.write_exr(str(tmp_path / "crop" / (nm + ".exr")), np.ones((6, 8, 3), np.float32))
     ds = mod.ParameterDataset(str(tmp_path) + "/", device="cpu")
     assert len(ds) == 2 and [os.path.basename(p[0]) for p in ds.pairs] == ["a.exr", "c.exr"]
+
+
+def test_genprojector_dataset_paths_and_mask(tmp_path):
+    """GenProjector/data.py:40-57 pairing (pickle <-> warped panorama) and :75-80 light mask; items need the GPU (gpu test)."""
+    import argparse
+    import importlib.util
+    here = os.path.join(os.path.dirname(__file__), "..", "emlight_b200", "dropin_genprojector", "data.py")
+    spec = importlib.util.spec_from_file_location("_dropin_gp_data", here)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for d in ("pkl", "warped", "crop"):
+        os.makedirs(tmp_path / d)
+    for nm in ("x", "y"):
+        with open(tmp_path / "pkl" / (nm + ".pickle"), "wb") as f:
+            pickle.dump({"distribution": np.ones(128, np.float32) / 128}, f)
+    wire.write_exr(str(tmp_path / "warped" / "y.exr"), np.ones((4, 8, 3), np.float32))
+    ds = mod.LavalIndoorDataset(argparse.Namespace(dataroot=str(tmp_path)))
+    assert len(ds) == 1 and ds.pairs[0][1].endswith("warped/y.exr")
+    hdr = np.zeros((4, 8, 3), np.float32)
+    hdr[1, 2] = (10, 10, 10)
+    hdr[3, 3] = (0.6, 0.6, 0.6)                 # above 5 % of the maximum
+    hdr[0, 0] = (0.4, 0.4, 0.4)                 # below
+    m = mod.light_mask(hdr)
+    assert m.shape == (1, 4, 8) and m.sum() == 2 and m[0, 1, 2] == 1 and m[0, 3, 3] == 1
+    loader = mod.create_dataloader(argparse.Namespace(dataroot=str(tmp_path), batchSize=1, serial_batches=True, isTrain=False))
+    assert len(loader) == 1
+
+
+def test_genprojector_util_shim_names():
+    import importlib.util
+    here = os.path.join(os.path.dirname(__file__), "..", "emlight_b200", "dropin_genprojector", "util.py")
+    spec = importlib.util.spec_from_file_location("_dropin_gp_util", here)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for name in ("TonemapHDR", "load_exr", "write_exr", "sphere_points", "convert_to_panorama", "tonemapping", "PanoramaHandler"):
+        assert hasattr(mod, name), name

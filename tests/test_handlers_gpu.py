@@ -47,3 +47,40 @@ def test_dataset_items_and_tonemapping(cuda, tmp_path):
     assert batch["crop"].shape == (1, 3, 48, 64)
     tm = handlers.tonemapping(crop)
     assert isinstance(tm, np.ndarray) and np.abs(tm - _np_tonemap(crop, 99, 0.8)[0]).max() <= 1e-5
+
+
+def test_genprojector_dataset_item(cuda, tmp_path):
+    """LavalIndoorDataset item against GenProjector/data.py:59-107 restated with the render oracle."""
+    import argparse
+    import emlight_b200 as E
+    from emlight_b200 import wire
+    from oracle import render_oracle as RO
+    here = os.path.join(os.path.dirname(__file__), "..", "emlight_b200", "dropin_genprojector", "data.py")
+    spec = importlib.util.spec_from_file_location("_dropin_gp_data_gpu", here)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(2)
+    for d in ("pkl", "warped", "crop"):
+        os.makedirs(tmp_path / d)
+    crop = np.exp(rng.normal(-1, 1, (96, 128, 3))).astype(np.float32)
+    pano = np.exp(rng.normal(-2, 1, (128, 256, 3))).astype(np.float32)
+    pano[20:24, 100:110] += 300
+    dist = rng.random(128).astype(np.float32)
+    dist /= dist.sum()
+    pkl = {"distribution": dist, "intensity": np.float32(420.0), "rgb_ratio": np.array([0.6, 0.6, 0.52], np.float32),
+           "ambient": np.array([900.0, 800.0, 700.0], np.float32)}
+    wire.write_exr(str(tmp_path / "crop" / "s.exr"), crop)
+    wire.write_exr(str(tmp_path / "warped" / "s.exr"), pano)
+    with open(tmp_path / "pkl" / "s.pickle", "wb") as f:
+        pickle.dump(pkl, f)
+    item = mod.LavalIndoorDataset(argparse.Namespace(dataroot=str(tmp_path)))[0]
+    _, alpha = _np_tonemap(crop, 50, 0.5)
+    assert item["name"] == "s" and item["input"].shape == (3, 128, 256) and item["crop"].shape == (3, 128, 128)
+    assert item["warped"].shape == (3, 128, 256) and item["map"].shape == (1, 128, 256)
+    assert np.allclose(item["warped"].numpy(), pano.transpose(2, 0, 1) * alpha, rtol=1e-5)
+    dirs = torch.from_numpy(E.sphere_points(128)).float().view(1, -1)
+    colors = (torch.from_numpy(dist).view(1, 128, 1) * (420.0 * 0.01) * torch.from_numpy(pkl["rgb_ratio"]).view(1, 1, 3)).reshape(1, -1)
+    want = (RO.convert_to_panorama_torch(dirs, torch.full((1, 128), 0.0025), colors)[0]
+            + torch.from_numpy(pkl["ambient"]).view(3, 1, 1) / (128 * 256)) * alpha
+    assert float((item["input"].cpu() - want).abs().max()) <= 1e-3 * float(want.abs().max())
+    assert torch.equal(item["distribution"].cpu(), torch.from_numpy(dist).view(1, 128, 1).repeat(1, 1, 3))
