@@ -390,3 +390,72 @@ def test_product_modules_do_not_use_the_stand_ins():
     with pytest.raises(Exception):
         G(torch.rand(1, 3, 128, 256), torch.rand(1, 3, 64, 64))
     assert np.isfinite(float(torch.zeros(1)))
+
+
+def test_pix2pix_model_training_iterations_on_stand_ins(sim, monkeypatch):
+    """The trainer's two steps through `Pix2PixModel` itself (pix2pix_model.py:40-141 + trainers): loss dictionaries with an autograd
+    node, backward, Adam, twice.  `.cuda()` is patched to identity so the dispatch code of genprojector.py runs on CPU tensors over
+    the stand-ins; first-iteration losses and the generator's gradients are compared with autograd of the oracle composition."""
+    import emlight_b200._lib as L
+    from emlight_b200.genprojector import Pix2PixModel
+    monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(L, "require_cuda", lambda *a: None)
+    ngf = ndf = 2
+    opt = _d_opt(ndf)
+    opt.__dict__.update(ngf=ngf, norm_G="spectralspadesyncbatch3x3", norm_E="spectralinstance", semantic_nc=3, num_upsampling_layers="normal",
+                        crop_size=256, aspect_ratio=2.0, isTrain=True, gan_mode="hinge", lr=0.0002, beta1=0.0, beta2=0.9, no_TTUR=False)
+    model = Pix2PixModel(opt)
+    sdg, sdd, sdv = GO.init_generator_state_dict(1, ngf), GO.init_discriminator_state_dict(2, ndf), GO.init_vgg_state_dict(3)
+    model.netG.load_state_dict(sdg)
+    model.netD.load_state_dict(sdd)
+    model.criterionVGG.vgg.load_state_dict({k[4:]: v for k, v in sdv.items()})
+    model.train()
+    model.autograd = True
+    og, od = model.create_optimizers(opt)
+    gen = torch.Generator().manual_seed(11)
+    data = {"input": torch.rand(1, 3, 128, 256, generator=gen) * 2, "crop": torch.rand(1, 3, 64, 64, generator=gen),
+            "warped": torch.rand(1, 3, 128, 256, generator=gen) * 20, "map": (torch.rand(1, 1, 128, 256, generator=gen) > 0.4).float()}
+    # ---- iteration 1, generator step, against the oracle
+    og.zero_grad()
+    g_losses, generated = model(data, "generator")
+    assert set(g_losses) == {"GAN", "GAN_Feat", "VGG", "COS"} and generated.shape == (1, 3, 128, 256)
+    assert all(v.requires_grad for v in g_losses.values())
+    sum(v.sum() for v in g_losses.values()).mean().backward()
+    sdg_r = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("weight_u", "weight_v", "running_mean", "running_var"))
+                 else v.clone()) for k, v in sdg.items()}
+    fake_ref = GO.generator_forward(sdg_r, data["input"], data["crop"], ngf=ngf, upd={})
+    sdd_now = {k: v.detach().clone() for k, v in model.netD.state_dict().items()}       # D after ITS power iteration (stored vectors)
+    want = GO.generator_losses(sdd_now, sdv, data["input"], fake_ref, data["warped"], data["map"])
+    for k, ref in want.items():
+        assert abs(float(g_losses[k].sum()) - float(ref)) <= 1e-3 * abs(float(ref)) + 1e-5, (k, float(g_losses[k].sum()), float(ref))
+    sum(v.sum() for v in want.values()).backward()
+    top = max(float(sdg_r[n].grad.abs().max()) for n, _ in model.netG.named_parameters())
+    for name, p in model.netG.named_parameters():
+        ref = sdg_r[name].grad
+        assert p.grad is not None, name
+        assert float((p.grad - ref).abs().max()) <= 5e-3 * max(float(ref.abs().max()), 1e-4 * top), name
+    assert all(p.grad is None for p in model.netD.parameters())                          # the G step leaves D's gradients alone
+    before = [p.detach().clone() for p in model.netG.parameters()]
+    og.step()
+    assert any(not torch.equal(a, b) for a, b in zip(before, model.netG.parameters()))
+    # ---- iteration 1, discriminator step (its no-grad generator forward is the forward-only product path: real kernels only, so
+    #      here it is replaced by the same network run over the stand-ins)
+    gt = sim
+    monkeypatch.setattr(model, "generate_fake", lambda inp, crop: gt.generator(gt.Tape(), model.netG, inp, crop, True))
+    od.zero_grad()
+    d_losses = model(data, "discriminator")
+    assert set(d_losses) == {"D_Fake", "D_real"}
+    sum(v.sum() for v in d_losses.values()).mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.netD.parameters())
+    od.step()
+    # ---- iteration 2 runs on fresh tapes
+    og.zero_grad()
+    g2, _ = model(data, "generator")
+    sum(v.sum() for v in g2.values()).mean().backward()
+    assert all(torch.isfinite(p.grad).all() for p in model.netG.parameters())
+    # ---- without the opt-in the model returns plain values (no graph), as before
+    monkeypatch.undo()
+    model.autograd = False
+    with pytest.raises(Exception):
+        model(data, "generator")                       # forward-only product path: CPU tensors are refused before any launch
