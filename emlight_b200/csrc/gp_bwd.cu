@@ -226,6 +226,123 @@ __global__ void inorm_bwd_apply_kernel(const float *__restrict__ g, int g_pitch,
     dx[row * dx_pitch + c] = is * (gv - static_cast<float>(s[c] / n) - xh * static_cast<float>(s[C + c] / n));
 }
 
+// ------------------------------------------------------------------------------------------------ nearest x2 upsample backward
+// dx[b,h,w,c] = sum_{i,j<2} g[b,2h+i,2w+j,c]   (generator.py:42,70 self.up)
+__global__ void upsample2_bwd_kernel(const float *__restrict__ g, int g_pitch, float *dx, int dx_pitch, long total, int H, int W, int C) {
+    const long tid = GLOBAL_TID;
+    if (tid >= total) return;
+    const int c = static_cast<int>(tid % C);
+    long t = tid / C;
+    const int w = static_cast<int>(t % W); t /= W;
+    const int h = static_cast<int>(t % H);
+    const long b = t / H;
+    const long W2 = 2L * W;
+    const float *r0 = g + ((b * 2 * H + 2 * h) * W2 + 2 * w) * g_pitch + c;
+    const float *r1 = r0 + W2 * g_pitch;
+    dx[tid / C * dx_pitch + c] = (r0[0] + r0[g_pitch]) + (r1[0] + r1[g_pitch]);
+}
+
+// ------------------------------------------------------------------------------------------------ out = (tanh(raw + bias) + 1) * scale backward
+// NCHW gradient / output -> NHWC gradient of raw; bias_sums[c] += sum (column workers over the HW*B rows)
+__global__ void tanh_nchw_bwd_kernel(const float *__restrict__ g, const float *__restrict__ out, float scale, float *d_raw, int pitch,
+                                     long B, long HW, int C, long nstrips, double *sums) {
+    const long w = GLOBAL_TID;
+    if (w >= nstrips * C) return;
+    const int c = static_cast<int>(w % C);
+    double acc = 0.0;
+    for (long r = w / C; r < B * HW; r += nstrips) {
+        const long b = r / HW, p = r % HW;
+        const long src = (b * C + c) * HW + p;
+        const float t = out[src] / scale - 1.0f;
+        const float v = g[src] * scale * (1.0f - t * t);
+        d_raw[r * pitch + c] = v;
+        acc += v;
+    }
+    if (sums) atomicAdd(sums + c, acc);
+}
+
+// ------------------------------------------------------------------------------------------------ pooling backward (gather form)
+// mode 0: avg_pool2d(3, stride 2, pad 1, count_include_pad=False): dx[y,x] = sum over windows (yo,xo) containing (y,x) of g / n(yo,xo)
+// mode 1: max_pool2d(2,2): dx[y,x] = g[y/2,x/2] if (y,x) is the FIRST maximum of its window in row-major order (ATen's choice)
+__global__ void pool2d_bwd_kernel(const float *__restrict__ g, int g_pitch, const float *__restrict__ x, int x_pitch, float *dx,
+                                  int dx_pitch, long total, int Hi, int Wi, int Ho, int Wo, int C, int mode) {
+    const long tid = GLOBAL_TID;
+    if (tid >= total) return;
+    const int c = static_cast<int>(tid % C);
+    long t = tid / C;
+    const int xx = static_cast<int>(t % Wi); t /= Wi;
+    const int y = static_cast<int>(t % Hi);
+    const long b = t / Hi;
+    float v = 0.0f;
+    if (mode == 0) {
+        for (int yo = y / 2; yo <= (y + 1) / 2; ++yo) {
+            if (yo >= Ho) continue;
+            const int ny = (2 * yo - 1 >= 0 ? 1 : 0) + 1 + (2 * yo + 1 < Hi ? 1 : 0);
+            for (int xo = xx / 2; xo <= (xx + 1) / 2; ++xo) {
+                if (xo >= Wo) continue;
+                const int nx = (2 * xo - 1 >= 0 ? 1 : 0) + 1 + (2 * xo + 1 < Wi ? 1 : 0);
+                v += g[((b * Ho + yo) * static_cast<long>(Wo) + xo) * g_pitch + c] / static_cast<float>(ny * nx);
+            }
+        }
+    } else {
+        const int yo = y / 2, xo = xx / 2;
+        const float *win = x + ((b * Hi + 2 * yo) * static_cast<long>(Wi) + 2 * xo) * x_pitch + c;
+        const float v00 = win[0], v01 = win[x_pitch], v10 = win[static_cast<long>(Wi) * x_pitch], v11 = win[(static_cast<long>(Wi) + 1) * x_pitch];
+        int arg = 0; float m = v00;
+        if (v01 > m) { m = v01; arg = 1; }
+        if (v10 > m) { m = v10; arg = 2; }
+        if (v11 > m) { m = v11; arg = 3; }
+        if (arg == (y & 1) * 2 + (xx & 1)) v = g[((b * Ho + yo) * static_cast<long>(Wo) + xo) * g_pitch + c];
+    }
+    dx[tid / C * dx_pitch + c] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ loss seeds
+// d a = coef * d(eml_loss_reduce(mode))/da  for the element-wise modes 0..4 (mode 5, the cosine distance, couples the channels)
+__global__ void loss_seed_kernel(const float *__restrict__ a, int a_pitch, const float *__restrict__ b, int b_pitch,
+                                 const float *__restrict__ mask, long M, int C, int mode, float coef,
+                                 const float *__restrict__ coef_dev, float *da, int da_pitch) {
+    const long tid = GLOBAL_TID;
+    if (tid >= M * C) return;
+    if (coef_dev) coef *= coef_dev[0];
+    const int c = static_cast<int>(tid % C);
+    const long r = tid / C;
+    const float av = a[r * a_pitch + c];
+    float d;
+    if (mode == 0) d = 1.0f;
+    else if (mode == 1) d = av < 1.0f ? 1.0f : 0.0f;
+    else if (mode == 2) d = av > -1.0f ? -1.0f : 0.0f;
+    else {
+        const float df = av - b[r * b_pitch + c];
+        d = df > 0.0f ? 1.0f : (df < 0.0f ? -1.0f : 0.0f);
+        if (mode == 4) { const float m = mask[r]; d *= m + (1.0f - m) * 50.0f; }
+    }
+    da[r * da_pitch + c] = coef * d;
+}
+
+// cosine distance over the channels as ATen computes it, 1 - ahat . bhat with ahat = a / max(|a|, eps), bhat = b / max(|b|, eps):
+//   |a| > eps: d/da = -(bhat - (ahat . bhat) ahat) / |a|;   |a| <= eps: d/da = -bhat / eps       (normalise first: no |a|^3 underflow)
+__global__ void cos_seed_kernel(const float *__restrict__ a, int a_pitch, const float *__restrict__ b, int b_pitch, long M, int C,
+                                float eps, float coef, const float *__restrict__ coef_dev, float *da, int da_pitch) {
+    const long r = GLOBAL_TID;
+    if (r >= M) return;
+    if (coef_dev) coef *= coef_dev[0];
+    float na = 0.0f, nb = 0.0f;
+    for (int c = 0; c < C; ++c) {
+        const float av = a[r * a_pitch + c], bv = b[r * b_pitch + c];
+        na += av * av; nb += bv * bv;
+    }
+    const float an = sqrtf(na);
+    const float ia = 1.0f / fmaxf(an, eps), ib = 1.0f / fmaxf(sqrtf(nb), eps);
+    float cosv = 0.0f;
+    for (int c = 0; c < C; ++c) cosv += (a[r * a_pitch + c] * ia) * (b[r * b_pitch + c] * ib);
+    for (int c = 0; c < C; ++c) {
+        const float ah = a[r * a_pitch + c] * ia, bh = b[r * b_pitch + c] * ib;
+        const float d = an > eps ? (bh - cosv * ah) * ia : bh * ia;
+        da[r * da_pitch + c] = -coef * d;
+    }
+}
+
 }  // namespace
 
 // =================================================================================================== C ABI
@@ -303,5 +420,55 @@ extern "C" int EML_API(eml_instance_norm_bwd)(const float *g, int g_pitch, const
     if (blocks_for(total) > 0x7fffffffL) return EML_E_SHAPE;
     EML_LAUNCH(inorm_bwd_apply_kernel, blocks_for(total), THREADS, stream, g, g_pitch, out, out_pitch, sums, static_cast<long>(B), HW,
                C, eps, leaky_relu, dx, dx_pitch);
+    return eml_launch_status();
+}
+
+extern "C" int EML_API(eml_upsample2_bwd)(const float *g, int g_pitch, float *dx, int dx_pitch, int B, int H, int W, int C, void *stream) {
+    EML_CHECK_PTR(g); EML_CHECK_PTR(dx);
+    if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || g_pitch < C || dx_pitch < C) return EML_E_SHAPE;
+    const long total = static_cast<long>(B) * H * W * C;
+    if (blocks_for(total) > 0x7fffffffL) return EML_E_SHAPE;
+    EML_LAUNCH(upsample2_bwd_kernel, blocks_for(total), THREADS, stream, g, g_pitch, dx, dx_pitch, total, H, W, C);
+    return eml_launch_status();
+}
+
+extern "C" int EML_API(eml_tanh_nchw_bwd)(const float *g_nchw, const float *out_nchw, float scale, float *d_raw, int pitch, int B,
+                                          long HW, int C, double *bias_sums, void *stream) {
+    EML_CHECK_PTR(g_nchw); EML_CHECK_PTR(out_nchw); EML_CHECK_PTR(d_raw);
+    if (B <= 0 || HW <= 0 || C <= 0 || pitch < C) return EML_E_SHAPE;
+    if (!(scale > 0.0f)) return EML_E_ARG;
+    const Strips s = make_strips(static_cast<long>(B) * HW, C);
+    EML_LAUNCH(tanh_nchw_bwd_kernel, s.blocks, THREADS, stream, g_nchw, out_nchw, scale, d_raw, pitch, static_cast<long>(B), HW, C,
+               s.nstrips, bias_sums);
+    return eml_launch_status();
+}
+
+extern "C" int EML_API(eml_pool2d_bwd)(const float *g, int g_pitch, const float *x, int x_pitch, float *dx, int dx_pitch, int Hi, int Wi,
+                                       int C, int B, int mode, void *stream) {
+    EML_CHECK_PTR(g); EML_CHECK_PTR(dx);
+    if (mode != 0 && mode != 1) return EML_E_ARG;
+    if (mode == 1) EML_CHECK_PTR(x);
+    if (B <= 0 || C <= 0 || Hi <= 0 || Wi <= 0 || g_pitch < C || dx_pitch < C || (mode == 1 && x_pitch < C)) return EML_E_SHAPE;
+    if (mode == 1 && ((Hi | Wi) & 1)) return EML_E_SHAPE;
+    const int Ho = mode == 0 ? (Hi + 1) / 2 : Hi / 2, Wo = mode == 0 ? (Wi + 1) / 2 : Wi / 2;
+    const long total = static_cast<long>(B) * Hi * Wi * C;
+    if (blocks_for(total) > 0x7fffffffL) return EML_E_SHAPE;
+    EML_LAUNCH(pool2d_bwd_kernel, blocks_for(total), THREADS, stream, g, g_pitch, x, x_pitch, dx, dx_pitch, total, Hi, Wi, Ho, Wo, C, mode);
+    return eml_launch_status();
+}
+
+extern "C" int EML_API(eml_loss_seed)(const float *a, int a_pitch, const float *b, int b_pitch, const float *mask, long M, int C, int mode,
+                                      float coef, const float *coef_dev, float *da, int da_pitch, void *stream) {
+    EML_CHECK_PTR(a); EML_CHECK_PTR(da);
+    if (mode < 0 || mode > 5) return EML_E_ARG;
+    if (mode >= 3) EML_CHECK_PTR(b);
+    if (mode == 4) EML_CHECK_PTR(mask);
+    if (M <= 0 || C <= 0 || a_pitch < C || da_pitch < C || (mode >= 3 && b_pitch < C)) return EML_E_SHAPE;
+    if (mode == 5) {
+        EML_LAUNCH(cos_seed_kernel, blocks_for(M), THREADS, stream, a, a_pitch, b, b_pitch, M, C, 1e-20f, coef, coef_dev, da, da_pitch);
+    } else {
+        if (blocks_for(M * C) > 0x7fffffffL) return EML_E_SHAPE;
+        EML_LAUNCH(loss_seed_kernel, blocks_for(M * C), THREADS, stream, a, a_pitch, b, b_pitch, mask, M, C, mode, coef, coef_dev, da, da_pitch);
+    }
     return eml_launch_status();
 }

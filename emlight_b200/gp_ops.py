@@ -222,3 +222,38 @@ def instance_norm_bwd(g, out, raw, B, HW, C, lrelu, eps=1e-5):
     _lib.check(_fn("eml_instance_norm_bwd")(_lib.ptr(g), g.shape[-1], _lib.ptr(out), out.shape[-1], _lib.ptr(raw), raw.shape[-1], B, HW, C,
                                             float(eps), int(lrelu), _lib.ptr(sums), _lib.ptr(dx), dx.shape[-1], _st()), "eml_instance_norm_bwd")
     return dx
+
+
+def upsample2_bwd(g, B, H, W, C):
+    """dx (B,H,W,pitch of g) = sum over the 2x2 blocks of g (B,2H,2W,pitch)."""
+    g = g.contiguous()
+    dx = torch.zeros(B, H, W, g.shape[-1], dtype=torch.float32, device=g.device)
+    _lib.check(_fn("eml_upsample2_bwd")(_lib.ptr(g), g.shape[-1], _lib.ptr(dx), dx.shape[-1], B, H, W, C, _st()), "eml_upsample2_bwd")
+    return dx
+
+
+def tanh_nchw_bwd(g_nchw, out_nchw, scale, B, HW, C, pitch, want_sums):
+    """(d_raw (B*HW rows, pitch) NHWC, bias sums float64 or None) from the NCHW gradient / output of tanh_to_nchw."""
+    g_nchw = g_nchw.contiguous().float()
+    d_raw = torch.zeros(B, HW, pitch, dtype=torch.float32, device=g_nchw.device)
+    sums = torch.zeros(C, dtype=torch.float64, device=g_nchw.device) if want_sums else None
+    _lib.check(_fn("eml_tanh_nchw_bwd")(_lib.ptr(g_nchw), _lib.ptr(out_nchw), float(scale), _lib.ptr(d_raw), pitch, B, HW, C, _lib.ptr(sums),
+                                        _st()), "eml_tanh_nchw_bwd")
+    return d_raw, sums
+
+
+def pool2d_bwd(g, x, B, H, W, C, mode):
+    """dx like x (B,H,W,pitch): adjoint of pool(x, mode) given g on the pooled grid."""
+    g = g.contiguous()
+    dx = torch.zeros_like(x)
+    _lib.check(_fn("eml_pool2d_bwd")(_lib.ptr(g), g.shape[-1], _lib.ptr(x), x.shape[-1], _lib.ptr(dx), dx.shape[-1], H, W, C, B, int(mode),
+                                     _st()), "eml_pool2d_bwd")
+    return dx
+
+
+def loss_seed(mode, a, M, C, coef, coef_dev, b=None, mask=None):
+    """da like a = coef * coef_dev[0] * d(loss_sum(mode))/da (coef_dev: 1-element float32 device tensor or None)."""
+    da = torch.zeros_like(a)
+    _lib.check(_fn("eml_loss_seed")(_lib.ptr(a), a.shape[-1], _lib.ptr(b), b.shape[-1] if b is not None else 0, _lib.ptr(mask), M, C, int(mode),
+                                    float(coef), _lib.ptr(coef_dev), _lib.ptr(da), da.shape[-1], _st()), "eml_loss_seed")
+    return da

@@ -13,8 +13,10 @@ Split of work in this first version:
 * the gather's adjoint (col2im through the sampling table), activation / bias, SPADE modulation, parameter-free BatchNorm and
   InstanceNorm adjoints are the kernels of `csrc/gp_bwd.cu` (`gp_ops.col2im`, `act_bwd`, `bias_act_bwd`, `spade_bwd`, `bn_free_bwd`,
   `instance_norm_bwd`);
-* the remaining glue -- nearest-upsample / latent / tanh adjoints, the two pooling adjoints (through ATen's own pooling backward),
-  loss seeds, batch slicing and layout permutes -- is device-agnostic torch tensor code on the same NHWC buffers.
+* nearest-upsample, tanh, the two pooling adjoints and the loss seeds (hinge / L1 / masked L1 / cosine; the upstream scalar gradient
+  is read on the device) are kernels of the same file (`upsample2_bwd`, `tanh_nchw_bwd`, `pool2d_bwd`, `loss_seed`);
+* what is left in torch tensor code is bookkeeping on the same buffers: batch slicing, NCHW <-> NHWC permutes at the image
+  boundary, the latent's 2 -> 8 column expansion, the spectral-norm quotient on the weight matrices and operand transposes.
 Semantics follow the reference's modules in `.train()`: batch-statistic (Sync)BatchNorm inside SPADE with the running-stat update and
 one all-reduce of the per-channel sums when several processes share the batch (forward AND backward), one spectral-norm power
 iteration per wrapped convolution per forward with `u`, `v` treated as constants in the backward (torch.nn.utils.spectral_norm).
@@ -299,7 +301,7 @@ def upsample2(tape, x, B, H, W, C):
     def bwd():
         g = tape.take(out)
         if g is not None:
-            tape.add(x, g.reshape(B, H, 2, W, 2, g.shape[-1]).sum((2, 4)))
+            tape.add(x, ops.upsample2_bwd(g, B, H, W, C))
 
     tape.record(bwd)
     return out
@@ -407,10 +409,10 @@ def generator(tape, G, guide, crop, training=True):
         g = tape.take(out)
         if g is None:
             return
-        t = out / 25.0 - 1.0
-        gr = (g * 25.0 * (1.0 - t * t)).permute(0, 2, 3, 1)
-        tape.add_param(last.bias, gr.sum((0, 1, 2)))
-        tape.add(raw, _pad_c(gr, raw.shape[-1]).contiguous())
+        d_raw, sums = ops.tanh_nchw_bwd(g, out, 25.0, B, H * W, 3, raw.shape[-1], last.bias.requires_grad)
+        if sums is not None:
+            tape.add_param(last.bias, sums.float())
+        tape.add(raw, d_raw.reshape(raw.shape))
 
     tape.record(bwd_out)
     return out
@@ -439,11 +441,7 @@ def _pool_with_grad(tape, x, B, H, W, C, mode):
         g = tape.take(out)
         if g is None:
             return
-        with torch.enable_grad():                                   # adjoint of the pooling through ATen's own pooling backward
-            xi = x[..., :C].permute(0, 3, 1, 2).detach().requires_grad_(True)
-            y = (F.avg_pool2d(xi, kernel_size=3, stride=2, padding=1, count_include_pad=False) if mode == 0 else F.max_pool2d(xi, 2, 2))
-            (gx,) = torch.autograd.grad(y, xi, g[..., :C].permute(0, 3, 1, 2))
-        tape.add(x, _pad_c(gx.permute(0, 2, 3, 1), x.shape[-1]))
+        tape.add(x, ops.pool2d_bwd(g, x, B, H, W, C, mode))
 
     tape.record(bwd)
     return out, ho, wo
@@ -508,15 +506,17 @@ def vgg_features(tape, vgg, x, B, H, W):
 
 
 # ============================================================================================================== losses
-def _mean_loss(tape, mode, a, M, C, count, grad_fn, b=None, mask=None, sign=1.0, scale=1.0):
-    """scalar = scale * sign/count * eml_loss_reduce(mode); `grad_fn()` -> d(sum)/da over a[..., :C] (before sign/count/scale)."""
-    val = (ops.loss_sum(mode, a, M, C, a.shape[-1], b, b.shape[-1] if b is not None else 0, mask) * (sign * scale / count)).float().reshape(())
+def _mean_loss(tape, mode, a, M, C, count, b=None, mask=None, sign=1.0, scale=1.0):
+    """scalar = scale * sign / count * eml_loss_reduce(mode); its adjoint seeds d/da through eml_loss_seed with the upstream scalar
+    gradient read on the device (no host synchronisation)."""
+    coef = sign * scale / count
+    val = (ops.loss_sum(mode, a, M, C, a.shape[-1], b, b.shape[-1] if b is not None else 0, mask) * coef).float().reshape(())
 
     def bwd():
         g = tape.take(val)
         if g is None:
             return
-        tape.add(a, _pad_c(grad_fn() * (g * (sign * scale / count)), a.shape[-1]))
+        tape.add(a, ops.loss_seed(mode, a, M, C, coef, g.reshape(1).float().contiguous(), b, mask))
 
     tape.record(bwd)
     return val
@@ -577,8 +577,7 @@ def generator_losses(tape, model, fake, guide, real, mask):
         t, h, w, c = fl[-1]
         tf = _slice_rows(tape, t, 0, B)
         n = B * h * w * c
-        gan.append(_mean_loss(tape, _RED_SUM, tf, B * h * w, c, n, lambda tf=tf, c=c: torch.ones_like(tf[..., :c]), sign=-1.0,
-                              scale=1.0 / num_D))
+        gan.append(_mean_loss(tape, _RED_SUM, tf, B * h * w, c, n, sign=-1.0, scale=1.0 / num_D))
     losses.append(_sum(tape, gan))
     if not opt.no_ganFeat_loss:
         m = mask.contiguous().float()
@@ -589,12 +588,7 @@ def generator_losses(tape, model, fake, guide, real, mask):
                 m = ops.resize_nearest(m, 1, mh, mw, h, w, 1, B, 0, 1)   # re-interpolated from its PREVIOUS size (pix2pix_model.py:111)
                 mh, mw = h, w
                 tf = _slice_rows(tape, t, 0, B)
-                tr = t[B:]
-
-                def gfn(tf=tf, tr=tr, m=m, c=c):
-                    return torch.sign(tf[..., :c] - tr[..., :c]) * (m + (1.0 - m) * 50.0)
-
-                fm.append(_mean_loss(tape, _RED_L1_MASKED, tf, B * h * w, c, B * h * w * c, gfn, b=tr, mask=m, scale=1.0 / num_D))
+                fm.append(_mean_loss(tape, _RED_L1_MASKED, tf, B * h * w, c, B * h * w * c, b=t[B:], mask=m, scale=1.0 / num_D))
         losses.append(_sum(tape, fm, (1,)))
     vin = torch.cat([fake, real], 0)
     xv = ops.nchw_to_nhwc(vin, 4)
@@ -609,9 +603,7 @@ def generator_losses(tape, model, fake, guide, real, mask):
     vl = []
     for wk, (t, h, w, c) in zip(model.criterionVGG.weights, vf):
         tf = _slice_rows(tape, t, 0, B)
-        tr = t[B:]
-        vl.append(_mean_loss(tape, _RED_L1, tf, B * h * w, c, B * h * w * c, lambda tf=tf, tr=tr, c=c: torch.sign(tf[..., :c] - tr[..., :c]),
-                             b=tr, scale=5.0 * wk))
+        vl.append(_mean_loss(tape, _RED_L1, tf, B * h * w, c, B * h * w * c, b=t[B:], scale=5.0 * wk))
     losses.append(_sum(tape, vl))
     a = ops.nchw_to_nhwc(fake, 4)
     bq = ops.nchw_to_nhwc(real, 4)
@@ -623,14 +615,7 @@ def generator_losses(tape, model, fake, guide, real, mask):
 
     tape.record(bwd_a)
 
-    def cos_grad():
-        with torch.enable_grad():
-            ai = a[..., :3].detach().requires_grad_(True)
-            s = (1.0 - F.cosine_similarity(ai, bq[..., :3], dim=-1, eps=1e-20)).sum()
-            (ga,) = torch.autograd.grad(s, ai)
-        return ga
-
-    losses.append(_mean_loss(tape, _RED_COS, a, B * H * W, 3, B * H * W, cos_grad, b=bq, scale=5.0))
+    losses.append(_mean_loss(tape, _RED_COS, a, B * H * W, 3, B * H * W, b=bq, scale=5.0))
     return losses
 
 
@@ -649,8 +634,6 @@ def discriminator_losses(tape, model, fake, guide, real):
         n = B * h * w * c
         tf, tr = _slice_rows(tape, t, 0, B), _slice_rows(tape, t, B, 2 * B)
         # hinge: D_Fake = -mean(min(-x-1, 0)) -> d/dx = [x > -1] / n ; D_real = -mean(min(x-1, 0)) -> d/dx = -[x < 1] / n
-        d_fake.append(_mean_loss(tape, _RED_HINGE_FAKE, tf, B * h * w, c, n, lambda tf=tf, c=c: -(tf[..., :c] > -1).float(), sign=-1.0,
-                                 scale=1.0 / num_D))
-        d_real.append(_mean_loss(tape, _RED_HINGE_REAL, tr, B * h * w, c, n, lambda tr=tr, c=c: (tr[..., :c] < 1).float(), sign=-1.0,
-                                 scale=1.0 / num_D))
+        d_fake.append(_mean_loss(tape, _RED_HINGE_FAKE, tf, B * h * w, c, n, sign=-1.0, scale=1.0 / num_D))
+        d_real.append(_mean_loss(tape, _RED_HINGE_REAL, tr, B * h * w, c, n, sign=-1.0, scale=1.0 / num_D))
     return [_sum(tape, d_fake), _sum(tape, d_real)]

@@ -291,7 +291,14 @@ int eml_wgrad_stem(const float *dZ, int dz_pitch, int O, const float *x_nchw, fl
  *     with sums = (2, C) [sum d_xhat, sum d_xhat * xhat] (all-reduced by the caller when several processes share the batch);
  *     sums == NULL: running-statistics mode, dx = inv_std * d_xhat.
  * eml_instance_norm_bwd: adjoint of eml_instance_norm (InstanceNorm2d(affine=False) + optional LeakyReLU) from its output and raw
- *     input; `sums` is a caller-zeroed (B, 4, C) double scratch. */
+ *     input; `sums` is a caller-zeroed (B, 4, C) double scratch.
+ * eml_upsample2_bwd: adjoint of the nearest x2 upsampling (generator.py:42,70): dx[b,h,w,c] = sum of the 2x2 block of g.
+ * eml_tanh_nchw_bwd: adjoint of eml_tanh_to_nchw from its NCHW output: d_raw (NHWC) = g * scale * (1 - tanh^2), bias_sums[c] += sum.
+ * eml_pool2d_bwd: adjoint of eml_pool2d; mode 0 (3x3 average, stride 2, pad 1, count_include_pad=False) needs only g, mode 1 (2x2 max)
+ *     routes g to the FIRST maximum of each window in row-major order (what ATen's max_pool2d backward does) and reads the input x.
+ * eml_loss_seed: da = coef * (coef_dev ? *coef_dev : 1) * d(eml_loss_reduce(mode))/da for modes 0..5 (coef_dev: the upstream scalar
+ *     gradient read on the device, so no host synchronisation is needed; mode 5: cosine distance with ATen's clamping,
+ *     1 - (a/max(|a|,eps)).(b/max(|b|,eps)), eps 1e-20 as in pix2pix_model.py:95); b / mask as for eml_loss_reduce. */
 int eml_col2im_lut(const float *dA, int Cp, const int *lut_idx, const float *lut_w, float *dx, int dx_pitch, int B, long out_pixels,
                    long in_pixels, void *stream);
 int eml_act_bwd(float *dx, int dx_pitch, const float *x, int x_pitch, const float *bias, int act, long M, int C, double *bias_sums,
@@ -305,6 +312,13 @@ int eml_bn_free_bwd(const float *d_xhat, int dxh_pitch, const float *x, int x_pi
                     const double *sums, double count, float *dx, int dx_pitch, long M, int C, void *stream);
 int eml_instance_norm_bwd(const float *g, int g_pitch, const float *out, int out_pitch, const float *raw, int raw_pitch, int B, long HW,
                           int C, float eps, int leaky_relu, double *sums, float *dx, int dx_pitch, void *stream);
+int eml_upsample2_bwd(const float *g, int g_pitch, float *dx, int dx_pitch, int B, int H, int W, int C, void *stream);
+int eml_tanh_nchw_bwd(const float *g_nchw, const float *out_nchw, float scale, float *d_raw, int pitch, int B, long HW, int C,
+                      double *bias_sums, void *stream);
+int eml_pool2d_bwd(const float *g, int g_pitch, const float *x, int x_pitch, float *dx, int dx_pitch, int Hi, int Wi, int C, int B,
+                   int mode, void *stream);
+int eml_loss_seed(const float *a, int a_pitch, const float *b, int b_pitch, const float *mask, long M, int C, int mode, float coef,
+                  const float *coef_dev, float *da, int da_pitch, void *stream);
 
 /* G6-G7 -- discriminator / loss building blocks (NHWC fp32).
  * eml_bias_act: out = act(x + bias[c]) (act 0 none, 1 ReLU, 2 LeakyReLU(0.2)); discriminator.py:91-92, VGG conv+ReLU.

@@ -23,7 +23,8 @@ def emu(tmp_path_factory):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DEML_EMULATE", "-x", "c++", SRC, "-o", out])
     lib = ctypes.CDLL(out)
     from emlight_b200 import _lib
-    for name in ("eml_col2im_lut", "eml_act_bwd", "eml_bias_act_bwd", "eml_spade_bwd", "eml_bn_free_bwd", "eml_instance_norm_bwd"):
+    for name in ("eml_col2im_lut", "eml_act_bwd", "eml_bias_act_bwd", "eml_spade_bwd", "eml_bn_free_bwd", "eml_instance_norm_bwd",
+                 "eml_upsample2_bwd", "eml_tanh_nchw_bwd", "eml_pool2d_bwd", "eml_loss_seed"):
         fn = getattr(lib, name + "_emu")
         fn.restype, fn.argtypes = _lib.SIGNATURES[name]          # the emulated entry points have the product's signatures
     return lib
@@ -145,6 +146,93 @@ def test_instance_norm_bwd_matches_autograd(emu, leaky, B, HW, C):
     assert float((dx[..., :C] - xr.grad).abs().max()) <= 2e-4 * float(xr.grad.abs().max()) + 1e-6
 
 
+def test_upsample2_and_tanh_bwd_match_autograd(emu):
+    gen = torch.Generator().manual_seed(4)
+    B, H, W, C, pitch = 2, 3, 5, 6, 8
+    x = torch.randn(B, C, H, W, generator=gen, requires_grad=True)
+    y = F.interpolate(x, scale_factor=2)
+    g = torch.randn(B, 2 * H, 2 * W, pitch, generator=gen)
+    y.backward(g[..., :C].permute(0, 3, 1, 2))
+    dx = torch.zeros(B, H, W, pitch)
+    assert emu.eml_upsample2_bwd_emu(P(g), pitch, P(dx), pitch, B, H, W, C, None) == 0
+    assert torch.allclose(dx[..., :C].permute(0, 3, 1, 2), x.grad, atol=1e-6) and not dx[..., C:].any()
+    # (tanh(raw + bias) + 1) * 25 -> NCHW
+    C, pitch = 3, 4
+    raw = torch.randn(B, H, W, C, generator=gen, requires_grad=True)
+    bias = torch.randn(C, generator=gen, requires_grad=True)
+    out = ((torch.tanh(raw + bias) + 1) * 25.0).permute(0, 3, 1, 2).contiguous()
+    gn = torch.randn(B, C, H, W, generator=gen)
+    out.backward(gn)
+    d_raw = torch.zeros(B, H, W, pitch)
+    sums = torch.zeros(C, dtype=torch.float64)
+    assert emu.eml_tanh_nchw_bwd_emu(P(gn), P(out.detach()), 25.0, P(d_raw), pitch, B, H * W, C, P(sums), None) == 0
+    assert torch.allclose(d_raw[..., :C], raw.grad, rtol=1e-4, atol=1e-5) and torch.allclose(sums.float(), bias.grad, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("Hi,Wi", [(8, 12), (7, 9), (1, 1), (2, 5)])
+def test_avg_pool_bwd_matches_autograd(emu, Hi, Wi):
+    gen = torch.Generator().manual_seed(Hi * Wi)
+    B, C, pitch = 2, 6, 8
+    x = torch.randn(B, C, Hi, Wi, generator=gen, requires_grad=True)
+    y = F.avg_pool2d(x, kernel_size=3, stride=2, padding=1, count_include_pad=False)
+    Ho, Wo = y.shape[2], y.shape[3]
+    g = torch.randn(B, Ho, Wo, pitch, generator=gen)
+    y.backward(g[..., :C].permute(0, 3, 1, 2))
+    dx = torch.zeros(B, Hi, Wi, pitch)
+    assert emu.eml_pool2d_bwd_emu(P(g), pitch, None, 0, P(dx), pitch, Hi, Wi, C, B, 0, None) == 0
+    assert torch.allclose(dx[..., :C].permute(0, 3, 1, 2), x.grad, atol=1e-6)
+
+
+def test_max_pool_bwd_matches_autograd_including_ties(emu):
+    gen = torch.Generator().manual_seed(8)
+    B, C, Hi, Wi, pitch = 2, 5, 6, 8, 8
+    x = torch.randn(B, C, Hi, Wi, generator=gen)
+    x = torch.relu(x)                                    # many exact ties at 0, like VGG's post-ReLU maps
+    x[0, 0, 0:2, 0:2] = 1.5                              # a 4-way tie at a positive value
+    xr = x.clone().requires_grad_(True)
+    y = F.max_pool2d(xr, 2, 2)
+    g = torch.randn(B, Hi // 2, Wi // 2, pitch, generator=gen)
+    y.backward(g[..., :C].permute(0, 3, 1, 2))
+    xn = F.pad(x.permute(0, 2, 3, 1), (0, pitch - C)).contiguous()
+    dx = torch.zeros(B, Hi, Wi, pitch)
+    assert emu.eml_pool2d_bwd_emu(P(g), pitch, P(xn), pitch, P(dx), pitch, Hi, Wi, C, B, 1, None) == 0
+    assert torch.equal(dx[..., :C].permute(0, 3, 1, 2), xr.grad)
+    assert emu.eml_pool2d_bwd_emu(P(g), pitch, P(xn), pitch, P(dx), pitch, 5, Wi, C, B, 1, None) < 0        # odd size
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
+def test_loss_seeds_match_autograd_of_the_reductions(emu, mode):
+    gen = torch.Generator().manual_seed(20 + mode)
+    M, C, pitch = 60, 3, 4
+    a = torch.randn(M, pitch, generator=gen) * 1.5
+    b = torch.randn(M, pitch, generator=gen)
+    mask = (torch.rand(M, generator=gen) > 0.5).float()
+    if mode == 5:
+        a[7, :C] = 0.0                                   # a zero vector: ATen clamps the norm
+    ar = a[:, :C].clone().requires_grad_(True)
+    bb = b[:, :C]
+    if mode == 0:
+        v = ar.sum()
+    elif mode == 1:
+        v = torch.clamp(ar - 1, max=0).sum()
+    elif mode == 2:
+        v = torch.clamp(-ar - 1, max=0).sum()
+    elif mode == 3:
+        v = (ar - bb).abs().sum()
+    elif mode == 4:
+        v = ((ar - bb).abs() * (mask + (1 - mask) * 50)[:, None]).sum()
+    else:
+        v = (1 - F.cosine_similarity(ar, bb, dim=1, eps=1e-20)).sum()
+    (v * 0.37).backward()
+    da = torch.zeros(M, pitch)
+    assert emu.eml_loss_seed_emu(P(a), pitch, P(b), pitch, P(mask), M, C, mode, 0.74, P(torch.tensor([0.5])), P(da), pitch, None) == 0
+    want = ar.grad
+    ok = torch.isfinite(want).all(1)
+    assert bool(ok.sum() >= M - 1)
+    assert float((da[:, :C][ok] - want[ok]).abs().max()) <= 1e-4 * float(want[ok].abs().max())
+    assert emu.eml_loss_seed_emu(P(a), pitch, None, pitch, P(mask), M, C, 3, 1.0, None, P(da), pitch, None) < 0
+
+
 def test_product_library_validates_the_same_arguments(lib):
     """The real (CUDA) entry points reject bad arguments before any launch -- no GPU needed."""
     z = ctypes.create_string_buffer(64)
@@ -156,4 +244,8 @@ def test_product_library_validates_the_same_arguments(lib):
     assert lib.eml_spade_bwd(a, 4, a, 4, a, 4, a, a, a, 4, None, a, a, 4, 4, 4, 0, a, None) < 0
     assert lib.eml_bn_free_bwd(a, 4, a, 4, a, a, a, 0.0, a, 4, 4, 4, None) < 0
     assert lib.eml_instance_norm_bwd(a, 4, a, 4, a, 4, 0, 4, 4, 1e-5, 0, a, a, 4, None) < 0
+    assert lib.eml_upsample2_bwd(a, 2, a, 4, 1, 2, 2, 4, None) < 0
+    assert lib.eml_tanh_nchw_bwd(a, a, 0.0, a, 4, 1, 4, 3, None, None) < 0
+    assert lib.eml_pool2d_bwd(a, 4, None, 4, a, 4, 4, 4, 4, 1, 1, None) < 0
+    assert lib.eml_loss_seed(a, 4, None, 4, None, 4, 4, 4, 1.0, None, a, 4, None) < 0
     assert np.isfinite(1.0) and c_double and c_float and c_int and c_long

@@ -142,7 +142,8 @@ def build_emu(outdir):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DEML_EMULATE", "-x", "c++", src, "-o", out])
     lib = ctypes.CDLL(out)
     fns = {}
-    for name in ("eml_col2im_lut", "eml_act_bwd", "eml_bias_act_bwd", "eml_spade_bwd", "eml_bn_free_bwd", "eml_instance_norm_bwd"):
+    for name in ("eml_col2im_lut", "eml_act_bwd", "eml_bias_act_bwd", "eml_spade_bwd", "eml_bn_free_bwd", "eml_instance_norm_bwd",
+                 "eml_upsample2_bwd", "eml_tanh_nchw_bwd", "eml_pool2d_bwd", "eml_loss_seed"):
         fn = getattr(lib, name + "_emu")
         fn.restype, fn.argtypes = _lib.SIGNATURES[name]
         fns[name] = fn
@@ -221,7 +222,7 @@ def test_conv_adjoint_matches_autograd(sim, stride, act, cin, cout):
 def test_instance_norm_pool_and_spectral_adjoints(sim):
     gt = sim
     gen = torch.Generator().manual_seed(3)
-    B, H, W, C = 2, 6, 8, 5
+    B, H, W, C = 2, 8, 12, 5
     x = torch.randn(B, C, H, W, generator=gen)
     xr = x.clone().requires_grad_(True)
     ref = F.max_pool2d(F.avg_pool2d(F.leaky_relu(F.instance_norm(xr, eps=1e-5), 0.2), 3, 2, 1, count_include_pad=False), 2, 2)

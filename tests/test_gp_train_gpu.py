@@ -197,3 +197,21 @@ def test_adjoint_kernels_match_their_host_emulation(cuda, lib, tmp_path):
     o = torch.nn.functional.leaky_relu((raw - raw.mean(1, keepdim=True)) * torch.rsqrt(raw.var(1, unbiased=False, keepdim=True) + 1e-5), 0.2).contiguous()
     c, g = both("eml_instance_norm_bwd", [gi, C, o, C, raw, C, Bn, HW, C, 1e-5, 1, torch.zeros(Bn, 4, C, dtype=torch.float64), torch.zeros(Bn, HW, C), C])
     assert torch.allclose(c[12], g[12], atol=1e-5)
+    Bq, Hq, Wq, C = 3, 16, 24, 10
+    gq = torch.randn(Bq, 2 * Hq, 2 * Wq, 12, generator=gen)
+    c, g = both("eml_upsample2_bwd", [gq, 12, torch.zeros(Bq, Hq, Wq, 12), 12, Bq, Hq, Wq, C])
+    assert torch.allclose(c[2], g[2], atol=1e-6)
+    on = (torch.tanh(torch.randn(Bq, 3, Hq, Wq, generator=gen)) + 1) * 25
+    gn = torch.randn(Bq, 3, Hq, Wq, generator=gen)
+    c, g = both("eml_tanh_nchw_bwd", [gn, on, 25.0, torch.zeros(Bq, Hq * Wq, 4), 4, Bq, Hq * Wq, 3, torch.zeros(3, dtype=torch.float64)])
+    assert torch.allclose(c[3], g[3], atol=1e-5) and torch.allclose(c[8], g[8], rtol=1e-6, atol=1e-6)
+    xq = torch.relu(torch.randn(Bq, Hq, Wq, 12, generator=gen))
+    for mode, (ho, wo) in ((0, ((Hq + 1) // 2, (Wq + 1) // 2)), (1, (Hq // 2, Wq // 2))):
+        gp = torch.randn(Bq, ho, wo, 12, generator=gen)
+        c, g = both("eml_pool2d_bwd", [gp, 12, xq, 12, torch.zeros(Bq, Hq, Wq, 12), 12, Hq, Wq, C, Bq, mode])
+        assert torch.allclose(c[4], g[4], atol=1e-6)
+    Mq = 5000
+    aq, bq, mq = torch.randn(Mq, 4, generator=gen), torch.randn(Mq, 4, generator=gen), (torch.rand(Mq, generator=gen) > 0.5).float()
+    for mode in range(6):
+        c, g = both("eml_loss_seed", [aq, 4, bq, 4, mq, Mq, 3, mode, 0.5, torch.tensor([0.25]), torch.zeros(Mq, 4), 4])
+        assert torch.allclose(c[10], g[10], rtol=1e-4, atol=1e-6), mode
