@@ -177,6 +177,92 @@ __global__ void __launch_bounds__(128) stem_kernel(const float *__restrict__ x, 
     }
 }
 
+// Variant 2 of the stem (selected with EML_STEM_V2=1 until it has been timed on a B200; results are bit-identical: same fmaf order).
+// SASS of stem_kernel shows 786 LDS for 896 FFMA -- the weights are read from shared memory one scalar per FMA ([o][tap] layout,
+// stride 27), so the kernel is bound by shared-memory issue (1 LDS / clk / SM against 4 FFMA warps / clk / SM).  Here the weights
+// are stored [tap][o]: one broadcast LDS.128 feeds four FMAs, and the output count is a template parameter so that the 8 dead
+// accumulators of C_out = 24 are gone.
+template <int CO>
+__global__ void __launch_bounds__(128) stem_kernel_v2(const float *__restrict__ x, const float *__restrict__ w,
+                                                      const float *__restrict__ scale, const float *__restrict__ shift,
+                                                      float *__restrict__ out, int out_pitch, double *stats_raw,
+                                                      double *stats_out, long so_stride, int B, int H, int W, int write_out,
+                                                      int relu) {
+    static_assert(CO % 4 == 0 && CO <= 32, "stem_kernel_v2: C_out must be a multiple of 4, at most 32");
+    __shared__ __align__(16) float s_w[27 * CO];
+    __shared__ float s_sc[CO], s_sh[CO];
+    __shared__ double s_red[4][CO][4];
+    for (int i = threadIdx.x; i < CO * 27; i += blockDim.x) s_w[(i % 27) * CO + i / 27] = w[i];      // w is [o][c][ky][kx]
+    for (int i = threadIdx.x; i < CO; i += blockDim.x) {
+        s_sc[i] = scale ? scale[i] : 1.f;
+        s_sh[i] = shift ? shift[i] : 0.f;
+    }
+    __syncthreads();
+    const long P = static_cast<long>(B) * H * W;
+    const long m = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+    const bool ok = m < P;
+    float acc[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) acc[o] = 0.f;
+    if (ok) {
+        const int xx = static_cast<int>(m % W), yy = static_cast<int>((m / W) % H);
+        const long b = m / (static_cast<long>(W) * H);
+        const float *xb = x + b * 3 * H * W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int sy = yy + ky - 1, sx = xx + kx - 1;
+                    float v = 0.f;
+                    if (sy >= 0 && sy < H && sx >= 0 && sx < W) v = __ldg(xb + (static_cast<long>(c) * H + sy) * W + sx);
+                    const float4 *wt = reinterpret_cast<const float4 *>(s_w + (c * 9 + ky * 3 + kx) * CO);
+#pragma unroll
+                    for (int o4 = 0; o4 < CO / 4; ++o4) {
+                        const float4 wv = wt[o4];
+                        acc[4 * o4 + 0] = fmaf(v, wv.x, acc[4 * o4 + 0]);
+                        acc[4 * o4 + 1] = fmaf(v, wv.y, acc[4 * o4 + 1]);
+                        acc[4 * o4 + 2] = fmaf(v, wv.z, acc[4 * o4 + 2]);
+                        acc[4 * o4 + 3] = fmaf(v, wv.w, acc[4 * o4 + 3]);
+                    }
+                }
+    }
+    float res[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+        res[o] = fmaf(acc[o], s_sc[o], s_sh[o]);
+        if (relu) res[o] = fmaxf(res[o], 0.f);
+    }
+    if (ok && write_out) {
+        float *op = out + m * out_pitch;
+        if ((out_pitch & 3) == 0) {
+#pragma unroll
+            for (int o = 0; o < CO; o += 4) *reinterpret_cast<float4 *>(op + o) = make_float4(res[o], res[o + 1], res[o + 2], res[o + 3]);
+        } else {
+#pragma unroll
+            for (int o = 0; o < CO; ++o) op[o] = res[o];
+        }
+    }
+    if (stats_raw != nullptr || stats_out != nullptr) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int o = 0; o < CO; ++o) {
+            double a0 = ok ? static_cast<double>(acc[o]) : 0.0, r0 = ok ? static_cast<double>(res[o]) : 0.0;
+            double t0 = warp_sum_d(a0), t1 = warp_sum_d(a0 * a0), t2 = warp_sum_d(r0), t3 = warp_sum_d(r0 * r0);
+            if (lane == 0) { s_red[0][o][warp] = t0; s_red[1][o][warp] = t1; s_red[2][o][warp] = t2; s_red[3][o][warp] = t3; }
+        }
+        __syncthreads();
+        if (threadIdx.x < CO) {
+            double t[4] = {0, 0, 0, 0};
+            for (int q = 0; q < 4; ++q)
+                for (int wv = 0; wv < 4; ++wv) t[q] += s_red[q][threadIdx.x][wv];
+            if (stats_raw) { atomicAdd(stats_raw + threadIdx.x, t[0]); atomicAdd(stats_raw + CO + threadIdx.x, t[1]); }
+            if (stats_out) { atomicAdd(stats_out + threadIdx.x, t[2]); atomicAdd(stats_out + so_stride + threadIdx.x, t[3]); }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- BN fold
 __global__ void bn_fold_kernel(const double *stats, long sstride, double count, const float *rmean, const float *rvar,
                                const float *gamma, const float *beta, const float *pre_scale,
@@ -298,6 +384,13 @@ extern "C" int eml_stem_forward(const float *x_nchw, const float *w_oihw, const 
     if (write_out) { EML_CHECK_PTR(out); EML_CHECK_ALIGN16(out); }
     if (B <= 0 || H <= 0 || W <= 0 || C_out <= 0 || C_out > 32 || out_pitch < C_out) return EML_E_SHAPE;
     const long P = static_cast<long>(B) * H * W;
+    static const bool v2 = eml_env_flag("EML_STEM_V2");
+    if (v2 && C_out == 24) {
+        stem_kernel_v2<24><<<static_cast<unsigned>((P + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+            x_nchw, w_oihw, scale, shift, out, out_pitch, stats_raw, stats_out, stats_out_stride > 0 ? stats_out_stride : C_out, B, H, W,
+            write_out, relu);
+        return eml_launch_status();
+    }
     stem_kernel<<<static_cast<unsigned>((P + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
         x_nchw, w_oihw, scale, shift, out, out_pitch, stats_raw, stats_out,
         stats_out_stride > 0 ? stats_out_stride : C_out, B, H, W, C_out, write_out, relu);

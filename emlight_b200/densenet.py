@@ -24,6 +24,7 @@ tcgen05 implicit-GEMM kernels with transposed / flipped weights, BatchNorm backw
 csrc/bwd_ops.cu, the 48-channel bottleneck is recomputed instead of stored, the tiny fc / head GEMMs use torch.matmul (cuBLAS).
 """
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -496,7 +497,16 @@ class DenseNet(nn.Module):
                 ws["fc_a"] = torch.empty(2, B, Kp, dtype=torch.bfloat16, device=dev)
             a_hi, a_lo = ws["fc_a"][0], (ws["fc_a"][1] if self.precision == "bf16x3" else None)
             _lib.check(lib.eml_split_bf16(_lib.ptr(ws["pooled"]), B, K, K, _lib.ptr(a_hi), _lib.ptr(a_lo), Kp, st), "eml_split_bf16(pooled)")
+            splitk = os.environ.get("EML_FC_SPLITK") == "1"          # experiment (off by default): M = B rows give only ceil(B/128) row
+            if splitk:                                               # tiles per 256-feature slice, i.e. 8 CTAs at B = 256; split K over the SMs
+                ws["fc"].zero_()                                     # (float atomics: no longer bit-reproducible run to run)
+                ks = max(1, min(Kp // 64, 148 // ((B + 127) // 128)))
             for n0, rows, buf in c["fc_pack"]:
+                if splitk:
+                    _lib.check(lib.eml_gemm_bf16_splitk(_lib.ptr(a_hi), _lib.ptr(a_lo), B, Kp, _lib.ptr(buf), rows, _lib.ptr(c["fc_b"][n0:n0 + rows]),
+                                                        _lib.ptr(ws["fc"]), self.fc.out_features, n0, _lib.PRECISIONS[self.precision], ks, st),
+                               "eml_gemm_bf16_splitk(fc)")
+                    continue
                 _lib.check(lib.eml_gemm_bf16(_lib.ptr(a_hi), _lib.ptr(a_lo), B, Kp, _lib.ptr(buf), rows, _lib.ptr(c["fc_b"][n0:n0 + rows]),
                                              _lib.ptr(ws["fc"]), self.fc.out_features, n0, _lib.PRECISIONS[self.precision], st), "eml_gemm_bf16(fc)")
         else:
