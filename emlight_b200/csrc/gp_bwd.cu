@@ -30,11 +30,16 @@ static inline int eml_launch_status() { return EML_OK; }
             for (unsigned t_ = 0; t_ < blockDim.x; ++t_) { blockIdx.x = b_; threadIdx.x = t_; kern(__VA_ARGS__); }     \
     } while (0)
 #define EML_API(name) name##_emu
+#include <string.h>
+static inline unsigned f2u(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 #else
 #include "common.cuh"
 #define EML_LAUNCH(kern, grid, block, stream, ...) \
     kern<<<static_cast<unsigned>(grid), (block), 0, static_cast<cudaStream_t>(stream)>>>(__VA_ARGS__)
 #define EML_API(name) name
+__device__ __forceinline__ unsigned f2u(float f) { return __float_as_uint(f); }
+__device__ __forceinline__ float u2f(unsigned u) { return __uint_as_float(u); }
 #endif
 
 namespace {
@@ -343,6 +348,48 @@ __global__ void cos_seed_kernel(const float *__restrict__ a, int a_pitch, const 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ transposed bf16 im2col (weight gradient)
+// The operand of the weight-gradient GEMM dWk^T = A^T dY has K = pixels, so it wants A TRANSPOSED: rows = (tap, channel), columns =
+// output pixels m.  This is eml_im2col_lut_bf16 writing the transpose directly, split into bf16 hi / lo (round to nearest even, the
+// same split as eml_split_bf16): thread = (m fastest, tap, channel quad) -> the four row writes of a warp are 64 contiguous bytes.
+//   hi/lo[(tap*Cp + c) * Mp + m] = bf16 split of sum_t w[p,tap,t] * act(x[b, idx[p,tap,t], c] + bias[c])     (columns >= M stay 0)
+#define BF16_RNE(f) static_cast<unsigned short>((f2u(f) + 0x7FFFu + ((f2u(f) >> 16) & 1u)) >> 16)
+__global__ void im2col_lut_bf16_t_kernel(const float *__restrict__ x, int x_pitch, int C, int Cp, const int *__restrict__ lut_idx,
+                                         const float *__restrict__ lut_w, const float *__restrict__ bias, int act,
+                                         unsigned short *hi, unsigned short *lo, long Mp, long M, long out_pixels, long in_pixels,
+                                         long total) {
+    const long tid = GLOBAL_TID;
+    if (tid >= total) return;
+    const long m = tid % M;
+    const long rest = tid / M;
+    const int tap = static_cast<int>(rest % 9);
+    const int cq = static_cast<int>(rest / 9);
+    const long p = m % out_pixels;
+    const long b = m / out_pixels;
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const long l = (p * 9 + tap) * 4;
+    for (int t = 0; t < 4; ++t) {
+        const int q = lut_idx[l + t];
+        const float w = lut_w[l + t];
+        if (q < 0 || w == 0.0f) continue;
+        const float *src = x + (b * in_pixels + q) * x_pitch + 4 * cq;
+        for (int j = 0; j < 4; ++j) {
+            const int c = 4 * cq + j;
+            if (c >= C) break;
+            float u = src[j] + (bias ? bias[c] : 0.0f);
+            if (act == 1) u = u > 0.0f ? u : 0.0f;
+            else if (act == 2) u = u > 0.0f ? u : 0.2f * u;
+            acc[j] += w * u;
+        }
+    }
+    for (int j = 0; j < 4; ++j) {
+        const long o = (static_cast<long>(tap) * Cp + 4 * cq + j) * Mp + m;
+        const unsigned short h = BF16_RNE(acc[j]);
+        hi[o] = h;
+        if (lo) { const float r = acc[j] - u2f(static_cast<unsigned>(h) << 16); lo[o] = BF16_RNE(r); }
+    }
+}
+
 }  // namespace
 
 // =================================================================================================== C ABI
@@ -470,5 +517,19 @@ extern "C" int EML_API(eml_loss_seed)(const float *a, int a_pitch, const float *
         if (blocks_for(M * C) > 0x7fffffffL) return EML_E_SHAPE;
         EML_LAUNCH(loss_seed_kernel, blocks_for(M * C), THREADS, stream, a, a_pitch, b, b_pitch, mask, M, C, mode, coef, coef_dev, da, da_pitch);
     }
+    return eml_launch_status();
+}
+
+extern "C" int EML_API(eml_im2col_lut_bf16_t)(const float *x, int x_pitch, int C, int Cp, const int *lut_idx, const float *lut_w,
+                                              const float *bias, int act, void *At_hi, void *At_lo, long Mp, int B, long out_pixels,
+                                              long in_pixels, void *stream) {
+    EML_CHECK_PTR(x); EML_CHECK_PTR(lut_idx); EML_CHECK_PTR(lut_w); EML_CHECK_PTR(At_hi);
+    if (act < 0 || act > 2) return EML_E_ARG;
+    const long M = static_cast<long>(B) * out_pixels;
+    if (B <= 0 || C <= 0 || Cp < C || (Cp & 3) || x_pitch < C || out_pixels <= 0 || in_pixels <= 0 || Mp < M) return EML_E_SHAPE;
+    const long total = M * 9 * (Cp >> 2);
+    if (blocks_for(total) > 0x7fffffffL) return EML_E_SHAPE;
+    EML_LAUNCH(im2col_lut_bf16_t_kernel, blocks_for(total), THREADS, stream, x, x_pitch, C, Cp, lut_idx, lut_w, bias, act,
+               static_cast<unsigned short *>(At_hi), static_cast<unsigned short *>(At_lo), Mp, M, out_pixels, in_pixels, total);
     return eml_launch_status();
 }

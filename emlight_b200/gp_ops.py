@@ -134,15 +134,25 @@ def mm_nt(a, b, precision="bf16x3"):
     a_hi = torch.empty(M, Kp, dtype=torch.bfloat16, device=a.device)
     a_lo = torch.empty_like(a_hi) if split else None
     _lib.check(lib.eml_split_bf16(_lib.ptr(a), M, K, K, _lib.ptr(a_hi), _lib.ptr(a_lo), Kp, st), "eml_split_bf16")
+    return mm_nt_split(a_hi, a_lo, M, K, b, precision)
+
+
+def mm_nt_split(a_hi, a_lo, M, K, b, precision="bf16x3"):
+    """(M,N) fp32 = A (M,K) @ b (N,K)^T with A already split into bf16 hi / lo rows of length Kp = round_up(K, 64) (zero padded)."""
+    lib = _lib.load()
+    st = _lib.stream_ptr()
+    b = b.contiguous().float()
+    N = b.shape[0]
+    Kp = a_hi.shape[1]
     pitch = _up4(N)
     mtiles = (M + 127) // 128
     ksplit = max(1, min(Kp // 64, 148 // mtiles))
     deep = ksplit > 1 and Kp >= 2048
-    out = (torch.zeros if deep else torch.empty)(M, pitch, dtype=torch.float32, device=a.device)
+    out = (torch.zeros if deep else torch.empty)(M, pitch, dtype=torch.float32, device=b.device)
     prec = _lib.PRECISIONS[precision]
     for n0 in range(0, N, 256):
         rows = min(256, N - n0)
-        buf = torch.empty(lib.eml_conv_wpack_bytes(rows, K, 1), dtype=torch.uint8, device=a.device)
+        buf = torch.empty(lib.eml_conv_wpack_bytes(rows, K, 1), dtype=torch.uint8, device=b.device)
         _lib.check(lib.eml_conv_pack_weights(_lib.ptr(b[n0:n0 + rows]), _lib.ptr(buf), rows, K, 1, st), "eml_conv_pack_weights(mm_nt)")
         if deep:
             _lib.check(lib.eml_gemm_bf16_splitk(_lib.ptr(a_hi), _lib.ptr(a_lo), M, Kp, _lib.ptr(buf), rows, None, _lib.ptr(out), pitch, n0,
@@ -257,3 +267,17 @@ def loss_seed(mode, a, M, C, coef, coef_dev, b=None, mask=None):
     _lib.check(_fn("eml_loss_seed")(_lib.ptr(a), a.shape[-1], _lib.ptr(b), b.shape[-1] if b is not None else 0, _lib.ptr(mask), M, C, int(mode),
                                     float(coef), _lib.ptr(coef_dev), _lib.ptr(da), da.shape[-1], _st()), "eml_loss_seed")
     return da
+
+
+def im2col_t(x, B, H, W, C, lut_, bias_in, act, split=True):
+    """(At_hi, At_lo or None): the im2col operand TRANSPOSED, (9*up4(C), Mp) bf16 with Mp = round_up(B*out_pixels, 64), for the
+    weight-gradient GEMM (K = pixels) -- no fp32 matrix, no transpose pass."""
+    idx, wgt, ho, wo = lut_
+    Cp = _up4(C)
+    M = B * ho * wo
+    Mp = (M + 63) // 64 * 64
+    hi = torch.zeros(9 * Cp, Mp, dtype=torch.bfloat16, device=x.device)
+    lo = torch.zeros_like(hi) if split else None
+    _lib.check(_fn("eml_im2col_lut_bf16_t")(_lib.ptr(x), x.shape[-1], C, Cp, _lib.ptr(idx), _lib.ptr(wgt), _lib.ptr(bias_in), int(act),
+                                            _lib.ptr(hi), _lib.ptr(lo), Mp, B, ho * wo, H * W, _st()), "eml_im2col_lut_bf16_t")
+    return hi, lo

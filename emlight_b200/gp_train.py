@@ -9,7 +9,8 @@ so `loss.backward()`, `optimizer.step()` and the gradient all-reduce of `paralle
 Split of work in this first version:
 * all contractions -- forward convolutions, data gradients `dA = dY Wk`, weight gradients `dWk^T = A^T dY` (K = pixels, split-K) --
   run on the TMA-fed tcgen05 GEMM through `gp_ops.mm_nt` / `gp_ops.conv_raw`; the im2col operand of the weight gradient is
-  recomputed with the forward's gather kernel instead of being stored;
+  recomputed instead of stored, written directly TRANSPOSED and split into bf16 hi/lo (`eml_im2col_lut_bf16_t`), so neither an
+  fp32 im2col matrix nor a transpose pass exists;
 * the gather's adjoint (col2im through the sampling table), activation / bias, SPADE modulation, parameter-free BatchNorm and
   InstanceNorm adjoints are the kernels of `csrc/gp_bwd.cu` (`gp_ops.col2im`, `act_bwd`, `bias_act_bwd`, `spade_bwd`, `bn_free_bwd`,
   `instance_norm_bwd`);
@@ -154,9 +155,14 @@ def conv(tape, x, B, H, W, C, w_eff, lut, bias_in, bias_in_param, act, precision
         M = B * ho * wo
         g2 = g[..., :O].reshape(M, O).contiguous()
         if on_dw is not None:
-            A = ops.im2col(x, B, H, W, C, lut, bias_in, act)                                  # (M, 9 Cp), recomputed
-            dwk_t = ops.mm_nt(A.t().contiguous(), g2.t().contiguous(), precision)            # (9 Cp, O), K = pixels
-            del A
+            if precision == "fp32":
+                A = ops.im2col(x, B, H, W, C, lut, bias_in, act)                              # (M, 9 Cp), recomputed
+                dwk_t = ops.mm_nt(A.t().contiguous(), g2.t().contiguous(), precision)        # (9 Cp, O), K = pixels
+                del A
+            else:                                                                             # operand recomputed straight into A^T bf16 hi/lo
+                at_hi, at_lo = ops.im2col_t(x, B, H, W, C, lut, bias_in, act, precision == "bf16x3")
+                dwk_t = ops.mm_nt_split(at_hi, at_lo, 9 * Cp, M, g2.t().contiguous(), precision)
+                del at_hi, at_lo
             on_dw(dwk_t.reshape(9, Cp, O)[:, :C, :].permute(2, 1, 0).reshape(O, C, 3, 3))
         need_b = bias_in_param is not None and bias_in_param.requires_grad
         if not (need_dx or need_b):

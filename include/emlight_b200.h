@@ -292,6 +292,9 @@ int eml_wgrad_stem(const float *dZ, int dz_pitch, int O, const float *x_nchw, fl
  *     sums == NULL: running-statistics mode, dx = inv_std * d_xhat.
  * eml_instance_norm_bwd: adjoint of eml_instance_norm (InstanceNorm2d(affine=False) + optional LeakyReLU) from its output and raw
  *     input; `sums` is a caller-zeroed (B, 4, C) double scratch.
+ * eml_im2col_lut_bf16_t: the eml_im2col_lut_bf16 gather written TRANSPOSED -- At[(tap*Cp + c), m], row length Mp >= B*out_pixels a
+ *     multiple of 64, bf16 hi / lo (At_lo may be NULL), caller-zeroed -- the A operand (rows = filter taps x channels, K = pixels) of the
+ *     weight-gradient GEMM dWk^T = A^T dY, so that no fp32 im2col matrix and no transpose pass exist.
  * eml_upsample2_bwd: adjoint of the nearest x2 upsampling (generator.py:42,70): dx[b,h,w,c] = sum of the 2x2 block of g.
  * eml_tanh_nchw_bwd: adjoint of eml_tanh_to_nchw from its NCHW output: d_raw (NHWC) = g * scale * (1 - tanh^2), bias_sums[c] += sum.
  * eml_pool2d_bwd: adjoint of eml_pool2d; mode 0 (3x3 average, stride 2, pad 1, count_include_pad=False) needs only g, mode 1 (2x2 max)
@@ -312,6 +315,8 @@ int eml_bn_free_bwd(const float *d_xhat, int dxh_pitch, const float *x, int x_pi
                     const double *sums, double count, float *dx, int dx_pitch, long M, int C, void *stream);
 int eml_instance_norm_bwd(const float *g, int g_pitch, const float *out, int out_pitch, const float *raw, int raw_pitch, int B, long HW,
                           int C, float eps, int leaky_relu, double *sums, float *dx, int dx_pitch, void *stream);
+int eml_im2col_lut_bf16_t(const float *x, int x_pitch, int C, int Cp, const int *lut_idx, const float *lut_w, const float *bias, int act,
+                          void *At_hi, void *At_lo, long Mp, int B, long out_pixels, long in_pixels, void *stream);
 int eml_upsample2_bwd(const float *g, int g_pitch, float *dx, int dx_pitch, int B, int H, int W, int C, void *stream);
 int eml_tanh_nchw_bwd(const float *g_nchw, const float *out_nchw, float scale, float *d_raw, int pitch, int B, long HW, int C,
                       double *bias_sums, void *stream);

@@ -24,7 +24,7 @@ def emu(tmp_path_factory):
     lib = ctypes.CDLL(out)
     from emlight_b200 import _lib
     for name in ("eml_col2im_lut", "eml_act_bwd", "eml_bias_act_bwd", "eml_spade_bwd", "eml_bn_free_bwd", "eml_instance_norm_bwd",
-                 "eml_upsample2_bwd", "eml_tanh_nchw_bwd", "eml_pool2d_bwd", "eml_loss_seed"):
+                 "eml_upsample2_bwd", "eml_tanh_nchw_bwd", "eml_pool2d_bwd", "eml_loss_seed", "eml_im2col_lut_bf16_t"):
         fn = getattr(lib, name + "_emu")
         fn.restype, fn.argtypes = _lib.SIGNATURES[name]          # the emulated entry points have the product's signatures
     return lib
@@ -231,6 +231,39 @@ def test_loss_seeds_match_autograd_of_the_reductions(emu, mode):
     assert bool(ok.sum() >= M - 1)
     assert float((da[:, :C][ok] - want[ok]).abs().max()) <= 1e-4 * float(want[ok].abs().max())
     assert emu.eml_loss_seed_emu(P(a), pitch, None, pitch, P(mask), M, C, 3, 1.0, None, P(da), pitch, None) < 0
+
+
+@pytest.mark.parametrize("kind,h,w,stride,C,act", [("sphere", 8, 16, 1, 5, 2), ("sphere", 8, 16, 2, 8, 0), ("conv", 9, 7, 2, 3, 1)])
+def test_transposed_bf16_im2col_matches_the_gather(emu, kind, h, w, stride, C, act):
+    """A^T in bf16 hi + lo == the fp32 gather to ~2^-16 relative; hi is the round-to-nearest-even bf16 of the value (the split of
+    eml_split_bf16); padding rows / columns stay zero."""
+    from emlight_b200.genprojector import _conv_lut, _sphere_lut
+    idx, wgt, ho, wo = (_sphere_lut if kind == "sphere" else _conv_lut)(h, w, stride)
+    idx, wgt = torch.from_numpy(idx).contiguous(), torch.from_numpy(wgt).contiguous()
+    B, Cp = 2, (C + 3) & ~3
+    gen = torch.Generator().manual_seed(h + w + C)
+    x = torch.randn(B, h * w, Cp, generator=gen)
+    bias = torch.randn(C, generator=gen)
+    M = B * ho * wo
+    Mp = (M + 63) // 64 * 64
+    hi = torch.zeros(9 * Cp, Mp, dtype=torch.bfloat16)
+    lo = torch.zeros(9 * Cp, Mp, dtype=torch.bfloat16)
+    assert emu.eml_im2col_lut_bf16_t_emu(P(x), Cp, C, Cp, P(idx), P(wgt), P(bias), act, P(hi), P(lo), Mp, B, ho * wo, h * w, None) == 0
+    u = x[..., :C] + bias
+    u = F.relu(u) if act == 1 else F.leaky_relu(u, 0.2) if act == 2 else u
+    u = F.pad(u, (0, Cp - C))
+    A = torch.zeros(B, ho * wo * 9, Cp)
+    for t in range(4):
+        A += u[:, idx[:, :, t].reshape(-1).clamp_min(0).long()] * wgt[:, :, t].reshape(1, -1, 1)
+    At = A.reshape(M, 9 * Cp).t()                                       # (9 Cp, M)
+    got = hi.float() + lo.float()
+    assert float((got[:, :M] - At).abs().max()) <= 2.0 ** -15 * float(At.abs().max())
+    assert torch.equal(hi[:, :M], At.to(torch.bfloat16)) or float((hi[:, :M].float() - At).abs().max()) <= 2.0 ** -8 * float(At.abs().max())
+    assert not got[:, M:].any()
+    only_hi = torch.zeros_like(hi)
+    assert emu.eml_im2col_lut_bf16_t_emu(P(x), Cp, C, Cp, P(idx), P(wgt), P(bias), act, P(only_hi), None, Mp, B, ho * wo, h * w, None) == 0
+    assert torch.equal(only_hi, hi)
+    assert emu.eml_im2col_lut_bf16_t_emu(P(x), Cp, C, Cp, P(idx), P(wgt), P(bias), act, P(hi), P(lo), M - 1, B, ho * wo, h * w, None) < 0
 
 
 def test_product_library_validates_the_same_arguments(lib):

@@ -131,6 +131,11 @@ def sim_tanh_to_nchw(raw, bias, B, H, W, C, scale):
     return ((torch.tanh(raw[..., :C] + bias) + 1) * scale).permute(0, 3, 1, 2).contiguous()
 
 
+def sim_mm_nt_split(a_hi, a_lo, M, K, b, precision="bf16x3"):
+    a = a_hi.float() + (a_lo.float() if a_lo is not None else 0)
+    return a[:M, :K] @ b.t()
+
+
 def build_emu(outdir):
     """csrc/gp_bwd.cu compiled for the host (EML_EMULATE): the adjoint KERNELS themselves run inside these tests."""
     import ctypes
@@ -143,7 +148,7 @@ def build_emu(outdir):
     lib = ctypes.CDLL(out)
     fns = {}
     for name in ("eml_col2im_lut", "eml_act_bwd", "eml_bias_act_bwd", "eml_spade_bwd", "eml_bn_free_bwd", "eml_instance_norm_bwd",
-                 "eml_upsample2_bwd", "eml_tanh_nchw_bwd", "eml_pool2d_bwd", "eml_loss_seed"):
+                 "eml_upsample2_bwd", "eml_tanh_nchw_bwd", "eml_pool2d_bwd", "eml_loss_seed", "eml_im2col_lut_bf16_t"):
         fn = getattr(lib, name + "_emu")
         fn.restype, fn.argtypes = _lib.SIGNATURES[name]
         fns[name] = fn
@@ -158,7 +163,7 @@ def install_sims(gp_ops, emu_fns, setter=setattr):
                          channel_sums=sim_channel_sums, spade_modulate=sim_spade_modulate, bias_residual=sim_bias_residual,
                          resize_nearest=sim_resize_nearest, resize_bilinear_nchw=sim_resize_bilinear_nchw,
                          tanh_to_nchw=sim_tanh_to_nchw, linear=lambda a, w, b: a @ w.t() + b,
-                         mm_nt=lambda a, b, precision="bf16x3": a @ b.t()).items():
+                         mm_nt=lambda a, b, precision="bf16x3": a @ b.t(), mm_nt_split=sim_mm_nt_split).items():
         setter(gp_ops, name, fn)
 
 

@@ -215,3 +215,12 @@ def test_adjoint_kernels_match_their_host_emulation(cuda, lib, tmp_path):
     for mode in range(6):
         c, g = both("eml_loss_seed", [aq, 4, bq, 4, mq, Mq, 3, mode, 0.5, torch.tensor([0.25]), torch.zeros(Mq, 4), 4])
         assert torch.allclose(c[10], g[10], rtol=1e-4, atol=1e-6), mode
+    h, w, C = 32, 64, 12
+    idx, wgt, ho, wo = _sphere_lut(h, w, 2)
+    idx, wgt = torch.from_numpy(idx).contiguous(), torch.from_numpy(wgt).contiguous()
+    Mq = 3 * ho * wo
+    Mp = (Mq + 63) // 64 * 64
+    xq = torch.randn(3, h * w, C, generator=gen)
+    c, g = both("eml_im2col_lut_bf16_t", [xq, C, 10, C, idx, wgt, torch.randn(10, generator=gen), 2, torch.zeros(9 * C, Mp, dtype=torch.bfloat16),
+                                          torch.zeros(9 * C, Mp, dtype=torch.bfloat16), Mp, 3, ho * wo, h * w])
+    assert torch.equal(c[8], g[8]) and torch.equal(c[9], g[9])
