@@ -390,6 +390,31 @@ __global__ void im2col_lut_bf16_t_kernel(const float *__restrict__ x, int x_pitc
     }
 }
 
+// ------------------------------------------------------------------------------------------------ col2im, gather form (no atomics)
+// The sampling table inverted on the host into CSR over INPUT pixels: for input pixel q the entries e in [offs[q], offs[q+1]) name the
+// im2col cell src[e] = p*9 + tap that read q with weight w[e].  One thread per (b, q, channel quad) sums its entries in a fixed order:
+// deterministic, one write per element, reads of dA rows coalesced over the channel quads.
+//   dx[b, q, c] = sum_e w[e] * dA[b*out_pixels + src[e]/9, (src[e]%9)*Cp + c]
+__global__ void col2im_csr_kernel(const float *__restrict__ dA, int Cp, const int *__restrict__ offs, const int *__restrict__ src,
+                                  const float *__restrict__ w, float *dx, int dx_pitch, long total, long out_pixels, long in_pixels) {
+    const long tid = GLOBAL_TID;
+    if (tid >= total) return;
+    const int q4 = Cp >> 2;
+    const int cq = static_cast<int>(tid % q4);
+    const long bq = tid / q4;
+    const long q = bq % in_pixels;
+    const long b = bq / in_pixels;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    const float *base = dA + b * out_pixels * 9L * Cp + 4 * cq;
+    for (int e = offs[q]; e < offs[q + 1]; ++e) {
+        const float *row = base + static_cast<long>(src[e]) * Cp;          // (p*9 + tap) * Cp
+        const float we = w[e];
+        a0 += we * row[0]; a1 += we * row[1]; a2 += we * row[2]; a3 += we * row[3];
+    }
+    float *dst = dx + bq * dx_pitch + 4 * cq;
+    dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
+}
+
 }  // namespace
 
 // =================================================================================================== C ABI
@@ -531,5 +556,15 @@ extern "C" int EML_API(eml_im2col_lut_bf16_t)(const float *x, int x_pitch, int C
     if (blocks_for(total) > 0x7fffffffL) return EML_E_SHAPE;
     EML_LAUNCH(im2col_lut_bf16_t_kernel, blocks_for(total), THREADS, stream, x, x_pitch, C, Cp, lut_idx, lut_w, bias, act,
                static_cast<unsigned short *>(At_hi), static_cast<unsigned short *>(At_lo), Mp, M, out_pixels, in_pixels, total);
+    return eml_launch_status();
+}
+
+extern "C" int EML_API(eml_col2im_csr)(const float *dA, int Cp, const int *offs, const int *src, const float *w, float *dx, int dx_pitch,
+                                       int B, long out_pixels, long in_pixels, void *stream) {
+    EML_CHECK_PTR(dA); EML_CHECK_PTR(offs); EML_CHECK_PTR(src); EML_CHECK_PTR(w); EML_CHECK_PTR(dx);
+    if (B <= 0 || out_pixels <= 0 || in_pixels <= 0 || Cp <= 0 || (Cp & 3) || dx_pitch < Cp) return EML_E_SHAPE;
+    const long total = static_cast<long>(B) * in_pixels * (Cp >> 2);
+    if (blocks_for(total) > 0x7fffffffL) return EML_E_SHAPE;
+    EML_LAUNCH(col2im_csr_kernel, blocks_for(total), THREADS, stream, dA, Cp, offs, src, w, dx, dx_pitch, total, out_pixels, in_pixels);
     return eml_launch_status();
 }

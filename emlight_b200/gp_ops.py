@@ -172,13 +172,37 @@ def _st():
     return _lib.stream_ptr()
 
 
-def col2im(dA, Cp, lut_, B, in_pixels):
-    """dx (B, in_pixels, Cp) = adjoint of the 4-tap gather applied to dA (B*out_pixels, 9*Cp)."""
+_CSR = {}
+
+
+def lut_csr(lut_, in_pixels):
+    """The sampling table inverted into CSR over input pixels (host, once per table): offs (in_pixels+1) int32, src = p*9 + tap int32,
+    w fp32, entries of one input pixel ordered by (p, tap, t) so that the summation order is fixed."""
     idx, wgt, ho, wo = lut_
+    key = (idx.data_ptr(), in_pixels, str(idx.device))
+    if key not in _CSR:
+        i = idx.reshape(-1).cpu().numpy().astype("int64")                   # (P*9*4,)
+        w = wgt.reshape(-1).cpu().numpy()
+        import numpy as np
+        keep = np.nonzero((i >= 0) & (w != 0))[0]
+        order = keep[np.argsort(i[keep], kind="stable")]
+        counts = np.bincount(i[order], minlength=in_pixels)
+        offs = np.concatenate(([0], np.cumsum(counts))).astype("int32")
+        src = (order // 4).astype("int32")
+        dev = idx.device
+        _CSR[key] = (torch.from_numpy(offs).to(dev), torch.from_numpy(src).to(dev), torch.from_numpy(w[order].astype("float32")).to(dev), idx)
+    return _CSR[key][:3]
+
+
+def col2im(dA, Cp, lut_, B, in_pixels):
+    """dx (B, in_pixels, Cp) = adjoint of the 4-tap gather applied to dA (B*out_pixels, 9*Cp): gather form over the inverted table
+    (eml_col2im_csr; no atomics, deterministic)."""
+    idx, wgt, ho, wo = lut_
+    offs, src, w = lut_csr(lut_, in_pixels)
     dA = dA.contiguous()
-    dx = torch.zeros(B, in_pixels, Cp, dtype=torch.float32, device=dA.device)
-    _lib.check(_fn("eml_col2im_lut")(_lib.ptr(dA), Cp, _lib.ptr(idx), _lib.ptr(wgt), _lib.ptr(dx), Cp, B, ho * wo, in_pixels, _st()),
-               "eml_col2im_lut")
+    dx = torch.empty(B, in_pixels, Cp, dtype=torch.float32, device=dA.device)
+    _lib.check(_fn("eml_col2im_csr")(_lib.ptr(dA), Cp, _lib.ptr(offs), _lib.ptr(src), _lib.ptr(w), _lib.ptr(dx), Cp, B, ho * wo, in_pixels,
+                                     _st()), "eml_col2im_csr")
     return dx
 
 

@@ -281,6 +281,9 @@ int eml_wgrad_stem(const float *dZ, int dz_pitch, int O, const float *x_nchw, fl
  *
  * eml_col2im_lut: adjoint of the eml_im2col_lut gather (sphere_cnn.py:111-124 grid_sample backward):
  *     dx[b, lut_idx[p,tap,t], c] += lut_w[p,tap,t] * dA[b*out_pixels + p, tap*Cp + c]      (float atomics; dx ZERO on entry)
+ * eml_col2im_csr: the same adjoint in gather form, without atomics: the table inverted on the host into CSR over input pixels
+ *     (offs (in_pixels+1), src = p*9 + tap, w), dx[b,q,c] = sum_{e in [offs[q], offs[q+1])} w[e] * dA[b*out_pixels + src[e]/9, (src[e]%9)*Cp + c];
+ *     every element of dx[..., :Cp] is written (no zeroing needed), deterministic summation order.
  * eml_act_bwd: dx *= act'(x + bias) in place (the activation eml_im2col_lut applies before gathering), bias_sums[c] += sum_m dx
  *     (act 0 with bias_sums != NULL: only the sums).
  * eml_bias_act_bwd: adjoint of eml_bias_act from its OUTPUT: dx = g * act'(out), bias_sums[c] += sum_m dx.
@@ -304,6 +307,8 @@ int eml_wgrad_stem(const float *dZ, int dz_pitch, int O, const float *x_nchw, fl
  *     1 - (a/max(|a|,eps)).(b/max(|b|,eps)), eps 1e-20 as in pix2pix_model.py:95); b / mask as for eml_loss_reduce. */
 int eml_col2im_lut(const float *dA, int Cp, const int *lut_idx, const float *lut_w, float *dx, int dx_pitch, int B, long out_pixels,
                    long in_pixels, void *stream);
+int eml_col2im_csr(const float *dA, int Cp, const int *offs, const int *src, const float *w, float *dx, int dx_pitch, int B,
+                   long out_pixels, long in_pixels, void *stream);
 int eml_act_bwd(float *dx, int dx_pitch, const float *x, int x_pitch, const float *bias, int act, long M, int C, double *bias_sums,
                 void *stream);
 int eml_bias_act_bwd(const float *g, int g_pitch, const float *out, int out_pitch, int act, float *dx, int dx_pitch, long M, int C,

@@ -24,7 +24,7 @@ def emu(tmp_path_factory):
     lib = ctypes.CDLL(out)
     from emlight_b200 import _lib
     for name in ("eml_col2im_lut", "eml_act_bwd", "eml_bias_act_bwd", "eml_spade_bwd", "eml_bn_free_bwd", "eml_instance_norm_bwd",
-                 "eml_upsample2_bwd", "eml_tanh_nchw_bwd", "eml_pool2d_bwd", "eml_loss_seed", "eml_im2col_lut_bf16_t"):
+                 "eml_upsample2_bwd", "eml_tanh_nchw_bwd", "eml_pool2d_bwd", "eml_loss_seed", "eml_im2col_lut_bf16_t", "eml_col2im_csr"):
         fn = getattr(lib, name + "_emu")
         fn.restype, fn.argtypes = _lib.SIGNATURES[name]          # the emulated entry points have the product's signatures
     return lib
@@ -63,6 +63,15 @@ def test_col2im_is_the_adjoint_of_the_gather(emu, kind, h, w, stride, C):
     for t in range(4):
         A += x[:, idx[:, :, t].reshape(-1).clamp_min(0).long()] * wgt[:, :, t].reshape(1, -1, 1)
     assert abs(float((A * d3).sum()) - float((x * dx).sum())) <= 1e-4 * float((A * d3).abs().sum())
+    # gather form over the inverted table: same result, every element written (start from garbage), deterministic
+    from emlight_b200 import gp_ops
+    offs, src, wv = gp_ops.lut_csr((idx, wgt, ho, wo), h * w)
+    assert int(offs[-1]) == int(((idx >= 0) & (wgt != 0)).sum()) and offs.dtype == torch.int32
+    dx2 = torch.full((B, h * w, Cp), 9.0)
+    assert emu.eml_col2im_csr_emu(P(dA), Cp, P(offs), P(src), P(wv), P(dx2), Cp, B, ho * wo, h * w, None) == 0
+    assert float((dx2 - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    dx3 = torch.zeros(B, h * w, Cp)
+    assert emu.eml_col2im_csr_emu(P(dA), Cp, P(offs), P(src), P(wv), P(dx3), Cp, B, ho * wo, h * w, None) == 0 and torch.equal(dx2, dx3)
     assert emu.eml_col2im_lut_emu(P(dA), 6, P(idx), P(wgt), P(dx), 8, B, ho * wo, h * w, None) < 0       # Cp must be a multiple of 4
     assert emu.eml_col2im_lut_emu(None, Cp, P(idx), P(wgt), P(dx), Cp, B, ho * wo, h * w, None) < 0
 
@@ -272,6 +281,7 @@ def test_product_library_validates_the_same_arguments(lib):
     a = ctypes.cast(z, c_void_p)
     assert lib.eml_col2im_lut(a, 6, a, a, a, 8, 1, 4, 4, None) < 0
     assert lib.eml_col2im_lut(None, 4, a, a, a, 4, 1, 4, 4, None) < 0
+    assert lib.eml_col2im_csr(a, 4, None, a, a, a, 4, 1, 4, 4, None) < 0
     assert lib.eml_act_bwd(a, 4, a, 4, None, 5, 4, 4, None, None) < 0
     assert lib.eml_bias_act_bwd(a, 2, a, 4, 1, a, 4, 4, 4, None, None) < 0
     assert lib.eml_spade_bwd(a, 4, a, 4, a, 4, a, a, a, 4, None, a, a, 4, 4, 4, 0, a, None) < 0

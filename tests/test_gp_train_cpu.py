@@ -148,7 +148,7 @@ def build_emu(outdir):
     lib = ctypes.CDLL(out)
     fns = {}
     for name in ("eml_col2im_lut", "eml_act_bwd", "eml_bias_act_bwd", "eml_spade_bwd", "eml_bn_free_bwd", "eml_instance_norm_bwd",
-                 "eml_upsample2_bwd", "eml_tanh_nchw_bwd", "eml_pool2d_bwd", "eml_loss_seed", "eml_im2col_lut_bf16_t"):
+                 "eml_upsample2_bwd", "eml_tanh_nchw_bwd", "eml_pool2d_bwd", "eml_loss_seed", "eml_im2col_lut_bf16_t", "eml_col2im_csr"):
         fn = getattr(lib, name + "_emu")
         fn.restype, fn.argtypes = _lib.SIGNATURES[name]
         fns[name] = fn
