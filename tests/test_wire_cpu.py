@@ -140,3 +140,58 @@ def test_dropin_util_exposes_exr_io():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.load_exr is wire.load_exr and mod.write_exr is wire.write_exr
+
+
+def _raw_exr(path, planes, x0=0, y0=0, line_order=0, ptype=2, shuffle=None):
+    """Hand-built uncompressed scan-line file (published layout): channels in `planes` (name -> (H,W) array), data window at (x0,y0),
+    chunks stored in `shuffle` order -- exercises what a writer other than ours may legally produce."""
+    import struct
+    names = sorted(planes)
+    h, w = planes[names[0]].shape
+    dt = {0: "<u4", 1: "<f2", 2: "<f4"}[ptype]
+
+    def attr(name, typ, payload):
+        return name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<i", len(payload)) + payload
+
+    chlist = b"".join(n.encode() + b"\0" + struct.pack("<iB3xii", ptype, 0, 1, 1) for n in names) + b"\0"
+    win = struct.pack("<4i", x0, y0, x0 + w - 1, y0 + h - 1)
+    header = struct.pack("<ii", 20000630, 2) + attr("channels", "chlist", chlist) + attr("compression", "compression", b"\0") + \
+        attr("dataWindow", "box2i", win) + attr("displayWindow", "box2i", win) + attr("lineOrder", "lineOrder", bytes([line_order])) + \
+        attr("pixelAspectRatio", "float", struct.pack("<f", 1.0)) + attr("screenWindowCenter", "v2f", struct.pack("<ff", 0, 0)) + \
+        attr("screenWindowWidth", "float", struct.pack("<f", 1.0)) + b"\0"
+    rows = list(range(h))
+    stored = list(shuffle) if shuffle is not None else (rows[::-1] if line_order == 1 else rows)
+    chunks = {}
+    for r in stored:
+        body = b"".join(np.ascontiguousarray(planes[n][r]).astype(dt).tobytes() for n in names)
+        chunks[r] = struct.pack("<ii", y0 + r, len(body)) + body
+    pos = len(header) + 8 * h
+    offs = {}
+    blob = b""
+    for r in stored:
+        offs[r] = pos + len(blob)
+        blob += chunks[r]
+    table_rows = rows[::-1] if line_order == 1 else rows                  # the offset table follows the line order
+    with open(path, "wb") as f:
+        f.write(header + struct.pack("<%dQ" % h, *[offs[r] for r in table_rows]) + blob)
+
+
+def test_reader_handles_window_offset_line_order_and_uint(tmp_path):
+    rng = np.random.default_rng(9)
+    planes = {c: rng.random((7, 5)).astype(np.float32) * 3 for c in "RGBA"}
+    want = np.stack([planes[c] for c in "RGB"], -1)
+    p = str(tmp_path / "w.exr")
+    _raw_exr(p, planes, x0=-3, y0=11)                                      # data window not at the origin
+    assert np.array_equal(wire.load_exr(p), want)
+    _raw_exr(p, planes, line_order=1)                                      # DECREASING_Y
+    assert np.array_equal(wire.load_exr(p), want)
+    _raw_exr(p, planes, shuffle=[3, 0, 6, 1, 5, 2, 4])                     # RANDOM_Y-style chunk order: rows are placed by their y
+    assert np.array_equal(wire.load_exr(p), want)
+    ids = {c: rng.integers(0, 2 ** 31, (4, 6)).astype(np.uint32) for c in "RGB"}
+    _raw_exr(p, ids, ptype=0)                                              # UINT channels convert to float like OpenEXR's FLOAT request
+    assert np.array_equal(wire.load_exr(p), np.stack([ids[c].astype(np.float32) for c in "RGB"], -1))
+    ch = wire.read_exr_channels(p)
+    assert ch["R"].dtype == np.uint32 and np.array_equal(ch["G"], ids["G"])
+    half = {c: rng.random((3, 4)).astype(np.float16) for c in "BGR"}
+    _raw_exr(p, half, ptype=1)
+    assert np.array_equal(wire.load_exr(p), np.stack([half[c].astype(np.float32) for c in "RGB"], -1))
