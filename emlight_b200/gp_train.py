@@ -33,7 +33,6 @@ import torch.nn.functional as F
 from . import gp_ops as ops
 from .genprojector import _RED_COS, _RED_HINGE_FAKE, _RED_HINGE_REAL, _RED_L1, _RED_L1_MASKED, _RED_SUM, _up4
 
-_LRELU = 0.2
 
 
 # ============================================================================================================== tape
@@ -106,14 +105,6 @@ def _pad_c(t, pitch):
     """(..., C) -> (..., pitch) zero padded."""
     C = t.shape[-1]
     return t if C == pitch else F.pad(t, (0, pitch - C))
-
-
-def _act_grad(u, act):
-    if act == 1:
-        return (u > 0).to(u.dtype)
-    if act == 2:
-        return torch.where(u > 0, torch.ones_like(u), torch.full_like(u, _LRELU))
-    return None
 
 
 def spectral_weight(module, update):
@@ -425,21 +416,6 @@ def generator(tape, G, guide, crop, training=True):
 
 
 # ============================================================================================================== discriminator / VGG
-def _to_nhwc_with_grad(tape, x_nchw, pitch, src=None):
-    """NCHW -> padded NHWC; when `src` (a tape tensor of the same NCHW shape) is given its gradient is routed back."""
-    out = ops.nchw_to_nhwc(x_nchw, pitch)
-    if src is not None:
-        C = x_nchw.shape[1]
-
-        def bwd():
-            g = tape.take(out)
-            if g is not None:
-                tape.add(src, g[..., :C].permute(0, 3, 1, 2))
-
-        tape.record(bwd)
-    return out
-
-
 def _pool_with_grad(tape, x, B, H, W, C, mode):
     out, ho, wo = ops.pool(x, B, H, W, C, mode)
 
