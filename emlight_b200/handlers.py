@@ -121,3 +121,75 @@ def polar_to_cartesian(phi_theta):
 def print_model_parm_nums(model):
     total = sum(p.nelement() for p in model.parameters())                                   # util.py:353-356
     print('  + Number of params: %.2fM' % (total / 1e6))
+
+
+# ------------------------------------------------------------------------------------------------- GenProjector/util.py output side
+def tonemapping_to_file(im, sv_path, gamma=2.4, percentile=50, max_mapping=0.5):
+    """GenProjector/util.py:226-245 `tonemapping(im, sv_path, ...)`: tone-map on the tonemap kernel and save as an 8-bit image."""
+    import torch
+    from PIL import Image
+    from .tonemap import TonemapHDR
+    x = im if torch.is_tensor(im) else torch.from_numpy(np.ascontiguousarray(im, dtype=np.float32))
+    y, _ = TonemapHDR(gamma=gamma, percentile=percentile, max_mapping=max_mapping)(x.cuda())
+    Image.fromarray((y.cpu().numpy() * 255.0).astype("uint8")).save(sv_path)
+
+
+def convert_visuals_to_numpy(visuals):
+    for key, t in visuals.items():                                                          # util.py:434-439: (C,H,W) tensor -> (H,W,C) array
+        visuals[key] = np.squeeze(t.permute(1, 2, 0).detach().cpu().numpy())
+    return visuals
+
+
+def print_current_errors(epoch, i, errors, t):
+    message = '(epoch: %d, iters: %d, time: %.3f)' % (epoch, i, t)                          # util.py:442-447
+    for k, v in errors.items():
+        message += '%s: %.3f ' % (k, v.mean().float())
+    print(message)
+
+
+def save_test_images(visuals, nm, out_dir="./results"):
+    """util.py:468-500 (what GenProjector/test.py:39 calls per image): `<nm>_fake_image.exr` (the HDR illumination map) plus
+    tone-mapped previews `<nm>_fake_image.jpg`, `<nm>_warped.jpg`, `<nm>_input.jpg`."""
+    import os
+    os.makedirs(out_dir, exist_ok=True)
+    visuals = convert_visuals_to_numpy(visuals)
+    for label, image in visuals.items():
+        base = os.path.join(out_dir, nm + '_' + label)
+        if label == 'fake_image':
+            tonemapping_to_file(image, base + '.jpg')
+            wire.write_exr(base + '.exr', image)
+        if label == 'warped':
+            tonemapping_to_file(image, base + '.jpg')
+        if label == 'input':
+            tonemapping_to_file(image * 255.0, base + '.jpg', percentile=99, max_mapping=0.99)
+
+
+def save_current_images(visuals, epoch, step, out_dir="./summary"):
+    """util.py:449-466: training-time previews."""
+    import os
+    from PIL import Image
+    os.makedirs(out_dir, exist_ok=True)
+    visuals = convert_visuals_to_numpy(visuals)
+    for label, image in visuals.items():
+        path = os.path.join(out_dir, 'epoch%.3d_iter%.3d_%s.png' % (epoch, step, label))
+        if label == 'input':
+            tonemapping_to_file(image, path, gamma=2.4, percentile=99, max_mapping=0.8)
+        elif label == 'im':
+            Image.fromarray((image * 255.0).astype('uint8')).save(path)
+        else:
+            tonemapping_to_file(image, path)
+
+
+def save_network(net, label, epoch, opt):
+    import os
+    import torch
+    path = os.path.join(opt.checkpoints_dir, opt.name, '%s_net_%s.pth' % (epoch, label))   # util.py:173-178 (state_dict on the CPU)
+    torch.save({k: v.cpu() for k, v in net.state_dict().items()}, path)
+
+
+def load_network(net, label, epoch, opt):
+    import os
+    import torch
+    path = os.path.join(opt.checkpoints_dir, opt.name, '%s_net_%s.pth' % (epoch, label))   # util.py:181-191
+    net.load_state_dict(torch.load(path))
+    return net

@@ -114,5 +114,23 @@ def test_genprojector_util_shim_names():
     spec = importlib.util.spec_from_file_location("_dropin_gp_util", here)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    for name in ("TonemapHDR", "load_exr", "write_exr", "sphere_points", "convert_to_panorama", "tonemapping", "PanoramaHandler"):
+    for name in ("TonemapHDR", "load_exr", "write_exr", "sphere_points", "convert_to_panorama", "tonemapping", "PanoramaHandler",
+                 "save_test_images", "save_current_images", "print_current_errors", "save_network", "load_network"):
         assert hasattr(mod, name), name
+
+
+def test_output_side_helpers_on_cpu(tmp_path, capsys):
+    import argparse
+    torch = pytest.importorskip("torch")
+    vis = handlers.convert_visuals_to_numpy({"a": torch.arange(24.0).reshape(3, 2, 4)})
+    assert vis["a"].shape == (2, 4, 3) and vis["a"][1, 2, 0] == 6.0
+    handlers.print_current_errors(3, 40, {"GAN": torch.tensor([1.5, 2.5]), "VGG": torch.tensor(0.25)}, 0.5)
+    assert "(epoch: 3, iters: 40, time: 0.500)GAN: 2.000 VGG: 0.250" in capsys.readouterr().out
+    opt = argparse.Namespace(checkpoints_dir=str(tmp_path), name="run")
+    os.makedirs(tmp_path / "run")
+    net = torch.nn.Linear(3, 2)
+    handlers.save_network(net, "G", "latest", opt)
+    assert os.path.exists(tmp_path / "run" / "latest_net_G.pth")
+    other = torch.nn.Linear(3, 2)
+    handlers.load_network(other, "G", "latest", opt)
+    assert torch.equal(other.weight, net.weight)

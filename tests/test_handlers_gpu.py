@@ -84,3 +84,21 @@ def test_genprojector_dataset_item(cuda, tmp_path):
             + torch.from_numpy(pkl["ambient"]).view(3, 1, 1) / (128 * 256)) * alpha
     assert float((item["input"].cpu() - want).abs().max()) <= 1e-3 * float(want.abs().max())
     assert torch.equal(item["distribution"].cpu(), torch.from_numpy(dist).view(1, 128, 1).repeat(1, 1, 3))
+
+
+def test_save_test_images_writes_the_reference_outputs(cuda, tmp_path):
+    """GenProjector/test.py:30-39 output stage: the HDR result as EXR (bit-exact round trip) plus the tone-mapped previews."""
+    from collections import OrderedDict
+    from PIL import Image
+    from emlight_b200 import handlers, wire
+    gen = torch.Generator().manual_seed(4)
+    fake = (torch.rand(3, 128, 256, generator=gen) * 50).to(cuda)
+    images = OrderedDict([("input", torch.rand(3, 128, 256, generator=gen).to(cuda)), ("fake_image", fake),
+                          ("warped", torch.rand(3, 128, 256, generator=gen).to(cuda) * 20), ("im", torch.rand(3, 128, 128, generator=gen).to(cuda))])
+    out = str(tmp_path / "results")
+    handlers.save_test_images(images, "scene7", out_dir=out)
+    assert sorted(os.listdir(out)) == ["scene7_fake_image.exr", "scene7_fake_image.jpg", "scene7_input.jpg", "scene7_warped.jpg"]
+    assert np.array_equal(wire.load_exr(os.path.join(out, "scene7_fake_image.exr")), fake.permute(1, 2, 0).cpu().numpy())
+    prev = np.asarray(Image.open(os.path.join(out, "scene7_fake_image.jpg")))
+    want, _ = _np_tonemap(fake.permute(1, 2, 0).cpu().numpy(), 50, 0.5)
+    assert prev.shape == (128, 256, 3) and np.abs(prev.astype(np.float32) - want * 255.0).mean() < 6.0       # JPEG is lossy
