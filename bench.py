@@ -313,6 +313,33 @@ def main():
             del nt, pn, cf
         except Exception as e:                                  # noqa: BLE001  (secondary workload: never fail the headline line)
             extra["config4_needlets_j3_b512"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        # BASELINE configs[3]'s GenProjector part (G step + D step: forward, tape backward of emlight_b200/gp_train.py, Adam).  Opt-in
+        # (EML_BENCH_GAN=1) until that path has had its first B200 run -- see DESIGN.md 4.2 / tools/gpu_pending.sh.
+        if os.environ.get("EML_BENCH_GAN") == "1":
+            try:
+                import argparse as _ap
+                from train_genprojector_synthetic import synthetic_batch as gan_batch
+                torch.cuda.empty_cache()
+                gopt = _ap.Namespace(ngf=64, ndf=64, norm_G="spectralspadesyncbatch3x3", norm_E="spectralinstance", norm_D="spectralinstance",
+                                     semantic_nc=3, label_nc=3, output_nc=3, num_upsampling_layers="normal", crop_size=256, aspect_ratio=2.0,
+                                     num_D=2, n_layers_D=4, netD_subarch="n_layer", no_ganFeat_loss=False, no_vgg_loss=False, gpu_ids=[0],
+                                     isTrain=True, gan_mode="hinge", lr=0.0002, beta1=0.0, beta2=0.9, no_TTUR=False)
+                gm = E.Pix2PixModel(gopt)
+                gm.train()
+                gm.autograd = True
+                og, od = gm.create_optimizers(gopt)
+                Bg = 4
+                gd = gan_batch(Bg, gen, dev)
+
+                def gan_iter():
+                    og.zero_grad(); gl, _ = gm(gd, "generator"); sum(gl.values()).mean().backward(); og.step()
+                    od.zero_grad(); dl = gm(gd, "discriminator"); sum(dl.values()).mean().backward(); od.step()
+                gan_iter()
+                ms_g = timed(gan_iter, 2) / 2
+                extra["config3_genprojector_G_step_plus_D_step_b4"] = {"ms_per_iteration": round(ms_g, 3), "maps_per_s": round(Bg / ms_g * 1e3, 2)}
+                del gm, og, od, gd
+            except Exception as e:                              # noqa: BLE001  (secondary workload: never fail the headline line)
+                extra["config3_genprojector_G_step_plus_D_step_b4"] = {"error": "%s: %s" % (type(e).__name__, e)}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt, threads = time_cpu(args.cpu_sample, 3, 1)

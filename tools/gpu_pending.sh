@@ -13,3 +13,4 @@ for flags in "" "EML_STEM_V2=1" "EML_FC_SPLITK=1" "EML_STEM_V2=1 EML_FC_SPLITK=1
 done
 timeout 300 python examples/make_gt_pickles.py --out-dir gpurun_out/pkl > gpurun_out/make_gt.log 2>&1; echo "make_gt_pickles exit $?"; tail -1 gpurun_out/make_gt.log
 timeout 900 python tools/profile_gan_step.py --batch 2 --ngf 32 --ndf 32 > gpurun_out/profile_gan.log 2>&1; echo "profile_gan exit $?"; tail -25 gpurun_out/profile_gan.log
+EML_BENCH_GAN=1 python bench.py --steps 5 --warmup 3 2> /dev/null | python -c "import sys, json; d = json.loads(sys.stdin.readline()); print(json.dumps(d[\"other_workloads\"], indent=1))"
