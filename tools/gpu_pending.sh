@@ -1,5 +1,6 @@
 # First B200 call of the next round: run the GPU tests that were written after round 1's GPU budget was spent (gated by
-# EML_PENDING_GPU), then the regular suite.  Usage:  gpurun --timeout 1500 -- 'bash tools/gpu_pending.sh'
+# EML_PENDING_GPU), the new examples, the A/B of the prepared switches and a per-entry-point profile of the GAN step (≈25 min of box time).
+# Usage:  gpurun --timeout 2400 -- 'bash tools/gpu_pending.sh'     (the regular suite + evidence run stay tools/gpu_final.sh)
 mkdir -p gpurun_out
 EML_PENDING_GPU=1 timeout 1200 python -m pytest tests/test_gp_train_gpu.py tests/test_handlers_gpu.py -q --timeout 900 -p no:cacheprovider > gpurun_out/pytest_pending.log 2>&1
 echo "pending exit $?"; tail -30 gpurun_out/pytest_pending.log
