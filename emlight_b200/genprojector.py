@@ -224,6 +224,7 @@ class SphereConv2D(nn.Module):
         else:
             self.register_parameter("bias", None)
         self.precision = "bf16x3"
+        self.autograd = False            # opt-in: forward recorded on a tape so that .backward() reaches weight, bias and input (gp_train.py)
         self.reset_parameters()
         self._pc = None
 
@@ -245,9 +246,15 @@ class SphereConv2D(nn.Module):
                 self._pc = (key, _PackedConv(self.effective_weight(), precision))
         return self._pc[1]
 
-    @torch.no_grad()
     def forward(self, x):
         _lib.require_cuda(x)
+        if self.autograd and torch.is_grad_enabled():
+            from . import gp_train
+            return gp_train.sphere_conv_module(self, x)
+        with torch.no_grad():
+            return self._forward_values(x)
+
+    def _forward_values(self, x):
         lib = _lib.load()
         B, C, H, W = x.shape
         xn = x.float().permute(0, 2, 3, 1).contiguous()

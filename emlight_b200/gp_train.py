@@ -619,3 +619,36 @@ def discriminator_losses(tape, model, fake, guide, real):
         d_fake.append(_mean_loss(tape, _RED_HINGE_FAKE, tf, B * h * w, c, n, sign=-1.0, scale=1.0 / num_D))
         d_real.append(_mean_loss(tape, _RED_HINGE_REAL, tr, B * h * w, c, n, sign=-1.0, scale=1.0 / num_D))
     return [_sum(tape, d_fake), _sum(tape, d_real)]
+
+
+def sphere_conv_module(mod, x):
+    """`SphereConv2D.forward` (sphere_cnn.py:111-124) with autograd: NCHW in / NCHW out, gradients for weight, bias and -- when it
+    requires them -- the input.  One tape node per call (opt-in: `SphereConv2D.autograd = True`)."""
+    B, C, H, W = x.shape
+    xd = x.detach().float()
+    box = {}
+
+    def runner(tape):
+        xn = ops.nchw_to_nhwc(xd, _up4(C))
+        box["xn"], box["tape"] = xn, tape
+        lut = ops.lut("sphere", H, W, mod.stride, xd.device)
+        raw, ho, wo = _sn_conv(tape, mod, xn, B, H, W, C, lut, mod.precision, mod.training, need_dx=x.requires_grad)
+        out = bias_act(tape, raw, mod.bias, 0, B, ho, wo, mod.out_c) if mod.bias is not None else raw
+        y = out[..., :mod.out_c].permute(0, 3, 1, 2).contiguous()
+
+        def bwd():
+            g = tape.take(y)
+            if g is not None:
+                tape.add(out, _pad_c(g.permute(0, 2, 3, 1), out.shape[-1]).contiguous())
+
+        tape.record(bwd)
+        if x.requires_grad:                                       # runs last in the reverse sweep: hand the input gradient to autograd
+            def bwd_x():
+                g = tape.take(xn)
+                if g is not None:
+                    tape.param_grads[x] = g[..., :C].permute(0, 3, 1, 2).contiguous().to(x.dtype)
+            tape.steps.insert(0, bwd_x)
+        return (y,)
+
+    params = [p for p in mod.parameters()] + ([x] if x.requires_grad else [])
+    return run_with_tape(runner, params)[0]

@@ -465,3 +465,34 @@ def test_pix2pix_model_training_iterations_on_stand_ins(sim, monkeypatch):
     model.autograd = False
     with pytest.raises(Exception):
         model(data, "generator")                       # forward-only product path: CPU tensors are refused before any launch
+
+
+@pytest.mark.parametrize("stride,bias", [(1, True), (2, False)])
+def test_sphere_conv_module_autograd(sim, monkeypatch, stride, bias):
+    """`SphereConv2D(...).autograd = True`: weight, bias and input gradients of the stand-alone layer vs autograd of the oracle."""
+    import emlight_b200._lib as L
+    from emlight_b200.genprojector import SphereConv2D
+    monkeypatch.setattr(L, "require_cuda", lambda *a: None)
+    gen = torch.Generator().manual_seed(5 + stride)
+    sc = SphereConv2D(6, 5, stride=stride, bias=bias)
+    with torch.no_grad():
+        sc.weight.copy_(torch.randn(5, 6, 3, 3, generator=gen))
+        if bias:
+            sc.bias.copy_(torch.randn(5, generator=gen))
+    sc.autograd = True
+    x = torch.randn(2, 6, 8, 16, generator=gen, requires_grad=True)
+    y = sc(x)
+    gy = torch.randn(y.shape, generator=gen)
+    (y * gy).sum().backward()
+    xr, wr = x.detach().clone().requires_grad_(True), sc.weight.detach().clone().requires_grad_(True)
+    br = sc.bias.detach().clone().requires_grad_(True) if bias else None
+    ref = GO.sphere_conv(xr, wr, br, stride)
+    assert _rel(y.detach(), ref.detach()) < 1e-5
+    (ref * gy).sum().backward()
+    assert _rel(x.grad, xr.grad) < 1e-4 and _rel(sc.weight.grad, wr.grad) < 1e-4
+    if bias:
+        assert _rel(sc.bias.grad, br.grad) < 1e-4
+    # without input gradients only the parameters receive them
+    sc.zero_grad()
+    (sc(x.detach()) * gy).sum().backward()
+    assert _rel(sc.weight.grad, wr.grad) < 1e-4

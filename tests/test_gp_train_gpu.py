@@ -60,6 +60,26 @@ def test_conv_adjoint_matches_oracle_autograd(cuda, stride, act, cin, cout):
     assert _l2rel(tape.param_grads[bin_].cpu(), br.grad) < 1e-3
 
 
+def test_sphere_conv_module_autograd(cuda):
+    """SphereConv2D with the autograd opt-in: weight / bias / input gradients vs autograd of the oracle layer."""
+    import emlight_b200 as E
+    gen = torch.Generator().manual_seed(7)
+    sc = E.SphereConv2D(6, 5, stride=2).to(cuda)
+    wt, b = torch.randn(5, 6, 3, 3, generator=gen) / 7, torch.randn(5, generator=gen)
+    sc.load_state_dict({"weight": wt, "bias": b})
+    sc.autograd = True
+    x0 = torch.randn(2, 6, 16, 32, generator=gen)
+    x = x0.to(cuda).requires_grad_(True)
+    y = sc(x)
+    gy = torch.randn(y.shape, generator=gen)
+    (y * gy.to(cuda)).sum().backward()
+    xr, wr, br = x0.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = GO.sphere_conv(xr, wr, br, 2)
+    (ref * gy).sum().backward()
+    assert _l2rel(y.detach().cpu(), ref.detach()) < 1e-4
+    assert _l2rel(x.grad.cpu(), xr.grad) < 1e-3 and _l2rel(sc.weight.grad.cpu(), wr.grad) < 1e-3 and _l2rel(sc.bias.grad.cpu(), br.grad) < 1e-3
+
+
 def _g_opt(ngf):
     return argparse.Namespace(ngf=ngf, norm_G="spectralspadesyncbatch3x3", norm_E="spectralinstance", semantic_nc=3,
                               num_upsampling_layers="normal", crop_size=256, aspect_ratio=2.0)
