@@ -73,3 +73,22 @@ def test_product_host_tables_match_oracle():
     th, ph = PN.pano_grid()
     tho, pho = NO.pano_grid()
     assert np.array_equal(th, tho) and np.array_equal(ph, pho)
+
+
+def test_healpix_known_answers_from_the_healpy_documentation():
+    """Published outputs of the third-party dependency the reference calls (healpy, unpinned; sphere_needlets.py:5,52-54): the
+    `healpy.pix2ang` documentation example  hp.pix2ang(16, [1440, 427, 1520, 0, 3071]) ->
+        theta = [1.52911759, 0.78550497, 1.57079633, 0.05103658, 3.09055608], phi = [0., 0.78539816, 1.61988371, 0.78539816, 5.49778714]
+    and the tutorial's  hp.pix2ang(16, 1440) -> (1.5291175943723188, 0.0).  Both the oracle's restatement of the RING scheme and the
+    product's closed form must reproduce them (the needlet levels use nside 1..8 of the same formulas)."""
+    from emlight_b200 import needlets as N
+    pix = [1440, 427, 1520, 0, 3071]
+    want_th = np.array([1.52911759, 0.78550497, 1.57079633, 0.05103658, 3.09055608])
+    want_ph = np.array([0., 0.78539816, 1.61988371, 0.78539816, 5.49778714])
+    th, ph = NO.pix2ang(16)
+    assert np.abs(th[pix] - want_th).max() < 5e-9 and np.abs(ph[pix] - want_ph).max() < 5e-9
+    assert th[1440] == 1.5291175943723188 and ph[1440] == 0.0
+    v = N.healpix_centres(16)                                   # (npix, 3), what healpy.pix2vec returns
+    th_p = np.arccos(v[:, 2])
+    ph_p = np.mod(np.arctan2(v[:, 1], v[:, 0]), 2 * np.pi)
+    assert np.abs(th_p[pix] - want_th).max() < 5e-9 and np.abs(ph_p[pix] - want_ph).max() < 5e-9
