@@ -1,5 +1,12 @@
-"""`models.pix2pix_model.Pix2PixModel` (GenProjector/models/pix2pix_model.py:12-186) -> emlight_b200.genprojector.Pix2PixModel."""
+"""`models.pix2pix_model.Pix2PixModel` (GenProjector/models/pix2pix_model.py:12-186) -> emlight_b200.genprojector.Pix2PixModel, built the
+way the reference builds it: networks through `networks.define_G / define_D` (print_network, init_weights(opt.init_type,
+opt.init_variance): :80-88), checkpoints loaded when testing or continuing (:84-87), modules left in training mode unless the script
+calls `.eval()` (the reference never calls `.train()`), `save(epoch)` (:72-74).  With `opt.isTrain` the loss dictionaries carry the
+autograd node of emlight_b200/gp_train.py, which is what lets `model_trainer.Trainer` run unchanged."""
+import torch
+
 import models.networks as networks  # noqa: F401  (the reference module exposes it too)
+import util
 from emlight_b200.genprojector import Pix2PixModel as _Pix2PixModel
 
 
@@ -8,3 +15,23 @@ class Pix2PixModel(_Pix2PixModel):
     def modify_commandline_options(parser, is_train):
         networks.modify_commandline_options(parser, is_train)
         return parser
+
+    def __init__(self, opt):
+        super().__init__(opt)
+        self.FloatTensor = torch.cuda.FloatTensor if self.use_gpu() else torch.FloatTensor
+        self.netG, self.netD = self.initialize_networks(opt)
+        self.train(True)
+        self.autograd = bool(opt.isTrain)
+
+    def initialize_networks(self, opt):
+        netG = networks.define_G(opt)
+        netD = networks.define_D(opt) if opt.isTrain else None
+        if not opt.isTrain or getattr(opt, "continue_train", False):
+            netG = util.load_network(netG, 'G', opt.which_epoch, opt)
+            if opt.isTrain:
+                netD = util.load_network(netD, 'D', opt.which_epoch, opt)
+        return netG, netD
+
+    def save(self, epoch):
+        util.save_network(self.netG, 'G', epoch, self.opt)
+        util.save_network(self.netD, 'D', epoch, self.opt)

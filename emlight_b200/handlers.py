@@ -193,3 +193,37 @@ def load_network(net, label, epoch, opt):
     path = os.path.join(opt.checkpoints_dir, opt.name, '%s_net_%s.pth' % (epoch, label))   # util.py:181-191
     net.load_state_dict(torch.load(path))
     return net
+
+
+# ------------------------------------------------------------------------------------------------- GenProjector/util.py small helpers
+def mkdir(path):
+    import os
+    if not os.path.exists(path):                                                            # util.py:127-129
+        os.makedirs(path)
+
+
+def mkdirs(paths):
+    for path in (paths if isinstance(paths, list) and not isinstance(paths, str) else [paths]):   # util.py:119-124
+        mkdir(path)
+
+
+def str2bool(v):
+    import argparse
+    if v.lower() in ('yes', 'true', 't', 'y', '1'):                                         # util.py:149-155
+        return True
+    if v.lower() in ('no', 'false', 'f', 'n', '0'):
+        return False
+    raise argparse.ArgumentTypeError('Boolean value expected.')
+
+
+def copyconf(default_opt, **kwargs):
+    import argparse
+    conf = argparse.Namespace(**vars(default_opt))                                          # util.py:40-45
+    for key, value in kwargs.items():
+        setattr(conf, key, value)
+    return conf
+
+
+def natural_sort(items):
+    import re
+    items.sort(key=lambda text: [int(c) if c.isdigit() else c for c in re.split(r'(\d+)', text)])   # util.py:132-146

@@ -1,0 +1,82 @@
+"""The reference's OWN GenProjector training scaffolding -- `options/train_options.py`, `options/base_options.py`, `model_trainer.py`,
+`iter_counter.py`, unchanged, imported from /root/reference -- running on the module-name shims of `emlight_b200/dropin_genprojector`
+(`models`, `models.networks[.sync_batchnorm]`, `util`, `data`): option parsing with the by-name network lookup, `Trainer(opt)`,
+`run_generator_one_step`, `run_discriminator_one_step`, `get_latest_losses`, `util.print_current_errors`, `update_learning_rate`,
+`save('latest')` and a reload through `--continue_train`.  CPU only: the device primitives are the stand-ins of test_gp_train_cpu
+(adjoint kernels through their host-emulation build), `.cuda()` is identity.  Skipped where the reference tree is absent (GPU box)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/GenProjector"
+
+SCRIPT = r'''
+import os, sys, tempfile
+root, ref, work = sys.argv[1], sys.argv[2], sys.argv[3]
+sys.argv = ["train.py", "--name", "run", "--checkpoints_dir", work, "--gpu_ids", "-1", "--ngf", "2", "--ndf", "2", "--batchSize", "1",
+            "--dataroot", work, "--niter", "1", "--niter_decay", "1"] + sys.argv[4:]
+sys.path[:0] = [os.path.join(root, "emlight_b200", "dropin_genprojector"), ref, root, os.path.join(root, "tests")]
+import torch
+torch.nn.Module.cuda = lambda self, *a, **k: self
+torch.Tensor.cuda = lambda self, *a, **k: self
+import test_gp_train_cpu as C
+from emlight_b200 import gp_ops, gp_train, genprojector, _lib
+C.install_sims(gp_ops, C.build_emu(tempfile.mkdtemp()))
+_lib.require_cuda = lambda *a: None
+# the D step's no-grad generator forward is the forward-only product path (real kernels): same network over the stand-ins here
+genprojector.Pix2PixModel.generate_fake = lambda self, inp, crop: gp_train.generator(gp_train.Tape(), self.netG, inp, crop, True)
+
+from options.train_options import TrainOptions          # the reference's files from here on
+from iter_counter import IterationCounter
+from model_trainer import Trainer
+import models, util
+assert models.__file__.startswith(os.path.join(root, "emlight_b200")) and util.__file__.startswith(os.path.join(root, "emlight_b200"))
+import options.base_options, model_trainer, iter_counter
+assert all(m.__file__.startswith(ref) for m in (options.base_options, model_trainer, iter_counter))
+
+opt = TrainOptions().parse()
+assert opt.norm_G == "spectralspadesyncbatch3x3" and opt.netD == "multiscale" and opt.num_D == 2 and opt.n_layers_D == 4
+trainer = Trainer(opt)
+model = trainer.pix2pix_model_on_one_gpu
+assert type(model).__module__ == "models.pix2pix_model" and model.training and model.autograd
+counter = IterationCounter(opt, 1)
+gen = torch.Generator().manual_seed(3)
+data_i = {"input": torch.rand(1, 3, 128, 256, generator=gen) * 2, "crop": torch.rand(1, 3, 128, 128, generator=gen),
+          "warped": torch.rand(1, 3, 128, 256, generator=gen) * 20, "map": (torch.rand(1, 1, 128, 256, generator=gen) > 0.9).float()}
+w0 = [p.detach().clone() for p in model.netG.parameters()]
+d0 = [p.detach().clone() for p in model.netD.parameters()]
+for epoch in counter.training_epochs():
+    counter.record_epoch_start(epoch)
+    counter.record_one_iteration()
+    trainer.run_generator_one_step(data_i)
+    trainer.run_discriminator_one_step(data_i)
+    losses = trainer.get_latest_losses()
+    util.print_current_errors(epoch, counter.epoch_iter, losses, counter.time_per_iter)
+    trainer.update_learning_rate(epoch)
+    counter.record_epoch_end()
+assert set(losses) == {"GAN", "GAN_Feat", "VGG", "COS", "D_Fake", "D_real"}
+assert all(torch.isfinite(v).all() for v in losses.values())
+assert any(not torch.equal(a, b) for a, b in zip(w0, model.netG.parameters()))
+assert any(not torch.equal(a, b) for a, b in zip(d0, model.netD.parameters()))
+assert trainer.get_latest_generated().shape == (1, 3, 128, 256)
+assert trainer.old_lr < opt.lr                                       # niter = 1, niter_decay = 1: the second epoch decays the rate
+trainer.save("latest")
+assert os.path.exists(os.path.join(work, "run", "latest_net_G.pth")) and os.path.exists(os.path.join(work, "run", "latest_net_D.pth"))
+print("TRAINER-OK", {k: round(float(v.mean()), 4) for k, v in losses.items()})
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree is only present in the build container")
+def test_reference_trainer_runs_unchanged_on_the_shims(tmp_path):
+    work = str(tmp_path)
+    r = subprocess.run([sys.executable, "-c", SCRIPT, ROOT, REF, work], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "TRAINER-OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+    assert "(epoch: 1, iters: 1, time:" in r.stdout and "update learning rate" in r.stdout
+    # --continue_train reloads what save('latest') wrote (pix2pix_model.py:84-87 through util.load_network)
+    r2 = subprocess.run([sys.executable, "-c", SCRIPT.replace('trainer.save("latest")', 'pass').replace(
+        "assert os.path.exists(os.path.join(work, \"run\", \"latest_net_G.pth\")) and os.path.exists(os.path.join(work, \"run\", \"latest_net_D.pth\"))", "pass"),
+                         ROOT, REF, work, "--continue_train"], capture_output=True, text=True, timeout=900)
+    assert r2.returncode == 0 and "TRAINER-OK" in r2.stdout, (r2.stdout[-1500:], r2.stderr[-3000:])
