@@ -17,9 +17,8 @@ class Pix2PixModel(_Pix2PixModel):
         return parser
 
     def __init__(self, opt):
-        super().__init__(opt)
+        super().__init__(opt)                      # builds the networks through initialize_networks() below
         self.FloatTensor = torch.cuda.FloatTensor if self.use_gpu() else torch.FloatTensor
-        self.netG, self.netD = self.initialize_networks(opt)
         self.train(True)
         self.autograd = bool(opt.isTrain)
 

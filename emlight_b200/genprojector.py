@@ -852,20 +852,24 @@ def cosine_loss(fake, real):
 
 class Pix2PixModel(nn.Module):
     """Drop-in for pix2pix_model.Pix2PixModel (pix2pix_model.py:12-186): mode dispatch 'inference' / 'generator' / 'discriminator'.
-    'inference' is the full product path.  'generator' and 'discriminator' EVALUATE the reference's loss dictionaries (same keys and
-    weights) on eval-mode networks; they carry no autograd graph -- GAN training (generator / discriminator backward, batch-statistic
-    SyncBN, spectral-norm power iteration) is not implemented in this round."""
+    'inference' is the full product path.  'generator' and 'discriminator' return the reference's loss dictionaries (same keys and
+    weights): plain values by default; with `self.autograd = True` (opt-in until its first B200 run) each call returns tensors attached
+    to one autograd node (emlight_b200/gp_train.py), so `sum(losses.values()).mean().backward()` + `create_optimizers()` train the
+    networks like GenProjector/model_trainer.py does."""
 
     def __init__(self, opt):
         super().__init__()
         self.opt = opt
         self.autograd = False            # opt-in: loss dictionaries carry an autograd node (gp_train.py) so the trainer's .backward() works
-        self.netG = SPADEGenerator(opt).cuda().eval()
-        self.netD = MultiscaleDiscriminator(opt).cuda().eval() if opt.isTrain else None
+        self.netG, self.netD = self.initialize_networks(opt)
         if opt.isTrain:
             self.criterionGAN = GANLoss(opt.gan_mode, opt=opt)
             if not getattr(opt, "no_vgg_loss", False):
                 self.criterionVGG = VGGLoss(getattr(opt, "gpu_ids", None))
+
+    def initialize_networks(self, opt):
+        """(netG, netD) -- pix2pix_model.py:80-88; the module-name shim overrides this with the reference's define_G / define_D flow."""
+        return SPADEGenerator(opt).cuda().eval(), (MultiscaleDiscriminator(opt).cuda().eval() if opt.isTrain else None)
 
     def forward(self, data, mode):
         input, crop, real_image, map = data["input"].cuda(), data["crop"].cuda(), data["warped"].cuda(), data["map"].cuda()
