@@ -80,3 +80,78 @@ def test_reference_trainer_runs_unchanged_on_the_shims(tmp_path):
         "assert os.path.exists(os.path.join(work, \"run\", \"latest_net_G.pth\")) and os.path.exists(os.path.join(work, \"run\", \"latest_net_D.pth\"))", "pass"),
                          ROOT, REF, work, "--continue_train"], capture_output=True, text=True, timeout=900)
     assert r2.returncode == 0 and "TRAINER-OK" in r2.stdout, (r2.stdout[-1500:], r2.stderr[-3000:])
+
+
+TEST_SCRIPT = r'''
+import os, pickle, runpy, sys, tempfile
+root, ref, work = sys.argv[1], sys.argv[2], sys.argv[3]
+sys.path[:0] = [os.path.join(root, "emlight_b200", "dropin_genprojector"), ref, root, os.path.join(root, "tests")]
+import numpy as np
+import torch
+torch.nn.Module.cuda = lambda self, *a, **k: self
+torch.Tensor.cuda = lambda self, *a, **k: self
+_orig_to = torch.Tensor.to
+torch.Tensor.to = lambda self, *a, **k: self if (a and isinstance(a[0], (str, torch.device)) and "cuda" in str(a[0])) else _orig_to(self, *a, **k)
+_orig_device = torch.device
+import test_gp_train_cpu as C
+from emlight_b200 import gp_ops, gp_train, genprojector, _lib, wire, tonemap, panorama
+from oracle import tonemap_oracle, render_oracle
+C.install_sims(gp_ops, C.build_emu(tempfile.mkdtemp()))
+_lib.require_cuda = lambda *a: None
+genprojector.Pix2PixModel.generate_fake = lambda self, inp, crop: gp_train.generator(gp_train.Tape(), self.netG, inp, crop, self.netG.training)
+
+
+def cpu_tonemap(self, img, clip=True, alpha=None, gamma=True):               # stand-in for eml_tonemap_hdr (the checker's restatement)
+    y, a = tonemap_oracle.tonemap_hdr(img.numpy(), self.gamma, self.percentile, self.max_mapping, clip, alpha, gamma)
+    return torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)), float(a)
+
+
+def cpu_guide(dist, inten, rgb, amb, alpha=1.0, dirs=None, size=0.0025):      # stand-in for the render kernel behind genprojector_guide
+    n = dist.shape[1]
+    d = torch.from_numpy(panorama.sphere_points(n)).float().view(1, -1)
+    col = (dist.view(1, n, 1) * (inten.view(1, 1, 1) * 0.01) * rgb.view(1, 1, 3)).reshape(1, -1)
+    env = render_oracle.convert_to_panorama_torch(d, torch.full((1, n), size), col)
+    return (env + amb.view(1, 3, 1, 1) / (128 * 256)) * alpha
+
+
+tonemap.TonemapHDR.__call__ = cpu_tonemap
+panorama.genprojector_guide = cpu_guide
+# ---- a two-sample dataset in the reference's layout + a checkpoint for --which_epoch latest
+rng = np.random.default_rng(0)
+for d in ("pkl", "warped", "crop", "ckpt/run"):
+    os.makedirs(os.path.join(work, d))
+for nm in ("a", "b"):
+    dist = rng.random(128).astype(np.float32); dist /= dist.sum()
+    with open(os.path.join(work, "pkl", nm + ".pickle"), "wb") as f:
+        pickle.dump({"distribution": dist, "intensity": np.float32(300.0), "rgb_ratio": np.array([0.6, 0.6, 0.5], np.float32),
+                     "ambient": np.array([500.0, 400.0, 300.0], np.float32)}, f)
+    wire.write_exr(os.path.join(work, "warped", nm + ".exr"), np.exp(rng.normal(-2, 1, (128, 256, 3))).astype(np.float32))
+    wire.write_exr(os.path.join(work, "crop", nm + ".exr"), np.exp(rng.normal(-1, 1, (96, 128, 3))).astype(np.float32))
+import argparse
+from models.networks.generator import SPADEGenerator
+g0 = SPADEGenerator(argparse.Namespace(ngf=2, norm_G="spectralspadesyncbatch3x3", norm_E="spectralinstance", semantic_nc=3,
+                                       num_upsampling_layers="normal", crop_size=256, aspect_ratio=2.0))
+torch.save(g0.state_dict(), os.path.join(work, "ckpt", "run", "latest_net_G.pth"))
+import data as data_shim
+import importlib
+data_shim = importlib.reload(data_shim)                                        # pick up the patched genprojector_guide
+os.chdir(work)
+sys.argv = ["test.py", "--name", "run", "--checkpoints_dir", os.path.join(work, "ckpt"), "--gpu_ids", "-1", "--ngf", "2", "--batchSize", "1",
+            "--dataroot", work + "/"]
+runpy.run_path(os.path.join(ref, "test.py"), run_name="__main__")              # the reference's test.py, unchanged
+out = sorted(os.listdir(os.path.join(work, "results")))
+print("TEST-OK", out)
+fake = wire.load_exr(os.path.join(work, "results", "a_fake_image.exr"))
+assert fake.shape == (128, 256, 3) and np.isfinite(fake).all() and fake.min() >= 0 and fake.max() <= 50
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree is only present in the build container")
+def test_reference_test_script_runs_unchanged_on_the_shims(tmp_path):
+    """GenProjector/test.py executed as-is (runpy): TestOptions, data.create_dataloader over pickle + EXR files, Pix2PixModel loaded from a
+    checkpoint, mode='inference', util.save_test_images -> results/<name>_fake_image.exr + previews.  Device work through CPU stand-ins."""
+    r = subprocess.run([sys.executable, "-c", TEST_SCRIPT, ROOT, REF, str(tmp_path)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "TEST-OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+    for nm in ("a", "b"):
+        for suffix in ("_fake_image.exr", "_fake_image.jpg", "_warped.jpg", "_input.jpg"):
+            assert nm + suffix in r.stdout, (nm + suffix, r.stdout[-600:])
