@@ -155,3 +155,20 @@ def test_reference_test_script_runs_unchanged_on_the_shims(tmp_path):
     for nm in ("a", "b"):
         for suffix in ("_fake_image.exr", "_fake_image.jpg", "_warped.jpg", "_input.jpg"):
             assert nm + suffix in r.stdout, (nm + suffix, r.stdout[-600:])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree is only present in the build container")
+def test_reference_train_script_runs_unchanged_on_the_shims(tmp_path):
+    """GenProjector/train.py executed as-is (runpy) for one epoch over a two-sample dataset: TrainOptions, data.create_dataloader,
+    Trainer, IterationCounter, util.print_current_errors / save_current_images, trainer.save('latest') and the per-epoch save."""
+    script = TEST_SCRIPT.replace('sys.argv = ["test.py",', 'sys.argv = ["train.py", "--ndf", "2", "--niter", "1", "--niter_decay", "0", "--print_freq", "1", '
+                                 '"--display_freq", "2", "--save_latest_freq", "2", "--save_epoch_freq", "1",')
+    script = script.replace('runpy.run_path(os.path.join(ref, "test.py"), run_name="__main__")', 'runpy.run_path(os.path.join(ref, "train.py"), run_name="__main__")')
+    script = script[:script.index('out = sorted(os.listdir(os.path.join(work, "results")))')] + \
+        'print("TRAIN-OK", sorted(os.listdir(os.path.join(work, "ckpt", "run"))), sorted(os.listdir(os.path.join(work, "summary"))))\n'
+    r = subprocess.run([sys.executable, "-c", script, ROOT, REF, str(tmp_path)], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and "TRAIN-OK" in r.stdout, (r.stdout[-2500:], r.stderr[-3000:])
+    assert "(epoch: 1, iters: 1, time:" in r.stdout and "(epoch: 1, iters: 2, time:" in r.stdout and "End of epoch 1 / 1" in r.stdout
+    for f in ("latest_net_G.pth", "latest_net_D.pth", "1_net_G.pth", "1_net_D.pth", "iter.txt", "opt.txt"):
+        assert f in r.stdout, (f, r.stdout[-800:])
+    assert "epoch001_iter002_fake_image.png" in r.stdout and "epoch001_iter002_input.png" in r.stdout
