@@ -23,14 +23,14 @@ class Pix2PixModel(_Pix2PixModel):
         self.autograd = bool(opt.isTrain)
 
     def initialize_networks(self, opt):
-        netG = networks.define_G(opt)
-        netD = networks.define_D(opt) if opt.isTrain else None
-        if not opt.isTrain or getattr(opt, "continue_train", False):
-            netG = util.load_network(netG, 'G', opt.which_epoch, opt)
-            if opt.isTrain:
-                netD = util.load_network(netD, 'D', opt.which_epoch, opt)
-        return netG, netD
+        training = bool(opt.isTrain)
+        nets = {"G": networks.define_G(opt), "D": networks.define_D(opt) if training else None}
+        if not training or getattr(opt, "continue_train", False):                 # test time, or resuming: read the checkpoints
+            for label in ("G", "D"):
+                if nets[label] is not None:
+                    nets[label] = util.load_network(nets[label], label, opt.which_epoch, opt)
+        return nets["G"], nets["D"]
 
     def save(self, epoch):
-        util.save_network(self.netG, 'G', epoch, self.opt)
-        util.save_network(self.netD, 'D', epoch, self.opt)
+        for label, net in (("G", self.netG), ("D", self.netD)):
+            util.save_network(net, label, epoch, self.opt)
