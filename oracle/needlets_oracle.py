@@ -1,13 +1,16 @@
 """CPU oracle for the spherical-needlet basis, projection and reconstruction (TEST INFRASTRUCTURE ONLY).
 
-PARITY UNPINNED.  The reference's Needlets/ code cannot run here or anywhere without its third-party dependencies:
-``healpy`` (unpinned -- the reference has no requirements file -- and absent from this image), ``scipy.special.lpmn``
-(removed from scipy 1.18, the installed one), and the pre-computed ``SN_Matrix3.npy`` (not shipped).  This file therefore
-restates (a) the *published* HEALPix RING pixelisation (Gorski et al. 2005, ApJ 622:759, eqs. 2-9: what
-``healpy.pix2ang / pix2vec / ringinfo`` return) and (b) the reference's own arithmetic, line by line, with
-``scipy.special.lpmv`` standing in for ``lpmn`` (same Condon-Shortley convention).  It is cross-checked only against itself:
-the line-by-line transcription (``spneedlet_eval``) against the closed form that the addition theorem gives
-(``needlet_matrix``), plus the basis' analytic properties (tests/test_needlets_cpu.py).
+PARITY: pinned against the reference's own files, except for healpy.  ``oracle/make_golden_needlets.py`` imports
+/root/reference/Needlets/sphere_needlets.py, sphere_harmonics.py and utils.py in place (shims: an ``lpmn`` with the documented contract
+over scipy's ``assoc_legendre_p_all`` because scipy 1.18 removed it; a ``healpy`` stub) and runs ``SNvertex`` at jmax = 3 on 24 points
+of the reference's 128x256 grid and at jmax = 2 on a whole 16x32 grid, then exec's the script lines gt_gen_j3.py:39-43,
+mat_gen2.py:43-51 and :55 on those arrays -> tests/golden/needlets.npz.  This file reproduces all of it to <= 2e-14
+(tests/test_needlets_cpu.py::test_oracle_matches_reference_golden).  What stays UNPINNED is third-party and absent from this image:
+``healpy`` (unpinned -- the reference has no requirements file): its ``pix2ang / pix2vec / ringinfo`` are restated here from the
+*published* HEALPix RING pixelisation (Gorski et al. 2005, ApJ 622:759, eqs. 2-9) and the golden run answers healpy's calls from
+this restatement; it is checked against the healpy documentation's own example outputs (nside = 16, 5 pixels to 5e-9, one to the
+last bit) and the scheme's symmetries only.  The pre-computed ``SN_Matrix3.npy``
+is not shipped by the reference.  ``scipy.special.lpmv`` stands in for ``lpmn`` below (same Condon-Shortley convention).
 
 Reference anchors (all under /root/reference/Needlets):
 * ``fun_b / compute_f2 / compute_f3``   sphere_needlets.py:10-29     window b(x) = sqrt(f3(x/B) - f3(x)), C-infinity bump via quad

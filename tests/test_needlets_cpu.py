@@ -1,10 +1,47 @@
-"""CPU: the needlets oracle (parity unpinned -- healpy / SN_Matrix3.npy are not available) is checked against itself
-(line-by-line transcription of sphere_needlets.py vs the addition-theorem closed form) and against analytic properties; the
+"""CPU: the needlets oracle is pinned against tests/golden/needlets.npz -- outputs of the reference's own Needlets/ files run by
+oracle/make_golden_needlets.py (healpy alone stays a restatement, checked against its documentation's examples) -- and checked against
+itself (line-by-line transcription of sphere_needlets.py vs the addition-theorem closed form) and against analytic properties; the
 product's host-side tables (emlight_b200.needlets) are checked against the oracle's independent implementations."""
+import os
 import numpy as np
 import pytest
 
 from oracle import needlets_oracle as NO
+
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "needlets.npz")
+
+
+def test_oracle_matches_reference_golden():
+    """Everything below was RETURNED by the reference's code (sphere_needlets.SNvertex / fun_b / spneedlet_pair, utils.getSolidAngleMap,
+    the exec'd script lines gt_gen_j3.py:39-43, mat_gen2.py:43-51,55); the oracle must reproduce it to rounding."""
+    g = np.load(GOLD)
+    SN3 = NO.needlet_matrix(g["theta3"], g["phi3"], 3)                      # jmax = 3: poles, the phi = 0 / 2 pi seam, random grid points
+    assert SN3.shape == g["SN_3"].shape == (24, 1021)
+    assert np.abs(SN3 - g["SN_3"]).max() < 1e-12
+    pair, use = NO.spneedlet_pair(3)
+    assert np.array_equal(pair, g["pair3"]) and np.array_equal(use, g["use3"])
+    assert np.abs(np.hstack((SN3[:, :1], SN3[:, 1:][:, use])) - g["SN1_3"]).max() < 1e-12
+    assert np.abs(np.hstack((SN3[:, :1], SN3[:, 1:][:, pair][:, use])) - g["SN2_3"]).max() < 1e-12
+    SN2 = NO.needlet_matrix(g["theta2"], g["phi2"], 2)                      # the whole 16x32 grid at jmax = 2
+    assert np.abs(SN2 - g["SN_2"]).max() < 1e-12
+    th, ph = NO.pano_grid(16, 32)
+    assert np.array_equal(th, g["theta2"]) and np.array_equal(ph, g["phi2"])
+    omega = NO.solid_angle_map(32)
+    assert np.array_equal(omega, g["omega2"])
+    coef = NO.project(g["pano2"], g["SN_2"], omega.reshape(-1))
+    assert np.abs(coef - g["coef2"]).max() < 1e-12 * np.abs(g["coef2"]).max()
+    assert np.abs(NO.reconstruct(g["SN_2"], g["coef2"]) - g["rec2"]).max() < 1e-12 * np.abs(g["rec2"]).max()
+    assert np.array_equal(NO.sparsify(g["sp_in"]), g["sp_out"])             # mask and values, bit for bit
+    assert np.array_equal(np.array([NO.fun_b(x) for x in g["b_x"]]), g["b_val"])
+
+
+def test_product_window_matches_reference_golden():
+    from emlight_b200 import needlets as PN
+    g = np.load(GOLD)
+    assert np.abs(np.array([PN.fun_b(x) for x in g["b_x"]]) - g["b_val"]).max() < 1e-15
+    pair, use = PN.spneedlet_pair(3)
+    assert np.array_equal(pair, g["pair3"]) and np.array_equal(use, g["use3"])
 
 
 def test_transcription_equals_closed_form():

@@ -1,5 +1,8 @@
-"""GPU: needlet basis kernel, projection / reconstruction GEMMs and sparsification through the C ABI vs the CPU oracle
-(oracle/needlets_oracle.py; parity unpinned -- see its header) and, at BASELINE config-5 size, vs float64 torch matmul."""
+"""GPU: needlet basis kernel, projection / reconstruction GEMMs and sparsification through the C ABI vs tests/golden/needlets.npz
+(outputs of the reference's own Needlets/ files, oracle/make_golden_needlets.py), vs the CPU oracle (oracle/needlets_oracle.py) and,
+at BASELINE config-5 size, vs float64 torch matmul."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -7,6 +10,39 @@ import torch
 from oracle import needlets_oracle as NO
 
 pytestmark = pytest.mark.gpu
+
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "needlets.npz")
+
+
+def test_matches_reference_golden(cuda):
+    """The reference's SNvertex outputs (jmax = 3 on grid points incl. poles / seam; jmax = 2 on a whole 16x32 grid) and its projection /
+    sparsification / reconstruction script lines, against the basis kernel and the tcgen05 GEMMs."""
+    from emlight_b200 import needlets as PN
+    g = np.load(GOLD)
+    SN1, SN2, SN = PN.SNvertex(g["theta3"], g["phi3"], 3, device=cuda)
+    assert np.abs(SN.cpu().numpy() - g["SN_3"]).max() < 1e-12
+    assert np.abs(SN1.cpu().numpy() - g["SN1_3"]).max() < 1e-12 and np.abs(SN2.cpu().numpy() - g["SN2_3"]).max() < 1e-12
+    tr = PN.NeedletTransform(jmax=2, h=16, w=32, device=cuda)
+    assert np.abs(tr.SN.cpu().numpy() - g["SN_2"]).max() < 1e-12
+    assert np.array_equal(tr.omega.cpu().numpy(), g["omega2"].reshape(-1))
+    pano = torch.from_numpy(g["pano2"]).float()[None]                                     # (1, P, 3) like im.reshape((-1, 3))
+    coef = tr.project(pano.to(cuda))
+    ref = (g["SN_2"] * g["omega2"].reshape(-1, 1)).T @ pano[0].double().numpy()            # same fp32-rounded input as the kernel saw
+    assert np.abs(ref - g["coef2"]).max() < 1e-6 * np.abs(g["coef2"]).max()
+    assert np.abs(coef[0].cpu().numpy() - g["coef2"]).max() < 1e-3 * np.abs(g["coef2"]).max()   # the north-star bar; bf16x3 measures ~1e-5
+    rec = tr.reconstruct(torch.from_numpy(g["coef2"]).float()[None].to(cuda))
+    assert np.abs(rec[0].cpu().numpy() - g["rec2"]).max() < 1e-3 * np.abs(g["rec2"]).max()
+    tr3 = PN.NeedletTransform.__new__(PN.NeedletTransform)                               # sparsify needs only the level table of jmax = 3
+    tr3.device, tr3.n, tr3.jmax, tr3.level_slices = torch.device(cuda), 1021, 3, [(1, 13), (13, 61), (61, 253), (253, 1021)]
+    sp = tr3.sparsify(torch.from_numpy(g["sp_in"]).float()[None].to(cuda))[0].cpu().numpy()
+    want = g["sp_out"]
+    edge = np.zeros(want.shape, dtype=bool)                                             # fp32 input: entries within rounding of a block's threshold
+    for lo, hi in ((253, 1021), (61, 253)):
+        blk = np.abs(g["sp_in"][lo:hi])
+        edge[lo:hi] = np.abs(blk - 0.1 * blk.max()) < 1e-6 * blk.max()
+    assert np.array_equal((sp != 0) | edge, (want != 0) | edge)
+    assert np.abs(sp - want)[~edge].max() <= 1e-6 * np.abs(want).max()
 
 
 def test_basis_matches_oracle(cuda):
