@@ -5,7 +5,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_lon
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libemlight_b200.so")
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 EML_CONV_1x1, EML_CONV_3x3, EML_CONV_POOL2 = 0, 1, 2
 EML_PREC_BF16, EML_PREC_BF16X3, EML_PREC_FP32 = 0, 1, 2
@@ -95,6 +95,7 @@ SIGNATURES = {
     "eml_tanh_nchw_bwd": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_long, c_int, c_void_p, c_void_p]),
     "eml_pool2d_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "eml_loss_seed": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_long, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p]),
+    "eml_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p]),
     "eml_loss_reduce": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_long, c_int, c_int, c_void_p, c_void_p]),
 }
 
@@ -138,6 +139,33 @@ def stream_ptr():
 
 
 def require_cuda(*tensors):
+    """Every tensor handed to a kernel lives on a CUDA device, and all of them on the same one."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("emlight_b200 runs on CUDA tensors only (sm_100a kernels; no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("emlight_b200: tensors on different devices (%s and %s)" % (dev, t.device))
+
+
+def on_tensor_device(fn):
+    """Decorator for the public entry points: run the call with the first CUDA tensor argument's device current, so that
+    `stream_ptr()` (the current device's stream), the workspaces allocated inside and the raw-pointer launches all refer to the
+    device the data is on -- a module on cuda:1 called while cuda:0 is current must not launch on cuda:0."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        import torch
+        for a in list(args) + list(kwargs.values()):
+            if torch.is_tensor(a) and a.is_cuda:
+                if a.device.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapper

@@ -149,8 +149,10 @@ class DenseNet(nn.Module):
         self.use_cuda_graph = False                    # eval mode only: replay the 104-launch forward as one CUDA graph per input shape
         self._graphs = {}
         self.fuse_dense_layers = True                  # eval mode: one composite-filter kernel per dense layer (csrc/dense_layer.cu)
+        self._grad_sink = None                         # parallel.FlatAdam.sink: receives finished gradients DURING the backward (per block)
 
     # ------------------------------------------------------------------ reference-facing API
+    @_lib.on_tensor_device
     def forward(self, x):
         _lib.require_cuda(x)
         if x.dim() != 4 or x.shape[1] != 3:
@@ -612,6 +614,9 @@ class DenseNet(nn.Module):
         P = self.fc.in_features // c_last
         out["fc.weight"] = (dfc.t() @ pooled).view(-1, P, c_last).permute(0, 2, 1).reshape(self.fc.out_features, -1).contiguous()
         out["fc.bias"] = dfc.sum(0)
+        sink = self._grad_sink
+        if sink is not None:                                                     # fc + heads = 90 % of the gradient bytes, finished first:
+            sink(out)                                                            # their all-reduce overlaps the whole convolutional backward
         dpool = dfc @ c["fc_w"]                                                  # (B, P*c_last) in (yo, xo, c) order
         hl, wl = ws["t_last"].shape[1], ws["t_last"].shape[2]
         k = self.avgpool_size
@@ -701,4 +706,6 @@ class DenseNet(nn.Module):
                 _lib.check(lib.eml_wgrad_stem(_lib.ptr(dz0), c0, c0, _lib.ptr(x), _lib.ptr(dw0), B, H, W, st), "eml_wgrad_stem")
                 out["features.conv0.weight"] = dw0
             del dS
+            if sink is not None:
+                sink(out)
         return out

@@ -18,6 +18,7 @@ spectral-norm vectors) and train (batch-statistic (Sync)BatchNorm with running-s
 convolution per forward).  Backward is not built: outputs carry no autograd graph.
 """
 import math
+import os
 import re
 from functools import lru_cache
 
@@ -246,6 +247,7 @@ class SphereConv2D(nn.Module):
                 self._pc = (key, _PackedConv(self.effective_weight(), precision))
         return self._pc[1]
 
+    @_lib.on_tensor_device
     def forward(self, x):
         _lib.require_cuda(x)
         if self.autograd and torch.is_grad_enabled():
@@ -495,7 +497,8 @@ class SPADEGenerator(nn.Module):
         self.opt = opt
         self.precision = precision
         self.use_cuda_graph = False      # replay the whole forward (hundreds of launches) as one CUDA graph per input shape
-        self.autograd = False            # opt-in: train-mode forward recorded on a tape so that .backward() works (gp_train.py)
+        self.autograd = False            # standalone use: set True to record the train-mode forward on a tape so that .backward() works
+                                         # (gp_train.py); Pix2PixModel drives the tape itself and does not need this
         self._graphs = {}
         nf = opt.ngf
         self.sw = opt.crop_size // 32
@@ -511,6 +514,7 @@ class SPADEGenerator(nn.Module):
         self.sphere_conv1 = SphereConv2D(nf, 3, stride=1)
         self.netE = ConvEncoder(opt)
 
+    @_lib.on_tensor_device
     def forward(self, input, crop):
         # training mode = the reference's train-mode FORWARD (batch-statistic BatchNorm inside SPADE with running-stat update,
         # one spectral-norm power iteration per wrapped convolution); the output carries no autograd graph -- backward is not built
@@ -658,6 +662,7 @@ class NLayerDiscriminator(nn.Module):
         outs.append((_bias_act(raw, conv.bias, 0, B * H * W, 3), H, W, 3))
         return outs
 
+    @_lib.on_tensor_device
     @torch.no_grad()
     def forward(self, input):
         _lib.require_cuda(input)
@@ -695,6 +700,7 @@ class MultiscaleDiscriminator(nn.Module):
             x, H, W = _pool(x, B, H, W, C, 0)
         return result
 
+    @_lib.on_tensor_device
     @torch.no_grad()
     def forward(self, input):
         _lib.require_cuda(input)
@@ -716,6 +722,7 @@ class GANLoss(nn.Module):
             raise NotImplementedError("emlight_b200.GANLoss: only gan_mode='hinge' (the reference default) is implemented")
         self.gan_mode, self.opt = gan_mode, opt
 
+    @_lib.on_tensor_device
     @torch.no_grad()
     def loss(self, input, target_is_real, for_discriminator=True):
         _lib.require_cuda(input)
@@ -795,6 +802,7 @@ class VGG19(nn.Module):
             outs.append((x, H, W, C))
         return outs
 
+    @_lib.on_tensor_device
     @torch.no_grad()
     def forward(self, X):
         _lib.require_cuda(X)
@@ -802,15 +810,67 @@ class VGG19(nn.Module):
         return [_to_nchw(t, c) for t, _, _, c in self.features_nhwc(_nchw_to_nhwc(X, 4), B, H, W)]
 
 
+def _find_vgg19_weights():
+    """Where an ImageNet VGG19 checkpoint may live on an offline box: $EML_VGG19_WEIGHTS, then torch hub's cache (what
+    torchvision.models.vgg19(pretrained=True) -- architecture.py:95 -- would have downloaded)."""
+    import glob
+    cand = [os.environ.get("EML_VGG19_WEIGHTS")]
+    hub = os.path.join(os.environ.get("TORCH_HOME", os.path.join(os.path.expanduser("~"), ".cache", "torch")), "hub", "checkpoints")
+    cand += sorted(glob.glob(os.path.join(hub, "vgg19-*.pth")))
+    for c in cand:
+        if c and os.path.exists(c):
+            return c
+    return None
+
+
 class VGGLoss(nn.Module):
     """Drop-in for loss.VGGLoss (loss.py:102-114): sum_k w_k * L1(vgg_k(x), vgg_k(y)), w = 1/32, 1/16, 1/8, 1/4, 1.  x and y run as
-    one 2B batch.  Value only (no autograd)."""
+    one 2B batch.  Value only here; the training tape (gp_train.py) differentiates it.
 
-    def __init__(self, gpu_ids=None, precision="bf16x3"):
+    Weights: the reference builds ``torchvision.models.vgg19(pretrained=True)`` (architecture.py:95).  ``weights`` = a path to that
+    checkpoint (torchvision's ``vgg19-dcbb9e9d.pth`` layout, ``features.N.weight``) or a state_dict; default = $EML_VGG19_WEIGHTS or
+    torch hub's cache.  When none is found the features stay randomly initialised -- fine for timing and parity tests, WRONG for real
+    training (the perceptual term would be measured in a random network's feature space) -- so that case warns loudly, and raises
+    when ``require_pretrained`` (or $EML_REQUIRE_VGG=1) is set."""
+
+    def __init__(self, gpu_ids=None, precision="bf16x3", weights=None, require_pretrained=None):
         super().__init__()
         self.vgg = VGG19(precision=precision).cuda()
         self.weights = [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0]
+        if require_pretrained is None:
+            require_pretrained = os.environ.get("EML_REQUIRE_VGG") == "1"
+        src = weights if weights is not None else _find_vgg19_weights()
+        self.pretrained = False
+        if src is not None:
+            sd = torch.load(src, map_location="cpu") if isinstance(src, (str, bytes, os.PathLike)) else src
+            self.load_torchvision_state_dict(sd)
+        elif require_pretrained:
+            raise RuntimeError("emlight_b200.VGGLoss: no ImageNet VGG19 checkpoint found (set EML_VGG19_WEIGHTS=/path/to/vgg19-dcbb9e9d.pth "
+                               "or pass weights=...); refusing to train against randomly initialised features")
+        else:
+            import warnings
+            warnings.warn("emlight_b200.VGGLoss: no ImageNet VGG19 checkpoint found (EML_VGG19_WEIGHTS / torch hub cache); the perceptual "
+                          "loss uses RANDOMLY INITIALISED features -- acceptable for benchmarks and parity tests only, not for training "
+                          "(reference: torchvision.models.vgg19(pretrained=True), architecture.py:95)", RuntimeWarning, stacklevel=2)
 
+    def load_torchvision_state_dict(self, sd):
+        """Load torchvision's vgg19 ``features.N.{weight,bias}`` (or the reference VGG19's ``sliceK.N.*``) into slice1..slice5."""
+        own = self.vgg.state_dict()
+        by_idx = {k.split(".", 1)[1]: k for k in own}                       # "N.weight" -> "sliceK.N.weight"
+        new, used = {}, 0
+        for k, v in sd.items():
+            if k.startswith("features.") and k[len("features."):] in by_idx:
+                new[by_idx[k[len("features."):]]] = v
+                used += 1
+            elif k in own:
+                new[k] = v
+                used += 1
+        if used != len(own):
+            raise RuntimeError("VGG19 checkpoint does not cover features[0:30]: matched %d of %d tensors" % (used, len(own)))
+        self.vgg.load_state_dict(new)
+        self.pretrained = True
+
+    @_lib.on_tensor_device
     @torch.no_grad()
     def forward(self, x, y):
         _lib.require_cuda(x, y)
@@ -853,14 +913,15 @@ def cosine_loss(fake, real):
 class Pix2PixModel(nn.Module):
     """Drop-in for pix2pix_model.Pix2PixModel (pix2pix_model.py:12-186): mode dispatch 'inference' / 'generator' / 'discriminator'.
     'inference' is the full product path.  'generator' and 'discriminator' return the reference's loss dictionaries (same keys and
-    weights): plain values by default; with `self.autograd = True` (opt-in until its first B200 run) each call returns tensors attached
-    to one autograd node (emlight_b200/gp_train.py), so `sum(losses.values()).mean().backward()` + `create_optimizers()` train the
-    networks like GenProjector/model_trainer.py does."""
+    weights).  When the model was built for training (`opt.isTrain`) and gradients are enabled, each call returns tensors attached to one
+    autograd node (emlight_b200/gp_train.py), so `sum(losses.values()).mean().backward()` + `create_optimizers()` train the networks
+    like GenProjector/model_trainer.py does (`self.autograd`; verified on B200 against autograd of the oracle,
+    tests/test_gp_train_gpu.py); under `torch.no_grad()` -- or with `self.autograd = False` -- the same calls return plain values."""
 
     def __init__(self, opt):
         super().__init__()
         self.opt = opt
-        self.autograd = False            # opt-in: loss dictionaries carry an autograd node (gp_train.py) so the trainer's .backward() works
+        self.autograd = bool(getattr(opt, "isTrain", False))   # loss dictionaries carry an autograd node (gp_train.py): the trainer's .backward() works
         self.netG, self.netD = self.initialize_networks(opt)
         if opt.isTrain:
             self.criterionGAN = GANLoss(opt.gan_mode, opt=opt)

@@ -112,6 +112,7 @@ def linear(a, w, bias):
     return out
 
 
+@_lib.on_tensor_device
 def mm_nt(a, b, precision="bf16x3"):
     """(M,N) fp32 = a (M,K) @ b (N,K)^T on the TMA-fed tcgen05 GEMM: `a` is split into bf16 hi/lo rows (eml_split_bf16), `b` is packed
     as the resident operand in slices of <= 256 rows (eml_conv_pack_weights); short-and-deep products (few row tiles, long K -- the

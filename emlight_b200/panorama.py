@@ -54,11 +54,13 @@ class _Render(torch.autograd.Function):
         return gd, gs, gc
 
 
+@_lib.on_tensor_device
 def convert_to_panorama(dirs, sizes, colors):
     """Same signature and result as the reference's util.convert_to_panorama (CUDA tensors only)."""
     return _Render.apply(dirs, sizes, colors)
 
 
+@_lib.on_tensor_device
 @torch.no_grad()
 def render_from_params(distribution, intensity, rgb_ratio, ambient=None, dirs=None, size=0.0025, gain=500.0):
     """Heads of the regression network -> (B,3,128,256) panorama in one launch (no (B,3N) colour tensor).
@@ -93,6 +95,7 @@ def render_from_params(distribution, intensity, rgb_ratio, ambient=None, dirs=No
     return out
 
 
+@_lib.on_tensor_device
 def genprojector_guide(distribution, intensity, rgb_ratio, ambient, alpha=1.0, dirs=None, size=0.0025):
     """The GenProjector's conditioning panorama from (predicted or ground-truth) light parameters -- GenProjector/data.py:86-102:
         env = (convert_to_panorama(dirs, 0.0025, dist * (intensity * 0.01) * rgb_ratio) + ambient / (128 * 256)) * alpha

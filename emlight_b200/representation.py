@@ -29,6 +29,7 @@ class extract_mesh:                                        # noqa: N801  (the re
         self._ster = torch.from_numpy(ster).to(self.device)
         self._idx = torch.from_numpy(self.idx.astype(np.int32).reshape(-1)).to(self.device)
 
+    @_lib.on_tensor_device
     @torch.no_grad()
     def compute(self, hdr):
         lib = _lib.load()

@@ -73,6 +73,7 @@ class SamplesLoss(Module):
             self._M[key] = anchor_distance_matrix(n).to(device)
         return self._M[key]
 
+    @_lib.on_tensor_device
     def forward(self, *args):
         if len(args) != 2:
             raise ValueError("A SamplesLoss accepts two (x, y) arguments here (uniform weights, samples_loss.py:62-70).")
@@ -85,6 +86,7 @@ class SamplesLoss(Module):
 class GMSamplesLoss(SamplesLoss):
     """gmloss variant: anchors scaled by a per-anchor depth ``geometry`` (rebuilt per call like the reference)."""
 
+    @_lib.on_tensor_device
     def forward(self, x, y, geometry):
         if x.dim() != 3 or x.shape[2] != 1 or x.shape != y.shape:
             raise ValueError("Input samples 'x' and 'y' should be encoded as (B,N,1) tensors of equal shape.")

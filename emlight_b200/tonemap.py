@@ -1,8 +1,10 @@
 """HDR tonemapping on the GPU -- drop-in for ``TonemapHDR`` of the reference (RegressionNetwork/util.py:36-66; the step right in front
 of the DenseNet: ``data.py:62-73`` tonemaps every crop and scales the intensity / ambient targets by the returned ``alpha``).
-SURVEY 8f rank 2.  Same constructor and call signature; accepts one image ``(H, W, C)`` like the reference or a batch ``(B, H, W, C)``
-of CUDA tensors and returns ``(tonemapped float32 tensor, alpha)`` -- ``alpha`` is a Python float for one image, a ``(B,)`` tensor for a
-batch.  The percentile is an exact per-image radix selection (``eml_tonemap_hdr``), interpolated like ``np.percentile``."""
+SURVEY 8f rank 2.  Same constructor and call signature.  A numpy ``(H, W, C)`` image -- what the reference's callers pass
+(``train.py:124,135``: ``tone(env)[0].transpose(...).astype('float32')``) -- is uploaded, tone-mapped by the kernel and comes back as
+``(numpy float32 array, float alpha)`` exactly like the reference; a CUDA tensor ``(H, W, C)`` or batch ``(B, H, W, C)`` stays on the
+device and returns ``(float32 tensor, alpha)`` -- ``alpha`` a Python float for one image, a ``(B,)`` tensor for a batch.  The percentile is an exact per-image radix selection (``eml_tonemap_hdr``), interpolated like ``np.percentile``."""
+import numpy as np
 import torch
 
 from . import _lib
@@ -14,9 +16,15 @@ class TonemapHDR:
         self.percentile = percentile
         self.max_mapping = max_mapping
 
+    @_lib.on_tensor_device
     @torch.no_grad()
     def __call__(self, img, clip=True, alpha=None, gamma=True):
         lib = _lib.load()
+        if isinstance(img, np.ndarray):                 # the reference's calling convention: numpy in -> numpy out (no CPU arithmetic:
+            if not torch.cuda.is_available():           # the array is uploaded and the kernel does the work)
+                raise RuntimeError("emlight_b200.TonemapHDR needs a CUDA device (sm_100a kernel; no CPU fallback)")
+            y, a = self(torch.from_numpy(np.ascontiguousarray(img, dtype=np.float32)).cuda(), clip=clip, alpha=alpha, gamma=gamma)
+            return y.cpu().numpy(), (a if not torch.is_tensor(a) else a.cpu().numpy())
         _lib.require_cuda(img)
         single = img.dim() == 3
         if img.dim() not in (3, 4):

@@ -374,6 +374,15 @@ int eml_extract_params(const float *hdr, const int *idx, const double *ster, int
 int eml_tonemap_hdr(const float *x, float *out, float *alpha, int B, long per_image, float gamma, float percentile, float max_mapping,
                     int use_gamma, int clip, int alpha_given, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training step epilogue -- torch.optim.Adam over ONE flat fp32 buffer holding all parameters of a network
+ * (RegressionNetwork/train.py:55-57 `Adam(lr=1e-4, betas=(0.9, 0.999))`, GenProjector/models/pix2pix_model.py:56-70 `betas=(0, 0.9)`),
+ * with the 1/world_size of the gradient all-reduce (replaces nn.DataParallel's gather, model_trainer.py:20-24) folded in:
+ *   g' = grad_scale * g ;  m = b1 m + (1-b1) g' ;  v = b2 v + (1-b2) g'^2 ;  p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps)
+ * p, g, m, v: n fp32 each, 16-byte aligned; step >= 1 is the 1-based update count (torch's state['step'] after increment). */
+int eml_adam_step(float *p, const float *g, float *m, float *v, long n, float lr, float beta1, float beta2, float eps, int step,
+                  float grad_scale, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

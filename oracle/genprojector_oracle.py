@@ -65,7 +65,7 @@ def sphere_grid(h, w, stride=1):
 
 
 def sphere_conv(x, weight, bias, stride=1):
-    grid = sphere_grid(x.shape[2], x.shape[3], stride).repeat(x.shape[0], 1, 1, 1)
+    grid = sphere_grid(x.shape[2], x.shape[3], stride).repeat(x.shape[0], 1, 1, 1).to(x.dtype)   # fp32 coordinates (as the reference); cast only for the fp64 debug runs
     s = F.grid_sample(x, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
     return F.conv2d(s, weight, bias, stride=3)
 

@@ -125,6 +125,34 @@ def test_vgg_features_and_loss_match_reference_golden(cuda, precision, tol):
     assert abs(float(loss) - float(g["loss_VGG"])) <= tol * float(g["loss_VGG"])
 
 
+def test_vgg_loss_loads_a_torchvision_checkpoint(cuda, tmp_path, monkeypatch):
+    """architecture.py:95 builds torchvision.models.vgg19(pretrained=True): a checkpoint in torchvision's `features.N.*` layout must load
+    into slice1..5 (path argument, $EML_VGG19_WEIGHTS), and its absence must warn -- or raise when pretrained weights are required."""
+    import torchvision
+    import emlight_b200 as E
+    torch.manual_seed(3)
+    tv = torchvision.models.vgg19(weights=None)
+    path = str(tmp_path / "vgg19-test.pth")
+    torch.save(tv.state_dict(), path)
+    monkeypatch.delenv("EML_VGG19_WEIGHTS", raising=False)
+    monkeypatch.setenv("TORCH_HOME", str(tmp_path / "no_hub"))
+    with pytest.warns(RuntimeWarning, match="RANDOMLY INITIALISED"):
+        crit0 = E.VGGLoss([0])
+    assert not crit0.pretrained
+    with pytest.raises(RuntimeError, match="no ImageNet VGG19 checkpoint"):
+        E.VGGLoss([0], require_pretrained=True)
+    monkeypatch.setenv("EML_VGG19_WEIGHTS", path)
+    crit = E.VGGLoss([0])
+    assert crit.pretrained
+    x = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        want = tv.features[:2](x)                                                     # conv1_1 + relu = slice1
+    got = crit.vgg(x.to(cuda))[0].cpu()
+    assert float((got - want).abs().max()) <= 1e-3 * float(want.abs().max())
+    with pytest.raises(RuntimeError, match="does not cover"):
+        crit.load_torchvision_state_dict({"features.0.weight": tv.state_dict()["features.0.weight"]})
+
+
 def test_pix2pix_model_modes_match_oracle(cuda):
     """Pix2PixModel.forward(data, mode) for the three modes (pix2pix_model.py:40-54) vs the oracle composition on small networks."""
     import emlight_b200 as E

@@ -1,5 +1,4 @@
-"""GPU: A/B switches prepared without a GPU (round 1's budget was spent) -- each must reproduce the default path's results before it
-can become the default.  PENDING FIRST B200 RUN: runs only with EML_PENDING_GPU=1 (`tools/gpu_pending.sh`).
+"""GPU: A/B switches -- each must reproduce the default path's results before it can become the default.
   EML_STEM_V2=1    stem with [tap][o] shared-memory weights (LDS.128 broadcast) and 24 accumulators: bit-identical by construction
   EML_FC_SPLITK=1  fc GEMM split over K (M = B rows fill only 8 CTAs otherwise): equal to fp32 summation order"""
 import os
@@ -8,8 +7,7 @@ import sys
 
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("EML_PENDING_GPU") != "1", reason="not yet run on a B200 (set EML_PENDING_GPU=1)")]
+pytestmark = [pytest.mark.gpu]
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CODE = r"""

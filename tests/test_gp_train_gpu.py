@@ -1,9 +1,8 @@
 """GPU: the GenProjector training tape (`emlight_b200/gp_train.py`) on the real kernels -- gradients against torch autograd through
 the CPU oracle, the trainer's two steps through `Pix2PixModel`.
 
-PENDING FIRST B200 RUN: this file was written after the round's GPU budget was spent; the algebra it exercises is pinned on CPU by
-`tests/test_gp_train_cpu.py`, but tolerances here (bf16x3 GEMMs, leaky-ReLU masks) have not been calibrated on hardware yet, so the
-tests only run when EML_PENDING_GPU=1 (`tools/gpu_pending.sh`).  Remove the gate once they are green on a B200."""
+The same algebra is pinned on CPU by `tests/test_gp_train_cpu.py` (torch stand-ins for the forward kernels); here every primitive is
+the real kernel.  First B200 run: round 2, call 0 (`gpurun_out/pytest_pending.log`); tolerances calibrated there."""
 import argparse
 import os
 
@@ -12,8 +11,7 @@ import torch
 
 from oracle import genprojector_oracle as GO
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("EML_PENDING_GPU") != "1", reason="not yet run on a B200 (set EML_PENDING_GPU=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _l2rel(a, b):
@@ -85,8 +83,19 @@ def _g_opt(ngf):
                               num_upsampling_layers="normal", crop_size=256, aspect_ratio=2.0)
 
 
-def test_generator_backward_matches_oracle_autograd(cuda):
+# (forward contraction precision, backward contraction precision, per-tensor L2 bound).  Measured on B200 (gpurun_out/gp_bwd_debug2.log):
+#   fp32 / fp32      worst 5.2e-4, median 3e-6    the tape algebra + every adjoint kernel on real hardware
+#   fp32 / bf16x3    worst 5.2e-4, median 1.5e-5  the backward tcgen05 GEMMs (dA = dY Wk, split-K dW = A^T dY) are fp32-grade
+#   bf16x3 / bf16x3  worst 2.4e-2, median 4e-3    the default.  Identical to bf16x3 / fp32 (2.4e-2): the whole difference is caused by
+#                    the FORWARD's 2.5e-5 rounding -- (leaky-)ReLU masks and batch statistics of a 2-image batch make the gradient a
+#                    discontinuous function of the forward values -- not by the backward kernels, which the second row isolates.
+_BWD_MODES = [({"fwd": "fp32", "bwd": "fp32"}, 2e-3), ({"fwd": "fp32"}, 2e-3), ({}, 6e-2)]
+
+
+@pytest.mark.parametrize("override,bound", _BWD_MODES, ids=["fp32_fp32", "fp32fwd_bf16x3bwd", "bf16x3_default"])
+def test_generator_backward_matches_oracle_autograd(cuda, override, bound):
     import emlight_b200 as E
+    from emlight_b200 import gp_train
     ngf = 4
     G = E.SPADEGenerator(_g_opt(ngf)).to(cuda).train()
     sd0 = GO.init_generator_state_dict(seed=4, ngf=ngf)
@@ -96,14 +105,19 @@ def test_generator_backward_matches_oracle_autograd(cuda):
     guide = torch.rand(2, 3, 128, 256, generator=gen) * 2
     crop = torch.rand(2, 3, 96, 112, generator=gen)
     gout = torch.randn(2, 3, 128, 256, generator=gen)
-    out = G(guide.to(cuda), crop.to(cuda))
-    assert out.requires_grad
-    (out * gout.to(cuda)).sum().backward()
+    gp_train.PRECISION_OVERRIDE.clear()
+    gp_train.PRECISION_OVERRIDE.update(override)
+    try:
+        out = G(guide.to(cuda), crop.to(cuda))
+        assert out.requires_grad
+        (out * gout.to(cuda)).sum().backward()
+    finally:
+        gp_train.PRECISION_OVERRIDE.clear()
     sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("weight_u", "weight_v", "running_mean", "running_var"))
               else v.clone()) for k, v in sd0.items()}
     upd = {}
     ref = GO.generator_forward(sd, guide, crop, ngf=ngf, upd=upd)
-    assert float((out.detach().cpu() - ref.detach()).abs().max()) / 50.0 < 1e-3
+    assert float((out.detach().cpu() - ref.detach()).abs().max()) / 50.0 < (1e-5 if "fwd" in override else 1e-3)
     (ref * gout).sum().backward()
     top = max(float(sd[n].grad.norm()) for n, _ in G.named_parameters())
     bad = {}
@@ -111,9 +125,9 @@ def test_generator_backward_matches_oracle_autograd(cuda):
         want = sd[name].grad
         assert p.grad is not None, name
         err = float((p.grad.cpu() - want).norm())
-        if err > 2e-2 * max(float(want.norm()), 1e-3 * top):      # leaky-ReLU / ReLU mask flips between the bf16x3 and fp32 forwards
+        if err > bound * max(float(want.norm()), 1e-3 * top):
             bad[name] = (err, float(want.norm()))
-    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1][0])[:8]
+    assert not bad, [(k, "%.3g" % (v[0] / max(v[1], 1e-30))) for k, v in bad.items()]
     buffers = dict(G.named_buffers())
     for k, v in upd.items():
         assert float((buffers[k].cpu() - v.detach()).abs().max()) <= 1e-3 * float(v.abs().max()) + 1e-6, k
@@ -243,9 +257,14 @@ def test_adjoint_kernels_match_their_host_emulation(cuda, lib, tmp_path):
     xq = torch.randn(3, h * w, C, generator=gen)
     c, g = both("eml_im2col_lut_bf16_t", [xq, C, 10, C, idx, wgt, torch.randn(10, generator=gen), 2, torch.zeros(9 * C, Mp, dtype=torch.bfloat16),
                                           torch.zeros(9 * C, Mp, dtype=torch.bfloat16), Mp, 3, ho * wo, h * w])
-    assert torch.equal(c[8], g[8]) and torch.equal(c[9], g[9])
+    # hi / lo planes: the GPU contracts the 4-tap interpolation into FMAs, the host build does not -> a value on a bf16 rounding
+    # boundary may land on the other side in `hi` with `lo` absorbing it; what the GEMM consumes is hi + lo (~16 mantissa bits)
+    cs, gs = c[8].float() + c[9].float(), g[8].float() + g[9].float()
+    assert float((cs - gs).abs().max()) <= 2e-5 * float(cs.abs().max())
+    assert float((c[8].float() - g[8].float()).abs().max()) <= 2.0 ** -7 * float(cs.abs().max())
     from emlight_b200 import gp_ops
     offs, src, wv = gp_ops.lut_csr((idx, wgt, ho, wo), h * w)
     dAq = torch.randn(3 * ho * wo, 9 * C, generator=gen)
     c, g = both("eml_col2im_csr", [dAq, C, offs, src, wv, torch.zeros(3, h * w, C), C, 3, ho * wo, h * w])
-    assert torch.equal(c[5], g[5])                                          # fixed summation order: bit-identical to the host run
+    # fixed summation order (no atomics); the GPU contracts w * dA + acc into FMAs, the host build does not -> equal to rounding
+    assert float((c[5] - g[5]).abs().max()) <= 2e-6 * float(c[5].abs().max())

@@ -1,5 +1,5 @@
 """GPU: the `data.ParameterDataset` / `util.tonemapping` shims (tone mapping on the kernel) against the reference arithmetic restated
-in numpy.  PENDING FIRST B200 RUN like tests/test_gp_train_gpu.py: runs only with EML_PENDING_GPU=1 (`tools/gpu_pending.sh`)."""
+in numpy."""
 import importlib.util
 import os
 import pickle
@@ -8,8 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("EML_PENDING_GPU") != "1", reason="not yet run on a B200 (set EML_PENDING_GPU=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _np_tonemap(img, percentile, max_mapping, gamma=2.4):
@@ -101,4 +100,9 @@ def test_save_test_images_writes_the_reference_outputs(cuda, tmp_path):
     assert np.array_equal(wire.load_exr(os.path.join(out, "scene7_fake_image.exr")), fake.permute(1, 2, 0).cpu().numpy())
     prev = np.asarray(Image.open(os.path.join(out, "scene7_fake_image.jpg")))
     want, _ = _np_tonemap(fake.permute(1, 2, 0).cpu().numpy(), 50, 0.5)
-    assert prev.shape == (128, 256, 3) and np.abs(prev.astype(np.float32) - want * 255.0).mean() < 6.0       # JPEG is lossy
+    # JPEG is lossy (white noise loses ~25 levels on average): compare with the same 8-bit image pushed through the same encoder
+    import io
+    buf = io.BytesIO()
+    Image.fromarray((want * 255.0).astype("uint8")).save(buf, format="JPEG")
+    same = np.asarray(Image.open(io.BytesIO(buf.getvalue())))
+    assert prev.shape == (128, 256, 3) and np.abs(prev.astype(np.float32) - same.astype(np.float32)).mean() < 1.0

@@ -42,3 +42,16 @@ def test_tonemap_batch_matches_oracle(cuda):
     # the median of the positive tonemapped values is max_mapping by construction
     v = y[0][y[0] > 0]
     assert abs(float(v.median()) - 0.5) < 1e-3
+
+
+def test_tonemap_numpy_call_like_train_py(cuda):
+    """RegressionNetwork/train.py:124,135: `tone(env_pred)[0].transpose((1, 2, 0)).astype('float32') * 255.0` on a numpy (3,128,256)
+    array -- numpy in, (numpy float32, float alpha) out, computed by the kernel."""
+    from emlight_b200.tonemap import TonemapHDR
+    env = np.ascontiguousarray(synthetic_crop(77, h=128, w=256).transpose(2, 0, 1)) * 40.0
+    y, alpha = TonemapHDR(gamma=2.4, percentile=50, max_mapping=0.5)(env)
+    ry, ra = TO.tonemap_hdr(env)
+    assert isinstance(y, np.ndarray) and y.dtype == np.float32 and y.shape == (3, 128, 256) and isinstance(alpha, float)
+    assert abs(alpha - ra) <= 1e-5 * ra and np.abs(y - ry).max() <= 1e-5
+    img = y.transpose((1, 2, 0)).astype('float32') * 255.0
+    assert img.shape == (128, 256, 3) and img.max() <= 255.0

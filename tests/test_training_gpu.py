@@ -71,3 +71,38 @@ def test_training_trajectory_matches_oracle(cuda):
     for name in ("features.conv0.weight", "features.denseblock2.denselayer5.conv1.weight", "fc.weight"):
         d = (dict(net.named_parameters())[name].detach().cpu() - params[name].detach()).abs().max().item()
         assert d <= 3 * 1e-4 * steps, (name, d)
+
+
+def test_flat_adam_with_sink_equals_torch_adam(cuda):
+    """parallel.FlatAdam on the GPU -- parameters / gradients as views of flat buffers, gradients delivered by DenseNet._backward through
+    the sink (the fc bucket before the convolutional backward starts), eml_adam_step -- against torch.optim.Adam on a twin network:
+    same kernels produce the gradients, so the two trajectories must agree to rounding of the update formula."""
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    import emlight_b200 as E
+    from emlight_b200 import parallel
+    from train_regression_synthetic import synthetic_batch
+    B, ln, steps = 2, 96, 3
+    sd = DO.init_state_dict(seed=0, n_anchors=ln)
+    gb = synthetic_batch(B, ln, torch.Generator().manual_seed(4), cuda)
+    sam = E.SamplesLoss("sinkhorn", p=2, blur=.025, batchsize=B)
+    nets = [E.DenseNet(n_anchors=ln, precision="bf16x3").to(cuda).train() for _ in range(2)]
+    for n in nets:
+        n.load_state_dict(sd)
+    ref = torch.optim.Adam(nets[0].parameters(), lr=1e-4, betas=(0.9, 0.999))
+    flat = parallel.FlatAdam(nets[1].named_parameters(), lr=1e-4, betas=(0.9, 0.999))
+    nets[1]._grad_sink = flat.sink
+    assert len(flat.buckets) == 2 and "fc.weight" in flat.buckets[0][2]          # heads + fc (34 MB) | everything else
+    losses = [[], []]
+    for _ in range(steps):
+        for i, (net, opt) in enumerate(zip(nets, (ref, flat))):
+            loss = _losses(net(gb[0]), gb, sam, ln)
+            opt.zero_grad(); loss.backward(); opt.step()
+            losses[i].append(float(loss))
+        assert flat.early_buckets == 2                                         # both buckets were complete before backward() returned
+    assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(*losses)), losses      # the packed-weight caches saw every update
+    pa, pb = dict(nets[0].named_parameters()), dict(nets[1].named_parameters())
+    for name in pa:
+        d = float((pa[name].detach() - pb[name].detach()).abs().max())
+        assert d <= 2e-6, (name, d)                                             # |update| ~ lr = 1e-4 per step
+        assert pb[name].data_ptr() >= flat.flat_p.data_ptr() and pb[name].grad.data_ptr() >= flat.flat_g.data_ptr()
+    assert torch.equal(nets[0].state_dict()["features.norm0.running_mean"], nets[1].state_dict()["features.norm0.running_mean"])
