@@ -64,14 +64,30 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def cpu_reference_step(batch, sd, x, dirs, threads):
+def reference_net():
+    """(callable x -> dict, kind): the reference's own RegressionNetwork/DenseNet.py when oracle/stage_ref.py staged it (oracle/_ref/,
+    git-ignored, travels with the snapshot) -- fc_dist widened to the workload's 128 anchors -- else the port (oracle/densenet_oracle.py)."""
+    import torch
+    from oracle import densenet_oracle as DO, stage_ref
+    sd = DO.init_state_dict(seed=0, n_anchors=N_ANCHORS)
+    mod = stage_ref.load()
+    if mod is not None:
+        net = mod.DenseNet()
+        net.fc_dist = torch.nn.Linear(1024, N_ANCHORS)
+        net.load_state_dict(sd)
+        net.eval()
+        return net, "reference"
+    return (lambda x: DO.densenet_forward(sd, x, training=False)), "port"
+
+
+def cpu_reference_step(batch, net, x, dirs, threads):
     """One pass of the reference path on the CPU: DenseNet forward (eval BN) -> colour composition -> SG render."""
     import numpy as np
     import torch
-    from oracle import densenet_oracle as DO, render_oracle as RO
+    from oracle import render_oracle as RO
     torch.set_num_threads(threads)
     with torch.no_grad():
-        out = DO.densenet_forward(sd, x, training=False)
+        out = net(x)
     # train.py:115-122: colours from the heads, shared anchors, size 0.0025, then the reference's light-by-light render
     cols = (out["distribution"][:, :, None] * (out["intensity"][:, :, None] * 500.0) * out["rgb_ratio"][:, None, :]).reshape(batch, -1)
     sizes = torch.full((batch, N_ANCHORS), 0.0025)
@@ -85,7 +101,7 @@ def time_cpu(sample, steps, warmup):
     import torch
     from oracle import densenet_oracle as DO, render_oracle as RO
     ncpu = os.cpu_count() or 1
-    sd = DO.init_state_dict(seed=0, n_anchors=N_ANCHORS)
+    sd, kind = reference_net()
     x = torch.rand(sample, 3, 192, 256, generator=torch.Generator().manual_seed(1234))
     dirs = RO.sphere_points(N_ANCHORS).astype(np.float32).reshape(1, -1)
     cands = sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)})
@@ -103,7 +119,198 @@ def time_cpu(sample, steps, warmup):
     for _ in range(steps):
         cpu_reference_step(sample, sd, x, dirs, threads)
     dt = (time.perf_counter() - t0) / steps
-    return sample / dt, dt, threads
+    return sample / dt, dt, threads, kind
+
+
+def cpu_sample_note(kind, sample, steps):
+    what = ("the reference's own RegressionNetwork/DenseNet.py (unmodified, staged in oracle/_ref; fc_dist widened to 128 anchors)" if kind == "reference"
+            else "oracle/ DenseNet forward (port: the same ATen ops in the same order)")
+    return ("best of {8,16,32,64,all} intra-op threads; %d crops per step x %d steps; %s, eval BN + light-by-light SG render "
+            "(port of util.py:222-245: the reference's util.py does not import), torch CPU ATen ops" % (sample, steps, what))
+
+
+def train_workloads(E, parallel, dev, rank, world, gen, timed, args):
+    """BASELINE configs[1] (regression train step, B = 64 per GPU) and the GenProjector part of configs[3] (G step + D step, ngf = 64,
+    B = 4 per GPU) at the current world size: forward + losses + backward + gradient all-reduce + Adam, with `parallel.FlatAdam`
+    (flat parameter / gradient views, buckets all-reduced in place and -- for the DenseNet -- launched from inside the backward)."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    from train_regression_synthetic import synthetic_batch
+    out = {}
+
+    def comm_alone(opts, reps=5):
+        """Device time of the gradient all-reduce by itself (every bucket, in place, back to back)."""
+        if world == 1:
+            return 0.0
+        def run():
+            for o in opts:
+                hs = [dist.all_reduce(o.flat_g[lo:hi], async_op=True) for lo, hi, _ in o.buckets]
+                for h in hs:
+                    h.wait()
+        run()
+        return timed(run, reps) / reps
+
+    # ---- configs[1]: DenseNet fwd (batch-statistic BN) + Sinkhorn EMD + 4 MSE terms + full backward + Adam (train.py:79-102)
+    Bt = 64
+    torch.manual_seed(0)                                        # identical initial weights on every rank
+    tnet = E.DenseNet(n_anchors=N_ANCHORS, precision=args.precision).to(dev).train()
+    opt = parallel.FlatAdam(tnet.named_parameters(), lr=1e-4, betas=(0.9, 0.999))
+    tnet._grad_sink = opt.sink
+    loss_fn = E.SamplesLoss("sinkhorn", p=2, blur=.025, batchsize=Bt)
+    l2 = torch.nn.MSELoss()
+    tb = synthetic_batch(Bt, N_ANCHORS, gen, dev)
+
+    def train_step():
+        crop, dist_gt, inten_gt, rgb_gt, amb_gt = tb
+        pred = tnet(crop)
+        dp = pred["distribution"].view(-1, N_ANCHORS, 1)
+        loss = (loss_fn(dp, dist_gt.view(-1, N_ANCHORS, 1)).sum() * 1000.0 + l2(dp, dist_gt.view(-1, N_ANCHORS, 1)) * 1000.0 +
+                l2(pred["intensity"], inten_gt) * 0.1 + l2(pred["rgb_ratio"], rgb_gt) * 100.0 + l2(pred["ambient"], amb_gt) * 1.0)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    for _ in range(2):
+        train_step()
+    ms_tr = timed(train_step, 3) / 3
+    ar = comm_alone([opt])
+    entry = {"ms_per_step": round(ms_tr, 3), "maps_per_s": round(Bt * world / ms_tr * 1e3, 1), "batch_per_gpu": Bt,
+             "allreduce_bytes": opt.comm_bytes, "allreduce_buckets": len(opt.buckets),
+             "buckets_launched_inside_backward": opt.early_buckets, "allreduce_alone_ms": round(ar, 3)}
+    if world > 1:
+        opt.comm = False                                          # the same step with the collective removed -> what the exchange costs
+        train_step()
+        ms_nc = timed(train_step, 3) / 3
+        opt.comm = True
+        exposed = max(0.0, ms_tr - ms_nc)
+        entry.update({"ms_per_step_without_allreduce": round(ms_nc, 3), "allreduce_exposed_ms": round(exposed, 3),
+                      "allreduce_overlapped_fraction": round(max(0.0, 1.0 - exposed / ar), 3) if ar > 0 else None,
+                      "allreduce_algbw_GBps": round(opt.comm_bytes / ar / 1e6, 1) if ar > 0 else None})
+    out["config1_train_step_fwd_bwd_allreduce_adam_b64_per_gpu"] = entry
+
+    def cfg1():                     # DenseNet fwd (batch-statistic BN, as train.py runs it) + Sinkhorn-EMD fwd + d/d(dist_pred) only
+        with torch.no_grad():
+            o = tnet(tb[0])
+        d = o["distribution"].detach().view(Bt, N_ANCHORS, 1).requires_grad_()
+        loss_fn(d, tb[1].view(Bt, N_ANCHORS, 1)).sum().backward()
+        return d.grad
+    if world == 1:
+        for _ in range(2):
+            cfg1()
+        ms1 = timed(cfg1, 5) / 5
+        out["config1_densenet_fwd_trainBN_plus_sinkhorn_fwd_bwd_b64"] = {"ms_per_step": round(ms1, 3), "maps_per_s": round(Bt / ms1 * 1e3, 1)}
+    del tnet, opt, tb
+    torch.cuda.empty_cache()
+
+    # ---- configs[3], GenProjector part: G step + D step (pix2pix_model.py:92-141 through model_trainer.py:34-50), ngf = ndf = 64
+    try:
+        import argparse as _ap
+        import warnings
+        from train_genprojector_synthetic import synthetic_batch as gan_batch
+        gopt = _ap.Namespace(ngf=64, ndf=64, norm_G="spectralspadesyncbatch3x3", norm_E="spectralinstance", norm_D="spectralinstance",
+                             semantic_nc=3, label_nc=3, output_nc=3, num_upsampling_layers="normal", crop_size=256, aspect_ratio=2.0,
+                             num_D=2, n_layers_D=4, netD_subarch="n_layer", no_ganFeat_loss=False, no_vgg_loss=False, gpu_ids=[0],
+                             isTrain=True, gan_mode="hinge", lr=0.0002, beta1=0.0, beta2=0.9, no_TTUR=False)
+        torch.manual_seed(0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")                     # VGG19 weights: none on the box (random features; timing only)
+            gm = E.Pix2PixModel(gopt)
+        gm.train()
+        og = parallel.FlatAdam(gm.netG.named_parameters(), lr=gopt.lr / 2, betas=(gopt.beta1, gopt.beta2))     # TTUR, pix2pix_model.py:62-66
+        od = parallel.FlatAdam(gm.netD.named_parameters(), lr=gopt.lr * 2, betas=(gopt.beta1, gopt.beta2))
+        Bg = 4
+        gd = gan_batch(Bg, gen, dev)
+
+        def gan_iter():
+            og.zero_grad(); gl, _ = gm(gd, "generator"); sum(gl.values()).mean().backward(); og.step()
+            od.zero_grad(); dl = gm(gd, "discriminator"); sum(dl.values()).mean().backward(); od.step()
+        gan_iter()
+        ms_g = timed(gan_iter, 2) / 2
+        ar = comm_alone([og, od], reps=3)
+        out["config3_genprojector_G_step_plus_D_step_b4_per_gpu"] = {
+            "ms_per_iteration": round(ms_g, 3), "maps_per_s": round(Bg * world / ms_g * 1e3, 2), "batch_per_gpu": Bg, "ngf": 64,
+            "allreduce_bytes": og.comm_bytes + od.comm_bytes, "allreduce_buckets": len(og.buckets) + len(od.buckets),
+            "allreduce_alone_ms": round(ar, 3), "allreduce_algbw_GBps": round((og.comm_bytes + od.comm_bytes) / ar / 1e6, 1) if ar > 0 else None,
+            "spade_stat_allreduces_per_iteration": 0 if world == 1 else "2 x (C) sums per SPADE norm, forward and backward (SynchronizedBatchNorm)"}
+        del gm, og, od, gd
+    except Exception as e:                              # noqa: BLE001  (secondary workload: never fail the headline line)
+        out["config3_genprojector_G_step_plus_D_step_b4_per_gpu"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    torch.cuda.empty_cache()
+    return out
+
+
+def eager_gpu_baseline(dev, B, value, extra):
+    """PyTorch eager on the SAME GPU -- the reference's ops (its own module when staged, else the port) on `cuda`,
+    fp32 with TF32 off (cuDNN / cuBLAS kernels), CUDA events.  A baseline leg like cpu_baseline: reported next to the product."""
+    import numpy as np
+    import torch
+    from oracle import densenet_oracle as DO, render_oracle as RO, stage_ref
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    net, kind = reference_net()
+    sd = DO.init_state_dict(seed=0, n_anchors=N_ANCHORS)
+    if kind == "reference":
+        net = net.to(dev)
+        fwd = net
+    else:
+        sdd = {k: v.to(dev) for k, v in sd.items()}
+        fwd = lambda t: DO.densenet_forward(sdd, t, training=False)           # noqa: E731
+    x = torch.rand(B, 3, 192, 256, generator=torch.Generator().manual_seed(1234)).to(dev)
+    dirs = torch.from_numpy(RO.sphere_points(N_ANCHORS).astype(np.float32).reshape(1, -1)).to(dev).repeat(B, 1)
+    sizes = torch.full((B, N_ANCHORS), 0.0025, device=dev)
+
+    def step():
+        with torch.no_grad():
+            o = fwd(x)
+            cols = (o["distribution"][:, :, None] * (o["intensity"][:, :, None] * 500.0) * o["rgb_ratio"][:, None, :]).reshape(B, -1)
+            return RO.convert_to_panorama_torch(dirs, sizes, cols)
+
+    def time_it(fn, n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    for _ in range(2):
+        step()
+    ms = time_it(step, 3)
+    res = {"kind": kind, "what": "reference ops on cuda:0 (torch eager, cuDNN/cuBLAS fp32, TF32 off), same B=%d workload as the headline" % B,
+           "ms_per_step": round(ms, 3), "maps_per_s": round(B / ms * 1e3, 1), "ours_over_eager": round(value / (B / ms * 1e3), 2)}
+    del x
+    torch.cuda.empty_cache()
+    # the train step (configs[1]): forward with batch-statistic BN + 4 MSE terms + Sinkhorn EMD (our kernel: 0.1 ms) + autograd backward + Adam
+    try:
+        import emlight_b200 as E
+        Bt = 64
+        params = {k: v.to(dev).clone().requires_grad_() for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+        state = {k: v.to(dev).clone() for k, v in sd.items()}
+        state.update(params)
+        opt = torch.optim.Adam(list(params.values()), lr=1e-4)
+        g = torch.Generator().manual_seed(5)
+        xt = torch.rand(Bt, 3, 192, 256, generator=g).to(dev)
+        yt = torch.softmax(3 * torch.randn(Bt, N_ANCHORS, generator=g), 1).view(Bt, N_ANCHORS, 1).to(dev)
+        sam = E.SamplesLoss("sinkhorn", p=2, blur=.025, batchsize=Bt)
+        l2 = torch.nn.functional.mse_loss
+
+        def tstep():
+            o = DO.densenet_forward(state, xt, training=True)
+            dp = o["distribution"].view(Bt, N_ANCHORS, 1)
+            loss = sam(dp, yt).sum() * 1000.0 + l2(dp, yt) * 1000.0 + l2(o["intensity"], torch.zeros_like(o["intensity"])) * 0.1 + \
+                l2(o["rgb_ratio"], torch.zeros_like(o["rgb_ratio"])) * 100.0 + l2(o["ambient"], torch.zeros_like(o["ambient"]))
+            opt.zero_grad(); loss.backward(); opt.step()
+        tstep()
+        ms_t = time_it(tstep, 3)
+        res["train_step_b64"] = {"ms_per_step": round(ms_t, 3), "maps_per_s": round(Bt / ms_t * 1e3, 1), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+        ours = extra.get("config1_train_step_fwd_bwd_allreduce_adam_b64_per_gpu", {}).get("ms_per_step")
+        if ours:
+            res["train_step_b64"]["ours_over_eager"] = round(ms_t / ours, 2)
+    except Exception as e:                              # noqa: BLE001  (e.g. out of memory: eager autograd keeps ~1.4 GB of activations per image)
+        res["train_step_b64"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -130,12 +337,12 @@ def main():
         if rank != 0:
             return
         sample = args.cpu_sample
-        v, dt, threads = time_cpu(sample, max(args.steps, 1), warmup)
+        v, dt, threads, kind = time_cpu(sample, max(args.steps, 1), warmup)
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "maps/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": dict(config, batch_per_gpu=sample, global_batch=sample),
-                "cpu_baseline": {"value": v, "unit": "maps/s", "cores": threads, "kind": "port",
-                                 "sample": "best of {8,16,32,64,all} intra-op threads; %d crops per step, oracle/ DenseNet forward + light-by-light SG render, torch CPU ATen ops (eval BN)" % sample},
+                "cpu_baseline": {"value": v, "unit": "maps/s", "cores": threads, "kind": kind,
+                                 "sample": cpu_sample_note(kind, sample, max(args.steps, 1))},
                 "e2e": {"value": v, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -238,12 +445,13 @@ def main():
     achieved = fam[top]["bytes"] / fam[top]["ms"] / 1e6
     # DRAM traffic of the dominant family per launch, from the committed ncu launch list of this same command (profiles/)
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tp) and B == 256:
+    tps = [os.path.join(ROOT, "profiles", n) for n in ("r02_traffic.json", "r01_traffic.json")]
+    tp = next((t for t in tps if os.path.exists(t)), None)
+    if tp is not None and B == 256:
         tj = json.load(open(tp))
         if top in tj["families"]:
             traffic = tj["families"][top]["traffic_bytes_per_launch"]
-            traffic_src = "profiles/r01_traffic.json (ncu dram__bytes_read+write, avg per launch); algorithmic bytes per launch = %d" % (
+            traffic_src = "profiles/" + os.path.basename(tp) + " (ncu dram__bytes_read+write, avg per launch); algorithmic bytes per launch = %d" % (
                 fam[top]["bytes"] // fam[top]["launches"])
     roofline = {"kernel": {"dense_layer": "dense_layer_kernel<SPLIT> (csrc/dense_layer.cu)",
                            "conv1x1": "conv1x1_persist_kernel<SPLIT,RELU>", "conv3x3": "conv3x3_roll_kernel<48,SPLIT>",
@@ -255,35 +463,15 @@ def main():
     fc_launches = 5 if (args.precision != "fp32" and B >= 32) else 1               # bf16 split + 4 GEMM slices, or the SIMT linear
     launches_per_step = 1 + sum(v["launches"] for v in fam.values()) + 1 + fc_launches + 1 + 1   # stem + convs + head_pool + fc + heads + render
 
-    # ---- secondary workloads (reported, not the headline): BASELINE configs[1] and configs[0]
+    # ---- secondary workloads (reported, not the headline).  The TRAINING steps run at every N: they are the workloads with a real
+    # exchange (one in-place bucketed all-reduce of the gradients, launched from inside the backward; SPADE's batch-statistic sums)
     extra = {}
+    if not args.no_cpu_baseline:                    # (the flag also skips every secondary workload: quick A/B runs of the headline)
+        torch.cuda.empty_cache()
+        extra.update(train_workloads(E, parallel, dev, rank, world, gen, timed, args))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        Bt = 64
-        xt = torch.rand(Bt, 3, 192, 256, generator=gen).to(dev)
-        yt = torch.softmax(3 * torch.randn(Bt, N_ANCHORS, generator=gen), 1).view(Bt, N_ANCHORS, 1).to(dev)
-        loss_fn = E.SamplesLoss("sinkhorn", p=2, blur=.025, batchsize=Bt)
-        net.train()
-
-        def cfg1():                     # DenseNet fwd (batch-statistic BN, as train.py runs it) + Sinkhorn-EMD fwd + d/d(dist_pred)
-            with torch.no_grad():
-                o = net(xt)
-            d = o["distribution"].detach().view(Bt, N_ANCHORS, 1).requires_grad_()
-            loss_fn(d, yt).sum().backward()
-            return d.grad
-        for _ in range(3):
-            cfg1()
-        ms1 = timed(cfg1, 5) / 5
-        # BASELINE configs[1]/[3] as train.py runs it: forward + 5-term loss + full backward + Adam step
-        sys.path.insert(0, os.path.join(ROOT, "examples"))
-        from train_regression_synthetic import synthetic_batch, train_step
-        opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.999))
-        tb = synthetic_batch(Bt, N_ANCHORS, gen, dev)
-        l2 = torch.nn.MSELoss()
-        for _ in range(2):
-            train_step(net, loss_fn, l2, opt, tb, N_ANCHORS, 1)
-        ms_tr = timed(lambda: train_step(net, loss_fn, l2, opt, tb, N_ANCHORS, 1), 3) / 3
         net.eval()
-        x1 = x[:1].contiguous()
+        x1 = x_host[:1].to(dev)
         for _ in range(3):
             step(x1)
         ms0 = timed(lambda: step(x1), 20) / 20
@@ -292,13 +480,11 @@ def main():
             step(x1)
         ms0g = timed(lambda: step(x1), 50) / 50
         net.use_cuda_graph = False
-        extra = {"config1_densenet_fwd_trainBN_plus_sinkhorn_fwd_bwd_b64": {"ms_per_step": round(ms1, 3), "maps_per_s": round(Bt / ms1 * 1e3, 1)},
-                 "train_step_fwd_bwd_adam_b64": {"ms_per_step": round(ms_tr, 3), "maps_per_s": round(Bt / ms_tr * 1e3, 1)},
-                 "config0_single_crop_latency_ms": round(ms0, 3), "config0_single_crop_latency_cuda_graph_ms": round(ms0g, 3)}
+        extra["config0_single_crop_latency_ms"] = round(ms0, 3)
+        extra["config0_single_crop_latency_cuda_graph_ms"] = round(ms0g, 3)
         # BASELINE configs[4] (per GPU share of B=512 over 8 GPUs = 64; here the whole 512 on one GPU): needlet j=3 projection + reconstruction
         try:
             from emlight_b200.needlets import NeedletTransform
-            del xt, yt, tb
             torch.cuda.empty_cache()
             nt = NeedletTransform(jmax=3, device=dev)
             pn = torch.exp(torch.randn(512, 3, 128, 256, device=dev))
@@ -313,38 +499,15 @@ def main():
             del nt, pn, cf
         except Exception as e:                                  # noqa: BLE001  (secondary workload: never fail the headline line)
             extra["config4_needlets_j3_b512"] = {"error": "%s: %s" % (type(e).__name__, e)}
-        # BASELINE configs[3]'s GenProjector part (G step + D step: forward, tape backward of emlight_b200/gp_train.py, Adam).  Opt-in
-        # (EML_BENCH_GAN=1) until that path has had its first B200 run -- see DESIGN.md 4.2 / tools/gpu_pending.sh.
-        if os.environ.get("EML_BENCH_GAN") == "1":
-            try:
-                import argparse as _ap
-                from train_genprojector_synthetic import synthetic_batch as gan_batch
-                torch.cuda.empty_cache()
-                gopt = _ap.Namespace(ngf=64, ndf=64, norm_G="spectralspadesyncbatch3x3", norm_E="spectralinstance", norm_D="spectralinstance",
-                                     semantic_nc=3, label_nc=3, output_nc=3, num_upsampling_layers="normal", crop_size=256, aspect_ratio=2.0,
-                                     num_D=2, n_layers_D=4, netD_subarch="n_layer", no_ganFeat_loss=False, no_vgg_loss=False, gpu_ids=[0],
-                                     isTrain=True, gan_mode="hinge", lr=0.0002, beta1=0.0, beta2=0.9, no_TTUR=False)
-                gm = E.Pix2PixModel(gopt)
-                gm.train()
-                gm.autograd = True
-                og, od = gm.create_optimizers(gopt)
-                Bg = 4
-                gd = gan_batch(Bg, gen, dev)
-
-                def gan_iter():
-                    og.zero_grad(); gl, _ = gm(gd, "generator"); sum(gl.values()).mean().backward(); og.step()
-                    od.zero_grad(); dl = gm(gd, "discriminator"); sum(dl.values()).mean().backward(); od.step()
-                gan_iter()
-                ms_g = timed(gan_iter, 2) / 2
-                extra["config3_genprojector_G_step_plus_D_step_b4"] = {"ms_per_iteration": round(ms_g, 3), "maps_per_s": round(Bg / ms_g * 1e3, 2)}
-                del gm, og, od, gd
-            except Exception as e:                              # noqa: BLE001  (secondary workload: never fail the headline line)
-                extra["config3_genprojector_G_step_plus_D_step_b4"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        torch.cuda.empty_cache()
+        try:
+            extra["eager_gpu_baseline"] = eager_gpu_baseline(dev, B, value, extra)
+        except Exception as e:                                  # noqa: BLE001
+            extra["eager_gpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, e)}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, threads = time_cpu(args.cpu_sample, 3, 1)
-        cpu = {"value": v, "unit": "maps/s", "cores": threads, "kind": "port",
-               "sample": "best of {8,16,32,64,all} intra-op threads; %d crops per step x 3 steps, oracle/ DenseNet forward + light-by-light SG render, torch CPU ATen ops (eval BN)" % args.cpu_sample}
+        v, dt, threads, kind = time_cpu(args.cpu_sample, 3, 1)
+        cpu = {"value": v, "unit": "maps/s", "cores": threads, "kind": kind, "sample": cpu_sample_note(kind, args.cpu_sample, 3)}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "maps/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -31,6 +31,16 @@
 //   warp 17     MMA     per 16-channel k-step three tcgen05.mma (hi*Bhi, lo*Bhi, hi*Blo): A descriptors are the stage base
 //                       + 32k bytes (hi) / + 64 + 32k bytes (lo); composite weights resident in shared memory
 //   warps 20-27 EPILOGUE one warpgroup per half row (stencil above)
+//
+// TS = true (default since round 2): the A operand lives in TENSOR MEMORY instead.  ncu on the smem-A version (profiles/
+// r01_ncu_full_dense_layer_v8.md) shows the shared-memory pipe as the roof: per 16 KB stage the converters read 16 KB and write 16 KB
+// (+ scale/shift reads) and the three MMAs per k-step re-read A (24 KB) and B (21 KB) -- 93 KB of shared-memory traffic per 16 KB of
+// HBM data.  With TS a converter THREAD owns one pixel row: it reads its 128-byte raw row (8 conflict-free LDS.128 through the
+// 128-byte swizzle), applies norm1 + ReLU, splits to bf16 hi/lo and writes the packed pairs with tcgen05.st into a ring of four
+// 32-column TMEM slots ([hi k0 | hi k1 | lo k0 | lo k1] x 8 columns; lane = pixel, column = channel pair -- layout validated by
+// tools/micro/ts_mma_test.cu); the MMAs take A from TMEM (tcgen05.mma [d], [a], b-desc).  Shared-memory traffic per stage drops to
+// 16 KB TMA write + 16 KB LDS + 21 KB B reads, the shared-memory stage is released as soon as it has been READ (not after the MMAs),
+// and the unused half of a partial last stage is skipped.  TMEM: 2 Z accumulators (224) + 4 partial-row slots (144) + A ring (128).
 #include <cuda.h>
 #include "common.cuh"
 #include "umma.cuh"
@@ -49,10 +59,16 @@ constexpr int F_THREADS = (F_EPI_WARP0 + 8) * 32;       // 896
 constexpr int F_G = 12;                                 // growth rate (output channels)
 constexpr int F_GRP = 3 * F_G;                          // 36 columns per dy group, ordered (dx, o)
 constexpr int F_NPAD = 112;
-constexpr int F_NZ = 3;                                 // Z accumulator buffers (tile j uses buffer j % 3)
 constexpr int F_ZSTRIDE = 112;                          // TMEM columns per Z buffer
-constexpr int F_UBASE = F_NZ * F_ZSTRIDE;               // 336: TMEM column of the partial-row slots
-constexpr int F_USTRIDE = 36;                           // [slot(2)][half(2)] x 36 columns -> 336 + 144 = 480 of 512 columns
+constexpr int F_USTRIDE = 36;                           // [slot(2)][half(2)] x 36 columns
+constexpr int F_NA = 4;                                 // TS: TMEM A-operand slots (one per converter warpgroup), 32 columns each
+constexpr int F_MAX_NZ = 3;
+// TMEM map.  smem-A: 3 Z (336) + partial rows (144) = 480.  TS: 2 Z (224) + partial rows (144) + A ring 4 x 32 (128) = 496 of 512.
+template <bool TS> struct FTmem {
+    static constexpr int NZ = TS ? 2 : 3;               // Z accumulator buffers (tile j uses buffer j % NZ)
+    static constexpr int UBASE = NZ * F_ZSTRIDE;        // partial-row slots
+    static constexpr int ABASE = UBASE + 4 * F_USTRIDE; // TS only: A ring
+};
 constexpr int F_MAX_C = 320;                            // 5 weight chunks of 64 channels
 constexpr int F_WCHUNK = 2 * F_NPAD * 128;              // bytes of one packed weight chunk [hi | lo] (64 channels)
 // floats per pixel in the row buffer: template parameter SROW = 36 (packed) or 44 (176 B = 48 B mod 128: the (pixel, quad) stream of the
@@ -114,6 +130,19 @@ template <> __device__ __forceinline__ void f_tmem_st<4>(uint32_t taddr, const f
 
 __device__ __forceinline__ void f_tmem_ld16(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
 __device__ __forceinline__ void f_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void f_tmem_st8u(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T: A = 128 lanes (rows) x 8 columns (16 bf16, pair (2c, 2c+1) in column c, low half first)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 
 // relu + truncation to bf16 in one instruction: d = {bf16(max(hi_in,0)), bf16(max(lo_in,0))}, round toward zero, so that for
 // v >= 0 the residual v - hi is >= 0 and exactly representable, and for v < 0 both parts are 0 after a second .relu convert.
@@ -194,10 +223,11 @@ __device__ __forceinline__ void band_init(BandIter &it, const FArgs &a, long ban
     it.m0 = (img * a.H + lo) * a.W;
 }
 
-template <bool SPLIT, bool POOL, int F_SROW>
+template <bool SPLIT, bool POOL, int F_SROW, bool TS>
 __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_constant__ CUtensorMap tmap, const FArgs a) {
+    constexpr int F_NZ = FTmem<TS>::NZ, F_UBASE = FTmem<TS>::UBASE, F_ABASE = FTmem<TS>::ABASE;
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long s_bar[3 * F_MAX_STAGES + 1 + 2 * F_NZ];
+    __shared__ __align__(8) unsigned long long s_bar[3 * F_MAX_STAGES + 1 + 2 * F_MAX_NZ + F_NA];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_scale[F_MAX_C], s_shift[F_MAX_C], s_bias[9 * F_G + 4];
 
@@ -213,12 +243,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
     const uint32_t bar_empty = smem_u32(&s_bar[2 * F_MAX_STAGES]);          // consumed by the MMAs
     const uint32_t bar_w = smem_u32(&s_bar[3 * F_MAX_STAGES]);
     const uint32_t bar_zfull = smem_u32(&s_bar[3 * F_MAX_STAGES + 1]);      // [F_NZ]
-    const uint32_t bar_zempty = smem_u32(&s_bar[3 * F_MAX_STAGES + 1 + F_NZ]);   // [F_NZ]
+    const uint32_t bar_zempty = smem_u32(&s_bar[3 * F_MAX_STAGES + 1 + F_MAX_NZ]);   // [F_NZ]
+    const uint32_t bar_afree = smem_u32(&s_bar[3 * F_MAX_STAGES + 1 + 2 * F_MAX_NZ]);    // [F_NA]  TS: MMAs that read TMEM A slot a are done
+    // TS reuses bar_ready[0 .. F_NA) as "A slot written" (4 converter warps arrive) and bar_empty[s] is armed by the converters (4 warps:
+    // the raw stage has been read), not by the MMA commits
 
     if (tid == 0) {
-        for (int s = 0; s < F_MAX_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_ready + 8 * s, 4); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < F_MAX_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_ready + 8 * s, 4); mbar_init(bar_empty + 8 * s, TS ? 4 : 1); }
+        for (int i = 0; i < F_NA; ++i) mbar_init(bar_afree + 8 * i, 1);
         mbar_init(bar_w, 1);
-        for (int i = 0; i < F_NZ; ++i) { mbar_init(bar_zfull + 8 * i, 1); mbar_init(bar_zempty + 8 * i, 4); }
+        for (int i = 0; i < F_MAX_NZ; ++i) { mbar_init(bar_zfull + 8 * i, 1); mbar_init(bar_zempty + 8 * i, 4); }
         fence_mbar_init();
     }
     for (int i = tid; i < F_MAX_C; i += F_THREADS) {
@@ -241,7 +275,66 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
     const uint32_t tmem_base = s_tmem;
     const int grid = static_cast<int>(gridDim.x);
 
-    if (warp < F_CWARPS) {
+    if (TS && warp < F_CWARPS) {
+        // =========================================================== CONVERTERS, TS: raw fp32 row (shared) -> bf16 hi/lo pairs (TMEM A slot)
+        // warpgroup cg converts stages g with g % 4 == cg into A slot cg; warp w4 = lane quarter, thread = pixel row of the tile.
+        // Every mbarrier here is observed in phase order: a warpgroup reaches stage g only after converting g - 4, all earlier
+        // stages have then landed (in-order TMA), so with a ring of >= 4 stages a parity wait can never be two phases early.
+        const int cg = warp >> 2, w4 = warp & 3;
+        const uint32_t row = static_cast<uint32_t>(w4 * 32 + lane);
+        const uint32_t r7 = row & 7u;
+        const uint32_t row_off = row * 128u;
+        const uint32_t ring = smem_u32(smem);
+        const uint32_t a_slot = tmem_base + F_ABASE + static_cast<uint32_t>(cg) * 32u + (static_cast<uint32_t>(w4 * 32) << 16);
+        uint32_t total = 0;
+        for (long band = blockIdx.x; band < a.nbands; band += grid) {
+            BandIter it;
+            band_init<POOL>(it, a, band);
+            total += static_cast<uint32_t>(it.nt) * static_cast<uint32_t>(POOL ? 2 * a.nstg : a.nstg);
+        }
+        const uint32_t nst_u = static_cast<uint32_t>(NST), nstg_u = static_cast<uint32_t>(a.nstg);
+        const int c16 = (a.C_in + 15) & ~15;                                     // channels the MMAs read (whole k-steps)
+        for (uint32_t g = static_cast<uint32_t>(cg); g < total; g += 4) {
+            const uint32_t s = g % nst_u, ph = (g / nst_u) & 1, aph = (g >> 2) & 1;
+            const int j = static_cast<int>(g % nstg_u);
+            const int halves = c16 - j * F_STAGE_C > 16 ? 2 : 1;                  // a partial last stage holds one k-step only
+            const uint32_t st = ring + s * F_STAGE_BYTES + row_off;
+            mbar_wait(bar_full + 8 * s, ph);
+            uint32_t hi[2][8], lo[2][8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h < halves) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float4 v;
+                        const uint32_t chunk = static_cast<uint32_t>(4 * h + q);
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(st + ((chunk ^ r7) << 4)) : "memory");
+                        const float4 sc = *reinterpret_cast<const float4 *>(&s_scale[j * F_STAGE_C + 16 * h + 4 * q]);
+                        const float4 sh = *reinterpret_cast<const float4 *>(&s_shift[j * F_STAGE_C + 16 * h + 4 * q]);
+                        uint2 hv, lv;
+                        f_convert_quad<SPLIT>(v, sc, sh, hv, lv);
+                        hi[h][2 * q] = hv.x; hi[h][2 * q + 1] = hv.y;
+                        lo[h][2 * q] = lv.x; lo[h][2 * q + 1] = lv.y;
+                    }
+                }
+            }
+            __syncwarp();                                                         // every lane's loads have been consumed
+            if (lane == 0) f_mbar_arrive(bar_empty + 8 * s);                      // raw stage free: the TMA warp may refill it
+            mbar_wait(bar_afree + 8 * cg, aph ^ 1);                               // MMAs of stage g - 4 have read this A slot
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h < halves) {
+                    f_tmem_st8u(a_slot + 8 * h, hi[h]);
+                    if (SPLIT) f_tmem_st8u(a_slot + 16 + 8 * h, lo[h]);
+                }
+            }
+            f_tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) f_mbar_arrive(bar_ready + 8 * cg);
+        }
+    } else if (warp < F_CWARPS) {
         // =========================================================== CONVERTERS (in place, raw fp32 -> [bf16 hi | bf16 lo])
         // warpgroup cg owns ring slots s with s % 4 == cg.  lane = (channel octet cp, row sub-index rs): per step a warp converts
         // 8 rows x 32 channels, 4 steps per stage; the 4 lanes of a row finish reading before any of them writes (__syncwarp).
@@ -351,24 +444,37 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
                 const int tpt = POOL ? 2 * a.nstg : a.nstg;
                 for (int jj = 0; jj < tpt; ++jj, ++g) {
                     const int j = POOL && jj >= a.nstg ? jj - a.nstg : jj;
-                    const uint32_t s = g % nst_u;
-                    const uint32_t ph = (g / nst_u) & 1;
+                    const uint32_t s = TS ? (g & 3u) : g % nst_u;                    // TS: A slot = warpgroup = g % 4
+                    const uint32_t ph = TS ? (g >> 2) & 1 : (g / nst_u) & 1;
                     mbar_wait(bar_ready + 8 * s, ph);
                     tc_fence_after();
                     if (leader) {
                         const int ks = min(2, ksteps_total - 2 * j);
-                        const uint64_t da = dA0 + static_cast<uint64_t>(s * stage16);
                         const uint64_t db_hi = dB0 + static_cast<uint64_t>(static_cast<uint32_t>(j >> 1) * wchunk16 + static_cast<uint32_t>(j & 1) * 4);
                         const uint64_t db_lo = db_hi + blo16;
-                        for (int k = 0; k < ks; ++k) {
-                            const uint64_t adv = static_cast<uint64_t>(k * 2);       // 32 bytes per k-step, in 16-byte units
-                            umma_bf16(d_tmem, da + adv, db_hi + adv, idesc, (jj | k) != 0 ? 1u : 0u);
-                            if (SPLIT) {
-                                umma_bf16(d_tmem, da + 4 + adv, db_hi + adv, idesc, 1u);   // lo half of the row: + 64 bytes
-                                umma_bf16(d_tmem, da + adv, db_lo + adv, idesc, 1u);
+                        if (TS) {
+                            const uint32_t ta = tmem_base + F_ABASE + s * 32u;
+                            for (int k = 0; k < ks; ++k) {
+                                const uint64_t adv = static_cast<uint64_t>(k * 2);
+                                umma_bf16_ts(d_tmem, ta + 8 * k, db_hi + adv, idesc, (jj | k) != 0 ? 1u : 0u);
+                                if (SPLIT) {
+                                    umma_bf16_ts(d_tmem, ta + 16 + 8 * k, db_hi + adv, idesc, 1u);
+                                    umma_bf16_ts(d_tmem, ta + 8 * k, db_lo + adv, idesc, 1u);
+                                }
                             }
+                            umma_commit(bar_afree + 8 * s);
+                        } else {
+                            const uint64_t da = dA0 + static_cast<uint64_t>(s * stage16);
+                            for (int k = 0; k < ks; ++k) {
+                                const uint64_t adv = static_cast<uint64_t>(k * 2);       // 32 bytes per k-step, in 16-byte units
+                                umma_bf16(d_tmem, da + adv, db_hi + adv, idesc, (jj | k) != 0 ? 1u : 0u);
+                                if (SPLIT) {
+                                    umma_bf16(d_tmem, da + 4 + adv, db_hi + adv, idesc, 1u);   // lo half of the row: + 64 bytes
+                                    umma_bf16(d_tmem, da + adv, db_lo + adv, idesc, 1u);
+                                }
+                            }
+                            umma_commit(bar_empty + 8 * s);
                         }
-                        umma_commit(bar_empty + 8 * s);
                         if (jj == tpt - 1) umma_commit(bar_zfull + 8 * zb);
                     }
                     __syncwarp();
@@ -642,9 +748,65 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
         return EML_OK;
     };
     int rc;
-    if (split) rc = wide_rows ? go(dense_layer_kernel<true, false, 44>) : go(dense_layer_kernel<true, false, F_GRP>);
-    else rc = wide_rows ? go(dense_layer_kernel<false, false, 44>) : go(dense_layer_kernel<false, false, F_GRP>);
+    if (eml_env_flag("EML_DENSE_SMEM_A")) {               // round-1 pipeline (A operand converted in place in shared memory), kept for A/B runs
+        if (split) rc = wide_rows ? go(dense_layer_kernel<true, false, 44, false>) : go(dense_layer_kernel<true, false, F_GRP, false>);
+        else rc = wide_rows ? go(dense_layer_kernel<false, false, 44, false>) : go(dense_layer_kernel<false, false, F_GRP, false>);
+    } else {
+        if (split) rc = wide_rows ? go(dense_layer_kernel<true, false, 44, true>) : go(dense_layer_kernel<true, false, F_GRP, true>);
+        else rc = wide_rows ? go(dense_layer_kernel<false, false, 44, true>) : go(dense_layer_kernel<false, false, F_GRP, true>);
+    }
     if (rc != EML_OK) return rc;
+    return eml_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------ composite filter (once per parameter version)
+// Weff[(dy,dx,o), c] = sum_b W2[o,b,dy,dx] * scale2[b] * W1[b,c]  and  bias9[rc][cc][o] = sum over the taps inside the image of
+// sum_b W2[o,b,dy,dx] * shift2[b]  (file header; RegressionNetwork/DenseNet.py:30-43 has no nonlinearity between conv1 and conv2),
+// accumulated in double and written STRAIGHT into the packed operand image the kernel above reads (the eml_conv_pack_weights layout for
+// C_out = 108 -> 112 rows, taps = 1: per 64-channel chunk [hi | lo], K-major SWIZZLE_128B).  One launch per layer instead of a dozen
+// float64 ATen kernels plus a pack launch.
+namespace {
+__global__ void __launch_bounds__(256) dense_compose_kernel(const float *__restrict__ w1, const float *__restrict__ w2, const float *__restrict__ s2,
+                                                            const float *__restrict__ t2, int nb, int C_in, unsigned char *__restrict__ out,
+                                                            float *__restrict__ bias9) {
+    const int cpt = (C_in + 63) / 64;
+    const long total = static_cast<long>(cpt) * F_NPAD * 64;
+    for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(idx % 64), n = static_cast<int>((idx / 64) % F_NPAD), ch = static_cast<int>(idx / (64L * F_NPAD));
+        const int ci = ch * 64 + k;
+        double acc = 0.0;
+        if (n < 9 * F_G && ci < C_in) {
+            const int tap = n / F_G, o = n - tap * F_G;
+            for (int b = 0; b < nb; ++b)
+                acc += static_cast<double>(w2[(static_cast<long>(o) * nb + b) * 9 + tap]) * static_cast<double>(s2[b]) *
+                       static_cast<double>(w1[static_cast<long>(b) * C_in + ci]);
+        }
+        const float v = static_cast<float>(acc);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        unsigned char *base = out + static_cast<size_t>(ch) * F_WCHUNK;
+        const uint32_t off = sw128_offset(n, k);
+        *reinterpret_cast<__nv_bfloat16 *>(base + off) = hi;
+        *reinterpret_cast<__nv_bfloat16 *>(base + static_cast<size_t>(F_NPAD) * 128 + off) = lo;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 9 * F_G) {       // (row class, column class, o): taps that fall inside the image
+        const int o = threadIdx.x % F_G, cc = (threadIdx.x / F_G) % 3, rc = threadIdx.x / (3 * F_G);
+        double acc = 0.0;
+        for (int dy = (rc == 0 ? 1 : 0); dy <= (rc == 2 ? 1 : 2); ++dy)
+            for (int dx = (cc == 0 ? 1 : 0); dx <= (cc == 2 ? 1 : 2); ++dx)
+                for (int b = 0; b < nb; ++b)
+                    acc += static_cast<double>(w2[(static_cast<long>(o) * nb + b) * 9 + dy * 3 + dx]) * static_cast<double>(t2[b]);
+        bias9[threadIdx.x] = static_cast<float>(acc);
+    }
+}
+}  // namespace
+
+extern "C" int eml_dense_layer_compose(const float *w1, const float *w2, const float *scale2, const float *shift2, int nb, int C_in,
+                                       int growth, void *wpack, float *bias9, void *stream) {
+    EML_CHECK_PTR(w1); EML_CHECK_PTR(w2); EML_CHECK_PTR(scale2); EML_CHECK_PTR(shift2); EML_CHECK_PTR(wpack); EML_CHECK_PTR(bias9);
+    EML_CHECK_ALIGN16(wpack);
+    if (growth != F_G || nb <= 0 || nb > 256 || C_in <= 0 || C_in > F_MAX_C) return EML_E_SHAPE;
+    dense_compose_kernel<<<64, 256, 0, static_cast<cudaStream_t>(stream)>>>(w1, w2, scale2, shift2, nb, C_in, static_cast<unsigned char *>(wpack), bias9);
     return eml_launch_status();
 }
 
@@ -700,15 +862,15 @@ int eml_dense_pool_forward(const eml_conv_params *p, cudaStream_t st) {
     const bool split = p->precision == EML_PREC_BF16X3;
     const size_t smem = fused_smem(a.nwchunks, p->W, a.stages);
     const unsigned grid = static_cast<unsigned>(a.nbands < sms ? a.nbands : sms);
-    cudaError_t e;
-    if (split) {
-        e = cudaFuncSetAttribute(dense_layer_kernel<true, true, F_GRP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    auto go = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);
-        dense_layer_kernel<true, true, F_GRP><<<grid, F_THREADS, smem, st>>>(tmap, a);
-    } else {
-        e = cudaFuncSetAttribute(dense_layer_kernel<false, true, F_GRP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return static_cast<int>(e);
-        dense_layer_kernel<false, true, F_GRP><<<grid, F_THREADS, smem, st>>>(tmap, a);
-    }
+        kern<<<grid, F_THREADS, smem, st>>>(tmap, a);
+        return EML_OK;
+    };
+    int rc;
+    if (eml_env_flag("EML_DENSE_SMEM_A")) rc = split ? go(dense_layer_kernel<true, true, F_GRP, false>) : go(dense_layer_kernel<false, true, F_GRP, false>);
+    else rc = split ? go(dense_layer_kernel<true, true, F_GRP, true>) : go(dense_layer_kernel<false, true, F_GRP, true>);
+    if (rc != EML_OK) return rc;
     return eml_launch_status();
 }

@@ -295,22 +295,23 @@ class DenseNet(nn.Module):
         st = _lib.stream_ptr()
         g = self.growth_rate
         c["fused"] = {}
-        valid = ((1, 2), (0, 1, 2), (0, 1))             # taps inside the image for the first / interior / last row or column
+        dev = c["aff"].device
+        nlayers = sum(self.block_config)
+        bias_all = torch.empty(nlayers, 9 * g, dtype=torch.float32, device=dev)
+        i = 0
         for b, c_in, _, _ in self._plan:
             blk = getattr(self.features, "denseblock%d" % b)
             for l, layer in enumerate(blk.children()):
                 ci = c_in + l * g
                 s2, t2 = self._aff(c, "b%d.l%d.norm2" % (b, l))
                 nb = layer.conv1.out_channels
-                w1 = layer.conv1.weight.detach().double().view(nb, ci)
-                w2 = layer.conv2.weight.detach().double()                                  # (g, nb, 3, 3)
-                weff = torch.einsum("obyx,b,bc->yxoc", w2, s2[:nb].double(), w1).reshape(9 * g, ci).float().contiguous()
-                beta = torch.einsum("obyx,b->yxo", w2, t2[:nb].double())                   # (3, 3, g)
-                bias9 = torch.stack([torch.stack([beta[list(valid[rc])][:, list(valid[cc])].sum((0, 1)) for cc in range(3)])
-                                     for rc in range(3)]).float().contiguous()
-                buf = torch.empty(lib.eml_conv_wpack_bytes(9 * g, ci, 1), dtype=torch.uint8, device=weff.device)
-                _lib.check(lib.eml_conv_pack_weights(_lib.ptr(weff), _lib.ptr(buf), 9 * g, ci, 1, st), "eml_conv_pack_weights(composite)")
-                c["fused"][(b, l)] = (buf, bias9)
+                buf = torch.empty(lib.eml_conv_wpack_bytes(9 * g, ci, 1), dtype=torch.uint8, device=dev)
+                # one launch per layer: fp64 composition written straight into the packed operand image (csrc/dense_layer.cu)
+                _lib.check(lib.eml_dense_layer_compose(_lib.ptr(c["w"]["b%d.l%d.conv1" % (b, l)]), _lib.ptr(c["w"]["b%d.l%d.conv2" % (b, l)]),
+                                                       _lib.ptr(s2), _lib.ptr(t2), nb, ci, g, _lib.ptr(buf), _lib.ptr(bias_all[i]), st),
+                           "eml_dense_layer_compose(b%d.l%d)" % (b, l))
+                c["fused"][(b, l)] = (buf, bias_all[i])
+                i += 1
 
     def _dense_layer(self, c, key, slab, pitch, h, w, B, ci):
         lib = _lib.load()

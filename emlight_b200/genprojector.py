@@ -915,7 +915,7 @@ class Pix2PixModel(nn.Module):
     'inference' is the full product path.  'generator' and 'discriminator' return the reference's loss dictionaries (same keys and
     weights).  When the model was built for training (`opt.isTrain`) and gradients are enabled, each call returns tensors attached to one
     autograd node (emlight_b200/gp_train.py), so `sum(losses.values()).mean().backward()` + `create_optimizers()` train the networks
-    like GenProjector/model_trainer.py does (`self.autograd`; verified on B200 against autograd of the oracle,
+    like GenProjector/model_trainer.py does (`self.autograd`; verified on B200 against torch autograd through the CPU restatement of the reference,
     tests/test_gp_train_gpu.py); under `torch.no_grad()` -- or with `self.autograd = False` -- the same calls return plain values."""
 
     def __init__(self, opt):

@@ -24,7 +24,7 @@ iteration per wrapped convolution per forward with `u`, `v` treated as constants
 
 STATUS: the algebra is checked on CPU against torch autograd of the reference restatement (`tests/test_gp_train_cpu.py`: torch
 stand-ins for the forward primitives, the adjoint kernels through their host-emulation build) and on B200 with the real kernels
-(`tests/test_gp_train_gpu.py`: every generator / discriminator parameter gradient against autograd of the oracle; with fp32 forward
+(`tests/test_gp_train_gpu.py`: every generator / discriminator parameter gradient against torch autograd through the CPU restatement of the reference; with fp32 forward
 contractions the bf16x3 backward agrees to 5e-4 worst / 1.5e-5 median per tensor).  `Pix2PixModel` built with `opt.isTrain` uses it by
 default; a standalone `SPADEGenerator` / `SphereConv2D` opts in with `.autograd = True`.
 """

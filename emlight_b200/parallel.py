@@ -132,6 +132,7 @@ class FlatAdam:
         self._reduced = [False] * len(self.buckets)
         self.comm_bytes = total * 4
         self.early_buckets = 0                          # buckets whose all-reduce was launched from inside the backward (last step)
+        self.comm = True                                # False: skip the collective (measurement of what the exchange costs; ranks then diverge)
 
     # ------------------------------------------------------------------ gradient side
     def zero_grad(self, set_to_none=False):
@@ -148,7 +149,7 @@ class FlatAdam:
         if self._reduced[i]:
             return
         self._reduced[i] = True
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if self.comm and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             lo, hi, _ = self.buckets[i]
             self._handles[i] = dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
 

@@ -155,6 +155,12 @@ typedef struct eml_dense_layer_params {
 } eml_dense_layer_params;
 int eml_dense_layer_supported(int H, int W, int C_in, int growth, int precision);
 int eml_dense_layer_forward(const eml_dense_layer_params *p, void *stream);
+/* The composite operands of eml_dense_layer_forward, built on the device once per parameter version (fp64 accumulation):
+ *   w1 (nb, C_in) = conv1.weight (DenseNet.py:37), w2 (growth, nb, 3, 3) = conv2.weight (:42), scale2 / shift2 (nb) = folded norm2 (:41)
+ *   wpack <- Weff[(dy,dx,o), c] = sum_b w2[o,b,dy,dx] scale2[b] w1[b,c], packed like eml_conv_pack_weights(C_out = 9 growth, taps = 1)
+ *            (eml_conv_wpack_bytes(9 * growth, C_in, 1) bytes);  bias9 (3,3,growth) <- the norm2 shift through the in-image taps. */
+int eml_dense_layer_compose(const float *w1, const float *w2, const float *scale2, const float *shift2, int nb, int C_in, int growth,
+                            void *wpack, float *bias9, void *stream);
 
 /* Stem: conv0 3x3 (3 -> C_out<=32) on the NCHW input image, fused affine (+ReLU when relu != 0), NHWC output at channel 0.
  * Replaces DenseNet.py:89-92 (conv0, norm0, relu0).  scale/shift NULL => raw convolution output.

@@ -83,10 +83,10 @@ def convert_to_panorama_torch(dirs, sizes, colors):
     """The same light-by-light accumulation written with torch CPU ops (what the reference executes, util.py:222-245);
     used as the timed CPU baseline.  dirs (B,3N), sizes (B,N), colors (B,3N) torch fp32 tensors."""
     import torch
-    xyz = torch.from_numpy(pixel_dirs(np.float32)).reshape(3, -1)
+    xyz = torch.from_numpy(pixel_dirs(np.float32)).reshape(3, -1).to(dirs.device)      # the reference's `.cuda()` at util.py:233
     B = colors.shape[0]
     n = colors.shape[1] // 3
-    out = torch.zeros(B, 3, PANO_H, PANO_W, dtype=dirs.dtype)
+    out = torch.zeros(B, 3, PANO_H, PANO_W, dtype=dirs.dtype, device=dirs.device)
     for k in range(n):
         d = torch.matmul(dirs[:, 3 * k:3 * k + 3], xyz).view(-1, PANO_H, PANO_W)
         out = out + colors[:, 3 * k:3 * k + 3][:, :, None, None] * torch.exp((d - 1) / sizes[:, k].view(-1, 1, 1))[:, None, :, :]

@@ -19,7 +19,8 @@ def test_reference_arm_prints_the_contract_line():
               "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "maps/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    staged = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "DenseNet.py"))      # oracle/stage_ref.py: the reference's own module
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == ("reference" if staged else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and "model" not in d["config"]
 

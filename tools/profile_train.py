@@ -23,6 +23,14 @@ class Wrap:
         if self.name == "eml_conv_forward":
             p = a[0]; p = p._obj if hasattr(p, "_obj") else p
             tag += "[mode%d,Cin%s,Cout%s%s]" % (p.mode, "<=64" if p.C_in <= 64 else ">64", "<=64" if p.C_out <= 64 else ">64", ",stats" if p.stats else "")
+        if self.name == "eml_wgrad_1x1":               # (dY, dy_pitch, N, x, x_pitch, C, scale, shift, relu, pool, H, W, dW, M, precision, stream)
+            C, pool, W = int(a[5]), int(a[9]), int(a[11])
+            tag += "[W%d,%s%s]" % (W, "C<=256" if C <= 256 else "C>256", ",pool" if pool else "")
+        if self.name in ("eml_bn_bwd_reduce", "eml_bn_bwd_apply"):   # (grad, g_pitch, x, x_pitch, pa, pb, mean, inv, gamma, beta, relu, pool, H, W, M, C, ...)
+            C, pool, W = int(a[15]), int(a[11]), int(a[13])
+            tag += "[W%d,%s%s]" % (W, "C<=48" if C <= 48 else "C>48", ",pool" if pool else "")
+        if self.name in ("eml_wgrad_3x3",):
+            tag += "[W%d]" % int(a[11])
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); r = self.fn(*a); e1.record(); rec.append((tag, e0, e1)); return r
 names = [n for n in _lib.SIGNATURES if n not in ("eml_version", "eml_error_string", "eml_device_ok", "eml_conv_wpack_bytes", "eml_sinkhorn_workspace_bytes")]
