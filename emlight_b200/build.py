@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libemlight_b200.so")
-SOURCES = ["capi_misc.cu", "dense_layer.cu", "needlets.cu", "extract.cu", "tonemap.cu", "sg_render.cu", "sinkhorn.cu", "conv_gemm.cu", "conv3x3_rows.cu", "conv1x1_persist.cu", "conv_simt.cu", "spade_ops.cu", "gp_bwd.cu", "gemm_tma.cu", "bwd_ops.cu", "wgrad1x1_tc.cu", "wgrad3x3_tc.cu"]
+SOURCES = ["capi_misc.cu", "dense_layer.cu", "dense_bwd1.cu", "needlets.cu", "extract.cu", "tonemap.cu", "sg_render.cu", "sinkhorn.cu", "conv_gemm.cu", "conv3x3_rows.cu", "conv1x1_persist.cu", "conv_simt.cu", "spade_ops.cu", "gp_bwd.cu", "gemm_tma.cu", "bwd_ops.cu", "wgrad1x1_tc.cu", "wgrad3x3_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

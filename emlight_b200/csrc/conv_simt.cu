@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(128) stem_kernel(const float *__restrict__ x, 
     }
 }
 
-// Variant 2 of the stem (selected with EML_STEM_V2=1 until it has been timed on a B200; results are bit-identical: same fmaf order).
+// Variant 2 of the stem: the default for C_out = 24 since round 2 (timed on B200: 55.66 -> 55.26 ms per B=256 step, outputs bit-identical to
+// variant 1 -- same fmaf order -- tests/test_experiments_gpu.py; EML_STEM_V1=1 selects the old kernel).
 // SASS of stem_kernel shows 786 LDS for 896 FFMA -- the weights are read from shared memory one scalar per FMA ([o][tap] layout,
 // stride 27), so the kernel is bound by shared-memory issue (1 LDS / clk / SM against 4 FFMA warps / clk / SM).  Here the weights
 // are stored [tap][o]: one broadcast LDS.128 feeds four FMAs, and the output count is a template parameter so that the 8 dead
@@ -384,7 +385,7 @@ extern "C" int eml_stem_forward(const float *x_nchw, const float *w_oihw, const 
     if (write_out) { EML_CHECK_PTR(out); EML_CHECK_ALIGN16(out); }
     if (B <= 0 || H <= 0 || W <= 0 || C_out <= 0 || C_out > 32 || out_pitch < C_out) return EML_E_SHAPE;
     const long P = static_cast<long>(B) * H * W;
-    static const bool v2 = eml_env_flag("EML_STEM_V2");
+    static const bool v2 = !eml_env_flag("EML_STEM_V1");
     if (v2 && C_out == 24) {
         stem_kernel_v2<24><<<static_cast<unsigned>((P + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
             x_nchw, w_oihw, scale, shift, out, out_pitch, stats_raw, stats_out, stats_out_stride > 0 ? stats_out_stride : C_out, B, H, W,

@@ -207,8 +207,8 @@ class DenseNet(nn.Module):
         for name, conv, taps in self._convs():
             w = conv.weight.detach().contiguous().float()
             c["w"][name] = w
-            if self.precision != "fp32":
-                nbytes = lib.eml_conv_wpack_bytes(w.shape[0], w.shape[1], taps)
+            if True:                                    # packed even in fp32 mode: the backward may run at another precision than the forward
+                nbytes = lib.eml_conv_wpack_bytes(w.shape[0], w.shape[1], taps)      # (tests isolate forward-rounding effects that way)
                 buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
                 _lib.check(lib.eml_conv_pack_weights(_lib.ptr(w), _lib.ptr(buf), w.shape[0], w.shape[1], taps, st),
                            "eml_conv_pack_weights")
@@ -660,6 +660,14 @@ class DenseNet(nn.Module):
             blk = getattr(f, "denseblock%d" % b)
             layers = list(blk.children())
             dN = torch.empty(B, h, w, g, dtype=torch.float32, device=dev)
+            prec = _lib.PRECISIONS[self.precision]
+            # fused conv1 backward (csrc/dense_bwd1.cu): dA never reaches memory, BatchNorm's mean terms are deferred as per-channel
+            # affine coefficients (coefA + coefB * x) applied when a channel range's gradient is read
+            fused1 = bool(lib.eml_dense_bwd1_supported(c_out, M, prec))
+            if fused1:
+                coef = torch.zeros(2, pitch, dtype=torch.float32, device=dev)
+                vec = torch.empty(5, pitch, dtype=torch.float32, device=dev)
+                w1pack = torch.empty(lib.eml_dense_bwd1_wpack_bytes(c_out), dtype=torch.uint8, device=dev)
             for l in range(len(layers) - 1, -1, -1):
                 layer = layers[l]
                 ci = c_in + l * gr
@@ -670,8 +678,13 @@ class DenseNet(nn.Module):
                 self._conv(c, "b%d.l%d.conv1" % (b, l), slab, pitch, h, w, B, ci, ws["bott"], g, 0, g, _lib.EML_CONV_1x1, 1, a1, None, g)
                 # gradient of this layer's 12 output channels; compacted because block 3's channel offsets (150 + 12 l) are not
                 # 16-byte aligned and the gather uses float4 loads
-                dy = torch.zeros(B, h, w, 16, dtype=torch.float32, device=dev)        # 12 -> 16 channels: what the rolling 3x3 kernel stages
-                dy[..., :gr] = dS[..., ci:ci + gr]
+                if fused1:
+                    dy = torch.empty(B, h, w, 16, dtype=torch.float32, device=dev)
+                    _lib.check(lib.eml_dense_bwd1_gather(_lib.ptr(dS), pitch, _lib.ptr(slab), pitch, _lib.ptr(coef[0]), _lib.ptr(coef[1]), ci, gr,
+                                                         _lib.ptr(dy), 16, 16, M, st), "eml_dense_bwd1_gather")
+                else:
+                    dy = torch.zeros(B, h, w, 16, dtype=torch.float32, device=dev)    # 12 -> 16 channels: what the rolling 3x3 kernel stages
+                    dy[..., :gr] = dS[..., ci:ci + gr]
                 w2 = layer.conv2.weight.detach().float()                          # (12, 48, 3, 3)
                 self._gemm_bwd(dy.data_ptr(), 16, B, h, w, gr, w2.permute(1, 0, 2, 3).flip(2, 3).contiguous(), dN, _lib.EML_CONV_3x3)
                 dw2 = torch.zeros(gr, g, 3, 3, dtype=torch.float32, device=dev)
@@ -680,15 +693,36 @@ class DenseNet(nn.Module):
                 out[pfx + ".conv2.weight"] = dw2
                 bn_bwd(n2, layer.norm2, pfx + ".norm2", _lib.ptr(dN), g, _lib.ptr(ws["bott"]), g, None, 0, 0, h, w, M, g, _lib.ptr(dN), g, 0)
                 w1 = layer.conv1.weight.detach().float()                          # (48, ci, 1, 1)
+                dw1 = torch.zeros(g, ci, dtype=torch.float32, device=dev)
+                if fused1:
+                    o0, _ = offs[n1]
+                    _lib.check(lib.eml_dense_bwd1_prep(_lib.ptr(a1[0]), _lib.ptr(a1[1]), _lib.ptr(pre[0]), _lib.ptr(pre[1]),
+                                                       _lib.ptr(mean_all[o0:o0 + ci]), _lib.ptr(inv_all[o0:o0 + ci]), _lib.ptr(layer.norm1.weight),
+                                                       ci, pitch, _lib.ptr(vec), st), "eml_dense_bwd1_prep")
+                    _lib.check(lib.eml_dense_bwd1_pack(_lib.ptr(w1), _lib.ptr(w1pack), ci, st), "eml_dense_bwd1_pack")
+                    sums.zero_()
+                    _lib.check(lib.eml_dense_bwd1(_lib.ptr(dN), _lib.ptr(slab), pitch, _lib.ptr(dS), pitch, _lib.ptr(w1pack), _lib.ptr(vec), pitch,
+                                                  ci, M, _lib.ptr(sums), cmax, prec, st), "eml_dense_bwd1(%s)" % pfx)
+                    _lib.check(lib.eml_wgrad_1x1(_lib.ptr(dN), g, g, _lib.ptr(slab), pitch, ci, _lib.ptr(a1[0]), _lib.ptr(a1[1]), 1, 0, h, w,
+                                                 _lib.ptr(dw1), M, _lib.PRECISIONS[self.precision], st), "eml_wgrad_1x1(conv1)")
+                    dgb = torch.empty(2, ci, dtype=torch.float32, device=dev)
+                    _lib.check(lib.eml_dense_bwd1_accum(_lib.ptr(sums), cmax, _lib.ptr(vec), pitch, float(M), ci, _lib.ptr(coef[0]),
+                                                        _lib.ptr(coef[1]), _lib.ptr(dgb[0]), _lib.ptr(dgb[1]), st), "eml_dense_bwd1_accum")
+                    out[pfx + ".norm1.weight"] = dgb[0]
+                    out[pfx + ".norm1.bias"] = dgb[1]
+                    out[pfx + ".conv1.weight"] = dw1.view(g, ci, 1, 1)
+                    continue
                 dA = torch.empty(B, h, w, _up4(ci), dtype=torch.float32, device=dev)
                 self._gemm_bwd(dN.data_ptr(), g, B, h, w, g, w1.permute(1, 0, 2, 3).contiguous(), dA, _lib.EML_CONV_1x1)
-                dw1 = torch.zeros(g, ci, dtype=torch.float32, device=dev)
                 _lib.check(lib.eml_wgrad_1x1(_lib.ptr(dN), g, g, _lib.ptr(slab), pitch, ci, _lib.ptr(a1[0]), _lib.ptr(a1[1]), 1, 0, h, w,
                                              _lib.ptr(dw1), M, _lib.PRECISIONS[self.precision], st), "eml_wgrad_1x1(conv1)")
                 out[pfx + ".conv1.weight"] = dw1.view(g, ci, 1, 1)
                 bn_bwd(n1, layer.norm1, pfx + ".norm1", _lib.ptr(dA), dA.shape[3], _lib.ptr(slab), pitch, pre, 1, 0, h, w, M, ci,
                        _lib.ptr(dS), pitch, 1)
                 del dA
+            if fused1:                                                            # the block-input channels' deferred BatchNorm mean terms
+                _lib.check(lib.eml_dense_bwd1_gather(_lib.ptr(dS), pitch, _lib.ptr(slab), pitch, _lib.ptr(coef[0]), _lib.ptr(coef[1]), 0, c_in,
+                                                     _lib.ptr(dS), pitch, c_in, M, st), "eml_dense_bwd1_gather(block input)")
             # ---- block input
             if bi > 0:
                 pb, _, _, ptr_c = self._plan[bi - 1]

@@ -279,6 +279,27 @@ int eml_wgrad_3x3(const float *dY, int dy_pitch, int N, const float *b, int b_pi
                   float *dW, int B, int H, int W, int precision, void *stream);
 int eml_wgrad_stem(const float *dZ, int dz_pitch, int O, const float *x_nchw, float *dW, int B, int H, int W, void *stream);
 
+/* Fused backward of norm1 -> relu1 -> conv1 (DenseNet.py:30-37) into the block's gradient slab (csrc/dense_bwd1.cu), training-mode BN:
+ *   dA = dN W1 on tensor cores, never written to memory;  g = dA * [sc x + sh > 0];  dS[:, c] += k1[c] g  (in place);
+ *   sums[c] += sum g (= d beta),  sums[sums_stride + c] += sum g xhat (= d gamma),  xhat = e x + f.
+ * BatchNorm's two mean terms are affine in the stored x with per-channel coefficients that add up over the layers reading a channel:
+ * eml_dense_bwd1_accum folds a layer's sums into coefA / coefB (and emits d gamma / d beta), eml_dense_bwd1_gather applies them when a
+ * channel range's gradient is read:  out[m, i] = dS[m, c0+i] + coefA[c0+i] + coefB[c0+i] x[m, c0+i]  (i < n; zero for n <= i < out_n).
+ *   dN (M, 48) contiguous; x / dS (M, pitch) with channels [0, C_in); wpack from eml_dense_bwd1_pack(conv1.weight viewed (48, C_in));
+ *   vec (5, vstride) from eml_dense_bwd1_prep: sc, sh (the forward's folded norm1 affine), e = pre_a inv, f = (pre_b - mean) inv,
+ *   k1 = gamma inv;  M % 128 == 0, C_in <= 352;  precision BF16 / BF16X3.  sums: double, zeroed by the caller. */
+size_t eml_dense_bwd1_wpack_bytes(int C_in);
+int eml_dense_bwd1_supported(int C_in, long M, int precision);
+int eml_dense_bwd1_pack(const float *w1, void *wpack, int C_in, void *stream);
+int eml_dense_bwd1_prep(const float *sc, const float *sh, const float *pre_a, const float *pre_b, const float *mean, const float *inv_std,
+                        const float *gamma, int C, int vstride, float *vec, void *stream);
+int eml_dense_bwd1(const float *dN, const float *x, int x_pitch, float *dS, int ds_pitch, const void *wpack, const float *vec, int vstride,
+                   int C_in, long M, double *sums, long sums_stride, int precision, void *stream);
+int eml_dense_bwd1_accum(const double *sums, long sums_stride, const float *vec, int vstride, double n, int C, float *coefA, float *coefB,
+                         float *dgamma, float *dbeta, void *stream);
+int eml_dense_bwd1_gather(const float *dS, int ds_pitch, const float *x, int x_pitch, const float *coefA, const float *coefB, int c0, int n,
+                          float *out, int out_pitch, int out_n, long M, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * G1-G6 backward -- adjoints used by the GenProjector training steps (pix2pix_model.py:92-141 -> trainers' loss.backward()).
  * The contractions (data gradient dA = dY Wk, weight gradient dWk^T = A^T dY) are eml_gemm_bf16[_splitk] on operands prepared with

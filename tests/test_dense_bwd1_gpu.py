@@ -1,0 +1,89 @@
+"""GPU: the fused conv1-backward kernel (csrc/dense_bwd1.cu: tcgen05 dA = dN W1 with A in tensor memory, ReLU mask, in-place dS update through
+TMA load / store, per-channel BatchNorm sums) and its helper entry points, through the C ABI, against the same algebra in float64 torch."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(dN, x, dS, w1, vec, ci):
+    sc, sh, e, f, k1 = [v[:ci].double() for v in vec]
+    xx = x[:, :ci].double()
+    dA = dN.double() @ w1.double()                                   # (M, ci)
+    z = torch.addcmul(sh.float(), x[:, :ci], sc.float())            # the kernel's fp32 fmaf decides the mask
+    g = dA * (z > 0)
+    out = dS.clone().double()
+    out[:, :ci] += k1 * g
+    return out, g.sum(0), (g * (e * xx + f)).sum(0)
+
+
+@pytest.mark.parametrize("ci,tiles,precision,tol", [(24, 3, "bf16x3", 2e-5), (36, 400, "bf16x3", 2e-5), (150, 300, "bf16x3", 2e-5),
+                                                    (204, 700, "bf16x3", 2e-5), (342, 310, "bf16x3", 2e-5), (108, 200, "bf16", 2e-2)])
+def test_dense_bwd1_matches_float64(cuda, lib, ci, tiles, precision, tol):
+    from emlight_b200 import _lib
+    P, st = _lib.ptr, _lib.stream_ptr()
+    M = 128 * tiles
+    pitch = (ci + 12 + 7) & ~7
+    gen = torch.Generator().manual_seed(ci)
+    dN = torch.randn(M, 48, generator=gen).to(cuda)
+    x = torch.randn(M, pitch, generator=gen).to(cuda)
+    dS0 = torch.randn(M, pitch, generator=gen).to(cuda)
+    w1 = (torch.randn(48, ci, generator=gen) / 7).to(cuda)
+    sc, sh = torch.randn(ci, generator=gen).to(cuda), (0.3 * torch.randn(ci, generator=gen)).to(cuda)
+    pa, pb = (0.5 + torch.rand(ci, generator=gen)).to(cuda), torch.randn(ci, generator=gen).to(cuda)
+    mean, inv, gamma = torch.randn(ci, generator=gen).to(cuda), (0.5 + torch.rand(ci, generator=gen)).to(cuda), torch.randn(ci, generator=gen).to(cuda)
+    vec = torch.empty(5, pitch, device=cuda)
+    _lib.check(lib.eml_dense_bwd1_prep(P(sc), P(sh), P(pa), P(pb), P(mean), P(inv), P(gamma), ci, pitch, P(vec), st), "prep")
+    assert torch.equal(vec[0, :ci], sc) and torch.equal(vec[1, :ci], sh)
+    assert torch.allclose(vec[2, :ci], pa * inv) and torch.allclose(vec[3, :ci], (pb - mean) * inv) and torch.allclose(vec[4, :ci], gamma * inv)
+    prec = _lib.PRECISIONS[precision]
+    assert lib.eml_dense_bwd1_supported(ci, M, prec) == 1 and lib.eml_dense_bwd1_supported(ci, M + 1, prec) == 0
+    wpack = torch.empty(lib.eml_dense_bwd1_wpack_bytes(ci), dtype=torch.uint8, device=cuda)
+    _lib.check(lib.eml_dense_bwd1_pack(P(w1), P(wpack), ci, st), "pack")
+    sums = torch.zeros(2, 352, dtype=torch.float64, device=cuda)
+    dS = dS0.clone()
+    _lib.check(lib.eml_dense_bwd1(P(dN), P(x), pitch, P(dS), pitch, P(wpack), P(vec), pitch, ci, M, P(sums), 352, prec, st), "eml_dense_bwd1")
+    want, s1, s2 = _ref(dN, x, dS0, w1, vec, ci)
+    scale = float((want[:, :ci] - dS0[:, :ci].double()).abs().max())
+    assert float((dS[:, :ci].double() - want[:, :ci]).abs().max()) <= tol * scale + 1e-6 * float(want.abs().max())
+    assert torch.equal(dS[:, ci:], dS0[:, ci:])                                  # channels past C_in are not touched (TMA store clips)
+    assert float((sums[0, :ci] - s1).abs().max()) <= max(tol, 1e-5) * float(s1.abs().max()) + 1e-3
+    assert float((sums[1, :ci] - s2).abs().max()) <= max(tol, 1e-5) * float(s2.abs().max()) + 1e-3
+    # accumulate the deferred affine terms, then read a channel range through them
+    coef = torch.zeros(2, pitch, device=cuda)
+    dgb = torch.empty(2, ci, device=cuda)
+    _lib.check(lib.eml_dense_bwd1_accum(P(sums), 352, P(vec), pitch, float(M), ci, P(coef[0]), P(coef[1]), P(dgb[0]), P(dgb[1]), st), "accum")
+    assert torch.allclose(dgb[0].double(), sums[1, :ci], rtol=1e-6) and torch.allclose(dgb[1].double(), sums[0, :ci], rtol=1e-6)
+    k1, e, f = vec[4, :ci].double(), vec[2, :ci].double(), vec[3, :ci].double()
+    assert torch.allclose(coef[0, :ci].double(), -k1 / M * (sums[0, :ci] + f * sums[1, :ci]), rtol=1e-5, atol=1e-7)
+    assert torch.allclose(coef[1, :ci].double(), -k1 / M * e * sums[1, :ci], rtol=1e-5, atol=1e-7)
+    c0 = max(0, ci - 12)
+    dy = torch.full((M, 16), 7.0, device=cuda)
+    _lib.check(lib.eml_dense_bwd1_gather(P(dS), pitch, P(x), pitch, P(coef[0]), P(coef[1]), c0, 12, P(dy), 16, 16, M, st), "gather")
+    ref = dS[:, c0:c0 + 12] + coef[0, c0:c0 + 12] + coef[1, c0:c0 + 12] * x[:, c0:c0 + 12]
+    assert torch.allclose(dy[:, :12], ref, rtol=1e-6, atol=1e-6) and float(dy[:, 12:].abs().max()) == 0.0
+    # full BatchNorm backward = masked term (kernel) + deferred affine terms: against autograd of relu(bn(pa x + pb)) . dA
+    if tiles <= 3:
+        xr = x[:, :ci].double().clone().requires_grad_(True)
+        u = pa.double() * xr + pb.double()
+        mu, var = u.mean(0), u.var(0, unbiased=False)
+        eps = 1e-5
+        zz = (u - mu) * torch.rsqrt(var + eps)
+        beta = torch.randn(ci, generator=gen).to(cuda).double()
+        a = torch.relu(gamma.double() * zz + beta)
+        dA = (dN.double() @ w1.double()).detach()
+        (a * dA).sum().backward()
+        # the same through the kernel with this BN's own statistics
+        inv2 = torch.rsqrt(var + eps).float()
+        sc2, sh2 = (gamma * inv2 * pa), (gamma * inv2 * (pb - mu.float()) + beta.float())
+        _lib.check(lib.eml_dense_bwd1_prep(P(sc2.contiguous()), P(sh2.contiguous()), P(pa), P(pb), P(mu.float().contiguous()), P(inv2.contiguous()),
+                                           P(gamma), ci, pitch, P(vec), st), "prep")
+        dS2 = torch.zeros(M, pitch, device=cuda)
+        sums.zero_()
+        _lib.check(lib.eml_dense_bwd1(P(dN), P(x), pitch, P(dS2), pitch, P(wpack), P(vec), pitch, ci, M, P(sums), 352, prec, st), "eml_dense_bwd1")
+        coef.zero_()
+        _lib.check(lib.eml_dense_bwd1_accum(P(sums), 352, P(vec), pitch, float(M), ci, P(coef[0]), P(coef[1]), P(dgb[0]), P(dgb[1]), st), "accum")
+        _lib.check(lib.eml_dense_bwd1_gather(P(dS2), pitch, P(x), pitch, P(coef[0]), P(coef[1]), 0, ci, P(dS2), pitch, ci, M, st), "gather in place")
+        du = dS2[:, :ci].double() * pa.double()                                    # dS holds d/du; autograd gave d/dx = pa * d/du
+        assert float((du - xr.grad).abs().max()) <= 1e-3 * float(xr.grad.abs().max())

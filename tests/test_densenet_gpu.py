@@ -62,16 +62,20 @@ def test_densenet_batch_independence_and_determinism(cuda):
     assert torch.equal(a[2:3], c)
 
 
-@pytest.mark.parametrize("precision,l2_tol,med_tol", [("fp32", 1.5e-2, 5e-3), ("bf16x3", 5e-2, 2.5e-2)])
-def test_densenet_backward_matches_oracle_autograd(cuda, precision, l2_tol, med_tol):
+@pytest.mark.parametrize("precision,bwd_precision,l2_tol,med_tol", [("fp32", "fp32", 1.5e-2, 5e-3), ("fp32", "bf16x3", 1.5e-2, 5e-3),
+                                                                     ("bf16x3", "bf16x3", 5e-2, 2.5e-2)],
+                         ids=["fp32", "fp32fwd_bf16x3bwd", "bf16x3"])
+def test_densenet_backward_matches_oracle_autograd(cuda, precision, bwd_precision, l2_tol, med_tol):
     """Training-mode BN (what train.py runs): every parameter gradient vs torch autograd through the CPU oracle.
 
     Conditioning: these B=2 gradients are sums over ReLU masks; the reference's OWN fp32 and fp64 gradients differ by
     median 1.3e-3 / p90 2.5e-3 (max-relative, forward agreeing to 9e-7) and a 1e-6 relative input perturbation moves them by
     1.9e-3 / 3.6e-3 (measured with oracle/).  The fp32 mode (forward error ~2e-6) lands on that floor
     (measured: median 1.9e-3, worst per-tensor L2 5.8e-3); bf16x3's forward differs by ~2e-5, flips ~20x more masks and lands at
-    ~1.2e-2.  Tensors whose true gradient is analytically ~0 (last_norm{1,2}: a BatchNorm feeding only BatchNorms) are compared
-    absolutely."""
+    ~1.2e-2.  The middle case ISOLATES that claim: forward in fp32 mode (the oracle's masks), backward with the bf16x3 tensor-core
+    kernels (dgrad GEMMs, MN-major wgrads) -- it must meet the fp32 bounds, i.e. the looser bf16x3 bound is a property of the forward's
+    rounding, not of the backward kernels.  Tensors whose true gradient is analytically ~0 (last_norm{1,2}: a BatchNorm feeding only
+    BatchNorms) are compared absolutely."""
     g = np.load(os.path.join(GOLDEN, "densenet.npz"))
     sd = DO.init_state_dict(seed=int(g["sd_seed"]), n_anchors=96)
     x = torch.rand(2, 3, 192, 256, generator=torch.Generator().manual_seed(21))
@@ -82,6 +86,7 @@ def test_densenet_backward_matches_oracle_autograd(cuda, precision, l2_tol, med_
     sum((out[k] * R[k]).sum() for k in KEYS).backward()
     net = _net(cuda, precision, g).train()
     o = net(x.to(cuda))
+    net.precision = bwd_precision                      # the backward reads the precision at call time; the packed weights exist in every mode
     sum((o[k] * R[k].to(cuda)).sum() for k in KEYS).backward()
     gmax = max(float(v.grad.abs().max()) for v in sdo.values() if getattr(v, "grad", None) is not None)
     l2s = []
@@ -101,6 +106,25 @@ def test_densenet_backward_matches_oracle_autograd(cuda, precision, l2_tol, med_
     for name in ("fc.weight", "fc_dist.weight", "fc_ambient.bias"):
         ref = sdo[name].grad
         assert float((dict(net.named_parameters())[name].grad.cpu() - ref).abs().max()) <= 1e-4 * float(ref.abs().max()), name
+
+
+def test_densenet_b256_rows_match_oracle(cuda):
+    """BASELINE configs[2] size: one B = 256 eval forward (fused dense layers, pair-mode block 3, transition on the TMA pipeline, tcgen05 fc)
+    against the CPU oracle on three of its rows -- samples are independent in eval mode -- plus bit-exact argmax."""
+    g = np.load(os.path.join(GOLDEN, "densenet.npz"))
+    net = _net(cuda, "bf16x3", g).eval()
+    x = torch.rand(256, 3, 192, 256, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        out = net(x.to(cuda))
+    rows = [0, 101, 255]
+    sd = DO.init_state_dict(seed=int(g["sd_seed"]), n_anchors=96)
+    with torch.no_grad():
+        ref = DO.densenet_forward(sd, x[rows], training=False)
+    for k in KEYS:
+        got = out[k][rows].cpu()
+        assert float((got - ref[k]).abs().max()) <= 1e-3 * float(ref[k].abs().max()), k
+    assert torch.equal(out["distribution"][rows].argmax(1).cpu(), ref["distribution"].argmax(1))
+    assert bool(torch.isfinite(out["distribution"]).all())
 
 
 def test_densenet_backward_contract(cuda):

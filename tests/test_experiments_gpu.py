@@ -1,5 +1,5 @@
 """GPU: A/B switches -- each must reproduce the default path's results before it can become the default.
-  EML_STEM_V2=1    stem with [tap][o] shared-memory weights (LDS.128 broadcast) and 24 accumulators: bit-identical by construction
+  EML_STEM_V1=1    the round-1 stem; the default is variant 2 ([tap][o] shared-memory weights, LDS.128 broadcast, 24 accumulators): bit-identical
   EML_FC_SPLITK=1  fc GEMM split over K (M = B rows fill only 8 CTAs otherwise): equal to fp32 summation order"""
 import os
 import subprocess
@@ -38,7 +38,7 @@ def _run(tmp_path, name, **env):
 def test_stem_v2_and_fc_splitk_reproduce_the_default_path(cuda, tmp_path):
     import torch
     base, base_t = _run(tmp_path, "base.pt")
-    stem, stem_t = _run(tmp_path, "stem.pt", EML_STEM_V2="1")
+    stem, stem_t = _run(tmp_path, "stem.pt", EML_STEM_V1="1")
     for k in base:
         assert torch.equal(base[k], stem[k]), k                         # same fmaf order -> bit-identical (eval and batch-stat BN)
         assert torch.allclose(base_t[k], stem_t[k], rtol=1e-5, atol=1e-6), k   # statistics go through atomics: summation order

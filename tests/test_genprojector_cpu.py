@@ -86,3 +86,16 @@ def test_generator_state_dict_contract():
     full = E.SPADEGenerator(_opt(64))
     assert sum(v.numel() for v in full.state_dict().values()) == 118430576            # reference: 253 tensors, 118.43 M values
     assert len(full.state_dict()) == 253
+
+
+def test_generator_oracle_matches_reference_golden_at_baseline_width():
+    """The restatement at ngf = 64 against the reference's own SPADEGenerator (oracle/make_golden_ngf64.py)."""
+    g = np.load(os.path.join(GOLDEN, "genprojector_w64.npz"))
+    w = int(g["width"])
+    sd = GO.init_generator_state_dict(seed=int(g["sd_seed"]), ngf=w)
+    gen = torch.Generator().manual_seed(int(g["in_seed"]))
+    guide = torch.rand(1, 3, 128, 256, generator=gen) * 2
+    crop = torch.rand(1, 3, 128, 128, generator=gen)
+    with torch.no_grad():
+        out = GO.generator_forward(sd, guide, crop, ngf=w)
+    assert np.abs(out.numpy()[:, :, ::4, ::4] - g["out"]).max() / 50.0 <= 1e-5

@@ -103,3 +103,34 @@ def test_generator_train_mode_forward_matches_reference_golden(cuda):
     G.eval()
     a = G(guide.to(cuda), crop.to(cuda))
     assert torch.equal(a, G(guide.to(cuda), crop.to(cuda)))
+
+
+def test_generator_and_discriminator_match_reference_golden_at_baseline_width(cuda):
+    """ngf = ndf = 64 (K up to 9216 per output, 4x the accumulation length of the ngf = 16 fixture): outputs of the
+    reference's own modules (oracle/make_golden_ngf64.py) vs the bf16x3 tcgen05 path, at the north-star tolerance 1e-3."""
+    import emlight_b200 as E
+    from test_discriminator_cpu import d_opt
+    g = np.load(os.path.join(GOLDEN, "genprojector_w64.npz"))
+    w = int(g["width"])
+    G = E.SPADEGenerator(_opt(w)).to(cuda).eval()
+    G.load_state_dict(GO.init_generator_state_dict(seed=int(g["sd_seed"]), ngf=w))
+    gen = torch.Generator().manual_seed(int(g["in_seed"]))
+    guide = torch.rand(1, 3, 128, 256, generator=gen) * 2
+    crop = torch.rand(1, 3, 128, 128, generator=gen)
+    with torch.no_grad():
+        out = G(guide.to(cuda), crop.to(cuda))
+    err = np.abs(out.cpu().numpy()[:, :, ::4, ::4] - g["out"]).max() / 50.0
+    assert err <= 1e-3, err
+    assert abs(float(out.double().mean()) - float(g["out_mean"])) <= 1e-3 * float(g["out_mean"])
+    del G
+    D = E.MultiscaleDiscriminator(d_opt(w)).to(cuda).eval()
+    D.load_state_dict(GO.init_discriminator_state_dict(int(g["sd_seed"]), w))
+    fake = torch.rand(1, 3, 128, 256, generator=gen) * 50 * torch.rand(1, 1, 128, 256, generator=gen) ** 4
+    with torch.no_grad():
+        feats = D(torch.cat([guide, fake], 1).to(cuda))
+    for i, fl in enumerate(feats):
+        for j, f in enumerate(fl):
+            want = g["d%d_%d" % (i, j)]
+            got = f.cpu().numpy()[:, ::max(1, f.shape[1] // 8), ::2, ::2]
+            assert got.shape == want.shape
+            assert np.abs(got - want).max() <= 1e-3 * np.abs(want).max(), (i, j, np.abs(got - want).max() / np.abs(want).max())
