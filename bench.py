@@ -468,7 +468,10 @@ def main():
     extra = {}
     if not args.no_cpu_baseline:                    # (the flag also skips every secondary workload: quick A/B runs of the headline)
         torch.cuda.empty_cache()
-        extra.update(train_workloads(E, parallel, dev, rank, world, gen, timed, args))
+        try:
+            extra.update(train_workloads(E, parallel, dev, rank, world, gen, timed, args))
+        except Exception as e:                                  # noqa: BLE001  (secondary workloads never fail the headline line)
+            extra["train_workloads_error"] = "%s: %s" % (type(e).__name__, str(e)[:300])
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         net.eval()
         x1 = x_host[:1].to(dev)

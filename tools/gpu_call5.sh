@@ -1,9 +1,12 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_dense_layer_gpu.py tests/test_densenet_gpu.py -q -x --timeout 600 -p no:cacheprovider > gpurun_out/pytest_dense.log 2>&1; echo "dense pytest exit $?"; tail -4 gpurun_out/pytest_dense.log
+timeout 600 python -m pytest tests/test_dense_bwd1_gpu.py -q --timeout 300 -p no:cacheprovider > gpurun_out/pytest_bwd1.log 2>&1; echo "bwd1 pytest exit $?"; tail -4 gpurun_out/pytest_bwd1.log; grep -E "^E  " gpurun_out/pytest_bwd1.log | head -8 | cut -c1-300
+timeout 900 python -m pytest tests/test_dense_layer_gpu.py tests/test_densenet_gpu.py -q --timeout 600 -p no:cacheprovider > gpurun_out/pytest_dense.log 2>&1; echo "dense pytest exit $?"; tail -6 gpurun_out/pytest_dense.log; grep -E "^E  " gpurun_out/pytest_dense.log | head -8 | cut -c1-300
 for flags in "EML_DENSE_SMEM_A=1" ""; do
   env $flags python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2> /dev/null | python -c "import sys, json; d = json.loads(sys.stdin.readline()); print('[$flags]', d['ms_per_step'], d['value'], d['roofline']['frac'], d['clocks'])"
 done
-timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider > gpurun_out/pytest_all.log 2>&1; echo "pytest exit $?"; tail -6 gpurun_out/pytest_all.log
+timeout 600 python tools/profile_train.py 64 > gpurun_out/profile_train_b64_fused.log 2>&1; echo "profile exit $?"; cat gpurun_out/profile_train_b64_fused.log
+EML_NO_FUSED_BWD1=1 timeout 600 python tools/profile_train.py 64 > gpurun_out/profile_train_b64_unfused.log 2>&1; echo "profile exit $?"; head -12 gpurun_out/profile_train_b64_unfused.log
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider > gpurun_out/pytest_all.log 2>&1; echo "pytest exit $?"; tail -8 gpurun_out/pytest_all.log
 timeout 1200 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit $?"; tail -3 gpurun_out/bench_n1.err
 python - <<'PY'
 import json
