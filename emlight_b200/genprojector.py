@@ -378,8 +378,9 @@ class SPADE(nn.Module):
             _lib.check(lib.eml_channel_stats(_lib.ptr(x), x.shape[-1], M, C, _lib.ptr(sums), _lib.stream_ptr()), "eml_channel_stats")
             n = float(M)
             if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+                from .parallel import global_count
                 torch.distributed.all_reduce(sums)
-                n *= torch.distributed.get_world_size()
+                n = float(global_count(B, x.device) * H * W)                                # shards may differ by one sample
             m_raw = sums[0] / n
             var = (sums[1] / n - m_raw * m_raw).clamp_min(0.0)
             mean = m_raw.float()                                                           # the bias shifts the mean and cancels

@@ -225,8 +225,9 @@ def spade(tape, mod, x, B, H, W, seg, x_bias, lrelu, precision, training):
     if training:
         sums = ops.channel_sums(x, M, C)
         if _world() > 1:
+            from .parallel import global_count
             torch.distributed.all_reduce(sums)
-            n *= _world()
+            n = float(global_count(B, x.device) * H * W)            # true global count: shards may differ by one sample
         m_raw = sums[0] / n
         var = (sums[1] / n - m_raw * m_raw).clamp_min(0.0)
         mean = m_raw.float()

@@ -40,6 +40,24 @@ def max_over_ranks(value, device=None):
     return float(t.item())
 
 
+_COUNT_CACHE = {}
+
+
+def global_count(local_n, device=None):
+    """Sum over ranks of a per-rank count (samples in this rank's shard).  Shards may differ by one sample when the batch does not
+    divide by the world size (`shard_range`), so synchronised batch statistics must divide by the TRUE global count, not by
+    local_n * world_size.  One tiny all-reduce + host read the first time a (local_n, world) pair is seen, cached afterwards: ranks
+    keep their shard sizes from step to step (drop_last loaders, `shard_range`)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return int(local_n)
+    key = (int(local_n), dist.get_world_size(), dist.get_rank())
+    if key not in _COUNT_CACHE:
+        t = torch.tensor([float(local_n)], dtype=torch.float64, device=device if device is not None else "cpu")
+        dist.all_reduce(t)
+        _COUNT_CACHE[key] = int(round(float(t.item())))
+    return _COUNT_CACHE[key]
+
+
 def allreduce_mean_(tensors, bucket_bytes=32 << 20):
     """In-place mean over ranks of a list of (gradient) tensors, flattened into buckets of ~bucket_bytes so that the
     collective count is set by launch latency, not by the parameter count (DenseNet: 9.3 M params = 37 MB fp32 -> 2 buckets)."""

@@ -54,22 +54,28 @@ def _inputs():
             torch.randn(B, H, W, FOUT, generator=g))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, split):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo")
     x, seg, gout = _inputs()
-    lo, hi = rank * B // world, (rank + 1) * B // world
+    lo, hi = (0, split) if rank == 0 else (split, B)
     out, dx, grads, rm, rv = _run_block(x[lo:hi].contiguous(), seg[lo:hi].contiguous(), gout[lo:hi].contiguous())
     q.put((rank, out.numpy(), dx.numpy(), {k: v.numpy() for k, v in grads.items()}, rm.numpy(), rv.numpy()))
     dist.destroy_process_group()
 
 
-def test_sharded_spade_block_equals_full_batch(monkeypatch):
+import pytest
+
+
+@pytest.mark.parametrize("split", [2, 3], ids=["even_2+2", "uneven_3+1"])
+def test_sharded_spade_block_equals_full_batch(monkeypatch, split):
+    """split = 3: shards of 3 and 1 samples (what parallel.shard_range yields when the batch does not divide): the synchronised
+    statistics must divide by the TRUE global count (parallel.global_count), not by local count x world size."""
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, split)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=300) for _ in procs), key=lambda r: r[0])
