@@ -52,10 +52,10 @@ constexpr int F_TILE_M = 128;
 constexpr int F_STAGE_C = 32;                           // channels per ring stage
 constexpr int F_STAGE_BYTES = F_TILE_M * F_STAGE_C * 4; // 16 KB: raw fp32 in, [hi | lo] bf16 out
 constexpr int F_MAX_STAGES = 12;
-constexpr int F_CWARPS = 16;                            // converter warps (4 warpgroups)
-constexpr int F_TMA_WARP = 16, F_MMA_WARP = 17;         // warps 18, 19 idle (keeps the epilogue warpgroups 4-aligned)
-constexpr int F_EPI_WARP0 = 20;
-constexpr int F_THREADS = (F_EPI_WARP0 + 8) * 32;       // 896
+// Warp roles for NCW converter warps (16 = four warpgroups; 8 = two, TS only: 640 threads leave 102 registers per thread, which lets
+// the epilogue keep 8-column TMEM pieces in flight): converters 0..NCW-1, TMA warp NCW, MMA warp NCW+1, two idle warps (keeps the
+// epilogue warpgroups 4-aligned), epilogue NCW+4 .. NCW+11.
+constexpr int f_threads(int ncw) { return (ncw + 12) * 32; }
 constexpr int F_G = 12;                                 // growth rate (output channels)
 constexpr int F_GRP = 3 * F_G;                          // 36 columns per dy group, ordered (dx, o)
 constexpr int F_NPAD = 112;
@@ -223,9 +223,13 @@ __device__ __forceinline__ void band_init(BandIter &it, const FArgs &a, long ban
     it.m0 = (img * a.H + lo) * a.W;
 }
 
-template <bool SPLIT, bool POOL, int F_SROW, bool TS>
-__global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_constant__ CUtensorMap tmap, const FArgs a) {
+template <bool SPLIT, bool POOL, int F_SROW, bool TS, int NCW = 16, int PW = 4>
+__global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __grid_constant__ CUtensorMap tmap, const FArgs a) {
     constexpr int F_NZ = FTmem<TS>::NZ, F_UBASE = FTmem<TS>::UBASE, F_ABASE = FTmem<TS>::ABASE;
+    constexpr int F_CWARPS = NCW, F_TMA_WARP = NCW, F_MMA_WARP = NCW + 1, F_EPI_WARP0 = NCW + 4, F_THREADS = f_threads(NCW);
+    constexpr int NCWG = NCW / 4;                          // converter warpgroups
+    static_assert(NCW == 16 || (TS && NCW == 8), "converter warps: 16, or 8 with the TMEM-resident A operand");
+    static_assert(PW == 4 || PW == 8, "stencil piece width");
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_bar[3 * F_MAX_STAGES + 1 + 2 * F_MAX_NZ + F_NA];
     __shared__ uint32_t s_tmem;
@@ -277,15 +281,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
 
     if (TS && warp < F_CWARPS) {
         // =========================================================== CONVERTERS, TS: raw fp32 row (shared) -> bf16 hi/lo pairs (TMEM A slot)
-        // warpgroup cg converts stages g with g % 4 == cg into A slot cg; warp w4 = lane quarter, thread = pixel row of the tile.
-        // Every mbarrier here is observed in phase order: a warpgroup reaches stage g only after converting g - 4, all earlier
-        // stages have then landed (in-order TMA), so with a ring of >= 4 stages a parity wait can never be two phases early.
+        // warpgroup cg converts stages g with g % NCWG == cg into A slot g % 4; warp w4 = lane quarter, thread = pixel row of the tile.
+        // Every mbarrier here is observed in phase order: a warpgroup reaches stage g only after converting g - NCWG, all earlier
+        // stages have then landed (in-order TMA), so with a ring of >= NCWG stages a parity wait can never be two phases early; an A
+        // slot always belongs to one warpgroup (NCWG divides 4).
         const int cg = warp >> 2, w4 = warp & 3;
         const uint32_t row = static_cast<uint32_t>(w4 * 32 + lane);
         const uint32_t r7 = row & 7u;
         const uint32_t row_off = row * 128u;
         const uint32_t ring = smem_u32(smem);
-        const uint32_t a_slot = tmem_base + F_ABASE + static_cast<uint32_t>(cg) * 32u + (static_cast<uint32_t>(w4 * 32) << 16);
+        const uint32_t a_lane = tmem_base + F_ABASE + (static_cast<uint32_t>(w4 * 32) << 16);
         uint32_t total = 0;
         for (long band = blockIdx.x; band < a.nbands; band += grid) {
             BandIter it;
@@ -294,8 +299,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
         }
         const uint32_t nst_u = static_cast<uint32_t>(NST), nstg_u = static_cast<uint32_t>(a.nstg);
         const int c16 = (a.C_in + 15) & ~15;                                     // channels the MMAs read (whole k-steps)
-        for (uint32_t g = static_cast<uint32_t>(cg); g < total; g += 4) {
-            const uint32_t s = g % nst_u, ph = (g / nst_u) & 1, aph = (g >> 2) & 1;
+        for (uint32_t g = static_cast<uint32_t>(cg); g < total; g += NCWG) {
+            const uint32_t s = g % nst_u, ph = (g / nst_u) & 1, as = g & 3u, aph = (g >> 2) & 1;
+            const uint32_t a_slot = a_lane + as * 32u;
             const int j = static_cast<int>(g % nstg_u);
             const int halves = c16 - j * F_STAGE_C > 16 ? 2 : 1;                  // a partial last stage holds one k-step only
             const uint32_t st = ring + s * F_STAGE_BYTES + row_off;
@@ -320,7 +326,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
             }
             __syncwarp();                                                         // every lane's loads have been consumed
             if (lane == 0) f_mbar_arrive(bar_empty + 8 * s);                      // raw stage free: the TMA warp may refill it
-            mbar_wait(bar_afree + 8 * cg, aph ^ 1);                               // MMAs of stage g - 4 have read this A slot
+            mbar_wait(bar_afree + 8 * as, aph ^ 1);                               // MMAs of stage g - 4 have read this A slot
             tc_fence_after();
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -332,7 +338,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
             f_tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) f_mbar_arrive(bar_ready + 8 * cg);
+            if (lane == 0) f_mbar_arrive(bar_ready + 8 * as);
         }
     } else if (warp < F_CWARPS) {
         // =========================================================== CONVERTERS (in place, raw fp32 -> [bf16 hi | bf16 lo])
@@ -556,9 +562,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) dense_layer_kernel(const __grid_
                     mbar_wait(bar_zfull + 8 * zb, zph);
                     __syncwarp();
                     tc_fence_after();
+                    if (PW == 8) {                                      // 8 columns x 5 arrays = 40 registers in flight per slice (NCW = 8 builds)
 #pragma unroll
-                    for (int piece = 0; piece < 9; ++piece)            // 4 columns x 5 arrays = 20 registers in flight per slice
-                        f_stencil_piece<4>(zc, us0, us1, piece * 4, srow, emit, init_next, upd, upd_add);
+                        for (int piece = 0; piece < 4; ++piece)
+                            f_stencil_piece<8>(zc, us0, us1, piece * 8, srow, emit, init_next, upd, upd_add);
+                        f_stencil_piece<4>(zc, us0, us1, 32, srow, emit, init_next, upd, upd_add);
+                    } else {
+#pragma unroll
+                        for (int piece = 0; piece < 9; ++piece)        // 4 columns x 5 arrays = 20 registers in flight per slice
+                            f_stencil_piece<4>(zc, us0, us1, piece * 4, srow, emit, init_next, upd, upd_add);
+                    }
                     f_tmem_wait_st();
                     tc_fence_before();
                     __syncwarp();
@@ -741,19 +754,24 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
     const size_t smem = fused_smem(a.nwchunks, p->W, a.stages, wide_rows ? 44 : F_GRP);
     const unsigned grid = static_cast<unsigned>(a.nbands < sms ? a.nbands : sms);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    auto go = [&](auto kern) -> int {
+    auto go = [&](auto kern, int threads) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);
-        kern<<<grid, F_THREADS, smem, st>>>(tmap, a);
+        kern<<<grid, threads, smem, st>>>(tmap, a);
         return EML_OK;
     };
     int rc;
+    const char *cw_env = getenv("EML_DENSE_CW");          // A/B switch: converter warps (16 default, 8 = two warpgroups + 8-column stencil pieces)
+    const int cw = cw_env ? atoi(cw_env) : 16;
     if (eml_env_flag("EML_DENSE_SMEM_A")) {               // round-1 pipeline (A operand converted in place in shared memory), kept for A/B runs
-        if (split) rc = wide_rows ? go(dense_layer_kernel<true, false, 44, false>) : go(dense_layer_kernel<true, false, F_GRP, false>);
-        else rc = wide_rows ? go(dense_layer_kernel<false, false, 44, false>) : go(dense_layer_kernel<false, false, F_GRP, false>);
+        if (split) rc = wide_rows ? go(dense_layer_kernel<true, false, 44, false>, f_threads(16)) : go(dense_layer_kernel<true, false, F_GRP, false>, f_threads(16));
+        else rc = wide_rows ? go(dense_layer_kernel<false, false, 44, false>, f_threads(16)) : go(dense_layer_kernel<false, false, F_GRP, false>, f_threads(16));
+    } else if (cw == 8) {
+        if (split) rc = wide_rows ? go(dense_layer_kernel<true, false, 44, true, 8, 8>, f_threads(8)) : go(dense_layer_kernel<true, false, F_GRP, true, 8, 8>, f_threads(8));
+        else rc = wide_rows ? go(dense_layer_kernel<false, false, 44, true, 8, 8>, f_threads(8)) : go(dense_layer_kernel<false, false, F_GRP, true, 8, 8>, f_threads(8));
     } else {
-        if (split) rc = wide_rows ? go(dense_layer_kernel<true, false, 44, true>) : go(dense_layer_kernel<true, false, F_GRP, true>);
-        else rc = wide_rows ? go(dense_layer_kernel<false, false, 44, true>) : go(dense_layer_kernel<false, false, F_GRP, true>);
+        if (split) rc = wide_rows ? go(dense_layer_kernel<true, false, 44, true>, f_threads(16)) : go(dense_layer_kernel<true, false, F_GRP, true>, f_threads(16));
+        else rc = wide_rows ? go(dense_layer_kernel<false, false, 44, true>, f_threads(16)) : go(dense_layer_kernel<false, false, F_GRP, true>, f_threads(16));
     }
     if (rc != EML_OK) return rc;
     return eml_launch_status();
@@ -865,7 +883,7 @@ int eml_dense_pool_forward(const eml_conv_params *p, cudaStream_t st) {
     auto go = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);
-        kern<<<grid, F_THREADS, smem, st>>>(tmap, a);
+        kern<<<grid, f_threads(16), smem, st>>>(tmap, a);
         return EML_OK;
     };
     int rc;

@@ -1,7 +1,8 @@
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_dense_bwd1_gpu.py -q --timeout 300 -p no:cacheprovider > gpurun_out/pytest_bwd1.log 2>&1; echo "bwd1 pytest exit $?"; tail -4 gpurun_out/pytest_bwd1.log; grep -E "^E  " gpurun_out/pytest_bwd1.log | head -8 | cut -c1-300
+EML_DENSE_CW=8 timeout 600 python -m pytest tests/test_dense_layer_gpu.py -q --timeout 300 -p no:cacheprovider > gpurun_out/pytest_dense_cw8.log 2>&1; echo "dense cw8 pytest exit $?"; tail -2 gpurun_out/pytest_dense_cw8.log
 timeout 900 python -m pytest tests/test_dense_layer_gpu.py tests/test_densenet_gpu.py -q --timeout 600 -p no:cacheprovider > gpurun_out/pytest_dense.log 2>&1; echo "dense pytest exit $?"; tail -6 gpurun_out/pytest_dense.log; grep -E "^E  " gpurun_out/pytest_dense.log | head -8 | cut -c1-300
-for flags in "EML_DENSE_SMEM_A=1" ""; do
+for flags in "EML_DENSE_SMEM_A=1" "" "EML_DENSE_CW=8"; do
   env $flags python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2> /dev/null | python -c "import sys, json; d = json.loads(sys.stdin.readline()); print('[$flags]', d['ms_per_step'], d['value'], d['roofline']['frac'], d['clocks'])"
 done
 timeout 600 python tools/profile_train.py 64 > gpurun_out/profile_train_b64_fused.log 2>&1; echo "profile exit $?"; cat gpurun_out/profile_train_b64_fused.log

@@ -3,6 +3,7 @@
 usage: python tools/launch_traffic.py gpurun_out/launches.csv profiles/r01_traffic.json"""
 import csv
 import json
+import re
 import sys
 
 FAMILIES = (("dense_layer", "dense_layer"), ("conv1x1_persist", "conv1x1"), ("conv3x3_roll", "conv3x3"), ("conv3x3_rows", "conv3x3"),
@@ -24,7 +25,7 @@ def main():
     for i in order:
         l = launches[i]
         name = next((f for key, f in FAMILIES if key in l["name"]), "other")
-        if name == "dense_layer" and "dense_layer_kernel<1, 1>" in l["name"].replace("(bool)", ""):
+        if name == "dense_layer" and re.search(r"dense_layer_kernel<\d, 1[,>]", l["name"].replace("(bool)", "").replace("(int)", "")):
             name = "pool1x1"                                  # dense_layer_kernel<SPLIT, POOL = true> is transition1 (eml_conv_forward POOL2)
         f = fam.setdefault(name, {"launches": 0, "time_ms": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0})
         f["launches"] += 1
