@@ -452,12 +452,14 @@ extern "C" int eml_dense_bwd1(const float *dN, const float *x, int x_pitch, floa
                               int vstride, int C_in, long M, double *sums, long sums_stride, int precision, void *stream) {
     EML_CHECK_PTR(dN); EML_CHECK_PTR(x); EML_CHECK_PTR(dS); EML_CHECK_PTR(wpack); EML_CHECK_PTR(vec); EML_CHECK_PTR(sums);
     EML_CHECK_ALIGN16(dN); EML_CHECK_ALIGN16(x); EML_CHECK_ALIGN16(dS); EML_CHECK_ALIGN16(wpack);
-    if (!eml_dense_bwd1_supported(C_in, M, precision) || (x_pitch & 3) || (ds_pitch & 3) || x_pitch < C_in || ds_pitch < C_in || vstride < C_in)
+    if (!eml_dense_bwd1_supported(C_in, M, precision) || (x_pitch & 3) || (ds_pitch & 3) || x_pitch < C_in || ds_pitch < ((C_in + 3) & ~3) || vstride < C_in)
         return EML_E_SHAPE;
     CUtensorMap tm_x, tm_ds;
     int rc = b1_make_map(&tm_x, x, C_in, M, x_pitch);
     if (rc != EML_OK) return rc;
-    rc = b1_make_map(&tm_ds, dS, C_in, M, ds_pitch);
+    // the TMA store clips at 16-byte granularity: with C_in = 2 (mod 4) -- block 3 -- it would zero the two channels behind C_in.  The dS
+    // map therefore covers whole channel quads: the extra channels are loaded with their true values, left unchanged (k1 = 0) and stored back
+    rc = b1_make_map(&tm_ds, dS, (C_in + 3) & ~3, M, ds_pitch);
     if (rc != EML_OK) return rc;
     const bool split = precision == EML_PREC_BF16X3;
     B1Args a{};

@@ -303,6 +303,9 @@ class DenseNet(nn.Module):
             blk = getattr(self.features, "denseblock%d" % b)
             for l, layer in enumerate(blk.children()):
                 ci = c_in + l * g
+                if not any(lib.eml_dense_layer_supported(2, wq, ci, g, _lib.PRECISIONS[self.precision]) for wq in (64, 128, 256)):
+                    i += 1                              # no geometry fuses this layer (block 3's last one, C_in = 330: more resident
+                    continue                            # weights than shared memory holds): it keeps the two-kernel path
                 s2, t2 = self._aff(c, "b%d.l%d.norm2" % (b, l))
                 nb = layer.conv1.out_channels
                 buf = torch.empty(lib.eml_conv_wpack_bytes(9 * g, ci, 1), dtype=torch.uint8, device=dev)
@@ -455,7 +458,7 @@ class DenseNet(nn.Module):
                 ci = c_in + l * self.growth_rate
                 n1, n2 = "b%d.l%d.norm1" % (b, l), "b%d.l%d.norm2" % (b, l)
                 mid = stats[so["b%d.l%d.mid" % (b, l)]:]
-                if (not train and "fused" in c and (w != 64 or B % 2 == 0) and    # W = 64 tiles hold a row of two images
+                if (not train and (b, l) in c.get("fused", ()) and (w != 64 or B % 2 == 0) and    # W = 64 tiles hold a row of two images
                         lib.eml_dense_layer_supported(h, w, ci, self.growth_rate, _lib.PRECISIONS[self.precision])):
                     self._dense_layer(c, (b, l), slab, pitch, h, w, B, ci)
                     continue

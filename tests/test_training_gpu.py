@@ -92,17 +92,28 @@ def test_flat_adam_with_sink_equals_torch_adam(cuda):
     flat = parallel.FlatAdam(nets[1].named_parameters(), lr=1e-4, betas=(0.9, 0.999))
     nets[1]._grad_sink = flat.sink
     assert len(flat.buckets) == 2 and "fc.weight" in flat.buckets[0][2]          # heads + fc (34 MB) | everything else
+    pa, pb = dict(nets[0].named_parameters()), dict(nets[1].named_parameters())
     losses = [[], []]
-    for _ in range(steps):
+    for step in range(steps):
         for i, (net, opt) in enumerate(zip(nets, (ref, flat))):
             loss = _losses(net(gb[0]), gb, sam, ln)
-            opt.zero_grad(); loss.backward(); opt.step()
+            opt.zero_grad(); loss.backward()
             losses[i].append(float(loss))
         assert flat.early_buckets == 2                                         # both buckets were complete before backward() returned
-    assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(*losses)), losses      # the packed-weight caches saw every update
-    pa, pb = dict(nets[0].named_parameters()), dict(nets[1].named_parameters())
-    for name in pa:
-        d = float((pa[name].detach() - pb[name].detach()).abs().max())
-        assert d <= 2e-6, (name, d)                                             # |update| ~ lr = 1e-4 per step
-        assert pb[name].data_ptr() >= flat.flat_p.data_ptr() and pb[name].grad.data_ptr() >= flat.flat_g.data_ptr()
+        # (1) the sink delivered what autograd delivers (same kernels; float atomics in the weight gradients -> summation-order noise)
+        gtop = max(float(p.grad.abs().max()) for p in pa.values())
+        for name in pa:
+            assert pb[name].grad.data_ptr() >= flat.flat_g.data_ptr() and pb[name].data_ptr() >= flat.flat_p.data_ptr(), name
+            d = float((pa[name].grad - pb[name].grad).abs().max())
+            assert d <= 1e-4 * max(float(pa[name].grad.abs().max()), 1e-3 * gtop), (name, d)
+        # (2) the fused update equals torch.optim.Adam on IDENTICAL gradients (Adam divides by sqrt(v): a 1e-6 difference in a
+        # near-zero gradient would otherwise move a weight by a good fraction of lr and hide formula errors behind a loose bound)
+        with torch.no_grad():
+            for name in pa:
+                pb[name].grad.copy_(pa[name].grad)
+        ref.step(); flat.step()
+        for name in pa:
+            d = float((pa[name].detach() - pb[name].detach()).abs().max())
+            assert d <= 2e-7 + 2e-6 * 1e-4 * (step + 1), (name, step, d)        # fp32 rounding of the update; |update| ~ lr = 1e-4
+    assert all(abs(a - b) <= 1e-4 * abs(a) for a, b in zip(*losses)), losses      # the packed-weight caches saw every update
     assert torch.equal(nets[0].state_dict()["features.norm0.running_mean"], nets[1].state_dict()["features.norm0.running_mean"])
