@@ -26,7 +26,8 @@ struct WArgs {
     const float *G; int g_pitch, N;            // gradient of the conv output, N <= 64 channels
     const float *x; int x_pitch, C;            // conv input (stored slab), C <= 256 channels
     const float *scale, *shift;
-    float *dW;                                 // (N, C)
+    float *dW;                                 // (N, dw_stride): this call fills columns [0, C)
+    int dw_stride;
     long M;
     int relu, nblk;                            // nblk = 2 * ceil(C / 128) channel blocks of 64 (zero padded)
     long ntiles;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) wgrad1x1_tc_kernel(const WArgs a
                     if (c < a.C) {
 #pragma unroll
                         for (int e = 0; e < 16; ++e)
-                            if (g16 + e < a.N) atomicAdd(a.dW + static_cast<long>(g16 + e) * a.C + c, v[e]);
+                            if (g16 + e < a.N) atomicAdd(a.dW + static_cast<long>(g16 + e) * a.dw_stride + c, v[e]);
                     }
                 }
             }
@@ -215,14 +216,31 @@ __global__ void __launch_bounds__(W_THREADS, 1) wgrad1x1_tc_kernel(const WArgs a
 
 }  // namespace
 
+// C > 256 (block 2 layers 14-16, block 3 layers 10-16: up to 342 input channels) runs as two passes over channel ranges of <= 256 -- the
+// 48-channel G operand is re-read, the slab columns are not -- instead of falling back to the SIMT kernel (round 1: 10 calls, 10.6 ms).
 bool eml_wgrad1x1_tc_supported(int N, int C, int pool, long M) {
-    return !pool && N <= 64 && C <= 256 && M >= W_KT && !eml_env_flag("EML_WGRAD_SIMT");
+    return !pool && N <= 64 && C <= 512 && M >= W_KT && !eml_env_flag("EML_WGRAD_SIMT");
 }
+
+static int wgrad1x1_tc_range(const float *G, int g_pitch, int N, const float *x, int x_pitch, int C, const float *scale, const float *shift,
+                             int relu, float *dW, int dw_stride, long M, int precision, cudaStream_t st);
 
 int eml_wgrad1x1_tc(const float *G, int g_pitch, int N, const float *x, int x_pitch, int C, const float *scale, const float *shift,
                     int relu, float *dW, long M, int precision, cudaStream_t st) {
+    for (int c0 = 0; c0 < C; c0 += 256) {
+        const int cc = C - c0 < 256 ? C - c0 : 256;
+        const int rc = wgrad1x1_tc_range(G, g_pitch, N, x + c0, x_pitch, cc, scale ? scale + c0 : nullptr, shift ? shift + c0 : nullptr, relu,
+                                         dW + c0, C, M, precision, st);
+        if (rc != EML_OK) return rc;
+    }
+    return EML_OK;
+}
+
+static int wgrad1x1_tc_range(const float *G, int g_pitch, int N, const float *x, int x_pitch, int C, const float *scale, const float *shift,
+                             int relu, float *dW, int dw_stride, long M, int precision, cudaStream_t st) {
     WArgs a{};
     a.G = G; a.g_pitch = g_pitch; a.N = N; a.x = x; a.x_pitch = x_pitch; a.C = C; a.scale = scale; a.shift = shift; a.dW = dW;
+    a.dw_stride = dw_stride;
     a.M = M; a.relu = relu;
     a.nblk = 2 * ((C + 127) / 128);
     a.ntiles = (M + W_KT - 1) / W_KT;

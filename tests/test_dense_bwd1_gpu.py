@@ -87,3 +87,20 @@ def test_dense_bwd1_matches_float64(cuda, lib, ci, tiles, precision, tol):
         _lib.check(lib.eml_dense_bwd1_gather(P(dS2), pitch, P(x), pitch, P(coef[0]), P(coef[1]), 0, ci, P(dS2), pitch, ci, M, st), "gather in place")
         du = dS2[:, :ci].double() * pa.double()                                    # dS holds d/du; autograd gave d/dx = pa * d/du
         assert float((du - xr.grad).abs().max()) <= 1e-3 * float(xr.grad.abs().max())
+
+
+@pytest.mark.parametrize("C,M", [(204, 128 * 150), (330, 128 * 96), (342, 6400)])
+def test_wgrad_1x1_tensor_core_ranges(cuda, lib, C, M):
+    """eml_wgrad_1x1 (conv1's weight gradient, K = pixels on MN-major tcgen05 operands): C > 256 runs as two channel ranges."""
+    from emlight_b200 import _lib
+    P, st = _lib.ptr, _lib.stream_ptr()
+    gen = torch.Generator().manual_seed(C)
+    pitch = (C + 12 + 7) & ~7
+    G = torch.randn(M, 48, generator=gen).to(cuda)
+    x = torch.randn(M, pitch, generator=gen).to(cuda)
+    sc, sh = torch.randn(C, generator=gen).to(cuda), (0.2 * torch.randn(C, generator=gen)).to(cuda)
+    dW = torch.zeros(48, C, device=cuda)
+    _lib.check(lib.eml_wgrad_1x1(P(G), 48, 48, P(x), pitch, C, P(sc), P(sh), 1, 0, 1, M, P(dW), M, _lib.PRECISIONS["bf16x3"], st), "eml_wgrad_1x1")
+    a = torch.relu(torch.addcmul(sh, x[:, :C], sc)).double()
+    want = G.double().t() @ a
+    assert float((dW.double() - want).abs().max()) <= 1e-4 * float(want.abs().max())
