@@ -21,7 +21,8 @@ actually runs -- running statistics in eval mode.
 
 Backward (training-mode BatchNorm, the mode train.py runs) is `_backward`: both data-gradient convolutions are the same
 tcgen05 implicit-GEMM kernels with transposed / flipped weights, BatchNorm backward and the weight gradients are the kernels of
-csrc/bwd_ops.cu, the 48-channel bottleneck is recomputed instead of stored, the tiny fc / head GEMMs use torch.matmul (cuBLAS).
+csrc/bwd_ops.cu and csrc/dense_bwd1.cu (fused conv1 backward), the 48-channel bottlenecks are kept by the training forward when memory
+allows (else recomputed), the tiny fc / head GEMMs use torch.matmul (cuBLAS).
 """
 import math
 import os
@@ -158,7 +159,8 @@ class DenseNet(nn.Module):
         if x.dim() != 4 or x.shape[1] != 3:
             raise ValueError("expected input (B,3,H,W), got %s" % (tuple(x.shape),))
         params = [p for p in self.parameters() if p.requires_grad]
-        if torch.is_grad_enabled() and (x.requires_grad or params):
+        self._for_backward = bool(torch.is_grad_enabled() and (x.requires_grad or params))
+        if self._for_backward:
             d, i, r, a = _DenseNetFn.apply(self, x, *params)
         elif self.use_cuda_graph and not self.training and self.launch_log is None:
             from .graphs import graphed_call
@@ -431,6 +433,17 @@ class DenseNet(nn.Module):
 
         if train:
             stats.zero_()
+        # Training keeps every layer's 48-channel bottleneck (conv1 output) for the backward when that fits comfortably -- 4 * 48 B per
+        # pixel and layer: 12.7 GB at B = 64 -- instead of recomputing it there (one more read of the layer's whole input slab per layer);
+        # otherwise one buffer is reused and the backward recomputes.
+        keep = None
+        if train and getattr(self, "_for_backward", False):
+            need = sum(B * hh * ww * g * 4 * n for (hh, ww), n in zip(ws["geom"], self.block_config))
+            free, _total = torch.cuda.mem_get_info(dev)
+            have = sum(t.numel() * 4 for t in ws.get("bott_keep", {}).values())
+            if os.environ.get("EML_RECOMPUTE_BOTTLENECK") != "1" and need - have < 0.5 * free:
+                keep = ws.setdefault("bott_keep", {})
+        ws["bott_kept"] = keep is not None
         # ---- stem (DenseNet.py:89-92)
         slab = ws["slab"][0]
         pitch = slab.shape[3]
@@ -464,11 +477,16 @@ class DenseNet(nn.Module):
                     continue
                 if train:
                     self._fold(c, n1, layer.norm1, stats=sstat, stride=pitch, count=count, pre=pre, mean_var=mv(layer.norm1, count))
-                self._conv(c, "b%d.l%d.conv1" % (b, l), slab, pitch, h, w, B, ci, ws["bott"], g, 0, g, _lib.EML_CONV_1x1, 1,
+                bott = ws["bott"]
+                if keep is not None:
+                    bott = keep.get((b, l))
+                    if bott is None or bott.shape[0] != B:
+                        bott = keep[(b, l)] = torch.empty(B, h, w, g, dtype=torch.float32, device=dev)
+                self._conv(c, "b%d.l%d.conv1" % (b, l), slab, pitch, h, w, B, ci, bott, g, 0, g, _lib.EML_CONV_1x1, 1,
                            self._aff(c, n1), mid if train else None, g)
                 if train:
                     self._fold(c, n2, layer.norm2, stats=mid, stride=g, count=count, mean_var=mv(layer.norm2, count))
-                self._conv(c, "b%d.l%d.conv2" % (b, l), ws["bott"], g, h, w, B, g, slab, pitch, ci, self.growth_rate,
+                self._conv(c, "b%d.l%d.conv2" % (b, l), bott, g, h, w, B, g, slab, pitch, ci, self.growth_rate,
                            _lib.EML_CONV_3x3, 0, self._aff(c, n2), sstat[ci:] if train else None, pitch)
             tr = getattr(f, "transition%d" % b)
             tn = "t%d.norm" % b
@@ -677,8 +695,11 @@ class DenseNet(nn.Module):
                 pfx = "features.denseblock%d.denselayer%d" % (b, l + 1)
                 n1, n2 = "b%d.l%d.norm1" % (b, l), "b%d.l%d.norm2" % (b, l)
                 a1, a2 = self._aff(c, n1), self._aff(c, n2)
-                # recompute the bottleneck (conv1 output) instead of having stored it
-                self._conv(c, "b%d.l%d.conv1" % (b, l), slab, pitch, h, w, B, ci, ws["bott"], g, 0, g, _lib.EML_CONV_1x1, 1, a1, None, g)
+                if ws.get("bott_kept"):
+                    bott = ws["bott_keep"][(b, l)]            # kept by the forward
+                else:                                         # recompute the bottleneck (conv1 output) instead of having stored it
+                    bott = ws["bott"]
+                    self._conv(c, "b%d.l%d.conv1" % (b, l), slab, pitch, h, w, B, ci, bott, g, 0, g, _lib.EML_CONV_1x1, 1, a1, None, g)
                 # gradient of this layer's 12 output channels; compacted because block 3's channel offsets (150 + 12 l) are not
                 # 16-byte aligned and the gather uses float4 loads
                 if fused1:
@@ -691,10 +712,10 @@ class DenseNet(nn.Module):
                 w2 = layer.conv2.weight.detach().float()                          # (12, 48, 3, 3)
                 self._gemm_bwd(dy.data_ptr(), 16, B, h, w, gr, w2.permute(1, 0, 2, 3).flip(2, 3).contiguous(), dN, _lib.EML_CONV_3x3)
                 dw2 = torch.zeros(gr, g, 3, 3, dtype=torch.float32, device=dev)
-                _lib.check(lib.eml_wgrad_3x3(_lib.ptr(dy), 16, gr, _lib.ptr(ws["bott"]), g, g, _lib.ptr(a2[0]), _lib.ptr(a2[1]), _lib.ptr(dw2),
+                _lib.check(lib.eml_wgrad_3x3(_lib.ptr(dy), 16, gr, _lib.ptr(bott), g, g, _lib.ptr(a2[0]), _lib.ptr(a2[1]), _lib.ptr(dw2),
                                              B, h, w, _lib.PRECISIONS[self.precision], st), "eml_wgrad_3x3")
                 out[pfx + ".conv2.weight"] = dw2
-                bn_bwd(n2, layer.norm2, pfx + ".norm2", _lib.ptr(dN), g, _lib.ptr(ws["bott"]), g, None, 0, 0, h, w, M, g, _lib.ptr(dN), g, 0)
+                bn_bwd(n2, layer.norm2, pfx + ".norm2", _lib.ptr(dN), g, _lib.ptr(bott), g, None, 0, 0, h, w, M, g, _lib.ptr(dN), g, 0)
                 w1 = layer.conv1.weight.detach().float()                          # (48, ci, 1, 1)
                 dw1 = torch.zeros(g, ci, dtype=torch.float32, device=dev)
                 if fused1:
