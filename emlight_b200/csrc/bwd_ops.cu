@@ -457,6 +457,54 @@ extern "C" int eml_wgrad_1x1(const float *G, int g_pitch, int N, const float *x,
     return eml_launch_status();
 }
 
+// out[b, y, x, c] = mean over the 2x2 window of relu(scale[c] * in[b, 2y+dy, 2x+dx, c] + shift[c])  -- the transition's pooled activation
+// (RegressionNetwork/DenseNet.py:14-21: norm -> relu -> conv -> avg_pool2d, the pooling commuted in front of the 1x1 conv), materialised
+// once for the transition's weight gradient so that it can run on the tensor-core wgrad kernel instead of the SIMT one.
+__global__ void __launch_bounds__(256) pool_act_kernel(const float *__restrict__ in, int in_pitch, const float *__restrict__ scale,
+                                                       const float *__restrict__ shift, int B, int H, int W, int C, float *__restrict__ out,
+                                                       int out_pitch) {
+    const int Hp = H >> 1, Wp = W >> 1, Q = (C + 3) >> 2;
+    const long total = static_cast<long>(B) * Hp * Wp * Q;
+    for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int q = static_cast<int>(idx % Q);
+        const long mp = idx / Q;
+        const int xp = static_cast<int>(mp % Wp);
+        const long t = mp / Wp;
+        const int yp = static_cast<int>(t % Hp);
+        const long b = t / Hp;
+        const int c = q * 4;
+        float sc[4], sh[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { sc[e] = c + e < C ? scale[c + e] : 0.f; sh[e] = c + e < C ? shift[c + e] : 0.f; }
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const float *p = in + ((b * H + 2 * yp + dy) * W + 2 * xp + dx) * in_pitch + c;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (c + 3 < C) { const float4 f = __ldg(reinterpret_cast<const float4 *>(p)); v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w; }
+                else for (int e = 0; e < 4; ++e) if (c + e < C) v[e] = p[e];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[e] += fmaxf(fmaf(v[e], sc[e], sh[e]), 0.f);
+            }
+        *reinterpret_cast<float4 *>(out + mp * out_pitch + c) = make_float4(0.25f * acc[0], 0.25f * acc[1], 0.25f * acc[2], 0.25f * acc[3]);
+    }
+}
+
+extern "C" int eml_pool_act(const float *in, int in_pitch, const float *scale, const float *shift, int B, int H, int W, int C, float *out,
+                            int out_pitch, void *stream) {
+    EML_CHECK_PTR(in); EML_CHECK_PTR(scale); EML_CHECK_PTR(shift); EML_CHECK_PTR(out);
+    EML_CHECK_ALIGN16(in); EML_CHECK_ALIGN16(out);
+    if (B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || C <= 0 || (in_pitch & 3) || (out_pitch & 3) || in_pitch < C ||
+        out_pitch < ((C + 3) & ~3))
+        return EML_E_SHAPE;
+    const long total = static_cast<long>(B) * (H / 2) * (W / 2) * ((C + 3) / 4);
+    long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pool_act_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, in_pitch, scale, shift, B, H, W, C, out, out_pitch);
+    return eml_launch_status();
+}
+
 bool eml_wgrad3x3_tc_supported(int N, int C);                                                            // wgrad3x3_tc.cu
 int eml_wgrad3x3_tc(const float *dY, int dy_pitch, int N, const float *b, int b_pitch, const float *scale, const float *shift,
                     float *dW, int B, int H, int W, int precision, cudaStream_t st);

@@ -470,7 +470,9 @@ extern "C" int eml_dense_bwd1(const float *dN, const float *x, int x_pitch, floa
     const size_t wbytes = static_cast<size_t>(a.Cpad) * 256;
     const size_t budget = 227 * 1024 - 12 * 1024;                   // static shared memory: vectors (7 KB), sums (2.8 KB), barriers
     int stages = B1_MAXST, ndn = 2;
-    while (stages > 2 && static_cast<size_t>(stages) * B1_STAGE + static_cast<size_t>(ndn) * B1_DNBYTES + wbytes + 1024 > budget) --stages;
+    // ring depth even: a ring slot is then always handled by the same epilogue warpgroup (stages alternate), i.e. every phase of its
+    // mbarriers has one in-order waiter (a parity wait cannot tell "two completions early" from "done")
+    while (stages > 2 && static_cast<size_t>(stages) * B1_STAGE + static_cast<size_t>(ndn) * B1_DNBYTES + wbytes + 1024 > budget) stages -= 2;
     if (static_cast<size_t>(stages) * B1_STAGE + static_cast<size_t>(ndn) * B1_DNBYTES + wbytes + 1024 > budget) ndn = 1;
     if (static_cast<size_t>(stages) * B1_STAGE + static_cast<size_t>(ndn) * B1_DNBYTES + wbytes + 1024 > budget) return EML_E_SHAPE;
     a.stages = stages; a.ndn = ndn;

@@ -282,9 +282,8 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
     if (TS && warp < F_CWARPS) {
         // =========================================================== CONVERTERS, TS: raw fp32 row (shared) -> bf16 hi/lo pairs (TMEM A slot)
         // warpgroup cg converts stages g with g % NCWG == cg into A slot g % 4; warp w4 = lane quarter, thread = pixel row of the tile.
-        // Every mbarrier here is observed in phase order: a warpgroup reaches stage g only after converting g - NCWG, all earlier
-        // stages have then landed (in-order TMA), so with a ring of >= NCWG stages a parity wait can never be two phases early; an A
-        // slot always belongs to one warpgroup (NCWG divides 4).
+        // The host makes the ring depth a multiple of NCWG, so a ring slot (g % NST) and an A slot (g % 4) always belong to the same
+        // warpgroup: every phase of their mbarriers is observed in order by one waiter.
         const int cg = warp >> 2, w4 = warp & 3;
         const uint32_t row = static_cast<uint32_t>(w4 * 32 + lane);
         const uint32_t r7 = row & 7u;
@@ -750,6 +749,14 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
     }
     a.stages = fused_stages(a.nwchunks, p->W);
     const bool wide_rows = fused_stages(a.nwchunks, p->W, 44) == a.stages && !eml_env_flag("EML_DENSE_PACKED_ROWS");
+    const char *cw_env = getenv("EML_DENSE_CW");          // A/B switch: converter warps (16 default, 8 = two warpgroups + 8-column stencil pieces)
+    const int cw = cw_env ? atoi(cw_env) : 16;
+    const bool ts = !eml_env_flag("EML_DENSE_SMEM_A");
+    // TS: the ring depth must be a multiple of the number of converter warpgroups, so that a ring slot is always converted by the same
+    // warpgroup and every phase of its mbarrier has one in-order waiter.  (A parity wait cannot tell "two completions early" from "done":
+    // with e.g. 5 slots and 4 warpgroups the waiter of round k on a slot may arrive before round k - 1 has even landed -- TMA loads of
+    // neighbouring stages complete out of order -- pass spuriously and read stale data: seen on B200 as run-to-run differences and hangs.)
+    if (ts) a.stages -= a.stages % (cw == 8 ? 2 : 4);
     const bool split = p->precision == EML_PREC_BF16X3;
     const size_t smem = fused_smem(a.nwchunks, p->W, a.stages, wide_rows ? 44 : F_GRP);
     const unsigned grid = static_cast<unsigned>(a.nbands < sms ? a.nbands : sms);
@@ -761,9 +768,7 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
         return EML_OK;
     };
     int rc;
-    const char *cw_env = getenv("EML_DENSE_CW");          // A/B switch: converter warps (16 default, 8 = two warpgroups + 8-column stencil pieces)
-    const int cw = cw_env ? atoi(cw_env) : 16;
-    if (eml_env_flag("EML_DENSE_SMEM_A")) {               // round-1 pipeline (A operand converted in place in shared memory), kept for A/B runs
+    if (!ts) {                                            // round-1 pipeline (A operand converted in place in shared memory), kept for A/B runs
         if (split) rc = wide_rows ? go(dense_layer_kernel<true, false, 44, false>, f_threads(16)) : go(dense_layer_kernel<true, false, F_GRP, false>, f_threads(16));
         else rc = wide_rows ? go(dense_layer_kernel<false, false, 44, false>, f_threads(16)) : go(dense_layer_kernel<false, false, F_GRP, false>, f_threads(16));
     } else if (cw == 8) {
@@ -876,6 +881,7 @@ int eml_dense_pool_forward(const eml_conv_params *p, cudaStream_t st) {
     a.nstg = (p->C_in + F_STAGE_C - 1) / F_STAGE_C;
     a.pool = 1; a.n_out = p->C_out;
     a.stages = fused_stages(a.nwchunks, p->W);
+    if (!eml_env_flag("EML_DENSE_SMEM_A")) a.stages &= ~3;          // TS: ring depth a multiple of the 4 converter warpgroups (see eml_dense_layer_forward)
     a.nbands = static_cast<long>(p->B) * (p->H / R);
     const bool split = p->precision == EML_PREC_BF16X3;
     const size_t smem = fused_smem(a.nwchunks, p->W, a.stages);

@@ -27,6 +27,7 @@ allows (else recomputed), the tiny fc / head GEMMs use torch.matmul (cuBLAS).
 import math
 import os
 from collections import OrderedDict
+from ctypes import c_void_p
 
 import torch
 import torch.nn as nn
@@ -671,8 +672,20 @@ class DenseNet(nn.Module):
             self._gemm_bwd(dt.data_ptr(), dt.shape[3], B, h // 2, w // 2, c_tr, wt.permute(1, 0, 2, 3).contiguous(), dp, _lib.EML_CONV_1x1)
             a_t = self._aff(c, "t%d.norm" % b)
             dwt = torch.zeros(c_tr, c_out, dtype=torch.float32, device=dev)
-            _lib.check(lib.eml_wgrad_1x1(_lib.ptr(dt), dt.shape[3], c_tr, _lib.ptr(slab), pitch, c_out, _lib.ptr(a_t[0]), _lib.ptr(a_t[1]),
-                                         1, 1, h, w, _lib.ptr(dwt), Mp, _lib.PRECISIONS[self.precision], st), "eml_wgrad_1x1(transition%d)" % b)
+            if self.precision != "fp32" and (dt.shape[3] & 3) == 0:
+                # pooled activation once, then the tensor-core wgrad (K = pooled pixels) per slice of <= 64 output channels
+                ap = torch.empty(B, h // 2, w // 2, _up4(c_out), dtype=torch.float32, device=dev)
+                _lib.check(lib.eml_pool_act(_lib.ptr(slab), pitch, _lib.ptr(a_t[0]), _lib.ptr(a_t[1]), B, h, w, c_out, _lib.ptr(ap), ap.shape[3], st),
+                           "eml_pool_act(transition%d)" % b)
+                for n0 in range(0, c_tr, 64):
+                    nn_ = min(64, c_tr - n0)
+                    _lib.check(lib.eml_wgrad_1x1(c_void_p(dt.data_ptr() + 4 * n0), dt.shape[3], nn_, _lib.ptr(ap), ap.shape[3], c_out, None, None,
+                                                 0, 0, h // 2, w // 2, c_void_p(dwt.data_ptr() + 4 * n0 * c_out), Mp, _lib.PRECISIONS[self.precision], st),
+                               "eml_wgrad_1x1(transition%d)" % b)
+                del ap
+            else:
+                _lib.check(lib.eml_wgrad_1x1(_lib.ptr(dt), dt.shape[3], c_tr, _lib.ptr(slab), pitch, c_out, _lib.ptr(a_t[0]), _lib.ptr(a_t[1]),
+                                             1, 1, h, w, _lib.ptr(dwt), Mp, _lib.PRECISIONS[self.precision], st), "eml_wgrad_1x1(transition%d)" % b)
             out["features.transition%d.conv.weight" % b] = dwt.view(c_tr, c_out, 1, 1)
             bn_bwd("t%d.norm" % b, tr.norm, "features.transition%d.norm" % b, _lib.ptr(dp), dp.shape[3], _lib.ptr(slab), pitch, pre, 1, 1,
                    h, w, M, c_out, _lib.ptr(dS), pitch, 1)

@@ -278,6 +278,11 @@ int eml_wgrad_1x1(const float *G, int g_pitch, int N, const float *x, int x_pitc
 int eml_wgrad_3x3(const float *dY, int dy_pitch, int N, const float *b, int b_pitch, int C, const float *scale, const float *shift,
                   float *dW, int B, int H, int W, int precision, void *stream);
 int eml_wgrad_stem(const float *dZ, int dz_pitch, int O, const float *x_nchw, float *dW, int B, int H, int W, void *stream);
+/* The transition's pooled activation (DenseNet.py:14-21, pooling commuted in front of the 1x1 conv), NHWC:
+ *   out[b, y, x, c] = mean_{2x2} relu(scale[c] in[b, 2y+dy, 2x+dx, c] + shift[c]);  out_pitch >= round_up4(C), channels C..round_up4(C) zero.
+ * Materialised once per transition so that its weight gradient runs on the tensor-core eml_wgrad_1x1 path (pool = 0 on `out`). */
+int eml_pool_act(const float *in, int in_pitch, const float *scale, const float *shift, int B, int H, int W, int C, float *out, int out_pitch,
+                 void *stream);
 
 /* Fused backward of norm1 -> relu1 -> conv1 (DenseNet.py:30-37) into the block's gradient slab (csrc/dense_bwd1.cu), training-mode BN:
  *   dA = dN W1 on tensor cores, never written to memory;  g = dA * [sc x + sh > 0];  dS[:, c] += k1[c] g  (in place);
