@@ -5,7 +5,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_lon
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libemlight_b200.so")
-ABI_VERSION = 19
+ABI_VERSION = 20
 
 EML_CONV_1x1, EML_CONV_3x3, EML_CONV_POOL2 = 0, 1, 2
 EML_PREC_BF16, EML_PREC_BF16X3, EML_PREC_FP32 = 0, 1, 2
@@ -44,6 +44,7 @@ SIGNATURES = {
     "eml_conv_forward": (c_int, [POINTER(ConvParams), c_void_p]),
     "eml_dense_layer_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "eml_dense_layer_forward": (c_int, [POINTER(DenseLayerParams), c_void_p]),
+    "eml_dense_layer_wpack_bytes": (c_size_t, [c_int]),
     "eml_dense_layer_compose": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "eml_stem_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_long,
                                  c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

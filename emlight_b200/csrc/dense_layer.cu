@@ -70,7 +70,12 @@ template <bool TS> struct FTmem {
     static constexpr int ABASE = UBASE + 4 * F_USTRIDE; // TS only: A ring
 };
 constexpr int F_MAX_C = 320;                            // 5 weight chunks of 64 channels
-constexpr int F_WCHUNK = 2 * F_NPAD * 128;              // bytes of one packed weight chunk [hi | lo] (64 channels)
+constexpr int F_WCHUNK = 2 * F_NPAD * 128;              // POOL (transition) weights: bytes of one eml_conv_pack_weights chunk [hi | lo] (64 channels, SWIZZLE_128B)
+// Dense-layer weights (eml_dense_layer_compose): one UNIT per 32-channel stage, [hi plane | lo plane], each plane 112 rows x 32 bf16 in the
+// K-major NO-SWIZZLE core-matrix layout: element (n, c) at (c / 8) * (112 * 16) + n * 16 + (c % 8) * 2 bytes (LBO = 1792, SBO = 128).
+// 32-channel granularity: C_in = 144 keeps 70 KB resident instead of three 64-channel chunks = 84 KB -- shared memory that goes to the TMA ring.
+constexpr int F_WPLANE = F_NPAD * 64;                   // 7168
+constexpr int F_WUNIT = 2 * F_WPLANE;                   // 14336
 // floats per pixel in the row buffer: template parameter SROW = 36 (packed) or 44 (176 B = 48 B mod 128: the (pixel, quad) stream of the
 // output pass and the per-pixel stores become bank-conflict free; chosen by the host whenever it does not cost a ring stage)
 
@@ -82,7 +87,8 @@ struct FArgs {
     float *out;
     int B, H, W, R;              // R = output rows per band (H % R == 0)
     int C_in, out_pitch, out_choff;
-    int nwchunks, nstg, stages;  // 64-channel weight chunks, 32-channel stages per tile, ring depth
+    int nwchunks, nstg, stages;  // 64-channel weight chunks (POOL), 32-channel stages per tile, ring depth
+    int wbytes;                  // resident weight bytes (dense: nstg units of F_WUNIT; POOL: nwchunks chunks of F_WCHUNK)
     int wide;                    // 0: store the 12 new channels (48 B per pixel); 1: also zero the 4 channels after them (64 B)
     long nbands;
     int pool;                    // transition mode (eml_transition_forward): tile = a PAIR of image rows accumulated into one Z buffer by
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     const int NST = a.stages;
     unsigned char *w_sm = smem + NST * F_STAGE_BYTES;
-    float *s_row = reinterpret_cast<float *>(w_sm + static_cast<size_t>(a.nwchunks) * F_WCHUNK);   // [(W + 2) pixels][36]
+    float *s_row = reinterpret_cast<float *>(w_sm + static_cast<size_t>(a.wbytes));                // [(W + 2) pixels][36]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int TPR = a.pair ? 1 : a.W / F_TILE_M;           // tiles per image row (1 or 2)
 
@@ -426,15 +432,17 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
         // =========================================================== MMA ISSUER
         const bool leader = elect_one();
         if (leader) {
-            const uint32_t bytes = static_cast<uint32_t>(a.nwchunks) * F_WCHUNK;
+            const uint32_t bytes = static_cast<uint32_t>(a.wbytes);
             mbar_expect_tx(bar_w, bytes);
             bulk_g2s(smem_u32(w_sm), a.wpack, bytes, bar_w);
         }
         mbar_wait(bar_w, 0);
         const uint32_t idesc = make_idesc_bf16(F_TILE_M, F_NPAD);
         const uint64_t dA0 = make_sw128_desc(smem_u32(smem));
-        const uint64_t dB0 = make_sw128_desc(smem_u32(w_sm));
-        const uint32_t stage16 = F_STAGE_BYTES >> 4, wchunk16 = F_WCHUNK >> 4, blo16 = (F_NPAD * 128) >> 4;
+        const uint64_t dB0 = POOL ? make_sw128_desc(smem_u32(w_sm)) : make_nosw_desc(smem_u32(w_sm), F_NPAD * 16, 128);
+        const uint32_t stage16 = F_STAGE_BYTES >> 4, wchunk16 = F_WCHUNK >> 4;
+        const uint32_t blo16 = POOL ? (F_NPAD * 128) >> 4 : F_WPLANE >> 4;             // hi -> lo image
+        const uint64_t kadv = POOL ? 2 : (2 * F_NPAD * 16) >> 4;                       // one 16-channel k-step, in 16-byte units
         const int ksteps_total = (a.C_in + 15) >> 4;
         uint32_t g = 0, jt = 0;
         const uint32_t nst_u = static_cast<uint32_t>(NST);
@@ -455,27 +463,29 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
                     tc_fence_after();
                     if (leader) {
                         const int ks = min(2, ksteps_total - 2 * j);
-                        const uint64_t db_hi = dB0 + static_cast<uint64_t>(static_cast<uint32_t>(j >> 1) * wchunk16 + static_cast<uint32_t>(j & 1) * 4);
+                        const uint64_t db_hi = dB0 + (POOL ? static_cast<uint64_t>(static_cast<uint32_t>(j >> 1) * wchunk16 + static_cast<uint32_t>(j & 1) * 4)
+                                                           : static_cast<uint64_t>(static_cast<uint32_t>(j) * (F_WUNIT >> 4)));
                         const uint64_t db_lo = db_hi + blo16;
                         if (TS) {
                             const uint32_t ta = tmem_base + F_ABASE + s * 32u;
                             for (int k = 0; k < ks; ++k) {
-                                const uint64_t adv = static_cast<uint64_t>(k * 2);
-                                umma_bf16_ts(d_tmem, ta + 8 * k, db_hi + adv, idesc, (jj | k) != 0 ? 1u : 0u);
+                                const uint64_t badv = static_cast<uint64_t>(k) * kadv;
+                                umma_bf16_ts(d_tmem, ta + 8 * k, db_hi + badv, idesc, (jj | k) != 0 ? 1u : 0u);
                                 if (SPLIT) {
-                                    umma_bf16_ts(d_tmem, ta + 16 + 8 * k, db_hi + adv, idesc, 1u);
-                                    umma_bf16_ts(d_tmem, ta + 8 * k, db_lo + adv, idesc, 1u);
+                                    umma_bf16_ts(d_tmem, ta + 16 + 8 * k, db_hi + badv, idesc, 1u);
+                                    umma_bf16_ts(d_tmem, ta + 8 * k, db_lo + badv, idesc, 1u);
                                 }
                             }
                             umma_commit(bar_afree + 8 * s);
                         } else {
                             const uint64_t da = dA0 + static_cast<uint64_t>(s * stage16);
                             for (int k = 0; k < ks; ++k) {
-                                const uint64_t adv = static_cast<uint64_t>(k * 2);       // 32 bytes per k-step, in 16-byte units
-                                umma_bf16(d_tmem, da + adv, db_hi + adv, idesc, (jj | k) != 0 ? 1u : 0u);
+                                const uint64_t adv = static_cast<uint64_t>(k * 2);       // A: 32 bytes per k-step, in 16-byte units
+                                const uint64_t badv = static_cast<uint64_t>(k) * kadv;
+                                umma_bf16(d_tmem, da + adv, db_hi + badv, idesc, (jj | k) != 0 ? 1u : 0u);
                                 if (SPLIT) {
-                                    umma_bf16(d_tmem, da + 4 + adv, db_hi + adv, idesc, 1u);   // lo half of the row: + 64 bytes
-                                    umma_bf16(d_tmem, da + adv, db_lo + adv, idesc, 1u);
+                                    umma_bf16(d_tmem, da + 4 + adv, db_hi + badv, idesc, 1u);  // lo half of the row: + 64 bytes
+                                    umma_bf16(d_tmem, da + adv, db_lo + badv, idesc, 1u);
                                 }
                             }
                             umma_commit(bar_empty + 8 * s);
@@ -660,14 +670,16 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
     }
 }
 
-size_t fused_smem(int nwchunks, int W, int stages, int srow = F_GRP) {
-    return static_cast<size_t>(stages) * F_STAGE_BYTES + static_cast<size_t>(nwchunks) * F_WCHUNK + static_cast<size_t>(W == 64 ? 2 * (W + 2) : W + 2) * srow * 4 + 1024;
+size_t fused_smem(size_t wbytes, int W, int stages, int srow = F_GRP) {
+    return static_cast<size_t>(stages) * F_STAGE_BYTES + wbytes + static_cast<size_t>(W == 64 ? 2 * (W + 2) : W + 2) * srow * 4 + 1024;
 }
-int fused_stages(int nwchunks, int W, int srow = F_GRP) {
+int fused_stages(size_t wbytes, int W, int srow = F_GRP) {
     for (int st = F_MAX_STAGES; st >= 4; --st)
-        if (fused_smem(nwchunks, W, st, srow) <= 227 * 1024 - 3400) return st;   // static shared memory (barriers, affine tables: 3344 B) counts too
+        if (fused_smem(wbytes, W, st, srow) <= 227 * 1024 - 3500) return st;     // static shared memory (barriers, affine tables: ~3.4 KB) counts too
     return 0;
 }
+inline size_t dense_wbytes(int C_in) { return static_cast<size_t>((C_in + F_STAGE_C - 1) / F_STAGE_C) * F_WUNIT; }
+inline size_t pool_wbytes(int C_in) { return static_cast<size_t>((C_in + 63) / 64) * F_WCHUNK; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -689,8 +701,10 @@ extern "C" int eml_dense_layer_supported(int H, int W, int C_in, int growth, int
     if (growth != F_G || (W != 64 && W != 128 && W != 256) || H < 2 || C_in <= 0 || C_in > F_MAX_C) return 0;
     if (W == 64 ? (C_in & 1) : (C_in & 3)) return 0;          // output channel offset: 8-byte (W = 64, float2 stores) or 16-byte aligned
     if (precision != EML_PREC_BF16 && precision != EML_PREC_BF16X3) return 0;
-    return fused_stages((C_in + 63) / 64, W) >= 4 ? 1 : 0;
+    return fused_stages(dense_wbytes(C_in), W) >= 4 ? 1 : 0;
 }
+
+extern "C" size_t eml_dense_layer_wpack_bytes(int C_in) { return C_in > 0 ? dense_wbytes(C_in) : 0; }
 
 extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *stream) {
     EML_CHECK_PTR(p); EML_CHECK_PTR(p->in); EML_CHECK_PTR(p->out); EML_CHECK_PTR(p->scale); EML_CHECK_PTR(p->shift);
@@ -747,18 +761,22 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
     if ((reinterpret_cast<uintptr_t>(p->out) & 31u) == 0 && (p->out_pitch & 7) == 0 && !eml_env_flag("EML_DENSE_NARROW_STORE")) {
         if (!pair && (p->out_choff & 7) == 0 && p->out_choff + F_G + 4 <= p->out_pitch) a.wide = 1;
     }
-    a.stages = fused_stages(a.nwchunks, p->W);
-    const bool wide_rows = fused_stages(a.nwchunks, p->W, 44) == a.stages && !eml_env_flag("EML_DENSE_PACKED_ROWS");
-    const char *cw_env = getenv("EML_DENSE_CW");          // A/B switch: converter warps (16 default, 8 = two warpgroups + 8-column stencil pieces)
-    const int cw = cw_env ? atoi(cw_env) : 16;
+    a.wbytes = static_cast<int>(dense_wbytes(p->C_in));
+    const char *cw_env = getenv("EML_DENSE_CW");          // converter warps: 8 (default: two warpgroups, 8-column stencil pieces, ring depth in steps of 2) or 16
+    const int cw = (cw_env && atoi(cw_env) == 16) ? 16 : 8;
     const bool ts = !eml_env_flag("EML_DENSE_SMEM_A");
+    const int gran = ts ? (cw == 8 ? 2 : 4) : 1;          // ring-depth granularity (see below)
+    const int st36 = fused_stages(a.wbytes, p->W), st44 = fused_stages(a.wbytes, p->W, 44);
+    a.stages = st36;
+    // 44-float row-buffer records (bank-conflict-free output pass) whenever that does not cost ring depth
+    const bool wide_rows = (st44 - st44 % gran) == (st36 - st36 % gran) && st44 >= 4 && !eml_env_flag("EML_DENSE_PACKED_ROWS");
     // TS: the ring depth must be a multiple of the number of converter warpgroups, so that a ring slot is always converted by the same
     // warpgroup and every phase of its mbarrier has one in-order waiter.  (A parity wait cannot tell "two completions early" from "done":
     // with e.g. 5 slots and 4 warpgroups the waiter of round k on a slot may arrive before round k - 1 has even landed -- TMA loads of
     // neighbouring stages complete out of order -- pass spuriously and read stale data: seen on B200 as run-to-run differences and hangs.)
-    if (ts) a.stages -= a.stages % (cw == 8 ? 2 : 4);
+    a.stages -= a.stages % gran;
     const bool split = p->precision == EML_PREC_BF16X3;
-    const size_t smem = fused_smem(a.nwchunks, p->W, a.stages, wide_rows ? 44 : F_GRP);
+    const size_t smem = fused_smem(a.wbytes, p->W, a.stages, wide_rows ? 44 : F_GRP);
     const unsigned grid = static_cast<unsigned>(a.nbands < sms ? a.nbands : sms);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto go = [&](auto kern, int threads) -> int {
@@ -785,18 +803,17 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
 // ------------------------------------------------------------------------------------------------ composite filter (once per parameter version)
 // Weff[(dy,dx,o), c] = sum_b W2[o,b,dy,dx] * scale2[b] * W1[b,c]  and  bias9[rc][cc][o] = sum over the taps inside the image of
 // sum_b W2[o,b,dy,dx] * shift2[b]  (file header; RegressionNetwork/DenseNet.py:30-43 has no nonlinearity between conv1 and conv2),
-// accumulated in double and written STRAIGHT into the packed operand image the kernel above reads (the eml_conv_pack_weights layout for
-// C_out = 108 -> 112 rows, taps = 1: per 64-channel chunk [hi | lo], K-major SWIZZLE_128B).  One launch per layer instead of a dozen
-// float64 ATen kernels plus a pack launch.
+// accumulated in double and written STRAIGHT into the packed operand image the kernel above reads (per 32-channel unit [hi | lo], 112 rows,
+// K-major no-swizzle core matrices: F_WUNIT).  One launch per layer instead of a dozen float64 ATen kernels plus a pack launch.
 namespace {
 __global__ void __launch_bounds__(256) dense_compose_kernel(const float *__restrict__ w1, const float *__restrict__ w2, const float *__restrict__ s2,
                                                             const float *__restrict__ t2, int nb, int C_in, unsigned char *__restrict__ out,
                                                             float *__restrict__ bias9) {
-    const int cpt = (C_in + 63) / 64;
-    const long total = static_cast<long>(cpt) * F_NPAD * 64;
+    const int nunits = (C_in + F_STAGE_C - 1) / F_STAGE_C;
+    const long total = static_cast<long>(nunits) * F_NPAD * F_STAGE_C;
     for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int k = static_cast<int>(idx % 64), n = static_cast<int>((idx / 64) % F_NPAD), ch = static_cast<int>(idx / (64L * F_NPAD));
-        const int ci = ch * 64 + k;
+        const int k = static_cast<int>(idx % F_STAGE_C), n = static_cast<int>((idx / F_STAGE_C) % F_NPAD), u = static_cast<int>(idx / (static_cast<long>(F_STAGE_C) * F_NPAD));
+        const int ci = u * F_STAGE_C + k;
         double acc = 0.0;
         if (n < 9 * F_G && ci < C_in) {
             const int tap = n / F_G, o = n - tap * F_G;
@@ -807,10 +824,10 @@ __global__ void __launch_bounds__(256) dense_compose_kernel(const float *__restr
         const float v = static_cast<float>(acc);
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        unsigned char *base = out + static_cast<size_t>(ch) * F_WCHUNK;
-        const uint32_t off = sw128_offset(n, k);
+        unsigned char *base = out + static_cast<size_t>(u) * F_WUNIT;
+        const uint32_t off = static_cast<uint32_t>((k >> 3) * (F_NPAD * 16) + n * 16 + (k & 7) * 2);       // no-swizzle core-matrix layout
         *reinterpret_cast<__nv_bfloat16 *>(base + off) = hi;
-        *reinterpret_cast<__nv_bfloat16 *>(base + static_cast<size_t>(F_NPAD) * 128 + off) = lo;
+        *reinterpret_cast<__nv_bfloat16 *>(base + F_WPLANE + off) = lo;
     }
     if (blockIdx.x == 0 && threadIdx.x < 9 * F_G) {       // (row class, column class, o): taps that fall inside the image
         const int o = threadIdx.x % F_G, cc = (threadIdx.x / F_G) % 3, rc = threadIdx.x / (3 * F_G);
@@ -844,7 +861,7 @@ bool eml_dense_pool_supported(const eml_conv_params *p) {
     if ((p->W != 128 && p->W != 256) || (p->H & 1) || p->C_in > F_MAX_C || (p->C_in & 3) || ((p->C_out + 15) & ~15) != F_NPAD) return false;
     if ((p->out_pitch & 3) || (p->out_choff & 3) || p->scale == nullptr || p->shift == nullptr) return false;
     if (eml_env_flag("EML_NO_TMA_TRANSITION")) return false;
-    return fused_stages((p->C_in + 63) / 64, p->W) >= 4;
+    return fused_stages(pool_wbytes(p->C_in), p->W) >= 4;
 }
 
 int eml_dense_pool_forward(const eml_conv_params *p, cudaStream_t st) {
@@ -880,11 +897,12 @@ int eml_dense_pool_forward(const eml_conv_params *p, cudaStream_t st) {
     a.nwchunks = (p->C_in + 63) / 64;
     a.nstg = (p->C_in + F_STAGE_C - 1) / F_STAGE_C;
     a.pool = 1; a.n_out = p->C_out;
-    a.stages = fused_stages(a.nwchunks, p->W);
+    a.wbytes = static_cast<int>(pool_wbytes(p->C_in));
+    a.stages = fused_stages(a.wbytes, p->W);
     if (!eml_env_flag("EML_DENSE_SMEM_A")) a.stages &= ~3;          // TS: ring depth a multiple of the 4 converter warpgroups (see eml_dense_layer_forward)
     a.nbands = static_cast<long>(p->B) * (p->H / R);
     const bool split = p->precision == EML_PREC_BF16X3;
-    const size_t smem = fused_smem(a.nwchunks, p->W, a.stages);
+    const size_t smem = fused_smem(a.wbytes, p->W, a.stages);
     const unsigned grid = static_cast<unsigned>(a.nbands < sms ? a.nbands : sms);
     auto go = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

@@ -311,7 +311,7 @@ class DenseNet(nn.Module):
                     continue                            # weights than shared memory holds): it keeps the two-kernel path
                 s2, t2 = self._aff(c, "b%d.l%d.norm2" % (b, l))
                 nb = layer.conv1.out_channels
-                buf = torch.empty(lib.eml_conv_wpack_bytes(9 * g, ci, 1), dtype=torch.uint8, device=dev)
+                buf = torch.empty(lib.eml_dense_layer_wpack_bytes(ci), dtype=torch.uint8, device=dev)
                 # one launch per layer: fp64 composition written straight into the packed operand image (csrc/dense_layer.cu)
                 _lib.check(lib.eml_dense_layer_compose(_lib.ptr(c["w"]["b%d.l%d.conv1" % (b, l)]), _lib.ptr(c["w"]["b%d.l%d.conv2" % (b, l)]),
                                                        _lib.ptr(s2), _lib.ptr(t2), nb, ci, g, _lib.ptr(buf), _lib.ptr(bias_all[i]), st),

@@ -157,8 +157,10 @@ int eml_dense_layer_supported(int H, int W, int C_in, int growth, int precision)
 int eml_dense_layer_forward(const eml_dense_layer_params *p, void *stream);
 /* The composite operands of eml_dense_layer_forward, built on the device once per parameter version (fp64 accumulation):
  *   w1 (nb, C_in) = conv1.weight (DenseNet.py:37), w2 (growth, nb, 3, 3) = conv2.weight (:42), scale2 / shift2 (nb) = folded norm2 (:41)
- *   wpack <- Weff[(dy,dx,o), c] = sum_b w2[o,b,dy,dx] scale2[b] w1[b,c], packed like eml_conv_pack_weights(C_out = 9 growth, taps = 1)
- *            (eml_conv_wpack_bytes(9 * growth, C_in, 1) bytes);  bias9 (3,3,growth) <- the norm2 shift through the in-image taps. */
+ *   wpack <- Weff[(dy,dx,o), c] = sum_b w2[o,b,dy,dx] scale2[b] w1[b,c] as bf16 hi / lo in the layout eml_dense_layer_forward reads
+ *            (eml_dense_layer_wpack_bytes(C_in) bytes; the only producer of that operand);  bias9 (3,3,growth) <- the norm2 shift
+ *            through the in-image taps. */
+size_t eml_dense_layer_wpack_bytes(int C_in);
 int eml_dense_layer_compose(const float *w1, const float *w2, const float *scale2, const float *shift2, int nb, int C_in, int growth,
                             void *wpack, float *bias9, void *stream);
 

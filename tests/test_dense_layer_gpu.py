@@ -30,7 +30,9 @@ def compose(w1, s2, t2, w2):
     return weff, bias9.float().contiguous()
 
 
-def run_fused(lib, cuda, x, c_in, s1, t1, weff, bias9, precision, rows=None):
+def run_fused(lib, cuda, x, c_in, s1, t1, w1, s2, t2, w2, precision, rows=None):
+    """The product path: eml_dense_layer_compose (composite filter + bias table on the device, written straight into the packed operand)
+    then eml_dense_layer_forward.  The device-built bias table is also checked against the host restatement above."""
     from emlight_b200 import _lib
     from emlight_b200._lib import DenseLayerParams
     B, H, W, pitch = x.shape
@@ -38,9 +40,13 @@ def run_fused(lib, cuda, x, c_in, s1, t1, weff, bias9, precision, rows=None):
     pad = (c_in + 3) & ~3
     sc = torch.zeros(pad, device=cuda); sc[:c_in] = s1.to(cuda)
     sh = torch.zeros(pad, device=cuda); sh[:c_in] = t1.to(cuda)
-    wd, bd = weff.to(cuda), bias9.to(cuda)
-    wp = torch.empty(lib.eml_conv_wpack_bytes(9 * G, c_in, 1), dtype=torch.uint8, device=cuda)
-    _lib.check(lib.eml_conv_pack_weights(_lib.ptr(wd), _lib.ptr(wp), 9 * G, c_in, 1, _lib.stream_ptr()))
+    wp = torch.empty(lib.eml_dense_layer_wpack_bytes(c_in), dtype=torch.uint8, device=cuda)
+    bd = torch.empty(9 * G, device=cuda)
+    _lib.check(lib.eml_dense_layer_compose(_lib.ptr(w1.reshape(NB, c_in).contiguous().to(cuda)), _lib.ptr(w2.contiguous().to(cuda)),
+                                           _lib.ptr(s2.to(cuda)), _lib.ptr(t2.to(cuda)), NB, c_in, G, _lib.ptr(wp), _lib.ptr(bd), _lib.stream_ptr()),
+               "eml_dense_layer_compose")
+    _, bias9 = compose(w1, s2, t2, w2)
+    assert float((bd.cpu() - bias9.reshape(-1)).abs().max()) <= 1e-5 * float(bias9.abs().max())
     p = DenseLayerParams()
     p.in_, p.scale, p.shift, p.wpack, p.bias9, p.out = (t.data_ptr() for t in (xd, sc, sh, wp, bd, xd))
     p.B, p.H, p.W, p.C_in, p.in_pitch = B, H, W, c_in, pitch
@@ -86,8 +92,7 @@ def test_dense_layer_matches_reference(lib, cuda, case, precision):
     t2 = 0.3 * torch.randn(NB, generator=g)
     w2 = torch.randn(G, NB, 3, 3, generator=g) / np.sqrt(9 * NB)
     ref = layer_ref(x, c_in, s1, t1, w1, s2, t2, w2)
-    weff, bias9 = compose(w1, s2, t2, w2)
-    out = run_fused(lib, cuda, x, c_in, s1, t1, weff, bias9, precision, rows)
+    out = run_fused(lib, cuda, x, c_in, s1, t1, w1, s2, t2, w2, precision, rows)
     got = out[..., c_in:c_in + G].double()
     err = (got - ref).abs().max().item() / ref.abs().max().item()
     assert err < TOL[precision], err
