@@ -71,11 +71,16 @@ template <bool TS> struct FTmem {
 };
 constexpr int F_MAX_C = 320;                            // 5 weight chunks of 64 channels
 constexpr int F_WCHUNK = 2 * F_NPAD * 128;              // POOL (transition) weights: bytes of one eml_conv_pack_weights chunk [hi | lo] (64 channels, SWIZZLE_128B)
-// Dense-layer weights (eml_dense_layer_compose): one UNIT per 32-channel stage, [hi plane | lo plane], each plane 112 rows x 32 bf16 in the
-// K-major NO-SWIZZLE core-matrix layout: element (n, c) at (c / 8) * (112 * 16) + n * 16 + (c % 8) * 2 bytes (LBO = 1792, SBO = 128).
-// 32-channel granularity: C_in = 144 keeps 70 KB resident instead of three 64-channel chunks = 84 KB -- shared memory that goes to the TMA ring.
-constexpr int F_WPLANE = F_NPAD * 64;                   // 7168
-constexpr int F_WUNIT = 2 * F_WPLANE;                   // 14336
+// Dense-layer weights (eml_dense_layer_compose): one UNIT per 32-channel stage, [hi plane | lo plane], each plane 120 rows x 32 bf16 in the
+// K-major NO-SWIZZLE core-matrix layout: element (n, c) at (c / 8) * (120 * 16) + n * 16 + (c % 8) * 2 bytes (LBO = 1920, SBO = 128).
+// 32-channel granularity: C_in = 144 keeps 75 KB resident instead of three 64-channel chunks = 84 KB -- shared memory that goes to the TMA ring.
+// The plane has 120 rows: rows 0-107 = (dy, dx, o), 12 zero rows behind them, because the row-sum kernels read one 36-row tap group
+// (dy) as an N = 48 operand -- rows are uniformly 16 B apart (SBO = 128), so a group is just a start-address shift of 36 * 16 B.
+constexpr int F_WROWS = 120;
+constexpr int F_WPLANE = F_WROWS * 64;                  // 7680
+constexpr int F_WUNIT = 2 * F_WPLANE;                   // 15360
+constexpr int F_RN = 48;                                // row-sum kernels: MMA N (36 used) = TMEM columns per output-row accumulator
+constexpr int F_NT = 8;                                 // row-sum kernels: ring of "tile done" barriers
 // floats per pixel in the row buffer: template parameter SROW = 36 (packed) or 44 (176 B = 48 B mod 128: the (pixel, quad) stream of the
 // output pass and the per-pixel stores become bank-conflict free; chosen by the host whenever it does not cost a ring stage)
 
@@ -89,7 +94,10 @@ struct FArgs {
     int C_in, out_pitch, out_choff;
     int nwchunks, nstg, stages;  // 64-channel weight chunks (POOL), 32-channel stages per tile, ring depth
     int wbytes;                  // resident weight bytes (dense: nstg units of F_WUNIT; POOL: nwchunks chunks of F_WCHUNK)
-    int wide;                    // 0: store the 12 new channels (48 B per pixel); 1: also zero the 4 channels after them (64 B)
+    int wide;                    // 0: store the 12 new channels (48 B per pixel); 1: also zero the 4 channels after them (64 B);
+                                 // 2: channels start mid-sector (offset = 4 mod 8): re-store the 4 channels IN FRONT with them (64 B, two
+                                 //    full sectors) from a stash of this layer's own raw input that the converters fill (TS, in == out)
+    int stash_rows;              // wide == 2: image rows in the stash ring
     long nbands;
     int pool;                    // transition mode (eml_transition_forward): tile = a PAIR of image rows accumulated into one Z buffer by
                                  // the tensor core (vertical half of the 2x2 average), epilogue = horizontal pair sum, x 0.25, N channels out
@@ -231,13 +239,16 @@ __device__ __forceinline__ void band_init(BandIter &it, const FArgs &a, long ban
 
 template <bool SPLIT, bool POOL, int F_SROW, bool TS, int NCW = 16, int PW = 4>
 __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __grid_constant__ CUtensorMap tmap, const FArgs a) {
-    constexpr int F_NZ = FTmem<TS>::NZ, F_UBASE = FTmem<TS>::UBASE, F_ABASE = FTmem<TS>::ABASE;
+    constexpr int F_NZ = FTmem<TS>::NZ, F_UBASE = FTmem<TS>::UBASE;
+    // row-sum kernels: 4 output rows x 2 half rows x 48 columns of accumulators (384), then the A ring (128) = all 512 columns
+    constexpr int F_ABASE = (TS && !POOL) ? 8 * F_RN : FTmem<TS>::ABASE;
     constexpr int F_CWARPS = NCW, F_TMA_WARP = NCW, F_MMA_WARP = NCW + 1, F_EPI_WARP0 = NCW + 4, F_THREADS = f_threads(NCW);
     constexpr int NCWG = NCW / 4;                          // converter warpgroups
     static_assert(NCW == 16 || (TS && NCW == 8), "converter warps: 16, or 8 with the TMEM-resident A operand");
     static_assert(PW == 4 || PW == 8, "stencil piece width");
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long s_bar[3 * F_MAX_STAGES + 1 + 2 * F_MAX_NZ + F_NA];
+    constexpr bool RS = TS && !POOL;                       // row-sum design: the MMAs add the three vertical taps into per-output-row accumulators
+    __shared__ __align__(8) unsigned long long s_bar[3 * F_MAX_STAGES + 1 + 2 * F_MAX_NZ + F_NA + F_NT + 8];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_scale[F_MAX_C], s_shift[F_MAX_C], s_bias[9 * F_G + 4];
 
@@ -255,12 +266,16 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
     const uint32_t bar_zfull = smem_u32(&s_bar[3 * F_MAX_STAGES + 1]);      // [F_NZ]
     const uint32_t bar_zempty = smem_u32(&s_bar[3 * F_MAX_STAGES + 1 + F_MAX_NZ]);   // [F_NZ]
     const uint32_t bar_afree = smem_u32(&s_bar[3 * F_MAX_STAGES + 1 + 2 * F_MAX_NZ]);    // [F_NA]  TS: MMAs that read TMEM A slot a are done
+    const uint32_t bar_tfull = smem_u32(&s_bar[3 * F_MAX_STAGES + 1 + 2 * F_MAX_NZ + F_NA]);          // [F_NT] RS: all MMAs of a tile are done
+    const uint32_t bar_rfree = smem_u32(&s_bar[3 * F_MAX_STAGES + 1 + 2 * F_MAX_NZ + F_NA + F_NT]);   // [8]    RS: a row accumulator was drained
     // TS reuses bar_ready[0 .. F_NA) as "A slot written" (4 converter warps arrive) and bar_empty[s] is armed by the converters (4 warps:
     // the raw stage has been read), not by the MMA commits
 
     if (tid == 0) {
         for (int s = 0; s < F_MAX_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_ready + 8 * s, 4); mbar_init(bar_empty + 8 * s, TS ? 4 : 1); }
         for (int i = 0; i < F_NA; ++i) mbar_init(bar_afree + 8 * i, 1);
+        for (int i = 0; i < F_NT; ++i) mbar_init(bar_tfull + 8 * i, 1);
+        for (int i = 0; i < 8; ++i) mbar_init(bar_rfree + 8 * i, 4);
         mbar_init(bar_w, 1);
         for (int i = 0; i < F_MAX_NZ; ++i) { mbar_init(bar_zfull + 8 * i, 1); mbar_init(bar_zempty + 8 * i, 4); }
         fence_mbar_init();
@@ -304,12 +319,21 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
         }
         const uint32_t nst_u = static_cast<uint32_t>(NST), nstg_u = static_cast<uint32_t>(a.nstg);
         const int c16 = (a.C_in + 15) & ~15;                                     // channels the MMAs read (whole k-steps)
+        // wide == 2: the raw values of the layer's last four input channels (= the four slab channels in front of its output) are kept per
+        // pixel in a ring of image rows, from where the output pass re-stores them together with the 12 new channels as two full sectors
+        const int js = (a.C_in - 4) / F_STAGE_C, qs = ((a.C_in - 4) % F_STAGE_C) >> 2;
+        float4 *s_stash = reinterpret_cast<float4 *>(s_row + (a.W + 2) * F_SROW);
+        long sb_band = blockIdx.x;
+        uint32_t sb_tile0 = 0, sb_row0 = 0, sb_nt = 0;
+        if (!POOL && a.wide == 2) { BandIter it; band_init<POOL>(it, a, sb_band); sb_nt = static_cast<uint32_t>(it.nt); }
         for (uint32_t g = static_cast<uint32_t>(cg); g < total; g += NCWG) {
             const uint32_t s = g % nst_u, ph = (g / nst_u) & 1, as = g & 3u, aph = (g >> 2) & 1;
             const uint32_t a_slot = a_lane + as * 32u;
             const int j = static_cast<int>(g % nstg_u);
             const int halves = c16 - j * F_STAGE_C > 16 ? 2 : 1;                  // a partial last stage holds one k-step only
             const uint32_t st = ring + s * F_STAGE_BYTES + row_off;
+            const bool stash = !POOL && a.wide == 2 && j == js;
+            float4 stash_v = make_float4(0.f, 0.f, 0.f, 0.f);
             mbar_wait(bar_full + 8 * s, ph);
             uint32_t hi[2][8], lo[2][8];
 #pragma unroll
@@ -320,6 +344,7 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
                         float4 v;
                         const uint32_t chunk = static_cast<uint32_t>(4 * h + q);
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(st + ((chunk ^ r7) << 4)) : "memory");
+                        if (stash && 4 * h + q == qs) stash_v = v;
                         const float4 sc = *reinterpret_cast<const float4 *>(&s_scale[j * F_STAGE_C + 16 * h + 4 * q]);
                         const float4 sh = *reinterpret_cast<const float4 *>(&s_shift[j * F_STAGE_C + 16 * h + 4 * q]);
                         uint2 hv, lv;
@@ -328,6 +353,16 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
                         lo[h][2 * q] = lv.x; lo[h][2 * q + 1] = lv.y;
                     }
                 }
+            }
+            if (stash) {                                                          // tile ordinal -> (row sequence number, half row)
+                const uint32_t tg = g / nstg_u, tpr = static_cast<uint32_t>(TPR);
+                while (tg >= sb_tile0 + sb_nt) {
+                    sb_tile0 += sb_nt; sb_row0 += sb_nt / tpr; sb_band += grid;
+                    BandIter it; band_init<POOL>(it, a, sb_band); sb_nt = static_cast<uint32_t>(it.nt);
+                }
+                const uint32_t tl = tg - sb_tile0;
+                const uint32_t rseq = sb_row0 + tl / tpr, half = tl % tpr;
+                s_stash[(rseq % static_cast<uint32_t>(a.stash_rows)) * a.W + half * F_TILE_M + row] = stash_v;
             }
             __syncwarp();                                                         // every lane's loads have been consumed
             if (lane == 0) f_mbar_arrive(bar_empty + 8 * s);                      // raw stage free: the TMA warp may refill it
@@ -439,13 +474,73 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
         mbar_wait(bar_w, 0);
         const uint32_t idesc = make_idesc_bf16(F_TILE_M, F_NPAD);
         const uint64_t dA0 = make_sw128_desc(smem_u32(smem));
-        const uint64_t dB0 = POOL ? make_sw128_desc(smem_u32(w_sm)) : make_nosw_desc(smem_u32(w_sm), F_NPAD * 16, 128);
+        const uint64_t dB0 = POOL ? make_sw128_desc(smem_u32(w_sm)) : make_nosw_desc(smem_u32(w_sm), F_WROWS * 16, 128);
         const uint32_t stage16 = F_STAGE_BYTES >> 4, wchunk16 = F_WCHUNK >> 4;
         const uint32_t blo16 = POOL ? (F_NPAD * 128) >> 4 : F_WPLANE >> 4;             // hi -> lo image
-        const uint64_t kadv = POOL ? 2 : (2 * F_NPAD * 16) >> 4;                       // one 16-channel k-step, in 16-byte units
+        const uint64_t kadv = POOL ? 2 : (2 * F_WROWS * 16) >> 4;                      // one 16-channel k-step, in 16-byte units
         const int ksteps_total = (a.C_in + 15) >> 4;
         uint32_t g = 0, jt = 0;
         const uint32_t nst_u = static_cast<uint32_t>(NST);
+        if constexpr (RS) {
+            // ---- row-sum issue loop.  Z row rho (image row rho) contributes through vertical tap dy to output row r = rho + 1 - dy:
+            //   R[r % 4][half] (+)= A(rho) * W[dy]^T      (N = 48: the tap group's 36 rows + 12 rows of the next group, columns never read)
+            // so the vertical part of the 3x3 stencil is done by the accumulate flag: the tap that reaches a row first (dy = 0 from the row
+            // above; dy = 1 for image row 0) initialises the accumulator, a row is complete when the tile BELOW it is done, and halo rows
+            // of a band issue one tap only.  The MMA warp runs up to two rows ahead of the epilogue, which merely drains finished rows.
+            const uint32_t idesc_rs = make_idesc_bf16(F_TILE_M, F_RN);
+            const uint64_t dBr = make_nosw_desc(smem_u32(w_sm), F_WROWS * 16, 128);
+            const uint64_t kadv_r = (2 * F_WROWS * 16) >> 4, blo_r = F_WPLANE >> 4, tap16 = (3 * F_G * 16) >> 4;
+            uint32_t rpar = 0;                                    // per accumulator: parity of its next "drained" wait
+            for (long band = blockIdx.x; band < a.nbands; band += grid) {
+                BandIter it;
+                band_init<POOL>(it, a, band);
+                const int bpi = a.H / a.R;
+                const int r0 = static_cast<int>(band % bpi) * a.R, rlo = max(r0 - 1, 0), rend = r0 + a.R - 1;
+                for (int t = 0; t < it.nt; ++t, ++jt) {
+                    const int rho = rlo + t / TPR, half = t % TPR;
+                    bool valid[3], init[3];
+                    uint32_t dcol[3];
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const int r = rho + 1 - dy;
+                        valid[dy] = r >= r0 && r <= rend;
+                        init[dy] = valid[dy] && (dy == 0 || (dy == 1 && rho == rlo));    // dy = 1 starts a row only when there is no row above (rho = rlo = r0 = 0)
+                        const uint32_t idx = static_cast<uint32_t>((r & 3) * 2 + half);
+                        dcol[dy] = tmem_base + idx * F_RN;
+                        if (init[dy]) {                                           // the accumulator's previous row must have been drained
+                            mbar_wait(bar_rfree + 8 * idx, ((rpar >> idx) & 1u) ^ 1u);
+                            rpar ^= 1u << idx;
+                        }
+                    }
+                    tc_fence_after();
+                    for (int jj = 0; jj < a.nstg; ++jj, ++g) {
+                        const uint32_t s = g & 3u, ph = (g >> 2) & 1;
+                        mbar_wait(bar_ready + 8 * s, ph);
+                        tc_fence_after();
+                        if (leader) {
+                            const int ks = min(2, ksteps_total - 2 * jj);
+                            const uint64_t db_hi = dBr + static_cast<uint64_t>(static_cast<uint32_t>(jj) * (F_WUNIT >> 4));
+                            const uint32_t ta = tmem_base + F_ABASE + s * 32u;
+                            for (int k = 0; k < ks; ++k) {
+#pragma unroll
+                                for (int dy = 0; dy < 3; ++dy) {
+                                    if (!valid[dy]) continue;
+                                    const uint64_t b = db_hi + static_cast<uint64_t>(k) * kadv_r + static_cast<uint64_t>(dy) * tap16;
+                                    umma_bf16_ts(dcol[dy], ta + 8 * k, b, idesc_rs, (init[dy] && (jj | k) == 0) ? 0u : 1u);
+                                    if (SPLIT) {
+                                        umma_bf16_ts(dcol[dy], ta + 16 + 8 * k, b, idesc_rs, 1u);
+                                        umma_bf16_ts(dcol[dy], ta + 8 * k, b + blo_r, idesc_rs, 1u);
+                                    }
+                                }
+                            }
+                            umma_commit(bar_afree + 8 * s);
+                            if (jj == a.nstg - 1) umma_commit(bar_tfull + 8 * (jt & (F_NT - 1)));
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        } else
         for (long band = blockIdx.x; band < a.nbands; band += grid) {
             BandIter it;
             band_init<POOL>(it, a, band);
@@ -549,12 +644,15 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
             }
         } else if (!POOL && active) {
             uint32_t j = 0;                                   // tile counter (all tiles of this CTA, both halves)
+            uint32_t rs = 0;                                  // row sequence number (all Z rows of this CTA): index into the stash ring
+            const float4 *s_stash = reinterpret_cast<const float4 *>(s_row + (a.W + 2) * F_SROW);
             for (long band = blockIdx.x; band < a.nbands; band += grid) {
                 const int bpi = a.H / a.R;
                 const long img = (band / bpi) * (a.pair ? 2 : 1);
                 const int r0 = static_cast<int>(band % bpi) * a.R;
                 const int rlo = max(r0 - 1, 0), rhi = min(r0 + a.R, a.H - 1), rend = r0 + a.R - 1;    // rend = last output row
                 for (int rho = rlo; rho <= rhi; ++rho) {
+                    const uint32_t rseq = rs++;
                     // ---- this warpgroup's tile of Z row rho
                     const uint32_t jt = j + static_cast<uint32_t>(wg);
                     j += static_cast<uint32_t>(TPR);
@@ -568,6 +666,31 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
                     const uint32_t us0 = lane_addr + F_UBASE + ((((rho + 1) & 1) * 2 + wg) * F_USTRIDE);   // U[rho-1] in, U[rho+1] out
                     const uint32_t us1 = lane_addr + F_UBASE + (((rho & 1) * 2 + wg) * F_USTRIDE);         // U[rho]
                     float *srow = s_row + (wg * F_TILE_M + px + 1 + (a.pair ? 2 * (px >> 6) : 0)) * F_SROW;
+                    if constexpr (RS) {
+                        // the tile of Z row rho is done -> output row rho - 1 is complete in its accumulator: copy it to the row buffer
+                        mbar_wait(bar_tfull + 8 * (jt & (F_NT - 1)), (jt / F_NT) & 1);
+                        __syncwarp();
+                        tc_fence_after();
+                        if (emit) {
+                            const uint32_t idx = static_cast<uint32_t>(((rho - 1) & 3) * 2 + wg);
+                            const uint32_t rc0 = lane_addr + idx * F_RN;
+                            float v0[8], v1[8], v2[8], v3[8], v4[4];
+                            f_tmem_ld<8>(rc0, v0); f_tmem_ld<8>(rc0 + 8, v1); f_tmem_ld<8>(rc0 + 16, v2); f_tmem_ld<8>(rc0 + 24, v3); f_tmem_ld<4>(rc0 + 32, v4);
+                            f_tmem_wait_ld<8>(v0); f_tmem_wait_ld<8>(v1); f_tmem_wait_ld<8>(v2); f_tmem_wait_ld<8>(v3); f_tmem_wait_ld<4>(v4);
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) f_mbar_arrive(bar_rfree + 8 * idx);    // the MMA warp may start another row in this accumulator
+                            *reinterpret_cast<float4 *>(srow) = make_float4(v0[0], v0[1], v0[2], v0[3]);
+                            *reinterpret_cast<float4 *>(srow + 4) = make_float4(v0[4], v0[5], v0[6], v0[7]);
+                            *reinterpret_cast<float4 *>(srow + 8) = make_float4(v1[0], v1[1], v1[2], v1[3]);
+                            *reinterpret_cast<float4 *>(srow + 12) = make_float4(v1[4], v1[5], v1[6], v1[7]);
+                            *reinterpret_cast<float4 *>(srow + 16) = make_float4(v2[0], v2[1], v2[2], v2[3]);
+                            *reinterpret_cast<float4 *>(srow + 20) = make_float4(v2[4], v2[5], v2[6], v2[7]);
+                            *reinterpret_cast<float4 *>(srow + 24) = make_float4(v3[0], v3[1], v3[2], v3[3]);
+                            *reinterpret_cast<float4 *>(srow + 28) = make_float4(v3[4], v3[5], v3[6], v3[7]);
+                            *reinterpret_cast<float4 *>(srow + 32) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+                        }
+                    } else {
                     mbar_wait(bar_zfull + 8 * zb, zph);
                     __syncwarp();
                     tc_fence_after();
@@ -585,6 +708,7 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) f_mbar_arrive(bar_zempty + 8 * zb);        // Z buffer drained: the MMA warp may refill it
+                    }
                     // ---- completed rows: U row -> shared row buffer -> 3-tap horizontal sum + bias -> slab
                     for (int pass = 0; pass < 2; ++pass) {
                         int orow;
@@ -593,22 +717,50 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
                             if (!flush) continue;
                             orow = rho;
                             float z4[4];
+                            const uint32_t fidx = static_cast<uint32_t>((rho & 3) * 2 + wg);
+                            const uint32_t fsrc = RS ? lane_addr + fidx * F_RN : us1;   // RS: the bottom row's own accumulator (complete: nothing below it)
 #pragma unroll
                             for (int piece = 0; piece < 4; ++piece) {            // rare (once per image): no need to batch
                                 float z[8];
-                                f_tmem_ld<8>(us1 + piece * 8, z);
+                                f_tmem_ld<8>(fsrc + piece * 8, z);
                                 f_tmem_wait_ld<8>(z);
                                 *reinterpret_cast<float4 *>(srow + piece * 8) = make_float4(z[0], z[1], z[2], z[3]);
                                 *reinterpret_cast<float4 *>(srow + piece * 8 + 4) = make_float4(z[4], z[5], z[6], z[7]);
                             }
-                            f_tmem_ld<4>(us1 + 32, z4);
+                            f_tmem_ld<4>(fsrc + 32, z4);
                             f_tmem_wait_ld<4>(z4);
                             *reinterpret_cast<float4 *>(srow + 32) = make_float4(z4[0], z4[1], z4[2], z4[3]);
+                            if constexpr (RS) {
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) f_mbar_arrive(bar_rfree + 8 * fidx);
+                            }
                         }
                         asm volatile("bar.sync 1, %0;" ::"r"(nE) : "memory");     // the whole row is staged
                         const int rc = orow == 0 ? 0 : (orow == a.H - 1 ? 2 : 1);
                         float *obase = a.out + ((img * a.H + orow) * a.W) * a.out_pitch + a.out_choff;
-                        if (a.wide == 0) {
+                        if (a.wide == 2) {
+                            // 64 bytes per pixel starting 4 channels IN FRONT of the new ones: [4 stashed raw channels | 12 new channels]
+                            const float4 *srow4 = s_stash + ((pass == 0 ? rseq - 1 : rseq) % static_cast<uint32_t>(a.stash_rows)) * a.W;
+                            for (int f = et; f < a.W * 4; f += nE) {
+                                const int x = f >> 2, qd = f & 3;                          // qd 0: the stashed quad; 1..3: quads of the new channels
+                                float *dst = obase + static_cast<long>(x) * a.out_pitch + (qd - 1) * 4;
+                                float4 o;
+                                if (qd == 0) {
+                                    o = srow4[x];
+                                } else {
+                                    const float *s0 = s_row + x * F_SROW + (qd - 1) * 4;
+                                    const float4 v0 = *reinterpret_cast<const float4 *>(s0);
+                                    const float4 v1 = *reinterpret_cast<const float4 *>(s0 + F_SROW + F_G);
+                                    const float4 v2 = *reinterpret_cast<const float4 *>(s0 + 2 * F_SROW + 2 * F_G);
+                                    const int cc = x == 0 ? 0 : (x == a.W - 1 ? 2 : 1);
+                                    const float4 bb = *reinterpret_cast<const float4 *>(&s_bias[(rc * 3 + cc) * F_G + (qd - 1) * 4]);
+                                    o.x = v0.x + v1.x + v2.x + bb.x; o.y = v0.y + v1.y + v2.y + bb.y;
+                                    o.z = v0.z + v1.z + v2.z + bb.z; o.w = v0.w + v1.w + v2.w + bb.w;
+                                }
+                                *reinterpret_cast<float4 *>(dst) = o;
+                            }
+                        } else if (a.wide == 0) {
                             const int npx = a.pair ? 2 * a.W : a.W;                    // pixels staged per row (pair mode: two images)
                             const bool al16 = (a.out_choff & 3) == 0;                  // block 3 starts its channels on an 8-byte boundary only
                             for (int f = et; f < npx * 3; f += nE) {
@@ -670,12 +822,12 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
     }
 }
 
-size_t fused_smem(size_t wbytes, int W, int stages, int srow = F_GRP) {
-    return static_cast<size_t>(stages) * F_STAGE_BYTES + wbytes + static_cast<size_t>(W == 64 ? 2 * (W + 2) : W + 2) * srow * 4 + 1024;
+size_t fused_smem(size_t wbytes, int W, int stages, int srow = F_GRP, size_t extra = 0) {
+    return static_cast<size_t>(stages) * F_STAGE_BYTES + wbytes + static_cast<size_t>(W == 64 ? 2 * (W + 2) : W + 2) * srow * 4 + extra + 1024;
 }
-int fused_stages(size_t wbytes, int W, int srow = F_GRP) {
+int fused_stages(size_t wbytes, int W, int srow = F_GRP, size_t extra = 0) {
     for (int st = F_MAX_STAGES; st >= 4; --st)
-        if (fused_smem(wbytes, W, st, srow) <= 227 * 1024 - 3500) return st;     // static shared memory (barriers, affine tables: ~3.4 KB) counts too
+        if (fused_smem(wbytes, W, st, srow, extra) <= 227 * 1024 - 3500) return st;   // static shared memory (barriers, affine tables: ~3.4 KB) counts too
     return 0;
 }
 inline size_t dense_wbytes(int C_in) { return static_cast<size_t>((C_in + F_STAGE_C - 1) / F_STAGE_C) * F_WUNIT; }
@@ -766,7 +918,19 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
     const int cw = (cw_env && atoi(cw_env) == 16) ? 16 : 8;
     const bool ts = !eml_env_flag("EML_DENSE_SMEM_A");
     const int gran = ts ? (cw == 8 ? 2 : 4) : 1;          // ring-depth granularity (see below)
-    const int st36 = fused_stages(a.wbytes, p->W), st44 = fused_stages(a.wbytes, p->W, 44);
+    // Layers whose channels start mid-sector (offset = 4 mod 8; every other layer of blocks 1 and 2): 48-byte stores leave a half-written
+    // 32-byte sector per pixel -- a read-modify-write in the memory system that costs 0.3-0.4 ms per block-1 layer at B = 256 (tools/
+    // layer_times.py).  With the TMEM-resident A operand the converters hold the layer's raw input in registers, so the 4 channels in front
+    // of the output are stashed (16 B per pixel, a ring of image rows) and re-stored with the new ones: 64 B = two full sectors.
+    size_t stash = 0;
+    if (ts && a.wide == 0 && !pair && (reinterpret_cast<uintptr_t>(p->out) & 31u) == 0 && (p->out_pitch & 7) == 0 && (p->out_choff & 7) == 4 &&
+        p->in == p->out && p->in_pitch == p->out_pitch && p->out_choff == p->C_in && a.nstg >= 2 && !eml_env_flag("EML_DENSE_NARROW_STORE") &&
+        !eml_env_flag("EML_DENSE_NO_STASH")) {
+        a.stash_rows = 1024 / p->W;                            // 4 rows (W = 256) / 8 rows (W = 128): more than the converters can run ahead
+        stash = static_cast<size_t>(a.stash_rows) * p->W * 16;
+        if (fused_stages(a.wbytes, p->W, F_GRP, stash) >= 4) a.wide = 2; else { stash = 0; a.stash_rows = 0; }
+    }
+    const int st36 = fused_stages(a.wbytes, p->W, F_GRP, stash), st44 = fused_stages(a.wbytes, p->W, 44, stash);
     a.stages = st36;
     // 44-float row-buffer records (bank-conflict-free output pass) whenever that does not cost ring depth
     const bool wide_rows = (st44 - st44 % gran) == (st36 - st36 % gran) && st44 >= 4 && !eml_env_flag("EML_DENSE_PACKED_ROWS");
@@ -776,7 +940,7 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
     // neighbouring stages complete out of order -- pass spuriously and read stale data: seen on B200 as run-to-run differences and hangs.)
     a.stages -= a.stages % gran;
     const bool split = p->precision == EML_PREC_BF16X3;
-    const size_t smem = fused_smem(a.wbytes, p->W, a.stages, wide_rows ? 44 : F_GRP);
+    const size_t smem = fused_smem(a.wbytes, p->W, a.stages, wide_rows ? 44 : F_GRP, stash);
     const unsigned grid = static_cast<unsigned>(a.nbands < sms ? a.nbands : sms);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto go = [&](auto kern, int threads) -> int {
@@ -810,9 +974,9 @@ __global__ void __launch_bounds__(256) dense_compose_kernel(const float *__restr
                                                             const float *__restrict__ t2, int nb, int C_in, unsigned char *__restrict__ out,
                                                             float *__restrict__ bias9) {
     const int nunits = (C_in + F_STAGE_C - 1) / F_STAGE_C;
-    const long total = static_cast<long>(nunits) * F_NPAD * F_STAGE_C;
+    const long total = static_cast<long>(nunits) * F_WROWS * F_STAGE_C;
     for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int k = static_cast<int>(idx % F_STAGE_C), n = static_cast<int>((idx / F_STAGE_C) % F_NPAD), u = static_cast<int>(idx / (static_cast<long>(F_STAGE_C) * F_NPAD));
+        const int k = static_cast<int>(idx % F_STAGE_C), n = static_cast<int>((idx / F_STAGE_C) % F_WROWS), u = static_cast<int>(idx / (static_cast<long>(F_STAGE_C) * F_WROWS));
         const int ci = u * F_STAGE_C + k;
         double acc = 0.0;
         if (n < 9 * F_G && ci < C_in) {
@@ -825,7 +989,7 @@ __global__ void __launch_bounds__(256) dense_compose_kernel(const float *__restr
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
         unsigned char *base = out + static_cast<size_t>(u) * F_WUNIT;
-        const uint32_t off = static_cast<uint32_t>((k >> 3) * (F_NPAD * 16) + n * 16 + (k & 7) * 2);       // no-swizzle core-matrix layout
+        const uint32_t off = static_cast<uint32_t>((k >> 3) * (F_WROWS * 16) + n * 16 + (k & 7) * 2);      // no-swizzle core-matrix layout
         *reinterpret_cast<__nv_bfloat16 *>(base + off) = hi;
         *reinterpret_cast<__nv_bfloat16 *>(base + F_WPLANE + off) = lo;
     }

@@ -42,9 +42,10 @@ def run_fused(lib, cuda, x, c_in, s1, t1, w1, s2, t2, w2, precision, rows=None):
     sh = torch.zeros(pad, device=cuda); sh[:c_in] = t1.to(cuda)
     wp = torch.empty(lib.eml_dense_layer_wpack_bytes(c_in), dtype=torch.uint8, device=cuda)
     bd = torch.empty(9 * G, device=cuda)
-    _lib.check(lib.eml_dense_layer_compose(_lib.ptr(w1.reshape(NB, c_in).contiguous().to(cuda)), _lib.ptr(w2.contiguous().to(cuda)),
-                                           _lib.ptr(s2.to(cuda)), _lib.ptr(t2.to(cuda)), NB, c_in, G, _lib.ptr(wp), _lib.ptr(bd), _lib.stream_ptr()),
-               "eml_dense_layer_compose")
+    w1d, w2d, s2d, t2d = w1.reshape(NB, c_in).contiguous().to(cuda), w2.contiguous().to(cuda), s2.to(cuda), t2.to(cuda)   # keep them alive
+    _lib.check(lib.eml_dense_layer_compose(_lib.ptr(w1d), _lib.ptr(w2d), _lib.ptr(s2d), _lib.ptr(t2d), NB, c_in, G, _lib.ptr(wp), _lib.ptr(bd),
+                                           _lib.stream_ptr()), "eml_dense_layer_compose")
+    torch.cuda.synchronize()
     _, bias9 = compose(w1, s2, t2, w2)
     assert float((bd.cpu() - bias9.reshape(-1)).abs().max()) <= 1e-5 * float(bias9.abs().max())
     p = DenseLayerParams()
