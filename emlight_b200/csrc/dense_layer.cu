@@ -825,10 +825,17 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
 size_t fused_smem(size_t wbytes, int W, int stages, int srow = F_GRP, size_t extra = 0) {
     return static_cast<size_t>(stages) * F_STAGE_BYTES + wbytes + static_cast<size_t>(W == 64 ? 2 * (W + 2) : W + 2) * srow * 4 + extra + 1024;
 }
-int fused_stages(size_t wbytes, int W, int srow = F_GRP, size_t extra = 0) {
-    for (int st = F_MAX_STAGES; st >= 4; --st)
-        if (fused_smem(wbytes, W, st, srow, extra) <= 227 * 1024 - 3500) return st;   // static shared memory (barriers, affine tables: ~3.4 KB) counts too
+int fused_stages(size_t wbytes, int W, int srow = F_GRP, size_t extra = 0, int min_stages = 4) {
+    for (int st = F_MAX_STAGES; st >= min_stages; --st)
+        if (fused_smem(wbytes, W, st, srow, extra) <= 227 * 1024 - 3700) return st;   // static shared memory (barriers, affine tables: ~3.6 KB) counts too
     return 0;
+}
+// Smallest ring the pipeline accepts: one slot per converter warpgroup.  The default build (TMEM-resident A, two converter warpgroups)
+// runs with 2 slots when the resident weights leave no more (block 3's widest layers, C_in up to 318: 150 KB of weights).
+inline int dense_min_stages() {
+    if (eml_env_flag("EML_DENSE_SMEM_A")) return 4;
+    const char *cw_env = getenv("EML_DENSE_CW");
+    return (cw_env && atoi(cw_env) == 16) ? 4 : 2;
 }
 inline size_t dense_wbytes(int C_in) { return static_cast<size_t>((C_in + F_STAGE_C - 1) / F_STAGE_C) * F_WUNIT; }
 inline size_t pool_wbytes(int C_in) { return static_cast<size_t>((C_in + 63) / 64) * F_WCHUNK; }
@@ -853,7 +860,7 @@ extern "C" int eml_dense_layer_supported(int H, int W, int C_in, int growth, int
     if (growth != F_G || (W != 64 && W != 128 && W != 256) || H < 2 || C_in <= 0 || C_in > F_MAX_C) return 0;
     if (W == 64 ? (C_in & 1) : (C_in & 3)) return 0;          // output channel offset: 8-byte (W = 64, float2 stores) or 16-byte aligned
     if (precision != EML_PREC_BF16 && precision != EML_PREC_BF16X3) return 0;
-    return fused_stages(dense_wbytes(C_in), W) >= 4 ? 1 : 0;
+    return fused_stages(dense_wbytes(C_in), W, F_GRP, 0, dense_min_stages()) >= dense_min_stages() ? 1 : 0;
 }
 
 extern "C" size_t eml_dense_layer_wpack_bytes(int C_in) { return C_in > 0 ? dense_wbytes(C_in) : 0; }
@@ -930,10 +937,11 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
         stash = static_cast<size_t>(a.stash_rows) * p->W * 16;
         if (fused_stages(a.wbytes, p->W, F_GRP, stash) >= 4) a.wide = 2; else { stash = 0; a.stash_rows = 0; }
     }
-    const int st36 = fused_stages(a.wbytes, p->W, F_GRP, stash), st44 = fused_stages(a.wbytes, p->W, 44, stash);
+    const int minst = dense_min_stages();
+    const int st36 = fused_stages(a.wbytes, p->W, F_GRP, stash, minst), st44 = fused_stages(a.wbytes, p->W, 44, stash, minst);
     a.stages = st36;
     // 44-float row-buffer records (bank-conflict-free output pass) whenever that does not cost ring depth
-    const bool wide_rows = (st44 - st44 % gran) == (st36 - st36 % gran) && st44 >= 4 && !eml_env_flag("EML_DENSE_PACKED_ROWS");
+    const bool wide_rows = (st44 - st44 % gran) == (st36 - st36 % gran) && st44 >= minst && !eml_env_flag("EML_DENSE_PACKED_ROWS");
     // TS: the ring depth must be a multiple of the number of converter warpgroups, so that a ring slot is always converted by the same
     // warpgroup and every phase of its mbarrier has one in-order waiter.  (A parity wait cannot tell "two completions early" from "done":
     // with e.g. 5 slots and 4 warpgroups the waiter of round k on a slot may arrive before round k - 1 has even landed -- TMA loads of
