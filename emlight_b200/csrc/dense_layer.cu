@@ -237,17 +237,17 @@ __device__ __forceinline__ void band_init(BandIter &it, const FArgs &a, long ban
     it.m0 = (img * a.H + lo) * a.W;
 }
 
-template <bool SPLIT, bool POOL, int F_SROW, bool TS, int NCW = 16, int PW = 4>
+template <bool SPLIT, bool POOL, int F_SROW, bool TS, int NCW = 16, int PW = 4, bool RSUM = false>
 __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __grid_constant__ CUtensorMap tmap, const FArgs a) {
     constexpr int F_NZ = FTmem<TS>::NZ, F_UBASE = FTmem<TS>::UBASE;
     // row-sum kernels: 4 output rows x 2 half rows x 48 columns of accumulators (384), then the A ring (128) = all 512 columns
-    constexpr int F_ABASE = (TS && !POOL) ? 8 * F_RN : FTmem<TS>::ABASE;
+    constexpr int F_ABASE = (TS && !POOL && RSUM) ? 8 * F_RN : FTmem<TS>::ABASE;
     constexpr int F_CWARPS = NCW, F_TMA_WARP = NCW, F_MMA_WARP = NCW + 1, F_EPI_WARP0 = NCW + 4, F_THREADS = f_threads(NCW);
     constexpr int NCWG = NCW / 4;                          // converter warpgroups
     static_assert(NCW == 16 || (TS && NCW == 8), "converter warps: 16, or 8 with the TMEM-resident A operand");
     static_assert(PW == 4 || PW == 8, "stencil piece width");
     extern __shared__ unsigned char smem_raw[];
-    constexpr bool RS = TS && !POOL;                       // row-sum design: the MMAs add the three vertical taps into per-output-row accumulators
+    constexpr bool RS = TS && !POOL && RSUM;               // row-sum design: the MMAs add the three vertical taps into per-output-row accumulators
     __shared__ __align__(8) unsigned long long s_bar[3 * F_MAX_STAGES + 1 + 2 * F_MAX_NZ + F_NA + F_NT + 8];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_scale[F_MAX_C], s_shift[F_MAX_C], s_bias[9 * F_G + 4];
@@ -962,8 +962,20 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
         if (split) rc = wide_rows ? go(dense_layer_kernel<true, false, 44, false>, f_threads(16)) : go(dense_layer_kernel<true, false, F_GRP, false>, f_threads(16));
         else rc = wide_rows ? go(dense_layer_kernel<false, false, 44, false>, f_threads(16)) : go(dense_layer_kernel<false, false, F_GRP, false>, f_threads(16));
     } else if (cw == 8) {
-        if (split) rc = wide_rows ? go(dense_layer_kernel<true, false, 44, true, 8, 8>, f_threads(8)) : go(dense_layer_kernel<true, false, F_GRP, true, 8, 8>, f_threads(8));
-        else rc = wide_rows ? go(dense_layer_kernel<false, false, 44, true, 8, 8>, f_threads(8)) : go(dense_layer_kernel<false, false, F_GRP, true, 8, 8>, f_threads(8));
+        // Two epilogue designs on the same TMA -> convert -> TMEM-A pipeline (measured per layer at B = 256, tools/layer_ab.py):
+        //  row-sum   the MMAs add the vertical taps into per-row accumulators (18 MMAs of N = 48 per stage): the epilogue only drains rows,
+        //            so the per-tile fixed cost is lowest -- wins while a tile has few stages (C_in <= EML_DENSE_RS_MAX_C, default 96);
+        //  Z stencil 6 MMAs of N = 112 per stage into a Z tile, vertical sum by the epilogue through TMEM: fewer, larger MMAs -- wins when
+        //            the tensor pipe would otherwise limit the wide layers.
+        const char *rs_env = getenv("EML_DENSE_RS_MAX_C");
+        const int rs_max_c = rs_env ? atoi(rs_env) : 96;
+        if (p->C_in <= rs_max_c) {
+            if (split) rc = wide_rows ? go(dense_layer_kernel<true, false, 44, true, 8, 8, true>, f_threads(8)) : go(dense_layer_kernel<true, false, F_GRP, true, 8, 8, true>, f_threads(8));
+            else rc = wide_rows ? go(dense_layer_kernel<false, false, 44, true, 8, 8, true>, f_threads(8)) : go(dense_layer_kernel<false, false, F_GRP, true, 8, 8, true>, f_threads(8));
+        } else {
+            if (split) rc = wide_rows ? go(dense_layer_kernel<true, false, 44, true, 8, 8>, f_threads(8)) : go(dense_layer_kernel<true, false, F_GRP, true, 8, 8>, f_threads(8));
+            else rc = wide_rows ? go(dense_layer_kernel<false, false, 44, true, 8, 8>, f_threads(8)) : go(dense_layer_kernel<false, false, F_GRP, true, 8, 8>, f_threads(8));
+        }
     } else {
         if (split) rc = wide_rows ? go(dense_layer_kernel<true, false, 44, true>, f_threads(16)) : go(dense_layer_kernel<true, false, F_GRP, true>, f_threads(16));
         else rc = wide_rows ? go(dense_layer_kernel<false, false, 44, true>, f_threads(16)) : go(dense_layer_kernel<false, false, F_GRP, true>, f_threads(16));

@@ -8,7 +8,8 @@ sys.path.insert(0, ROOT)
 import torch
 import emlight_b200 as E
 
-VARIANTS = [("smemA_r1", {"EML_DENSE_SMEM_A": "1"}), ("rowsum", {}), ("rowsum_nostash", {"EML_DENSE_NO_STASH": "1"})]
+VARIANTS = [("smemA_r1", {"EML_DENSE_SMEM_A": "1"}), ("zstencil_all", {"EML_DENSE_RS_MAX_C": "0"}), ("rowsum<=96", {"EML_DENSE_RS_MAX_C": "96"}),
+            ("rowsum<=144", {"EML_DENSE_RS_MAX_C": "144"}), ("rowsum_all", {"EML_DENSE_RS_MAX_C": "400"})]
 KEYS = sorted({k for _, env in VARIANTS for k in env})
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -29,7 +30,7 @@ with torch.no_grad():
             for fam, lname, abytes, flops, a, b in net.launch_log:
                 acc[name].setdefault(lname, []).append(a.elapsed_time(b))
             net.launch_log = None
-names = list(acc[VARIANTS[0][0]])
+names = [n for n in acc[VARIANTS[0][0]] if all(n in acc[v] for v, _ in VARIANTS)]      # layers every variant runs as the same family
 print("%-14s" % "layer" + "".join("%16s" % n for n, _ in VARIANTS))
 tot = {n: 0.0 for n, _ in VARIANTS}
 for ln in names:
