@@ -962,13 +962,15 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
         if (split) rc = wide_rows ? go(dense_layer_kernel<true, false, 44, false>, f_threads(16)) : go(dense_layer_kernel<true, false, F_GRP, false>, f_threads(16));
         else rc = wide_rows ? go(dense_layer_kernel<false, false, 44, false>, f_threads(16)) : go(dense_layer_kernel<false, false, F_GRP, false>, f_threads(16));
     } else if (cw == 8) {
-        // Two epilogue designs on the same TMA -> convert -> TMEM-A pipeline (measured per layer at B = 256, tools/layer_ab.py):
+        // Two epilogue designs on the same TMA -> convert -> TMEM-A pipeline, chosen per layer from an interleaved in-process A/B at B = 256
+        // (tools/layer_ab.py, profiles/r02_layer_ab.txt):
         //  row-sum   the MMAs add the vertical taps into per-row accumulators (18 MMAs of N = 48 per stage): the epilogue only drains rows,
-        //            so the per-tile fixed cost is lowest -- wins while a tile has few stages (C_in <= EML_DENSE_RS_MAX_C, default 96);
-        //  Z stencil 6 MMAs of N = 112 per stage into a Z tile, vertical sum by the epilogue through TMEM: fewer, larger MMAs -- wins when
-        //            the tensor pipe would otherwise limit the wide layers.
+        //            so the fixed cost per tile is lowest -- wins while a tile has few stages: C_in <= 60 at W = 256 (block 1, layers 1-4:
+        //            0.97-1.28 ms against 1.16-1.38 ms), C_in <= 156 at W = 128 (block 2, layers 1-5);
+        //  Z stencil 6 MMAs of N = 112 per stage into a Z tile, vertical sum by the epilogue through TMEM: fewer, larger MMAs -- wins for the
+        //            wide layers, where the 18 small MMAs per stage hold the converters back (ncu: converters wait for a free A slot).
         const char *rs_env = getenv("EML_DENSE_RS_MAX_C");
-        const int rs_max_c = rs_env ? atoi(rs_env) : 96;
+        const int rs_max_c = rs_env ? atoi(rs_env) : (p->W == 256 ? 60 : (p->W == 128 ? 156 : 0));
         if (p->C_in <= rs_max_c) {
             if (split) rc = wide_rows ? go(dense_layer_kernel<true, false, 44, true, 8, 8, true>, f_threads(8)) : go(dense_layer_kernel<true, false, F_GRP, true, 8, 8, true>, f_threads(8));
             else rc = wide_rows ? go(dense_layer_kernel<false, false, 44, true, 8, 8, true>, f_threads(8)) : go(dense_layer_kernel<false, false, F_GRP, true, 8, 8, true>, f_threads(8));
