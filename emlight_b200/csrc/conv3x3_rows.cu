@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(ROWS_THREADS) conv3x3_rows_kernel(const RowsAr
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Persistent ROLLING-ROW variant (no statistics epilogue).
+// Persistent ROLLING-ROW variant (statistics epilogue for C_out <= 16: per-thread double sums over the CTA's pixels, round 2).
 // A CTA owns a vertical band (image b, 128-pixel column block, RB consecutive output rows) and walks down it: output row
 // y needs input rows y-1, y, y+1, of which y-1 and y are already staged from the previous step -- so every new output row
 // stages exactly ONE new halo row (130 px) into a 4-slot ring instead of three (3x fewer loads, conversions and
@@ -415,6 +415,12 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv3x3_roll_kernel(const RollA
         // ======================================================= EPILOGUE
         const int q4 = warp & 3;
         const bool vec_ok = ((a.out_pitch | a.out_choff) & 3) == 0;
+        // batch-statistic BatchNorm downstream (training forward): per-channel sum / sum of squares of the outputs, accumulated per thread
+        // (= per pixel column) in double over the CTA's whole pixel range, reduced once at the end (N_pad <= 16 only: conv2's 12 channels)
+        const bool want_stats = a.stats != nullptr;
+        double st1[16], st2[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { st1[e] = 0.0; st2[e] = 0.0; }
         uint32_t j = 0;
         for (long unit = blockIdx.x; unit < ra.nunits; unit += gridDim.x) {
             long b; int x0, y0, nrows;
@@ -452,7 +458,26 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv3x3_roll_kernel(const RollA
                                     if (n + e < a.C_out) orow[n + e] = v[qq * 4 + e];
                             }
                         }
+                        if (want_stats && g16 == 0) {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) { const double d = static_cast<double>(v[e]); st1[e] += d; st2[e] += d * d; }
+                        }
                     }
+                }
+            }
+        }
+        if (want_stats) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                double s1 = st1[e], s2 = st2[e];
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+                }
+                if (lane == 0 && e < a.C_out) {
+                    atomicAdd(a.stats + e, s1);
+                    atomicAdd(a.stats + a.stats_stride + e, s2);
                 }
             }
         }
@@ -532,7 +557,7 @@ int eml_rows_pack(const float *w_oihw, unsigned char *dst, int C_out, int C_in, 
 
 bool eml_rows_supported(const eml_conv_params *p) {
     if (p->mode != EML_CONV_3x3) return false;
-    const bool persist_ok = p->stats == nullptr && !eml_env_flag("EML_NO_PERSIST");
+    const bool persist_ok = (p->stats == nullptr || (p->C_out <= 16 && !eml_env_flag("EML_NO_PERSIST_STATS"))) && !eml_env_flag("EML_NO_PERSIST");
     // 12 -> 48 data gradient (conv2's dgrad): input pitch must give 16 readable, zero-padded channels
     if (p->C_in <= 16 && p->in_pitch >= 16 && p->C_out <= 64 && persist_ok && p->scale == nullptr && p->shift == nullptr &&
         (p->precision == EML_PREC_BF16 || p->precision == EML_PREC_BF16X3))
@@ -557,7 +582,7 @@ int eml_rows_forward(const eml_conv_params *p, const unsigned char *wplanar, cud
     const long tiles = static_cast<long>(p->B) * p->H * (p->W / ROWS_TILE);
     if (tiles >= (1L << 31)) return EML_E_SHAPE;
     cudaError_t e;
-    if (a.stats == nullptr && !eml_env_flag("EML_NO_PERSIST")) {
+    if ((a.stats == nullptr || (p->C_out <= 16 && !eml_env_flag("EML_NO_PERSIST_STATS"))) && !eml_env_flag("EML_NO_PERSIST")) {
         RollArgs ra{};
         ra.r = a;
         ra.wcat = wplanar + rows_planar_bytes(p->C_out, p->C_in);

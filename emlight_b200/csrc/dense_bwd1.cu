@@ -404,6 +404,27 @@ __global__ void __launch_bounds__(256) dense_bwd1_gather_kernel(const float *__r
     }
 }
 
+// float4 variant: c0, n, out_n, every pitch multiples of 4 and 16-byte aligned bases -- thread = (pixel, channel quad)
+__global__ void __launch_bounds__(256) dense_bwd1_gather4_kernel(const float *__restrict__ dS, int ds_pitch, const float *__restrict__ x, int x_pitch,
+                                                                 const float *__restrict__ coefA, const float *__restrict__ coefB, int c0, int n,
+                                                                 float *out, int out_pitch, int out_n, long M) {
+    const int Q = out_n >> 2;
+    const long total = M * Q;
+    for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+        const long m = idx / Q;
+        const int i = static_cast<int>(idx - m * Q) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) {
+            const int c = c0 + i;
+            const float4 d = *reinterpret_cast<const float4 *>(dS + m * ds_pitch + c);
+            const float4 xv = __ldg(reinterpret_cast<const float4 *>(x + m * x_pitch + c));
+            const float4 a = *reinterpret_cast<const float4 *>(coefA + c), b = *reinterpret_cast<const float4 *>(coefB + c);
+            v = make_float4(fmaf(b.x, xv.x, d.x + a.x), fmaf(b.y, xv.y, d.y + a.y), fmaf(b.z, xv.z, d.z + a.z), fmaf(b.w, xv.w, d.w + a.w));
+        }
+        *reinterpret_cast<float4 *>(out + m * out_pitch + i) = v;
+    }
+}
+
 }  // namespace
 
 extern "C" size_t eml_dense_bwd1_wpack_bytes(int C_in) { return static_cast<size_t>((C_in + 31) & ~31) * 256; }
@@ -441,6 +462,16 @@ extern "C" int eml_dense_bwd1_gather(const float *dS, int ds_pitch, const float 
                                      int c0, int n, float *out, int out_pitch, int out_n, long M, void *stream) {
     EML_CHECK_PTR(dS); EML_CHECK_PTR(x); EML_CHECK_PTR(coefA); EML_CHECK_PTR(coefB); EML_CHECK_PTR(out);
     if (n <= 0 || out_n < n || out_pitch < out_n || M <= 0 || c0 < 0) return EML_E_SHAPE;
+    const bool vec = ((c0 | n | out_n | ds_pitch | x_pitch | out_pitch) & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(dS) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                       reinterpret_cast<uintptr_t>(coefA) | reinterpret_cast<uintptr_t>(coefB)) & 15) == 0;
+    if (vec) {
+        long blocks4 = (M * (out_n / 4) + 255) / 256;
+        if (blocks4 > 148 * 16) blocks4 = 148 * 16;
+        dense_bwd1_gather4_kernel<<<static_cast<unsigned>(blocks4), 256, 0, static_cast<cudaStream_t>(stream)>>>(dS, ds_pitch, x, x_pitch, coefA, coefB, c0, n,
+                                                                                                              out, out_pitch, out_n, M);
+        return eml_launch_status();
+    }
     long blocks = (M * out_n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     dense_bwd1_gather_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(dS, ds_pitch, x, x_pitch, coefA, coefB, c0, n,
