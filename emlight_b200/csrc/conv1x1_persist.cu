@@ -39,6 +39,7 @@ struct PArgs {
     int C_out, N_pad, out_pitch, out_choff;
     int nchunks;
     int relu;
+    double *stats; long stats_stride;   // optional per-output-channel sum / sum of squares (batch-statistic BatchNorm downstream)
     int stages;          // A-ring depth (3 or 4, whatever fits next to the resident weights and the output staging)
     long ntiles;
 };
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_bar[2 * P_MAX_STAGES + 1 + 4];
     __shared__ uint32_t s_tmem;
+    __shared__ double s_stat[2][64];
 
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * P_A_TILE;
@@ -239,6 +241,14 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
         const bool direct = !(((a.out_pitch | a.out_choff) & 3) == 0 && (a.C_out & 3) == 0);
         float *stage = reinterpret_cast<float *>(smem + out_stage_off);      // [nq planes][129 x 16 B]
         constexpr int PLANE_F = 129 * 4;                               // floats per plane (one 16-byte pad slot)
+        // statistics epilogue (round 2: the training forward's conv1): in the write-out every thread keeps ONE channel quad -- rows
+        // are dealt round-robin in groups of 128 / cq -- so the per-channel sums live in 8 double registers over all the CTA's tiles
+        const bool want_stats = a.stats != nullptr && !direct;
+        const int cqs = a.C_out >> 2;
+        const int rows_per_pass = cqs > 0 ? 128 / cqs : 0;
+        const int my_q = cqs > 0 ? et % cqs : 0, my_r = cqs > 0 ? et / cqs : 0;
+        double st1[4] = {0.0, 0.0, 0.0, 0.0}, st2[4] = {0.0, 0.0, 0.0, 0.0};
+        if (et < 64) { s_stat[0][et] = 0.0; s_stat[1][et] = 0.0; }
         uint32_t j = 0;
         for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++j) {
             const uint32_t buf = j & 1, aph = (j >> 1) & 1;
@@ -293,16 +303,43 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
             asm volatile("bar.sync 1, 128;" ::: "memory");               // staging complete (epilogue warps only)
             // 2. coalesced write-out: consecutive threads take consecutive float4 of the (row, quad) stream
             const int cq = a.C_out >> 2;                                  // valid quads per row
-            const int total = P_TILE_M * cq;
-            for (int f = et; f < total; f += 128) {
-                const int r = f / cq, qd = f - r * cq;
-                const long m = m0 + r;
-                if (m < a.M) {
-                    const float4 val = *reinterpret_cast<const float4 *>(stage + qd * PLANE_F + r * 4);
-                    *reinterpret_cast<float4 *>(a.out + m * a.out_pitch + a.out_choff + qd * 4) = val;
+            if (want_stats) {
+                if (my_r < rows_per_pass) {
+                    for (int r = my_r; r < P_TILE_M; r += rows_per_pass) {   // same (row, quad) stream as below, fixed quad per thread
+                        const long m = m0 + r;
+                        if (m < a.M) {
+                            const float4 val = *reinterpret_cast<const float4 *>(stage + my_q * PLANE_F + r * 4);
+                            *reinterpret_cast<float4 *>(a.out + m * a.out_pitch + a.out_choff + my_q * 4) = val;
+                            const double d0 = val.x, d1 = val.y, d2 = val.z, d3 = val.w;
+                            st1[0] += d0; st1[1] += d1; st1[2] += d2; st1[3] += d3;
+                            st2[0] += d0 * d0; st2[1] += d1 * d1; st2[2] += d2 * d2; st2[3] += d3 * d3;
+                        }
+                    }
+                }
+            } else {
+                const int total = P_TILE_M * cq;
+                for (int f = et; f < total; f += 128) {
+                    const int r = f / cq, qd = f - r * cq;
+                    const long m = m0 + r;
+                    if (m < a.M) {
+                        const float4 val = *reinterpret_cast<const float4 *>(stage + qd * PLANE_F + r * 4);
+                        *reinterpret_cast<float4 *>(a.out + m * a.out_pitch + a.out_choff + qd * 4) = val;
+                    }
                 }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");               // staging buffer free for the next tile
+        }
+        if (want_stats) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");               // s_stat zeroed by every epilogue thread's store above
+            if (my_r < rows_per_pass) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { atomicAdd(&s_stat[0][my_q * 4 + e], st1[e]); atomicAdd(&s_stat[1][my_q * 4 + e], st2[e]); }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et < a.C_out) {
+                atomicAdd(a.stats + et, s_stat[0][et]);
+                atomicAdd(a.stats + a.stats_stride + et, s_stat[1][et]);
+            }
         }
     }
     tc_fence_before();
@@ -326,7 +363,9 @@ static int persist_stages(int nchunks, int N_pad, bool split) {
 }
 
 bool eml_persist_supported(const eml_conv_params *p) {
-    if (p->mode != EML_CONV_1x1 || p->stats != nullptr) return false;
+    if (p->mode != EML_CONV_1x1) return false;
+    if (p->stats != nullptr && ((p->C_out & 3) || ((p->out_pitch | p->out_choff) & 3) || p->C_out > 64 || eml_env_flag("EML_NO_PERSIST_STATS")))
+        return false;                                 // the statistics epilogue lives in the staged (float4) write-out
     if (p->precision != EML_PREC_BF16 && p->precision != EML_PREC_BF16X3) return false;
     const int N_pad = (p->C_out + 15) & ~15;
     const int nchunks = (p->C_in + P_CHUNK_K - 1) / P_CHUNK_K;
@@ -342,6 +381,7 @@ int eml_persist_forward(const eml_conv_params *p, cudaStream_t st) {
     a.C_out = p->C_out; a.N_pad = (p->C_out + 15) & ~15; a.out_pitch = p->out_pitch; a.out_choff = p->out_choff;
     a.nchunks = (p->C_in + P_CHUNK_K - 1) / P_CHUNK_K;
     a.relu = p->relu;
+    a.stats = p->stats; a.stats_stride = p->stats_stride > 0 ? p->stats_stride : p->C_out;
     a.ntiles = (a.M + P_TILE_M - 1) / P_TILE_M;
     const bool split = p->precision == EML_PREC_BF16X3;
     a.stages = persist_stages(a.nchunks, a.N_pad, split);
