@@ -151,6 +151,8 @@ class FlatAdam:
         self.comm_bytes = total * 4
         self.early_buckets = 0                          # buckets whose all-reduce was launched from inside the backward (last step)
         self.comm = True                                # False: skip the collective (measurement of what the exchange costs; ranks then diverge)
+        self.measure = False                            # True: CUDA events around the wait for the collectives in step() -> exposed_ms()
+        self._wait_events = []
 
     # ------------------------------------------------------------------ gradient side
     def zero_grad(self, set_to_none=False):
@@ -185,15 +187,32 @@ class FlatAdam:
                 self._launch(i)
                 self.early_buckets += 1
 
+    def exposed_ms(self):
+        """Mean device time per step() that the compute stream spent WAITING for the gradient all-reduce (measure = True): the part of
+        the exchange that the backward did not hide.  Synchronises."""
+        if not self._wait_events:
+            return 0.0
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self._wait_events) / len(self._wait_events)
+        self._wait_events = []
+        return ms
+
     # ------------------------------------------------------------------ update
     @torch.no_grad()
     def step(self):
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         for i in range(len(self.buckets)):
             self._launch(i)
+        timed = self.measure and self.flat_p.is_cuda
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         for h in self._handles:
             if h is not None:
-                h.wait()
+                h.wait()                                 # the compute stream waits for the NCCL stream: time exposed = not overlapped
+        if timed:
+            e1.record()
+            self._wait_events.append((e0, e1))
         self.t += 1
         b1, b2 = self.betas
         if self.flat_p.is_cuda:
