@@ -240,6 +240,18 @@ def train_workloads(E, parallel, dev, rank, world, gen, timed, args):
             "allreduce_alone_ms": round(ar, 3), "allreduce_algbw_GBps": round((og.comm_bytes + od.comm_bytes) / ar / 1e6, 1) if ar > 0 else None,
             "allreduce_exposed_wait_ms": round(wait_g, 3),
             "spade_stat_allreduces_per_iteration": 0 if world == 1 else "2 x (C) sums per SPADE norm, forward and backward (SynchronizedBatchNorm)"}
+        # the same iteration at the single-pass bf16 tier (BASELINE configs[3] names bf16; F7: ~3e-3 relative error per conv instead of
+        # ~1e-5 for the three-pass split) -- reported next to the parity-grade number, never instead of it
+        try:
+            gm.netG.precision = "bf16"; gm.netD.precision = "bf16"
+            if getattr(gm, "criterionVGG", None) is not None:
+                gm.criterionVGG.vgg.precision = "bf16"
+            gan_iter()
+            ms_b = timed(gan_iter, 2) / 2
+            out["config3_genprojector_G_step_plus_D_step_b4_per_gpu"]["bf16_single_pass_ms_per_iteration"] = round(ms_b, 3)
+            out["config3_genprojector_G_step_plus_D_step_b4_per_gpu"]["bf16_single_pass_maps_per_s"] = round(Bg * world / ms_b * 1e3, 2)
+        except Exception as e:                          # noqa: BLE001
+            out["config3_genprojector_G_step_plus_D_step_b4_per_gpu"]["bf16_single_pass_error"] = "%s: %s" % (type(e).__name__, e)
         del gm, og, od, gd
     except Exception as e:                              # noqa: BLE001  (secondary workload: never fail the headline line)
         out["config3_genprojector_G_step_plus_D_step_b4_per_gpu"] = {"error": "%s: %s" % (type(e).__name__, e)}

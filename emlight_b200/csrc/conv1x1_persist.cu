@@ -106,12 +106,19 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv1x1_persist_kernel(const PAr
             const int ch = c0 + sub * 4;
             const bool lane_ok = sub * 4 < ksteps * 16 && ch < a.C_in;
             const float *rowp = a.in + (m0 + rgrp) * a.in_pitch + ch;
+            const int nv = a.C_in - ch;
             unsigned m = 0;
 #pragma unroll
             for (int i = 0; i < P_NROWS; ++i) {
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (lane_ok && (m0 + rgrp + RSTEP * i) < a.M) {
-                    v[i] = __ldg(reinterpret_cast<const float4 *>(rowp + static_cast<long>(RSTEP * i) * a.in_pitch));
+                    const float *src = rowp + static_cast<long>(RSTEP * i) * a.in_pitch;
+                    if (nv >= 4) v[i] = __ldg(reinterpret_cast<const float4 *>(src));
+                    else {                                           // ragged last quad (C_in % 4 != 0): the channels behind C_in belong to
+                        v[i].x = __ldg(src);                         // a layer that has not run yet -- never touch them (initcheck-clean)
+                        if (nv > 1) v[i].y = __ldg(src + 1);
+                        if (nv > 2) v[i].z = __ldg(src + 2);
+                    }
                     m |= 1u << i;
                 }
             }

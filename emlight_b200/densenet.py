@@ -223,11 +223,14 @@ class DenseNet(nn.Module):
         c["fc_w"] = self.fc.weight.detach().float().view(-1, c_tr, P).permute(0, 2, 1).reshape(self.fc.out_features, -1).contiguous()
         c["fc_b"] = self.fc.bias.detach().float().contiguous()
         if self.precision != "fp32":
-            # fc as a TMA-fed tcgen05 GEMM (eml_gemm_bf16): weights packed in slices of <= 256 output features
+            # fc as a TMA-fed tcgen05 GEMM (eml_gemm_bf16): weights packed in slices of <= 256 output features.  (Narrower slices do not
+            # help: the launches serialise on the stream and each is bound by its 8208-deep K loop -- 16 x 64 features took 1.25 ms
+            # against 0.62 ms for 4 x 256, profiles/r02_profile_train_b64_wgrad3x3_v2.txt.)
             c["fc_pack"] = []
             K = self.fc.in_features
-            for n0 in range(0, self.fc.out_features, 256):
-                rows = min(256, self.fc.out_features - n0)
+            step = int(os.environ.get("EML_FC_SLICE", "256"))
+            for n0 in range(0, self.fc.out_features, step):
+                rows = min(step, self.fc.out_features - n0)
                 buf = torch.empty(lib.eml_conv_wpack_bytes(rows, K, 1), dtype=torch.uint8, device=device)
                 _lib.check(lib.eml_conv_pack_weights(_lib.ptr(c["fc_w"][n0:n0 + rows]), _lib.ptr(buf), rows, K, 1, st), "eml_conv_pack_weights(fc)")
                 c["fc_pack"].append((n0, rows, buf))

@@ -104,3 +104,27 @@ def test_wgrad_1x1_tensor_core_ranges(cuda, lib, C, M):
     a = torch.relu(torch.addcmul(sh, x[:, :C], sc)).double()
     want = G.double().t() @ a
     assert float((dW.double() - want).abs().max()) <= 1e-4 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-4), ("bf16", 2e-2), ("fp32", 1e-5)])
+@pytest.mark.parametrize("B,H,W,N", [(2, 5, 64, 12), (1, 37, 256, 12), (3, 4, 130, 12), (2, 3, 8, 12), (1, 70, 32, 16), (2, 9, 256, 7), (5, 1, 16, 12)])
+def test_wgrad_3x3(cuda, lib, B, H, W, N, precision, tol):
+    """eml_wgrad_3x3 (conv2's weight gradient, DenseNet.py:33-34 backward): dW[n,c,ky,kx] = sum_p dY[p,n] * N2[p+(ky-1,kx-1), c] with
+    N2 = scale*b + shift inside the image and 0 outside.  Shapes cover every ring-slot case (H >= 4 rows), ragged widths (W = 130:
+    a second 2-pixel tile), N < 12 with an unaligned tail, one-row images and bands (H = 70 > 32 rows)."""
+    from emlight_b200 import _lib
+    P, st = _lib.ptr, _lib.stream_ptr()
+    gen = torch.Generator().manual_seed(B * 1000 + H * 10 + W)
+    dY = torch.randn(B, H, W, 16, generator=gen).to(cuda)
+    b = torch.randn(B, H, W, 48, generator=gen).to(cuda)
+    sc, sh = torch.randn(48, generator=gen).to(cuda), (0.3 * torch.randn(48, generator=gen)).to(cuda)
+    dW = torch.zeros(N, 48, 3, 3, device=cuda)
+    _lib.check(lib.eml_wgrad_3x3(P(dY), 16, N, P(b), 48, 48, P(sc), P(sh), P(dW), B, H, W, _lib.PRECISIONS[precision], st), "eml_wgrad_3x3")
+    n2 = torch.addcmul(sh, b, sc).double().permute(0, 3, 1, 2)                                   # (B, 48, H, W)
+    w = torch.zeros(N, 48, 3, 3, dtype=torch.float64, device=cuda, requires_grad=True)
+    y = torch.nn.functional.conv2d(n2, w, padding=1)
+    y.backward(dY[..., :N].double().permute(0, 3, 1, 2))
+    assert float((dW.double() - w.grad).abs().max()) <= tol * float(w.grad.abs().max())
+    # accumulates into dW (the caller zeroes): a second call doubles it
+    _lib.check(lib.eml_wgrad_3x3(P(dY), 16, N, P(b), 48, 48, P(sc), P(sh), P(dW), B, H, W, _lib.PRECISIONS[precision], st), "eml_wgrad_3x3")
+    assert float((dW.double() - 2 * w.grad).abs().max()) <= 2 * tol * float(w.grad.abs().max())
