@@ -356,6 +356,47 @@ __global__ void __launch_bounds__(256) linear_kernel(const float *__restrict__ a
         }
 }
 
+// Few rows (M <= 16: the ConvEncoder's fc at batch <= 16, generator.py:124): the 64x64 tiling leaves N/64 CTAs walking all of K
+// serially (1.4 ms for 16 x 8192 x 256).  Here one warp owns one output feature: it streams that weight row once (float4 per lane,
+// coalesced), keeps M partial sums per lane against the L1/L2-resident activations and reduces them with shuffles.
+__global__ void __launch_bounds__(256) linear_rows_kernel(const float *__restrict__ a, const float *__restrict__ w,
+                                                          const float *__restrict__ bias, float *__restrict__ out,
+                                                          int M, int N, int K) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (n >= N) return;
+    float acc[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) acc[m] = 0.f;
+    const float *wr = w + static_cast<long>(n) * K;
+    if ((K & 3) == 0) {
+        for (int k = lane * 4; k < K; k += 128) {
+            const float4 wv = __ldg(reinterpret_cast<const float4 *>(wr + k));
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                if (m < M) {
+                    const float4 av = __ldg(reinterpret_cast<const float4 *>(a + static_cast<long>(m) * K + k));
+                    acc[m] = fmaf(av.x, wv.x, fmaf(av.y, wv.y, fmaf(av.z, wv.z, fmaf(av.w, wv.w, acc[m]))));
+                }
+            }
+        }
+    } else {
+        for (int k = lane; k < K; k += 32) {
+            const float wv = __ldg(wr + k);
+#pragma unroll
+            for (int m = 0; m < 16; ++m)
+                if (m < M) acc[m] = fmaf(__ldg(a + static_cast<long>(m) * K + k), wv, acc[m]);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        float v = acc[m];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && m < M) out[static_cast<long>(m) * N + n] = v + (bias ? bias[n] : 0.f);
+    }
+}
+
 }  // namespace
 
 int eml_conv_forward_simt(const eml_conv_params *p, cudaStream_t st) {
@@ -428,6 +469,10 @@ extern "C" int eml_linear_fp32(const float *a, const float *w, const float *bias
                                void *stream) {
     EML_CHECK_PTR(a); EML_CHECK_PTR(w); EML_CHECK_PTR(out);
     if (M <= 0 || N <= 0 || K <= 0) return EML_E_SHAPE;
+    if (M <= 16 && (((K & 3) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0) || (K & 3))) {
+        linear_rows_kernel<<<(N + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, w, bias, out, M, N, K);
+        return eml_launch_status();
+    }
     dim3 grid((N + 63) / 64, (M + 63) / 64);
     linear_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, w, bias, out, M, N, K);
     return eml_launch_status();

@@ -34,6 +34,8 @@ struct GArgs {
     int nchunks, stages;
     long mtiles;
     int ksplit, cps;                // split-K: work item = (m-tile, K range of cps chunks); partial sums are added with red.global
+    int nslices;                    // output-channel slices of N columns each in ONE launch: work item = (slice, K range, m-tile);
+    long slice_bytes;               // slice s reads wpack + s * slice_bytes, bias + s * N and writes at out_choff + s * N
 };
 
 __device__ __forceinline__ void g_mbar_arrive(uint32_t bar) {
@@ -77,7 +79,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tma_kernel(const __grid_con
         // ================================================================ LOADER
         const bool leader = elect_one();
         uint32_t g = 0;
-        for (long t = blockIdx.x; t < a.mtiles * a.ksplit; t += gridDim.x) {
+        const long per_slice = a.mtiles * a.ksplit;
+        for (long ts = blockIdx.x; ts < per_slice * a.nslices; ts += gridDim.x) {
+            const long t = ts % per_slice;
+            const unsigned char *wp = a.wpack + (ts / per_slice) * a.slice_bytes;
             const int m0 = static_cast<int>((t % a.mtiles) * G_TILE_M);
             const int c_lo = static_cast<int>(t / a.mtiles) * a.cps, c_hi = min(a.nchunks, c_lo + a.cps);
             for (int c = c_lo; c < c_hi; ++c, ++g) {
@@ -89,7 +94,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tma_kernel(const __grid_con
                     mbar_expect_tx(bar, static_cast<uint32_t>(stage_bytes));
                     tma_load_2d(smem_u32(st), &tm_hi, c * G_CHUNK_K, m0, bar);
                     if (SPLIT) tma_load_2d(smem_u32(st + G_A_TILE), &tm_lo, c * G_CHUNK_K, m0, bar);
-                    bulk_g2s(smem_u32(st + (SPLIT ? 2 : 1) * G_A_TILE), a.wpack + static_cast<size_t>(c) * 2 * b_tile,
+                    bulk_g2s(smem_u32(st + (SPLIT ? 2 : 1) * G_A_TILE), wp + static_cast<size_t>(c) * 2 * b_tile,
                              static_cast<uint32_t>((SPLIT ? 2 : 1) * b_tile), bar);
                 }
                 __syncwarp();
@@ -103,7 +108,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tma_kernel(const __grid_con
         const uint32_t stage16 = static_cast<uint32_t>(stage_bytes) >> 4, alo16 = G_A_TILE >> 4;
         const uint32_t bhi16 = static_cast<uint32_t>((SPLIT ? 2 : 1) * G_A_TILE) >> 4, blo16 = static_cast<uint32_t>(b_tile) >> 4;
         uint32_t g = 0, j = 0;
-        for (long t = blockIdx.x; t < a.mtiles * a.ksplit; t += gridDim.x, ++j) {
+        const long per_slice = a.mtiles * a.ksplit;
+        for (long ts = blockIdx.x; ts < per_slice * a.nslices; ts += gridDim.x, ++j) {
+            const long t = ts % per_slice;
             const uint32_t buf = j & 1, aph = (j >> 1) & 1;
             mbar_wait(bar_accempty + 8 * buf, aph ^ 1);
             const uint32_t d_tmem = tmem_base + buf * acc_cols;
@@ -135,7 +142,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tma_kernel(const __grid_con
         const int q = warp & 3;
         const bool vec_ok = ((a.out_pitch | a.out_choff) & 3) == 0;
         uint32_t j = 0;
-        for (long t = blockIdx.x; t < a.mtiles * a.ksplit; t += gridDim.x, ++j) {
+        const long per_slice = a.mtiles * a.ksplit;
+        for (long ts = blockIdx.x; ts < per_slice * a.nslices; ts += gridDim.x, ++j) {
+            const long t = ts % per_slice;
+            const int n_off = static_cast<int>(ts / per_slice) * a.N;
+            const float *bias = a.bias ? a.bias + n_off : nullptr;
             const uint32_t buf = j & 1, aph = (j >> 1) & 1;
             mbar_wait(bar_accfull + 8 * buf, aph);
             __syncwarp();
@@ -143,7 +154,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tma_kernel(const __grid_con
             const bool first_k = t < a.mtiles;                  // the K range that also adds the bias
             const long m = (t % a.mtiles) * G_TILE_M + q * 32 + lane;
             const bool row_ok = m < a.M;
-            float *orow = a.out + (row_ok ? m : 0) * a.out_pitch + a.out_choff;
+            float *orow = a.out + (row_ok ? m : 0) * a.out_pitch + a.out_choff + n_off;
             for (int g16 = 0; g16 < a.N_pad; g16 += 16) {
                 float v[16];
                 tmem_ld16(tmem_base + buf * acc_cols + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g16), v);
@@ -152,11 +163,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tma_kernel(const __grid_con
                     for (int qq = 0; qq < 4; ++qq) {
                         const int n = g16 + qq * 4;
                         float4 o = make_float4(v[qq * 4], v[qq * 4 + 1], v[qq * 4 + 2], v[qq * 4 + 3]);
-                        if (a.bias != nullptr && first_k) {
-                            if (n < a.N) o.x += a.bias[n];
-                            if (n + 1 < a.N) o.y += a.bias[n + 1];
-                            if (n + 2 < a.N) o.z += a.bias[n + 2];
-                            if (n + 3 < a.N) o.w += a.bias[n + 3];
+                        if (bias != nullptr && first_k) {
+                            if (n < a.N) o.x += bias[n];
+                            if (n + 1 < a.N) o.y += bias[n + 1];
+                            if (n + 2 < a.N) o.z += bias[n + 2];
+                            if (n + 3 < a.N) o.w += bias[n + 3];
                         }
                         if (a.ksplit > 1) {                     // partial sum of one K range: accumulate (out zeroed by the caller)
                             if (n < a.N) atomicAdd(orow + n, o.x);
@@ -218,10 +229,14 @@ int make_map(CUtensorMap *map, const void *base, long M, int Kp) {
 }  // namespace
 
 static int gemm_impl(const void *A_hi, const void *A_lo, long M, int Kp, const void *wpack, int N, const float *bias,
-                     float *out, int out_pitch, int out_choff, int precision, int ksplit, void *stream) {
+                     float *out, int out_pitch, int out_choff, int precision, int ksplit, void *stream, int nslices = 1,
+                     long slice_bytes = 0) {
     EML_CHECK_PTR(A_hi); EML_CHECK_PTR(wpack); EML_CHECK_PTR(out);
     EML_CHECK_ALIGN16(A_hi); EML_CHECK_ALIGN16(wpack);
-    if (M <= 0 || Kp <= 0 || (Kp % G_CHUNK_K) || N <= 0 || N > 256 || out_pitch < out_choff + N || out_choff < 0) return EML_E_SHAPE;
+    if (M <= 0 || Kp <= 0 || (Kp % G_CHUNK_K) || N <= 0 || N > 256 || nslices < 1 || out_choff < 0 ||
+        out_pitch < out_choff + static_cast<long>(N) * nslices)
+        return EML_E_SHAPE;
+    if (nslices > 1 && ((N & 15) || (slice_bytes & 15) || slice_bytes < static_cast<long>(Kp / G_CHUNK_K) * 2 * N * 128)) return EML_E_SHAPE;
     const bool split = precision == EML_PREC_BF16X3;
     if (!split && precision != EML_PREC_BF16) return EML_E_ARG;
     if (split) { EML_CHECK_PTR(A_lo); EML_CHECK_ALIGN16(A_lo); }
@@ -233,6 +248,7 @@ static int gemm_impl(const void *A_hi, const void *A_lo, long M, int Kp, const v
     GArgs a{};
     a.wpack = static_cast<const unsigned char *>(wpack); a.bias = bias; a.out = out; a.M = M;
     a.N = N; a.N_pad = (N + 15) & ~15; a.out_pitch = out_pitch; a.out_choff = out_choff;
+    a.nslices = nslices; a.slice_bytes = slice_bytes;
     a.nchunks = Kp / G_CHUNK_K;
     a.mtiles = (M + G_TILE_M - 1) / G_TILE_M;
     if (ksplit < 1 || ksplit > a.nchunks) return EML_E_ARG;
@@ -247,7 +263,7 @@ static int gemm_impl(const void *A_hi, const void *A_lo, long M, int Kp, const v
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long items = a.mtiles * a.ksplit;
+    const long items = a.mtiles * a.ksplit * nslices;
     const unsigned grid = static_cast<unsigned>(items < sms ? items : sms);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
@@ -266,6 +282,14 @@ static int gemm_impl(const void *A_hi, const void *A_lo, long M, int Kp, const v
 extern "C" int eml_gemm_bf16(const void *A_hi, const void *A_lo, long M, int Kp, const void *wpack, int N, const float *bias,
                              float *out, int out_pitch, int out_choff, int precision, void *stream) {
     return gemm_impl(A_hi, A_lo, M, Kp, wpack, N, bias, out, out_pitch, out_choff, precision, 1, stream);
+}
+
+// `nslices` output slices of exactly N (a multiple of 16, <= 256) columns in ONE launch: slice s multiplies the same A by the
+// packed weights at wpack + s * slice_bytes and writes columns [out_choff + s*N, out_choff + (s+1)*N).  Wide layers at low
+// resolution (M = B*H*W small, O = 512 / 1024) otherwise run as O/256 launches of ceil(M/128) CTAs each, one after the other.
+extern "C" int eml_gemm_bf16_slices(const void *A_hi, const void *A_lo, long M, int Kp, const void *wpack, long slice_bytes, int nslices,
+                                    int N, const float *bias, float *out, int out_pitch, int out_choff, int precision, void *stream) {
+    return gemm_impl(A_hi, A_lo, M, Kp, wpack, N, bias, out, out_pitch, out_choff, precision, 1, stream, nslices, slice_bytes);
 }
 
 // Split-K variant for short-and-deep products (needlet projection: M = 3 B rows, K = 32768 pixels): the K chunks are dealt to

@@ -76,76 +76,110 @@ __global__ void __launch_bounds__(256) im2col_lut_kernel(const float *__restrict
 
 // Same gather, emitting the GEMM operand already split into bf16 hi / lo matrices of row length Kp (a multiple of 64;
 // columns >= 9*Cp are zero) -- the layout gemm_tma.cu's tensor maps describe.  A_lo may be NULL (single-pass bf16).
-// One warp per output pixel: the 9 LUT entries are warp-broadcast loads, lanes walk the channel quads, so the four source
-// reads are 512-byte coalesced segments and the hi/lo writes are 256-byte coalesced; no per-element integer division.
+// A block takes I2_TP consecutive output pixels: their 9 LUT entries go to shared memory once, then the threads walk the
+// tile's (pixel, k-quad) items FLATTENED -- consecutive threads = consecutive 8-byte pieces of an A row, whatever C is
+// (the 3-channel label map has ONE quad per tap: a warp-per-pixel loop left 31 lanes idle there) -- four items per
+// thread in flight (16 independent 16-byte gathers) before any is converted and stored.
+constexpr int I2_TP = 32;
 __global__ void __launch_bounds__(256) im2col_lut_bf16_kernel(const float *__restrict__ x, int x_pitch, int C, int Cp,
                                                               const int *__restrict__ idx, const float *__restrict__ wgt,
                                                               const float *__restrict__ bias, int act,
                                                               __nv_bfloat16 *__restrict__ A_hi, __nv_bfloat16 *__restrict__ A_lo, int Kp,
                                                               int Mo_img, long in_img_pixels, long M) {
-    const int cq = Cp >> 2, kq = Kp >> 2;
-    const int lane = threadIdx.x & 31;
+    __shared__ int4 s_idx[I2_TP * 9];
+    __shared__ float4 s_w[I2_TP * 9];
+    __shared__ long s_xoff[I2_TP];
+    const int cq = Cp >> 2, kq = Kp >> 2, kdata = 9 * cq;
+    const int cq_shift = (cq & (cq - 1)) == 0 ? __ffs(cq) - 1 : -1;
     const bool vec = (x_pitch & 3) == 0;
-    for (long m = blockIdx.x * 8L + (threadIdx.x >> 5); m < M; m += gridDim.x * 8L) {
-        const long b = m / Mo_img;
-        const int mp = static_cast<int>(m - b * Mo_img);
-        const float *xb = x + b * in_img_pixels * x_pitch;
-        __nv_bfloat16 *row_hi = A_hi + m * Kp;
-        __nv_bfloat16 *row_lo = A_lo ? A_lo + m * Kp : nullptr;
-        for (int tap = 0; tap < 9; ++tap) {
-            const int4 id = __ldg(reinterpret_cast<const int4 *>(idx + (static_cast<long>(mp) * 9 + tap) * 4));
-            const float4 w = __ldg(reinterpret_cast<const float4 *>(wgt + (static_cast<long>(mp) * 9 + tap) * 4));
-            const int ids[4] = {id.x, id.y, id.z, id.w};
-            const float ws[4] = {w.x, w.y, w.z, w.w};
-            for (int q = lane; q < cq; q += 32) {
-                const int c = q * 4;
-                float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (bias != nullptr) {
-                    bs.x = bias[c];
-                    if (c + 1 < C) bs.y = bias[c + 1];
-                    if (c + 2 < C) bs.z = bias[c + 2];
-                    if (c + 3 < C) bs.w = bias[c + 3];
-                }
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                const bool full = vec && c + 3 < C;
+    const long ntiles = (M + I2_TP - 1) / I2_TP;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long m0 = tile * I2_TP;
+        const int npx = static_cast<int>(min(static_cast<long>(I2_TP), M - m0));
+        __syncthreads();                                             // previous tile's readers are done
+        for (int e = threadIdx.x; e < npx * 9; e += blockDim.x) {
+            const int px = e / 9, tap = e - px * 9;
+            const long m = m0 + px;
+            const long b = m / Mo_img;
+            const long mp = m - b * Mo_img;
+            s_idx[e] = __ldg(reinterpret_cast<const int4 *>(idx + (mp * 9 + tap) * 4));
+            s_w[e] = __ldg(reinterpret_cast<const float4 *>(wgt + (mp * 9 + tap) * 4));
+            if (tap == 0) s_xoff[px] = b * in_img_pixels * x_pitch;
+        }
+        __syncthreads();
+        const int items = npx * kq;
+        for (int it0 = threadIdx.x; it0 < items; it0 += 4 * blockDim.x) {
+            float4 v[4][4], bs[4], w[4];
+            int qk[4], px[4], c[4];
+            unsigned live = 0;                                       // bit u*4+t: gather t of item u is in flight
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int it = it0 + u * blockDim.x;
+                px[u] = -1;
+                if (it >= items) continue;
+                px[u] = it / kq;
+                qk[u] = it - px[u] * kq;
+                if (qk[u] >= kdata) continue;                        // K padding: zeros
+                const int tap = cq_shift >= 0 ? (qk[u] >> cq_shift) : qk[u] / cq;
+                c[u] = (qk[u] - tap * cq) * 4;
+                const int4 id = s_idx[px[u] * 9 + tap];
+                w[u] = s_w[px[u] * 9 + tap];
+                const int ids[4] = {id.x, id.y, id.z, id.w};
+                const float *xb = x + s_xoff[px[u]] + c[u];
+                const bool full = vec && c[u] + 3 < C;
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    if (ids[t] < 0) continue;
-                    const float *p = xb + static_cast<long>(ids[t]) * x_pitch + c;
-                    float4 v;
+                    if (ids[t] < 0) continue;                        // zero padding (grid_sample padding_mode='zeros' / conv padding)
+                    const float *p = xb + static_cast<long>(ids[t]) * x_pitch;
                     if (full) {
-                        v = __ldg(reinterpret_cast<const float4 *>(p));
+                        v[u][t] = __ldg(reinterpret_cast<const float4 *>(p));
                     } else {
-                        v.x = p[0];
-                        v.y = c + 1 < C ? p[1] : 0.f;
-                        v.z = c + 2 < C ? p[2] : 0.f;
-                        v.w = c + 3 < C ? p[3] : 0.f;
+                        v[u][t].x = p[0];
+                        v[u][t].y = c[u] + 1 < C ? p[1] : 0.f;
+                        v[u][t].z = c[u] + 2 < C ? p[2] : 0.f;
+                        v[u][t].w = c[u] + 3 < C ? p[3] : 0.f;
                     }
-                    acc.x = fmaf(ws[t], apply_act(v.x + bs.x, act), acc.x);
-                    acc.y = fmaf(ws[t], apply_act(v.y + bs.y, act), acc.y);
-                    acc.z = fmaf(ws[t], apply_act(v.z + bs.z, act), acc.z);
-                    acc.w = fmaf(ws[t], apply_act(v.w + bs.w, act), acc.w);
+                    live |= 1u << (u * 4 + t);
                 }
-                if (c + 1 >= C) acc.y = 0.f;
-                if (c + 2 >= C) acc.z = 0.f;
-                if (c + 3 >= C) acc.w = 0.f;
+                bs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias != nullptr) {
+                    bs[u].x = bias[c[u]];
+                    if (c[u] + 1 < C) bs[u].y = bias[c[u] + 1];
+                    if (c[u] + 2 < C) bs[u].z = bias[c[u] + 2];
+                    if (c[u] + 3 < C) bs[u].w = bias[c[u] + 3];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (px[u] < 0) continue;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (qk[u] < kdata) {
+                    const float ws[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        if (!((live >> (u * 4 + t)) & 1u)) continue;
+                        acc.x = fmaf(ws[t], apply_act(v[u][t].x + bs[u].x, act), acc.x);
+                        acc.y = fmaf(ws[t], apply_act(v[u][t].y + bs[u].y, act), acc.y);
+                        acc.z = fmaf(ws[t], apply_act(v[u][t].z + bs[u].z, act), acc.z);
+                        acc.w = fmaf(ws[t], apply_act(v[u][t].w + bs[u].w, act), acc.w);
+                    }
+                    if (c[u] + 1 >= C) acc.y = 0.f;
+                    if (c[u] + 2 >= C) acc.z = 0.f;
+                    if (c[u] + 3 >= C) acc.w = 0.f;
+                }
                 __nv_bfloat162 h01 = __floats2bfloat162_rn(acc.x, acc.y), h23 = __floats2bfloat162_rn(acc.z, acc.w);
                 uint2 hv;
                 hv.x = *reinterpret_cast<uint32_t *>(&h01); hv.y = *reinterpret_cast<uint32_t *>(&h23);
-                const int ko = (tap * cq + q) * 4;
-                *reinterpret_cast<uint2 *>(row_hi + ko) = hv;
-                if (row_lo != nullptr) {
+                const long ko = (m0 + px[u]) * Kp + qk[u] * 4;
+                *reinterpret_cast<uint2 *>(A_hi + ko) = hv;
+                if (A_lo != nullptr) {
                     __nv_bfloat162 l01 = __floats2bfloat162_rn(acc.x - __low2float(h01), acc.y - __high2float(h01));
                     __nv_bfloat162 l23 = __floats2bfloat162_rn(acc.z - __low2float(h23), acc.w - __high2float(h23));
                     uint2 lv;
                     lv.x = *reinterpret_cast<uint32_t *>(&l01); lv.y = *reinterpret_cast<uint32_t *>(&l23);
-                    *reinterpret_cast<uint2 *>(row_lo + ko) = lv;
+                    *reinterpret_cast<uint2 *>(A_lo + ko) = lv;
                 }
             }
-        }
-        for (int qk = 9 * cq + lane; qk < kq; qk += 32) {                 // zero the K padding
-            *reinterpret_cast<uint2 *>(row_hi + qk * 4) = make_uint2(0u, 0u);
-            if (row_lo != nullptr) *reinterpret_cast<uint2 *>(row_lo + qk * 4) = make_uint2(0u, 0u);
         }
     }
 }
@@ -168,6 +202,117 @@ __global__ void __launch_bounds__(256) spade_modulate_kernel(const float *__rest
         float v = fmaf(n, 1.f + g, b);
         if (lrelu) v = v > 0.f ? v : 0.2f * v;
         out[m * out_pitch + c] = v;
+    }
+}
+
+// Fast path of the same operand: no bias, no activation (eml_bias_act applies them ONCE per source value beforehand instead of once
+// per bilinear tap and filter tap, 36x), whole channel quads.  The general kernel above is issue-bound (ncu: 67 % issue slots, L2 at
+// 13 %): here a warp owns one output pixel, lanes stride the row's k-quads (no division by the row length), the LUT is staged as
+// ready-made float offsets, and an item is 2 LDS + 4 LDG + 16 FMA + the bf16 split.
+__global__ void __launch_bounds__(256) im2col_lut_bf16_plain_kernel(const float *__restrict__ x, int x_pitch, int Cp,
+                                                                    const int *__restrict__ idx, const float *__restrict__ wgt,
+                                                                    __nv_bfloat16 *__restrict__ A_hi, __nv_bfloat16 *__restrict__ A_lo, int Kp,
+                                                                    int Mo_img, long in_img_pixels, long M) {
+    __shared__ int4 s_off[I2_TP * 9];
+    __shared__ float4 s_w[I2_TP * 9];
+    __shared__ long s_xoff[I2_TP];
+    const int cq = Cp >> 2, kq = Kp >> 2, kdata = 9 * cq;
+    const int cq_shift = (cq & (cq - 1)) == 0 ? __ffs(cq) - 1 : -1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long ntiles = (M + I2_TP - 1) / I2_TP;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long m0 = tile * I2_TP;
+        const int npx = static_cast<int>(min(static_cast<long>(I2_TP), M - m0));
+        __syncthreads();
+        for (int e = threadIdx.x; e < npx * 9; e += blockDim.x) {
+            const int px = e / 9, tap = e - px * 9;
+            const long m = m0 + px;
+            const long b = m / Mo_img;
+            const long mp = m - b * Mo_img;
+            int4 id = __ldg(reinterpret_cast<const int4 *>(idx + (mp * 9 + tap) * 4));
+            id.x = id.x < 0 ? -1 : id.x * x_pitch; id.y = id.y < 0 ? -1 : id.y * x_pitch;
+            id.z = id.z < 0 ? -1 : id.z * x_pitch; id.w = id.w < 0 ? -1 : id.w * x_pitch;
+            s_off[e] = id;
+            s_w[e] = __ldg(reinterpret_cast<const float4 *>(wgt + (mp * 9 + tap) * 4));
+            if (tap == 0) s_xoff[px] = b * in_img_pixels * x_pitch;
+        }
+        __syncthreads();
+        for (int px = warp; px < npx; px += 8) {
+            const float *xb = x + s_xoff[px];
+            __nv_bfloat16 *row_hi = A_hi + (m0 + px) * Kp;
+            __nv_bfloat16 *row_lo = A_lo ? A_lo + (m0 + px) * Kp : nullptr;
+            for (int q0 = lane; q0 < kq; q0 += 128) {
+                float4 v[4][4], w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int qk = q0 + 32 * u;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) v[u][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (qk < kdata) {
+                        const int tap = cq_shift >= 0 ? (qk >> cq_shift) : qk / cq;
+                        const int c = (qk - tap * cq) * 4;
+                        const int4 o = s_off[px * 9 + tap];
+                        w[u] = s_w[px * 9 + tap];
+                        if (o.x >= 0) v[u][0] = __ldg(reinterpret_cast<const float4 *>(xb + o.x + c));
+                        if (o.y >= 0) v[u][1] = __ldg(reinterpret_cast<const float4 *>(xb + o.y + c));
+                        if (o.z >= 0) v[u][2] = __ldg(reinterpret_cast<const float4 *>(xb + o.z + c));
+                        if (o.w >= 0) v[u][3] = __ldg(reinterpret_cast<const float4 *>(xb + o.w + c));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int qk = q0 + 32 * u;
+                    if (qk >= kq) continue;
+                    const float ws[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        acc.x = fmaf(ws[t], v[u][t].x, acc.x); acc.y = fmaf(ws[t], v[u][t].y, acc.y);
+                        acc.z = fmaf(ws[t], v[u][t].z, acc.z); acc.w = fmaf(ws[t], v[u][t].w, acc.w);
+                    }
+                    __nv_bfloat162 h01 = __floats2bfloat162_rn(acc.x, acc.y), h23 = __floats2bfloat162_rn(acc.z, acc.w);
+                    uint2 hv;
+                    hv.x = *reinterpret_cast<uint32_t *>(&h01); hv.y = *reinterpret_cast<uint32_t *>(&h23);
+                    *reinterpret_cast<uint2 *>(row_hi + qk * 4) = hv;
+                    if (row_lo != nullptr) {
+                        __nv_bfloat162 l01 = __floats2bfloat162_rn(acc.x - __low2float(h01), acc.y - __high2float(h01));
+                        __nv_bfloat162 l23 = __floats2bfloat162_rn(acc.z - __low2float(h23), acc.w - __high2float(h23));
+                        uint2 lv;
+                        lv.x = *reinterpret_cast<uint32_t *>(&l01); lv.y = *reinterpret_cast<uint32_t *>(&l23);
+                        *reinterpret_cast<uint2 *>(row_lo + qk * 4) = lv;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// out = act(x + bias[c])  (act: 0 none, 1 ReLU, 2 LeakyReLU(0.2)): discriminator model0 (SphereConv + LeakyReLU, discriminator.py:91-92),
+// VGG conv + ReLU, and the input transform of a SphereConv applied once per value (see the fast path above).  `out` may be `x`.
+__global__ void __launch_bounds__(256) bias_act_kernel(const float *x, int x_pitch, const float *__restrict__ bias, int act,
+                                                       float *out, int out_pitch, long M, int C) {
+    if (((x_pitch | out_pitch | C) & 3) == 0) {
+        const int cq = C >> 2;
+        const long total = M * cq;
+        for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+            const int c = static_cast<int>(i % cq) * 4;
+            const long m = i / cq;
+            float4 v = *reinterpret_cast<const float4 *>(x + m * x_pitch + c);
+            if (bias != nullptr) {
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + c));
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
+            *reinterpret_cast<float4 *>(out + m * out_pitch + c) = v;
+        }
+        return;
+    }
+    const long total = M * C;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        const long m = i / C;
+        out[m * out_pitch + c] = apply_act(x[m * x_pitch + c] + (bias ? bias[c] : 0.f), act);
     }
 }
 
@@ -283,17 +428,6 @@ __global__ void __launch_bounds__(256) tanh_out_kernel(const float *__restrict__
 }
 
 
-// out = act(x + bias[c])   (discriminator model0: SphereConv + LeakyReLU, discriminator.py:91-92; VGG conv + ReLU)
-__global__ void __launch_bounds__(256) bias_act_kernel(const float *__restrict__ x, int x_pitch, const float *__restrict__ bias, int act,
-                                                       float *__restrict__ out, int out_pitch, long M, int C) {
-    const long total = M * C;
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(i % C);
-        const long m = i / C;
-        out[m * out_pitch + c] = apply_act(x[m * x_pitch + c] + (bias ? bias[c] : 0.f), act);
-    }
-}
-
 // mode 0: avg_pool2d(k=3, s=2, p=1, count_include_pad=False) (discriminator.py:48-51); mode 1: max_pool2d(k=2, s=2) (VGG19)
 __global__ void __launch_bounds__(256) pool_kernel(const float *__restrict__ x, int x_pitch, int Hi, int Wi, float *__restrict__ out,
                                                    int out_pitch, int Ho, int Wo, int C, long B, int mode) {
@@ -399,7 +533,13 @@ extern "C" int eml_im2col_lut_bf16(const float *x, int x_pitch, int C, int Cp, c
     if ((x_pitch & 3) == 0) EML_CHECK_ALIGN16(x);
     if (out_pixels >= (1L << 31)) return EML_E_SHAPE;
     const long M = static_cast<long>(B) * out_pixels;
-    im2col_lut_bf16_kernel<<<grid_for(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    if (bias == nullptr && act == 0 && C == Cp && (x_pitch & 3) == 0 && in_pixels * x_pitch < (1L << 31) && !eml_env_flag("EML_IM2COL_GENERAL")) {
+        im2col_lut_bf16_plain_kernel<<<grid_for(M, I2_TP), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            x, x_pitch, Cp, lut_idx, lut_w, static_cast<__nv_bfloat16 *>(A_hi), static_cast<__nv_bfloat16 *>(A_lo), Kp,
+            static_cast<int>(out_pixels), in_pixels, M);
+        return eml_launch_status();
+    }
+    im2col_lut_bf16_kernel<<<grid_for(M, I2_TP), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         x, x_pitch, C, Cp, lut_idx, lut_w, bias, act, static_cast<__nv_bfloat16 *>(A_hi), static_cast<__nv_bfloat16 *>(A_lo), Kp,
         static_cast<int>(out_pixels), in_pixels, M);
     return eml_launch_status();
@@ -413,6 +553,15 @@ extern "C" int eml_spade_modulate(const float *x, int x_pitch, const float *mean
     if (M <= 0 || C <= 0 || x_pitch < C || gb_pitch < 2 * C || out_pitch < C) return EML_E_SHAPE;
     spade_modulate_kernel<<<grid_for(M * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_pitch, mean, inv_std, gamma_beta, gb_pitch,
                                                                                        bias_gamma, bias_beta, out, out_pitch, M, C, leaky_relu);
+    return eml_launch_status();
+}
+
+extern "C" int eml_bias_act(const float *x, int x_pitch, const float *bias, int act, float *out, int out_pitch, long M, int C, void *stream) {
+    EML_CHECK_PTR(x); EML_CHECK_PTR(out);
+    if (M <= 0 || C <= 0 || x_pitch < C || out_pitch < C) return EML_E_SHAPE;
+    if (act < 0 || act > 2) return EML_E_ARG;
+    if (((x_pitch | out_pitch | C) & 3) == 0) { EML_CHECK_ALIGN16(x); EML_CHECK_ALIGN16(out); if (bias) EML_CHECK_ALIGN16(bias); }
+    bias_act_kernel<<<grid_for(M * ((C + 3) / 4)), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_pitch, bias, act, out, out_pitch, M, C);
     return eml_launch_status();
 }
 
@@ -459,14 +608,6 @@ extern "C" int eml_tanh_to_nchw(const float *x, int x_pitch, const float *bias, 
     if (B <= 0 || C <= 0 || HW <= 0 || x_pitch < C) return EML_E_SHAPE;
     const long total = static_cast<long>(B) * C * HW;
     tanh_out_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_pitch, bias, out, B, HW, C, scale);
-    return eml_launch_status();
-}
-
-extern "C" int eml_bias_act(const float *x, int x_pitch, const float *bias, int act, float *out, int out_pitch, long M, int C, void *stream) {
-    EML_CHECK_PTR(x); EML_CHECK_PTR(out);
-    if (M <= 0 || C <= 0 || x_pitch < C || out_pitch < C) return EML_E_SHAPE;
-    if (act < 0 || act > 2) return EML_E_ARG;
-    bias_act_kernel<<<grid_for(M * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_pitch, bias, act, out, out_pitch, M, C);
     return eml_launch_status();
 }
 

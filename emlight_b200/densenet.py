@@ -359,6 +359,8 @@ class DenseNet(nn.Module):
         h, w = H, W
         for b, c_in, c_out, c_tr in self._plan:
             ws["slab"].append(torch.empty(B, h, w, _up8(c_out), dtype=torch.float32, device=device))
+            if _up8(c_out) > c_out:
+                ws["slab"][-1][..., c_out:].zero_()        # pitch padding: quad loads of the last channels reach it (masked, but defined)
             ws["geom"].append((h, w))
             h, w = h // 2, w // 2
         ws["bott"] = torch.empty(B, H, W, 4 * self.growth_rate, dtype=torch.float32, device=device)
@@ -672,6 +674,8 @@ class DenseNet(nn.Module):
             tr = getattr(f, "transition%d" % b)
             wt = tr.conv.weight.detach().float()                                  # (c_tr, c_out, 1, 1)
             dp = torch.empty(B, h // 2, w // 2, _up4(c_out), dtype=torch.float32, device=dev)
+            if _up4(c_out) > c_out:
+                dp[..., c_out:].zero_()                    # pitch padding: read as part of the last channel quad (masked, but defined)
             self._gemm_bwd(dt.data_ptr(), dt.shape[3], B, h // 2, w // 2, c_tr, wt.permute(1, 0, 2, 3).contiguous(), dp, _lib.EML_CONV_1x1)
             a_t = self._aff(c, "t%d.norm" % b)
             dwt = torch.zeros(c_tr, c_out, dtype=torch.float32, device=dev)

@@ -138,12 +138,20 @@ class _PackedConv:
         self.K = K
         self.slices = []
         st = _lib.stream_ptr()
+        # equal slices live in ONE buffer at a fixed stride, so eml_gemm_bf16_slices can run them all in one launch
+        self.pack_all, self.slice_bytes = None, 0
+        if precision != "fp32" and O > _MAX_N and O % _MAX_N == 0:
+            self.slice_bytes = lib.eml_conv_wpack_bytes(_MAX_N, K, 1)
+            self.pack_all = torch.empty(self.slice_bytes * (O // _MAX_N), dtype=torch.uint8, device=weight.device)
         for n0 in range(0, O, _MAX_N):
             n = min(_MAX_N, O - n0)
             w_s = self.wk[n0:n0 + n].contiguous()
             pack = None
             if precision != "fp32":
-                pack = torch.empty(lib.eml_conv_wpack_bytes(n, K, 1), dtype=torch.uint8, device=weight.device)
+                if self.pack_all is not None:
+                    pack = self.pack_all[(n0 // _MAX_N) * self.slice_bytes:(n0 // _MAX_N + 1) * self.slice_bytes]
+                else:
+                    pack = torch.empty(lib.eml_conv_wpack_bytes(n, K, 1), dtype=torch.uint8, device=weight.device)
                 _lib.check(lib.eml_conv_pack_weights(_lib.ptr(w_s), _lib.ptr(pack), n, K, 1, st), "eml_conv_pack_weights")
             self.slices.append((n0, n, w_s, pack))
 
@@ -195,11 +203,21 @@ def _conv_raw(x, B, H, W, pc, lut, bias_in, act, precision):
         _gemm(A, M, pc, out, out.shape[-1], 0, precision)
         return out
     split = precision == "bf16x3"
+    st = _lib.stream_ptr()
+    if (bias_in is not None or act) and pc.C == pc.Cp and x.shape[-1] % 4 == 0:
+        # the input transform once per value (not once per filter tap x bilinear tap): the gather then takes its plain fast path
+        xt = torch.empty(B, H, W, pc.Cp, dtype=torch.float32, device=x.device)
+        _lib.check(lib.eml_bias_act(_lib.ptr(x), x.shape[-1], _lib.ptr(bias_in), act, _lib.ptr(xt), pc.Cp, B * H * W, pc.C, st), "eml_bias_act")
+        x, bias_in, act = xt, None, 0
     a_hi = torch.empty(M, pc.K, dtype=torch.bfloat16, device=x.device)
     a_lo = torch.empty(M, pc.K, dtype=torch.bfloat16, device=x.device) if split else None
-    st = _lib.stream_ptr()
     _lib.check(lib.eml_im2col_lut_bf16(_lib.ptr(x), x.shape[-1], pc.C, pc.Cp, _lib.ptr(idx), _lib.ptr(wgt), _lib.ptr(bias_in), act,
                                        _lib.ptr(a_hi), _lib.ptr(a_lo), pc.K, B, ho * wo, H * W, st), "eml_im2col_lut_bf16")
+    if pc.pack_all is not None:
+        _lib.check(lib.eml_gemm_bf16_slices(_lib.ptr(a_hi), _lib.ptr(a_lo), M, pc.K, _lib.ptr(pc.pack_all), pc.slice_bytes, len(pc.slices), _MAX_N,
+                                            None, _lib.ptr(out), out.shape[-1], 0, _lib.PRECISIONS[precision], st),
+                   "eml_gemm_bf16_slices(%dx%dx%d)" % (M, pc.O, pc.K))
+        return out
     for n0, n, w_s, pack in pc.slices:
         _lib.check(lib.eml_gemm_bf16(_lib.ptr(a_hi), _lib.ptr(a_lo), M, pc.K, _lib.ptr(pack), n, None, _lib.ptr(out), out.shape[-1], n0,
                                      _lib.PRECISIONS[precision], st), "eml_gemm_bf16(%dx%dx%d)" % (M, n, pc.K))

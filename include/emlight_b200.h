@@ -221,6 +221,13 @@ int eml_gemm_bf16(const void *A_hi, const void *A_lo, long M, int Kp, const void
 int eml_gemm_bf16_splitk(const void *A_hi, const void *A_lo, long M, int Kp, const void *wpack, int N, const float *bias, float *out,
                          int out_pitch, int out_choff, int precision, int ksplit, void *stream);
 
+/* `nslices` output slices of exactly N columns (N a multiple of 16, <= 256) in ONE launch: slice s multiplies the same A by the packed
+ * weights at wpack + s * slice_bytes (each slice packed by eml_conv_pack_weights as its own (N, Kp) matrix), adds bias[s*N + n] and writes
+ * columns [out_choff + s*N, out_choff + (s+1)*N).  The wide low-resolution SphereConv layers (O = 512 / 1024 at 4x8 .. 16x32,
+ * generator.py:40-52) otherwise run as O/256 launches of ceil(M/128) CTAs each; results are bit-identical to per-slice eml_gemm_bf16. */
+int eml_gemm_bf16_slices(const void *A_hi, const void *A_lo, long M, int Kp, const void *wpack, long slice_bytes, int nslices, int N,
+                         const float *bias, float *out, int out_pitch, int out_choff, int precision, void *stream);
+
 /* SPADE.forward (models/networks/normalization.py:101-115) after the gamma/beta convolutions:
  *   out = ((x - mean[c]) * inv_std[c]) * (1 + gamma + bias_gamma[c]) + (beta + bias_beta[c]), optional LeakyReLU(0.2);
  * gamma_beta (M, gb_pitch) holds gamma in channels [0,C) and beta in [C,2C) (one GEMM with concatenated weights). */
@@ -365,7 +372,9 @@ int eml_loss_seed(const float *a, int a_pitch, const float *b, int b_pitch, cons
                   const float *coef_dev, float *da, int da_pitch, void *stream);
 
 /* G6-G7 -- discriminator / loss building blocks (NHWC fp32).
- * eml_bias_act: out = act(x + bias[c]) (act 0 none, 1 ReLU, 2 LeakyReLU(0.2)); discriminator.py:91-92, VGG conv+ReLU.
+ * eml_bias_act: out = act(x + bias[c]) (act 0 none, 1 ReLU, 2 LeakyReLU(0.2)); discriminator.py:91-92, VGG conv+ReLU; also the input
+ *   transform of a SphereConv (relu(mlp_shared(seg)) in SPADE.forward, normalization.py:104-106) applied ONCE per value so that
+ *   eml_im2col_lut_bf16 takes its bias-free fast path instead of re-applying it for each of the 36 (filter tap, bilinear tap) reads.
  * eml_pool2d : mode 0 = avg_pool2d(3, stride 2, pad 1, count_include_pad=False) (discriminator.py:48-51), mode 1 = max_pool2d(2,2) (VGG19).
  * eml_loss_reduce: *acc += sum of  0: a | 1: min(a-1,0) | 2: min(-a-1,0) | 3: |a-b| | 4: |a-b|*(m+(1-m)*50), m = mask[pixel] |
  *                  5: per pixel 1 - cos(a,b) over channels   (loss.py:57-82,109-114; pix2pix_model.py:101-122); caller divides by the count. */

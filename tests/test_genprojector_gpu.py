@@ -134,3 +134,47 @@ def test_generator_and_discriminator_match_reference_golden_at_baseline_width(cu
             got = f.cpu().numpy()[:, ::max(1, f.shape[1] // 8), ::2, ::2]
             assert got.shape == want.shape
             assert np.abs(got - want).max() <= 1e-3 * np.abs(want).max(), (i, j, np.abs(got - want).max() / np.abs(want).max())
+
+
+@pytest.mark.parametrize("B,h,w,C,stride,kind,act", [(3, 5, 9, 3, 1, "sphere", 0), (2, 16, 32, 64, 1, "sphere", 2), (2, 8, 16, 10, 2, "sphere", 1),
+                                                      (1, 32, 64, 128, 1, "sphere", 1), (2, 12, 20, 36, 2, "conv", 2), (1, 4, 8, 1024, 1, "sphere", 0),
+                                                      (2, 7, 11, 20, 1, "sphere", 1)])
+def test_im2col_bf16_operand_equals_fp32_im2col(cuda, B, h, w, C, stride, kind, act):
+    """eml_im2col_lut_bf16 (the GEMM operand the tensor-core path reads: bf16 hi | lo, row length Kp, zero K padding) against
+    eml_im2col_lut (fp32, checked against the CPU restatement through the fp32 generator tests): hi == bf16(value) bit for bit, hi + lo
+    reconstructs the value to 2^-16, pad columns are zero.  Shapes: one channel quad per tap (C = 3), ragged quads (C = 10), tiles that
+    cross an image boundary (45 pixels per image, tiles of 32), the widest layer (C = 1024), regular-grid LUT with stride 2."""
+    from emlight_b200 import _lib, genprojector as GP
+    lib, P, st = _lib.load(), _lib.ptr, _lib.stream_ptr()
+    gen = torch.Generator().manual_seed(C * 3 + h)
+    Cp = (C + 3) // 4 * 4
+    x = torch.randn(B, h, w, Cp, generator=gen).to(cuda)
+    bias = torch.randn(C, generator=gen).to(cuda)
+    idx, wgt, ho, wo = GP._LUTS.get(kind, h, w, stride, cuda)
+    M, K = B * ho * wo, 9 * Cp
+    Kp = (K + 63) // 64 * 64
+    A = torch.full((M, K), float("nan"), device=cuda)
+    _lib.check(lib.eml_im2col_lut(P(x), Cp, C, Cp, P(idx), P(wgt), P(bias), act, P(A), B, ho * wo, h * w, st), "eml_im2col_lut")
+    hi = torch.full((M, Kp), float("nan"), dtype=torch.bfloat16, device=cuda)
+    lo = torch.full((M, Kp), float("nan"), dtype=torch.bfloat16, device=cuda)
+    _lib.check(lib.eml_im2col_lut_bf16(P(x), Cp, C, Cp, P(idx), P(wgt), P(bias), act, P(hi), P(lo), Kp, B, ho * wo, h * w, st), "eml_im2col_lut_bf16")
+    assert torch.equal(hi[:, :K], A.to(torch.bfloat16))
+    assert float((hi[:, :K].float() + lo[:, :K].float() - A).abs().max()) <= 2.0 ** -16 * float(A.abs().max())
+    assert float(hi[:, K:].float().abs().sum()) == 0.0 and float(lo[:, K:].float().abs().sum()) == 0.0
+    only = torch.full((M, Kp), float("nan"), dtype=torch.bfloat16, device=cuda)
+    _lib.check(lib.eml_im2col_lut_bf16(P(x), Cp, C, Cp, P(idx), P(wgt), P(bias), act, P(only), None, Kp, B, ho * wo, h * w, st), "eml_im2col_lut_bf16")
+    assert torch.equal(only, hi)                                                                    # single-pass bf16 tier: A_lo = NULL
+    if C == Cp:
+        # what _conv_raw runs: the input transform once per value (eml_bias_act), then the bias-free / activation-free fast path of the
+        # gather -- same operand, bit for bit (the blend sees identical values in identical order)
+        xt = torch.full((B, h, w, Cp), float("nan"), device=cuda)
+        _lib.check(lib.eml_bias_act(P(x), Cp, P(bias), act, P(xt), Cp, B * h * w, C, st), "eml_bias_act")
+        want = x + bias
+        want = torch.relu(want) if act == 1 else (torch.where(want > 0, want, 0.2 * want) if act == 2 else want)
+        assert torch.equal(xt, want)
+        h2 = torch.full((M, Kp), float("nan"), dtype=torch.bfloat16, device=cuda)
+        l2 = torch.full((M, Kp), float("nan"), dtype=torch.bfloat16, device=cuda)
+        _lib.check(lib.eml_im2col_lut_bf16(P(xt), Cp, C, Cp, P(idx), P(wgt), None, 0, P(h2), P(l2), Kp, B, ho * wo, h * w, st), "eml_im2col_lut_bf16 (plain)")
+        assert torch.equal(h2, hi) and torch.equal(l2, lo)
+        _lib.check(lib.eml_im2col_lut_bf16(P(xt), Cp, C, Cp, P(idx), P(wgt), None, 0, P(h2), None, Kp, B, ho * wo, h * w, st), "eml_im2col_lut_bf16 (plain)")
+        assert torch.equal(h2, hi)

@@ -35,7 +35,10 @@ if args.profile:
         def __init__(self, name, fn): self.name, self.fn = name, fn
         def __call__(self, *a):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); r = self.fn(*a); e1.record(); rec.append((self.name, e0, e1)); return r
+            key = self.name
+            if self.name == "eml_im2col_lut_bf16": key += "[C=%d,px=%d]" % (a[2], a[12])          # channels, output pixels per image
+            if self.name == "eml_gemm_bf16": key += "[M=%d,K=%d,N=%d]" % (a[2], a[3], a[5])
+            e0.record(); r = self.fn(*a); e1.record(); rec.append((key, e0, e1)); return r
     names = [n for n in _lib.SIGNATURES if n not in ("eml_version", "eml_error_string", "eml_device_ok", "eml_conv_wpack_bytes", "eml_sinkhorn_workspace_bytes")]
     orig = {n: getattr(lib, n) for n in names}
     for n in names: setattr(lib, n, Wrap(n, orig[n]))
@@ -46,7 +49,11 @@ if args.profile:
     agg = collections.Counter(); cnt = collections.Counter()
     for n, a, b in rec: agg[n] += a.elapsed_time(b); cnt[n] += 1
     print("profile: host time to enqueue one forward %.2f ms, %d C-ABI calls" % (t_cpu * 1e3, len(rec)))
-    for n, v in agg.most_common(): print("  %-28s x%4d %8.3f ms" % (n, cnt[n], v))
+    fam = collections.Counter()
+    for n, v in agg.items(): fam[n.split("[")[0]] += v
+    for n, v in fam.most_common(): print("  %-44s       %8.3f ms" % (n, v))
+    print("  by shape:")
+    for n, v in agg.most_common(40): print("  %-44s x%4d %8.3f ms" % (n, cnt[n], v))
 if args.graph:
     G.use_cuda_graph = True
     for _ in range(3): out = G(guide, crop)
