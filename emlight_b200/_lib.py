@@ -64,7 +64,8 @@ SIGNATURES = {
     "eml_im2col_lut_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
                                     c_long, c_long, c_void_p]),
     "eml_gemm_bf16": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "eml_gemm_bf16_slices": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p, c_long, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "eml_gemm_bf16_slices": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p, c_long, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "eml_gemm_pack_slices": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_void_p]),
     "eml_gemm_bf16_splitk": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "eml_spade_modulate": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_long,
                                    c_int, c_int, c_void_p]),

@@ -331,6 +331,49 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, unsigned char *
     }
 }
 
+// The same image for a plain (N, K) row-major matrix (taps = 1: GEMM operands of the GenProjector path, ~1350 packs per G+D
+// iteration, many of them activations), `nslices` slices of `rows` rows each at a fixed stride: one thread converts one 16-byte
+// swizzle chunk (8 consecutive k of one row: two float4 reads, one 16-byte hi store, one 16-byte lo store) instead of one element
+// with 2-byte stores.
+__global__ void __launch_bounds__(256) pack_matrix_kernel(const float *__restrict__ w, unsigned char *__restrict__ out, int rows, int K,
+                                                          int N_pad, int nchunks, int nslices, long slice_bytes) {
+    const long per_slice = static_cast<long>(nchunks) * N_pad * 8;
+    const long total = per_slice * nslices;
+    const bool vec = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0;
+    for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int sl = static_cast<int>(idx / per_slice);
+        const long r = idx - sl * per_slice;
+        const int kc = static_cast<int>(r & 7);
+        const int n = static_cast<int>((r >> 3) % N_pad);
+        const int c = static_cast<int>((r >> 3) / N_pad);
+        const int k0 = c * CHUNK_K + kc * 8;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (n < rows && k0 < K) {
+            const float *src = w + (static_cast<long>(sl) * rows + n) * K + k0;
+            if (vec && k0 + 8 <= K) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(src)), b = __ldg(reinterpret_cast<const float4 *>(src + 4));
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (k0 + i < K) v[i] = src[i];
+            }
+        }
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - __low2float(hh), v[2 * i + 1] - __high2float(hh));
+            h[i] = *reinterpret_cast<const uint32_t *>(&hh);
+            l[i] = *reinterpret_cast<const uint32_t *>(&ll);
+        }
+        unsigned char *base = out + sl * slice_bytes + static_cast<size_t>(c) * 2 * N_pad * 128;
+        const uint32_t off = sw128_offset(n, kc * 8);
+        *reinterpret_cast<uint4 *>(base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(base + static_cast<size_t>(N_pad) * 128 + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
 inline int pad16(int n) { return (n + 15) & ~15; }
 inline int tmem_cols_for(int n) { int c = 32; while (c < n) c <<= 1; return c; }
 
@@ -380,6 +423,13 @@ extern "C" int eml_conv_pack_weights(const float *w_oihw, void *wpack, int C_out
     EML_CHECK_ALIGN16(wpack);
     if (C_out <= 0 || C_out > 256 || C_in <= 0 || (taps != 1 && taps != 9)) return EML_E_SHAPE;
     const int cpt = (C_in + CHUNK_K - 1) / CHUNK_K;
+    if (taps == 1 && !eml_env_flag("EML_PACK_V1")) {
+        const long items = static_cast<long>(cpt) * pad16(C_out) * 8;
+        const unsigned grid = static_cast<unsigned>(items / 256 + 1 < 148 * 8 ? items / 256 + 1 : 148 * 8);
+        pack_matrix_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w_oihw, static_cast<unsigned char *>(wpack), C_out, C_in,
+                                                                             pad16(C_out), cpt, 1, 0);
+        return eml_launch_status();
+    }
     pack_weights_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         w_oihw, static_cast<unsigned char *>(wpack), C_out, C_in, taps, pad16(C_out), cpt);
     int rc = eml_launch_status();
@@ -389,6 +439,21 @@ extern "C" int eml_conv_pack_weights(const float *w_oihw, void *wpack, int C_out
     return rc;
 }
 
+
+// `nslices` slices of `rows` rows each (rows a multiple of 16, <= 256) of a row-major (nslices*rows, K) matrix, slice s packed at
+// wpack + s * slice_bytes exactly as eml_conv_pack_weights(w + s*rows*K, ..., rows, K, 1) would: ONE launch (eml_gemm_bf16_slices).
+extern "C" int eml_gemm_pack_slices(const float *w, void *wpack, int nslices, int rows, int K, long slice_bytes, void *stream) {
+    EML_CHECK_PTR(w); EML_CHECK_PTR(wpack);
+    EML_CHECK_ALIGN16(wpack);
+    if (nslices <= 0 || rows <= 0 || rows > 256 || (rows & 15) || K <= 0) return EML_E_SHAPE;
+    const int cpt = (K + CHUNK_K - 1) / CHUNK_K;
+    if ((slice_bytes & 15) || slice_bytes < static_cast<long>(generic_wpack_bytes(rows, K, 1))) return EML_E_SHAPE;
+    const long items = static_cast<long>(cpt) * rows * 8 * nslices;
+    const unsigned grid = static_cast<unsigned>(items / 256 + 1 < 148 * 8 ? items / 256 + 1 : 148 * 8);
+    pack_matrix_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<unsigned char *>(wpack), rows, K, rows, cpt, nslices,
+                                                                         slice_bytes);
+    return eml_launch_status();
+}
 
 extern "C" int eml_conv_forward(const eml_conv_params *p, void *stream) {
     EML_CHECK_PTR(p); EML_CHECK_PTR(p->in); EML_CHECK_PTR(p->out);

@@ -287,9 +287,11 @@ extern "C" int eml_gemm_bf16(const void *A_hi, const void *A_lo, long M, int Kp,
 // `nslices` output slices of exactly N (a multiple of 16, <= 256) columns in ONE launch: slice s multiplies the same A by the
 // packed weights at wpack + s * slice_bytes and writes columns [out_choff + s*N, out_choff + (s+1)*N).  Wide layers at low
 // resolution (M = B*H*W small, O = 512 / 1024) otherwise run as O/256 launches of ceil(M/128) CTAs each, one after the other.
+// ksplit > 1 additionally deals the K chunks to `ksplit` work items per (slice, tile) as eml_gemm_bf16_splitk does (`out` ZERO on entry).
 extern "C" int eml_gemm_bf16_slices(const void *A_hi, const void *A_lo, long M, int Kp, const void *wpack, long slice_bytes, int nslices,
-                                    int N, const float *bias, float *out, int out_pitch, int out_choff, int precision, void *stream) {
-    return gemm_impl(A_hi, A_lo, M, Kp, wpack, N, bias, out, out_pitch, out_choff, precision, 1, stream, nslices, slice_bytes);
+                                    int N, const float *bias, float *out, int out_pitch, int out_choff, int precision, int ksplit,
+                                    void *stream) {
+    return gemm_impl(A_hi, A_lo, M, Kp, wpack, N, bias, out, out_pitch, out_choff, precision, ksplit, stream, nslices, slice_bytes);
 }
 
 // Split-K variant for short-and-deep products (needlet projection: M = 3 B rows, K = 32768 pixels): the K chunks are dealt to

@@ -40,6 +40,10 @@ static inline float u2f(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 #define EML_API(name) name
 __device__ __forceinline__ unsigned f2u(float f) { return __float_as_uint(f); }
 __device__ __forceinline__ float u2f(unsigned u) { return __uint_as_float(u); }
+// spade_ops.cu: the shared-memory-transposed form of eml_im2col_lut_bf16_t (CUDA build only)
+bool eml_im2col_t_tiled_ok(int x_pitch, int C, int Cp, const void *bias, int act, const void *hi, const void *lo, long Mp);
+int eml_im2col_t_tiled(const float *x, int x_pitch, int Cp, const int *lut_idx, const float *lut_w, void *hi, void *lo, long Mp, long M,
+                       long out_pixels, long in_pixels, cudaStream_t st);
 #endif
 
 namespace {
@@ -552,6 +556,10 @@ extern "C" int EML_API(eml_im2col_lut_bf16_t)(const float *x, int x_pitch, int C
     if (act < 0 || act > 2) return EML_E_ARG;
     const long M = static_cast<long>(B) * out_pixels;
     if (B <= 0 || C <= 0 || Cp < C || (Cp & 3) || x_pitch < C || out_pixels <= 0 || in_pixels <= 0 || Mp < M) return EML_E_SHAPE;
+#ifndef EML_EMULATE
+    if (eml_im2col_t_tiled_ok(x_pitch, C, Cp, bias, act, At_hi, At_lo, Mp))
+        return eml_im2col_t_tiled(x, x_pitch, Cp, lut_idx, lut_w, At_hi, At_lo, Mp, M, out_pixels, in_pixels, static_cast<cudaStream_t>(stream));
+#endif
     const long total = M * 9 * (Cp >> 2);
     if (blocks_for(total) > 0x7fffffffL) return EML_E_SHAPE;
     EML_LAUNCH(im2col_lut_bf16_t_kernel, blocks_for(total), THREADS, stream, x, x_pitch, C, Cp, lut_idx, lut_w, bias, act,

@@ -288,6 +288,84 @@ __global__ void __launch_bounds__(256) im2col_lut_bf16_plain_kernel(const float 
     }
 }
 
+// The TRANSPOSED operand of the weight-gradient GEMM (rows = (tap, channel), columns = output pixels; eml_im2col_lut_bf16_t in
+// gp_bwd.cu holds the reference form, one thread per (pixel, tap, quad) with 2-byte stores).  Tiled: a block takes 64 pixels x one
+// filter tap x 64 channels, gathers like the fast path above (16 lanes = 16 consecutive channel quads of one source pixel: 256-byte
+// reads), splits into bf16 hi / lo, transposes through shared memory and writes 64 rows of 128 contiguous bytes.  No bias, no
+// activation (eml_bias_act first), whole quads, Mp % 8 == 0.
+constexpr int IT_PX = 64, IT_CH = 64, IT_LD = IT_PX + 2;
+__global__ void __launch_bounds__(256) im2col_lut_bf16_t_tiled_kernel(const float *__restrict__ x, int x_pitch, int Cp,
+                                                                      const int *__restrict__ idx, const float *__restrict__ wgt,
+                                                                      unsigned short *__restrict__ hi, unsigned short *__restrict__ lo,
+                                                                      long Mp, long M, long out_pixels, long in_pixels, int cgroups) {
+    __shared__ __align__(16) unsigned short s_hi[IT_CH][IT_LD];
+    __shared__ __align__(16) unsigned short s_lo[IT_CH][IT_LD];
+    long blk = blockIdx.x;
+    const int cg = static_cast<int>(blk % cgroups); blk /= cgroups;
+    const int tap = static_cast<int>(blk % 9);
+    const long m0 = (blk / 9) * IT_PX;
+    const int c0 = cg * IT_CH;
+    const int nch = min(IT_CH, Cp - c0);
+    const int cql = threadIdx.x & 15, pxl0 = threadIdx.x >> 4;
+    float4 v[4][4], w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long m = m0 + pxl0 + 16 * i;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) v[i][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < M && cql * 4 < nch) {
+            const long b = m / out_pixels;
+            const long p = m - b * out_pixels;
+            const int4 id = __ldg(reinterpret_cast<const int4 *>(idx + (p * 9 + tap) * 4));
+            w[i] = __ldg(reinterpret_cast<const float4 *>(wgt + (p * 9 + tap) * 4));
+            const float *xb = x + b * in_pixels * x_pitch + c0 + cql * 4;
+            if (id.x >= 0) v[i][0] = __ldg(reinterpret_cast<const float4 *>(xb + static_cast<long>(id.x) * x_pitch));
+            if (id.y >= 0) v[i][1] = __ldg(reinterpret_cast<const float4 *>(xb + static_cast<long>(id.y) * x_pitch));
+            if (id.z >= 0) v[i][2] = __ldg(reinterpret_cast<const float4 *>(xb + static_cast<long>(id.z) * x_pitch));
+            if (id.w >= 0) v[i][3] = __ldg(reinterpret_cast<const float4 *>(xb + static_cast<long>(id.w) * x_pitch));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int px = pxl0 + 16 * i;
+        const float ws[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            acc[0] = fmaf(ws[t], v[i][t].x, acc[0]); acc[1] = fmaf(ws[t], v[i][t].y, acc[1]);
+            acc[2] = fmaf(ws[t], v[i][t].z, acc[2]); acc[3] = fmaf(ws[t], v[i][t].w, acc[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(acc[j]);
+            s_hi[cql * 4 + j][px] = __bfloat16_as_ushort(h);
+            s_lo[cql * 4 + j][px] = __bfloat16_as_ushort(__float2bfloat16_rn(acc[j] - __bfloat162float(h)));
+        }
+    }
+    __syncthreads();
+    const int r = threadIdx.x >> 2, seg = threadIdx.x & 3;
+    if (r >= nch) return;
+    const long mcol = m0 + seg * 16;
+    if (mcol >= M) return;
+    const long o = (static_cast<long>(tap) * Cp + c0 + r) * Mp + mcol;
+    const uint32_t *rh = reinterpret_cast<const uint32_t *>(&s_hi[r][seg * 16]);
+    const uint32_t *rl = reinterpret_cast<const uint32_t *>(&s_lo[r][seg * 16]);
+    if (mcol + 16 <= M) {
+        *reinterpret_cast<uint4 *>(hi + o) = make_uint4(rh[0], rh[1], rh[2], rh[3]);
+        *reinterpret_cast<uint4 *>(hi + o + 8) = make_uint4(rh[4], rh[5], rh[6], rh[7]);
+        if (lo != nullptr) {
+            *reinterpret_cast<uint4 *>(lo + o) = make_uint4(rl[0], rl[1], rl[2], rl[3]);
+            *reinterpret_cast<uint4 *>(lo + o + 8) = make_uint4(rl[4], rl[5], rl[6], rl[7]);
+        }
+    } else {
+        for (int k = 0; mcol + k < M; ++k) {
+            hi[o + k] = s_hi[r][seg * 16 + k];
+            if (lo != nullptr) lo[o + k] = s_lo[r][seg * 16 + k];
+        }
+    }
+}
+
 // out = act(x + bias[c])  (act: 0 none, 1 ReLU, 2 LeakyReLU(0.2)): discriminator model0 (SphereConv + LeakyReLU, discriminator.py:91-92),
 // VGG conv + ReLU, and the input transform of a SphereConv applied once per value (see the fast path above).  `out` may be `x`.
 __global__ void __launch_bounds__(256) bias_act_kernel(const float *x, int x_pitch, const float *__restrict__ bias, int act,
@@ -553,6 +631,21 @@ extern "C" int eml_spade_modulate(const float *x, int x_pitch, const float *mean
     if (M <= 0 || C <= 0 || x_pitch < C || gb_pitch < 2 * C || out_pitch < C) return EML_E_SHAPE;
     spade_modulate_kernel<<<grid_for(M * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_pitch, mean, inv_std, gamma_beta, gb_pitch,
                                                                                        bias_gamma, bias_beta, out, out_pitch, M, C, leaky_relu);
+    return eml_launch_status();
+}
+
+// called by eml_im2col_lut_bf16_t (gp_bwd.cu) when the operand qualifies for the tiled kernel
+bool eml_im2col_t_tiled_ok(int x_pitch, int C, int Cp, const void *bias, int act, const void *hi, const void *lo, long Mp) {
+    return bias == nullptr && act == 0 && C == Cp && (x_pitch & 3) == 0 && (Mp & 7) == 0 && (reinterpret_cast<uintptr_t>(hi) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(lo) & 15) == 0 && !eml_env_flag("EML_IM2COL_GENERAL");
+}
+int eml_im2col_t_tiled(const float *x, int x_pitch, int Cp, const int *lut_idx, const float *lut_w, void *hi, void *lo, long Mp, long M,
+                       long out_pixels, long in_pixels, cudaStream_t st) {
+    const int cgroups = (Cp + IT_CH - 1) / IT_CH;
+    const long blocks = ((M + IT_PX - 1) / IT_PX) * 9 * cgroups;
+    if (blocks > 0x7fffffffL) return EML_E_SHAPE;
+    im2col_lut_bf16_t_tiled_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, x_pitch, Cp, lut_idx, lut_w, static_cast<unsigned short *>(hi),
+                                                                               static_cast<unsigned short *>(lo), Mp, M, out_pixels, in_pixels, cgroups);
     return eml_launch_status();
 }
 

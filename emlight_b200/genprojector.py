@@ -143,16 +143,18 @@ class _PackedConv:
         if precision != "fp32" and O > _MAX_N and O % _MAX_N == 0:
             self.slice_bytes = lib.eml_conv_wpack_bytes(_MAX_N, K, 1)
             self.pack_all = torch.empty(self.slice_bytes * (O // _MAX_N), dtype=torch.uint8, device=weight.device)
+            _lib.check(lib.eml_gemm_pack_slices(_lib.ptr(self.wk), _lib.ptr(self.pack_all), O // _MAX_N, _MAX_N, K, self.slice_bytes, st),
+                       "eml_gemm_pack_slices")
         for n0 in range(0, O, _MAX_N):
             n = min(_MAX_N, O - n0)
-            w_s = self.wk[n0:n0 + n].contiguous()
+            w_s = self.wk[n0:n0 + n]                   # a row range of a contiguous matrix: contiguous
             pack = None
             if precision != "fp32":
                 if self.pack_all is not None:
                     pack = self.pack_all[(n0 // _MAX_N) * self.slice_bytes:(n0 // _MAX_N + 1) * self.slice_bytes]
                 else:
                     pack = torch.empty(lib.eml_conv_wpack_bytes(n, K, 1), dtype=torch.uint8, device=weight.device)
-                _lib.check(lib.eml_conv_pack_weights(_lib.ptr(w_s), _lib.ptr(pack), n, K, 1, st), "eml_conv_pack_weights")
+                    _lib.check(lib.eml_conv_pack_weights(_lib.ptr(w_s), _lib.ptr(pack), n, K, 1, st), "eml_conv_pack_weights")
             self.slices.append((n0, n, w_s, pack))
 
 
@@ -215,7 +217,7 @@ def _conv_raw(x, B, H, W, pc, lut, bias_in, act, precision):
                                        _lib.ptr(a_hi), _lib.ptr(a_lo), pc.K, B, ho * wo, H * W, st), "eml_im2col_lut_bf16")
     if pc.pack_all is not None:
         _lib.check(lib.eml_gemm_bf16_slices(_lib.ptr(a_hi), _lib.ptr(a_lo), M, pc.K, _lib.ptr(pc.pack_all), pc.slice_bytes, len(pc.slices), _MAX_N,
-                                            None, _lib.ptr(out), out.shape[-1], 0, _lib.PRECISIONS[precision], st),
+                                            None, _lib.ptr(out), out.shape[-1], 0, _lib.PRECISIONS[precision], 1, st),
                    "eml_gemm_bf16_slices(%dx%dx%d)" % (M, pc.O, pc.K))
         return out
     for n0, n, w_s, pack in pc.slices:

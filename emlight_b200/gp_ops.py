@@ -151,7 +151,17 @@ def mm_nt_split(a_hi, a_lo, M, K, b, precision="bf16x3"):
     deep = ksplit > 1 and Kp >= 2048
     out = (torch.zeros if deep else torch.empty)(M, pitch, dtype=torch.float32, device=b.device)
     prec = _lib.PRECISIONS[precision]
-    for n0 in range(0, N, 256):
+    n_start = 0
+    nfull = N // 256
+    if nfull >= 2:
+        # all whole 256-row slices of b: one pack launch, one GEMM launch (work item = (slice, K range, 128-row tile))
+        sb = lib.eml_conv_wpack_bytes(256, K, 1)
+        buf = torch.empty(sb * nfull, dtype=torch.uint8, device=b.device)
+        _lib.check(lib.eml_gemm_pack_slices(_lib.ptr(b), _lib.ptr(buf), nfull, 256, K, sb, st), "eml_gemm_pack_slices(mm_nt)")
+        _lib.check(lib.eml_gemm_bf16_slices(_lib.ptr(a_hi), _lib.ptr(a_lo), M, Kp, _lib.ptr(buf), sb, nfull, 256, None, _lib.ptr(out), pitch, 0,
+                                            prec, ksplit if deep else 1, st), "eml_gemm_bf16_slices(%dx%dx%d)" % (M, nfull * 256, K))
+        n_start = nfull * 256
+    for n0 in range(n_start, N, 256):
         rows = min(256, N - n0)
         buf = torch.empty(lib.eml_conv_wpack_bytes(rows, K, 1), dtype=torch.uint8, device=b.device)
         _lib.check(lib.eml_conv_pack_weights(_lib.ptr(b[n0:n0 + rows]), _lib.ptr(buf), rows, K, 1, st), "eml_conv_pack_weights(mm_nt)")
@@ -301,8 +311,17 @@ def im2col_t(x, B, H, W, C, lut_, bias_in, act, split=True):
     Cp = _up4(C)
     M = B * ho * wo
     Mp = (M + 63) // 64 * 64
-    hi = torch.zeros(9 * Cp, Mp, dtype=torch.bfloat16, device=x.device)
-    lo = torch.zeros_like(hi) if split else None
+    if (bias_in is not None or act) and C == Cp and x.shape[-1] % 4 == 0:
+        # the input transform once per value, then the tiled (shared-memory transposed) form of the gather
+        xt = torch.empty(B, H, W, Cp, dtype=torch.float32, device=x.device)
+        _lib.check(_fn("eml_bias_act")(_lib.ptr(x), x.shape[-1], _lib.ptr(bias_in), int(act), _lib.ptr(xt), Cp, B * H * W, C, _st()), "eml_bias_act")
+        x, bias_in, act = xt, None, 0
+    hi = torch.empty(9 * Cp, Mp, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi) if split else None
+    if Mp > M:                                                     # the K padding of the weight-gradient GEMM
+        hi[:, M:].zero_()
+        if split:
+            lo[:, M:].zero_()
     _lib.check(_fn("eml_im2col_lut_bf16_t")(_lib.ptr(x), x.shape[-1], C, Cp, _lib.ptr(idx), _lib.ptr(wgt), _lib.ptr(bias_in), int(act),
                                             _lib.ptr(hi), _lib.ptr(lo), Mp, B, ho * wo, H * W, _st()), "eml_im2col_lut_bf16_t")
     return hi, lo

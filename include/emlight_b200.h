@@ -226,7 +226,11 @@ int eml_gemm_bf16_splitk(const void *A_hi, const void *A_lo, long M, int Kp, con
  * columns [out_choff + s*N, out_choff + (s+1)*N).  The wide low-resolution SphereConv layers (O = 512 / 1024 at 4x8 .. 16x32,
  * generator.py:40-52) otherwise run as O/256 launches of ceil(M/128) CTAs each; results are bit-identical to per-slice eml_gemm_bf16. */
 int eml_gemm_bf16_slices(const void *A_hi, const void *A_lo, long M, int Kp, const void *wpack, long slice_bytes, int nslices, int N,
-                         const float *bias, float *out, int out_pitch, int out_choff, int precision, void *stream);
+                         const float *bias, float *out, int out_pitch, int out_choff, int precision, int ksplit, void *stream);
+/* Packs `nslices` slices of `rows` rows (a multiple of 16, <= 256) of the row-major (nslices*rows, K) fp32 matrix w in one launch:
+ * slice s lands at wpack + s * slice_bytes (slice_bytes >= eml_conv_wpack_bytes(rows, K, 1)) in eml_conv_pack_weights' layout.
+ * ksplit of eml_gemm_bf16_slices: 1, or the split-K factor of eml_gemm_bf16_splitk (then `out` must be ZERO on entry). */
+int eml_gemm_pack_slices(const float *w, void *wpack, int nslices, int rows, int K, long slice_bytes, void *stream);
 
 /* SPADE.forward (models/networks/normalization.py:101-115) after the gamma/beta convolutions:
  *   out = ((x - mean[c]) * inv_std[c]) * (1 + gamma + bias_gamma[c]) + (beta + bias_beta[c]), optional LeakyReLU(0.2);

@@ -61,7 +61,7 @@ def test_gemm_slices_in_one_launch_equal_per_slice_launches(cuda, lib, M, K, nsl
     pitch = nsl * N + 4
     one = torch.zeros(M, pitch, device=cuda)
     ref = torch.zeros(M, pitch, device=cuda)
-    _lib.check(lib.eml_gemm_bf16_slices(P(hi), P(lo), M, Kp, P(pack_all), sb, nsl, N, P(bias), P(one), pitch, 4, _lib.PRECISIONS["bf16x3"], st),
+    _lib.check(lib.eml_gemm_bf16_slices(P(hi), P(lo), M, Kp, P(pack_all), sb, nsl, N, P(bias), P(one), pitch, 4, _lib.PRECISIONS["bf16x3"], 1, st),
                "eml_gemm_bf16_slices")
     for s in range(nsl):
         _lib.check(lib.eml_gemm_bf16(P(hi), P(lo), M, Kp, P(pack_all[s * sb:(s + 1) * sb]), N, P(bias[s * N:(s + 1) * N]), P(ref), pitch, 4 + s * N,
@@ -70,8 +70,16 @@ def test_gemm_slices_in_one_launch_equal_per_slice_launches(cuda, lib, M, K, nsl
     want = A.double() @ W.double().t() + bias.double()
     assert float((one[:, 4:].double() - want).abs().max()) <= 2e-5 * float(want.abs().max())
     # argument checks: slices must be whole 16-column groups and fit the row pitch
-    assert lib.eml_gemm_bf16_slices(P(hi), P(lo), M, Kp, P(pack_all), sb, nsl, N, P(bias), P(one), pitch - 8, 4, _lib.PRECISIONS["bf16x3"], st) < 0
-    assert lib.eml_gemm_bf16_slices(P(hi), P(lo), M, Kp, P(pack_all), sb, nsl, N - 4, P(bias), P(one), pitch, 4, _lib.PRECISIONS["bf16x3"], st) < 0
+    assert lib.eml_gemm_bf16_slices(P(hi), P(lo), M, Kp, P(pack_all), sb, nsl, N, P(bias), P(one), pitch - 8, 4, _lib.PRECISIONS["bf16x3"], 1, st) < 0
+    assert lib.eml_gemm_bf16_slices(P(hi), P(lo), M, Kp, P(pack_all), sb, nsl, N - 4, P(bias), P(one), pitch, 4, _lib.PRECISIONS["bf16x3"], 1, st) < 0
+    # one pack launch for all slices == per-slice packs, byte for byte; split-K over the slices matches to summation order
+    again = torch.zeros_like(pack_all)
+    _lib.check(lib.eml_gemm_pack_slices(P(Wp), P(again), nsl, N, Kp, sb, st), "eml_gemm_pack_slices")
+    assert torch.equal(again, pack_all)
+    sk = torch.zeros(M, pitch, device=cuda)
+    _lib.check(lib.eml_gemm_bf16_slices(P(hi), P(lo), M, Kp, P(pack_all), sb, nsl, N, P(bias), P(sk), pitch, 4, _lib.PRECISIONS["bf16x3"],
+                                        min(3, Kp // 64), st), "eml_gemm_bf16_slices(split-K)")
+    assert float((sk[:, 4:].double() - want).abs().max()) <= 2e-5 * float(want.abs().max())
 
 
 def test_gemm_split_k_matches_single_pass(cuda, lib):
@@ -102,3 +110,18 @@ def test_linear_fp32(cuda, lib, M, K, N):
     assert float((out.double() - want).abs().max()) <= 1e-5 * float(want.abs().max())
     _lib.check(lib.eml_linear_fp32(P(a), P(w), None, P(out), M, N, K, st), "eml_linear_fp32")
     assert float((out.double() - (want - b.double())).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("N,K", [(256, 1152), (100, 70), (16, 64), (37, 9216)])
+def test_matrix_pack_equals_the_elementwise_pack(cuda, lib, N, K, monkeypatch):
+    """eml_conv_pack_weights with taps = 1 runs the 16-byte-chunk kernel; EML_PACK_V1=1 keeps the element-per-thread one: same bytes."""
+    from emlight_b200 import _lib
+    gen = torch.Generator().manual_seed(N + K)
+    W = torch.randn(N, K, generator=gen).to(cuda)
+    nbytes = lib.eml_conv_wpack_bytes(N, K, 1)
+    a = torch.full((nbytes,), 0xAB, dtype=torch.uint8, device=cuda)
+    b = torch.full((nbytes,), 0xCD, dtype=torch.uint8, device=cuda)
+    _lib.check(lib.eml_conv_pack_weights(_lib.ptr(W), _lib.ptr(a), N, K, 1, _lib.stream_ptr()), "pack")
+    monkeypatch.setenv("EML_PACK_V1", "1")
+    _lib.check(lib.eml_conv_pack_weights(_lib.ptr(W), _lib.ptr(b), N, K, 1, _lib.stream_ptr()), "pack v1")
+    assert torch.equal(a, b)

@@ -178,3 +178,15 @@ def test_im2col_bf16_operand_equals_fp32_im2col(cuda, B, h, w, C, stride, kind, 
         assert torch.equal(h2, hi) and torch.equal(l2, lo)
         _lib.check(lib.eml_im2col_lut_bf16(P(xt), Cp, C, Cp, P(idx), P(wgt), None, 0, P(h2), None, Kp, B, ho * wo, h * w, st), "eml_im2col_lut_bf16 (plain)")
         assert torch.equal(h2, hi)
+        # the weight-gradient GEMM's operand is the TRANSPOSE (rows = (tap, channel), columns = pixels padded to 64): the tiled kernel
+        # writes exactly the transposed forward operand and leaves the pad columns to the caller
+        Mp = (M + 63) // 64 * 64
+        ht = torch.full((K, Mp), 3.0, dtype=torch.bfloat16, device=cuda)
+        lt = torch.full((K, Mp), 3.0, dtype=torch.bfloat16, device=cuda)
+        _lib.check(lib.eml_im2col_lut_bf16_t(P(xt), Cp, C, Cp, P(idx), P(wgt), None, 0, P(ht), P(lt), Mp, B, ho * wo, h * w, st), "eml_im2col_lut_bf16_t")
+        assert torch.equal(ht[:, :M], hi[:, :K].t()) and torch.equal(lt[:, :M], lo[:, :K].t())
+        assert bool((ht[:, M:] == 3.0).all()) and bool((lt[:, M:] == 3.0).all())
+        from emlight_b200 import gp_ops
+        gh, gl = gp_ops.im2col_t(x, B, h, w, C, (idx, wgt, ho, wo), bias, act)                      # the host wrapper: transform + pad zeroing
+        assert torch.equal(gh[:, :M], hi[:, :K].t()) and torch.equal(gl[:, :M], lo[:, :K].t())
+        assert float(gh[:, M:].float().abs().sum()) == 0.0 and float(gl[:, M:].float().abs().sum()) == 0.0

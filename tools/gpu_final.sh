@@ -18,3 +18,7 @@ timeout 600 python tools/profile_train.py 64 > gpurun_out/profile_train_b64.log 
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 3000 -c 1400 --csv --log-file gpurun_out/launches_train_b64.csv \
     python tools/profile_train.py 64 > gpurun_out/ncu_train.log 2>&1; echo "ncu train exit $?"
 ls -la gpurun_out | head -40
+# GenProjector: generator forward (eval) per-shape profile, and the G + D iteration
+timeout 600 python tools/bench_generator.py --batch 16 --profile > gpurun_out/profile_generator_fwd_b16.log 2>&1; echo "gen exit $?"; tail -1 gpurun_out/profile_generator_fwd_b16.log
+timeout 600 python tools/bench_generator.py --batch 16 --precision bf16 > gpurun_out/generator_fwd_b16_bf16.log 2>&1; tail -1 gpurun_out/generator_fwd_b16_bf16.log
+timeout 600 python tools/profile_gan_step.py --ngf 64 --ndf 64 --batch 4 > gpurun_out/profile_gan_step_b4_ngf64.log 2>&1; echo "gan exit $?"; tail -2 gpurun_out/profile_gan_step_b4_ngf64.log

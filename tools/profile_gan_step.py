@@ -59,3 +59,13 @@ total = s0.elapsed_time(s1)
 print("one iteration: %.1f ms on the device, %.1f ms of host time to enqueue, %d C-ABI calls, %.1f ms inside them" % (total, host * 1e3, len(rec), sum(agg.values())))
 for n, v in agg.most_common(): print("  %-28s x%5d %9.3f ms" % (n, cnt[n], v))
 print(json.dumps({"ms_per_iteration": total, "abi_ms": sum(agg.values()), "batch": a.batch, "ngf": a.ngf, "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30}))
+# clean timing (no per-call events): 3 iterations back to back
+iteration()
+torch.cuda.synchronize()
+c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0 = time.perf_counter(); c0.record()
+for _ in range(3):
+    iteration()
+c1.record(); host = (time.perf_counter() - t0) / 3
+torch.cuda.synchronize()
+print(json.dumps({"clean_ms_per_iteration": c0.elapsed_time(c1) / 3, "host_enqueue_ms": host * 1e3}))
