@@ -170,7 +170,7 @@ def train_workloads(E, parallel, dev, rank, world, gen, timed, args):
         opt.zero_grad()
         loss.backward()
         opt.step()
-    for _ in range(2):
+    for _ in range(3):
         train_step()
     opt.measure = world > 1
     ms_tr = timed(train_step, 3) / 3
@@ -228,9 +228,10 @@ def train_workloads(E, parallel, dev, rank, world, gen, timed, args):
         def gan_iter():
             og.zero_grad(); gl, _ = gm(gd, "generator"); sum(gl.values()).mean().backward(); og.step()
             od.zero_grad(); dl = gm(gd, "discriminator"); sum(dl.values()).mean().backward(); od.step()
-        gan_iter()
+        for _ in range(3):                              # the caching allocator still grows during the second iteration (tape of ~1400 buffers)
+            gan_iter()
         og.measure = od.measure = world > 1
-        ms_g = timed(gan_iter, 2) / 2
+        ms_g = timed(gan_iter, 3) / 3
         wait_g = og.exposed_ms() + od.exposed_ms()
         og.measure = od.measure = False
         ar = comm_alone([og, od], reps=3)
@@ -246,8 +247,9 @@ def train_workloads(E, parallel, dev, rank, world, gen, timed, args):
             gm.netG.precision = "bf16"; gm.netD.precision = "bf16"
             if getattr(gm, "criterionVGG", None) is not None:
                 gm.criterionVGG.vgg.precision = "bf16"
-            gan_iter()
-            ms_b = timed(gan_iter, 2) / 2
+            for _ in range(2):
+                gan_iter()
+            ms_b = timed(gan_iter, 3) / 3
             out["config3_genprojector_G_step_plus_D_step_b4_per_gpu"]["bf16_single_pass_ms_per_iteration"] = round(ms_b, 3)
             out["config3_genprojector_G_step_plus_D_step_b4_per_gpu"]["bf16_single_pass_maps_per_s"] = round(Bg * world / ms_b * 1e3, 2)
         except Exception as e:                          # noqa: BLE001
