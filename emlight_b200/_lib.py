@@ -5,7 +5,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_lon
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libemlight_b200.so")
-ABI_VERSION = 21
+ABI_VERSION = 22
 
 EML_CONV_1x1, EML_CONV_3x3, EML_CONV_POOL2 = 0, 1, 2
 EML_PREC_BF16, EML_PREC_BF16X3, EML_PREC_FP32 = 0, 1, 2
@@ -65,6 +65,7 @@ SIGNATURES = {
                                     c_long, c_long, c_void_p]),
     "eml_gemm_bf16": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "eml_gemm_bf16_slices": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p, c_long, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "eml_spectral_norm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "eml_gemm_pack_slices": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_void_p]),
     "eml_gemm_bf16_splitk": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "eml_spade_modulate": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_long,
@@ -148,7 +149,11 @@ def ptr(t):
 
 
 def stream_ptr():
+    """The current device's current stream as a raw cudaStream_t (what every launch in the library takes)."""
     import torch
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:                                       # no Stream object per call (~1000 calls per GenProjector iteration)
+        return c_void_p(raw(torch.cuda.current_device()))
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

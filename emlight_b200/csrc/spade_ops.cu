@@ -583,6 +583,73 @@ inline unsigned grid_for(long total, int per_block = 256) {
     return static_cast<unsigned>(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// ------------------------------------------------------------------------------------------------ spectral norm
+// torch.nn.utils.spectral_norm on a (O, K) weight matrix (architecture.py:37-40, normalization.py:29): one power iteration
+//     v <- normalize(W^T u),  u <- normalize(W v),  sigma = u . (W v)
+// as four small deterministic kernels behind ONE C-ABI call (the torch formulation is ~12 tensor ops per wrapped convolution and
+// forward: ~140 convolutions per G+D iteration).  (1) t = W^T u: one thread per column, rows walked 8 at a time (coalesced over the
+// columns); (2) one block: v = t / max(|t|, eps); (3) s = W v: one warp per row; (4) one block: u = s / max(|s|, eps), sigma = u . s.
+__global__ void __launch_bounds__(256) sn_wtu_kernel(const float *__restrict__ w, const float *__restrict__ u, float *__restrict__ t, int O, int K) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int o = 0;
+    for (; o + 8 <= O; o += 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(__ldg(w + static_cast<long>(o + i) * K + k), __ldg(u + o + i), acc[i]);
+    }
+    for (; o < O; ++o) acc[0] = fmaf(__ldg(w + static_cast<long>(o) * K + k), __ldg(u + o), acc[0]);
+    t[k] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+}
+__device__ __forceinline__ float sn_block_sum(float v, float *red) {           // 1024 threads, fixed order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = threadIdx.x < 32 ? red[threadIdx.x] : 0.f;
+    if (threadIdx.x < 32) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        if (threadIdx.x == 0) red[0] = r;
+    }
+    __syncthreads();
+    r = red[0];
+    __syncthreads();
+    return r;
+}
+// out = in / max(|in|, eps); if sigma != NULL also *sigma = out . in
+__global__ void __launch_bounds__(1024) sn_normalize_kernel(const float *__restrict__ in, float *__restrict__ out, int n, float eps, float *sigma) {
+    __shared__ float red[32];
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < n; i += 1024) ss = fmaf(in[i], in[i], ss);
+    const float nrm = sqrtf(sn_block_sum(ss, red));
+    const float inv = 1.f / fmaxf(nrm, eps);
+    float dot = 0.f;
+    for (int i = threadIdx.x; i < n; i += 1024) { const float o = in[i] * inv; out[i] = o; dot = fmaf(o, in[i], dot); }
+    if (sigma != nullptr) {
+        dot = sn_block_sum(dot, red);
+        if (threadIdx.x == 0) *sigma = dot;
+    }
+}
+__global__ void __launch_bounds__(256) sn_wv_kernel(const float *__restrict__ w, const float *__restrict__ v, float *__restrict__ s, int O, int K) {
+    const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (o >= O) return;
+    const float *wr = w + static_cast<long>(o) * K;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(__ldg(wr + k), __ldg(v + k), acc);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) s[o] = acc;
+}
+// eval mode: sigma = u . s with the stored u (no update)
+__global__ void __launch_bounds__(1024) sn_dot_kernel(const float *__restrict__ a, const float *__restrict__ b, int n, float *out) {
+    __shared__ float red[32];
+    float d = 0.f;
+    for (int i = threadIdx.x; i < n; i += 1024) d = fmaf(a[i], b[i], d);
+    d = sn_block_sum(d, red);
+    if (threadIdx.x == 0) *out = d;
+}
+
 }  // namespace
 
 extern "C" int eml_im2col_lut(const float *x, int x_pitch, int C, int Cp, const int *lut_idx, const float *lut_w,
@@ -631,6 +698,24 @@ extern "C" int eml_spade_modulate(const float *x, int x_pitch, const float *mean
     if (M <= 0 || C <= 0 || x_pitch < C || gb_pitch < 2 * C || out_pitch < C) return EML_E_SHAPE;
     spade_modulate_kernel<<<grid_for(M * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_pitch, mean, inv_std, gamma_beta, gb_pitch,
                                                                                        bias_gamma, bias_beta, out, out_pitch, M, C, leaky_relu);
+    return eml_launch_status();
+}
+
+extern "C" int eml_spectral_norm(const float *w, int O, int K, float *u, float *v, int training, float eps, float *scratch, float *sigma,
+                                 void *stream) {
+    EML_CHECK_PTR(w); EML_CHECK_PTR(u); EML_CHECK_PTR(v); EML_CHECK_PTR(scratch); EML_CHECK_PTR(sigma);
+    if (O <= 0 || K <= 0) return EML_E_SHAPE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *t = scratch, *sv = scratch + K;                                     // K + O floats
+    if (training) {
+        sn_wtu_kernel<<<(K + 255) / 256, 256, 0, st>>>(w, u, t, O, K);
+        sn_normalize_kernel<<<1, 1024, 0, st>>>(t, v, K, eps, nullptr);
+        sn_wv_kernel<<<(O + 7) / 8, 256, 0, st>>>(w, v, sv, O, K);
+        sn_normalize_kernel<<<1, 1024, 0, st>>>(sv, u, O, eps, sigma);
+    } else {
+        sn_wv_kernel<<<(O + 7) / 8, 256, 0, st>>>(w, v, sv, O, K);
+        sn_dot_kernel<<<1, 1024, 0, st>>>(u, sv, O, sigma);
+    }
     return eml_launch_status();
 }
 

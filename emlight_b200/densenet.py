@@ -229,8 +229,16 @@ class DenseNet(nn.Module):
             c["fc_pack"] = []
             K = self.fc.in_features
             step = int(os.environ.get("EML_FC_SLICE", "256"))
-            for n0 in range(0, self.fc.out_features, step):
-                rows = min(step, self.fc.out_features - n0)
+            nfc = self.fc.out_features
+            if (nfc % step == 0 and nfc > step and step % 16 == 0 and os.environ.get("EML_FC_SERIAL") != "1" and
+                    os.environ.get("EML_FC_SPLITK") != "1"):
+                # all slices in one buffer at a fixed stride: ONE launch runs them side by side (eml_gemm_bf16_slices; same bits)
+                sb = lib.eml_conv_wpack_bytes(step, K, 1)
+                buf = torch.empty(sb * (nfc // step), dtype=torch.uint8, device=device)
+                _lib.check(lib.eml_gemm_pack_slices(_lib.ptr(c["fc_w"]), _lib.ptr(buf), nfc // step, step, K, sb, st), "eml_gemm_pack_slices(fc)")
+                c["fc_slices"] = (buf, sb, nfc // step, step)
+            for n0 in range(0, nfc if "fc_slices" not in c else 0, step):
+                rows = min(step, nfc - n0)
                 buf = torch.empty(lib.eml_conv_wpack_bytes(rows, K, 1), dtype=torch.uint8, device=device)
                 _lib.check(lib.eml_conv_pack_weights(_lib.ptr(c["fc_w"][n0:n0 + rows]), _lib.ptr(buf), rows, K, 1, st), "eml_conv_pack_weights(fc)")
                 c["fc_pack"].append((n0, rows, buf))
@@ -531,6 +539,11 @@ class DenseNet(nn.Module):
             if splitk:                                               # tiles per 256-feature slice, i.e. 8 CTAs at B = 256; split K over the SMs
                 ws["fc"].zero_()                                     # (float atomics: no longer bit-reproducible run to run)
                 ks = max(1, min(Kp // 64, 148 // ((B + 127) // 128)))
+            if "fc_slices" in c and not splitk:
+                buf, sb, nsl, step = c["fc_slices"]
+                _lib.check(lib.eml_gemm_bf16_slices(_lib.ptr(a_hi), _lib.ptr(a_lo), B, Kp, _lib.ptr(buf), sb, nsl, step, _lib.ptr(c["fc_b"]),
+                                                    _lib.ptr(ws["fc"]), self.fc.out_features, 0, _lib.PRECISIONS[self.precision], 1, st),
+                           "eml_gemm_bf16_slices(fc)")
             for n0, rows, buf in c["fc_pack"]:
                 if splitk:
                     _lib.check(lib.eml_gemm_bf16_splitk(_lib.ptr(a_hi), _lib.ptr(a_lo), B, Kp, _lib.ptr(buf), rows, _lib.ptr(c["fc_b"][n0:n0 + rows]),

@@ -289,10 +289,34 @@ class SphereConv2D(nn.Module):
         return out[..., :self.out_c].permute(0, 3, 1, 2).contiguous()
 
 
+_TORCH_SPECTRAL = os.environ.get("EML_TORCH_SPECTRAL") == "1"     # A/B: the tensor-op formulation
+
+
+def _sn_kernel_ok(wm):
+    return wm.is_cuda and wm.dtype == torch.float32 and wm.is_contiguous() and not _TORCH_SPECTRAL
+
+
+def _sn_sigma_kernel(module, wm, update):
+    """sigma (0-dim tensor) of the (O, K) weight `wm` through eml_spectral_norm: one C-ABI call (four small kernels) instead of ~12
+    tensor ops per wrapped convolution and forward; with `update` the power iteration rewrites module.weight_u / weight_v in place."""
+    O, K = wm.shape
+    scratch = torch.empty(O + K + 1, dtype=torch.float32, device=wm.device)
+    sigma = scratch[O + K:]
+    with torch.no_grad():
+        _lib.check(_lib.load().eml_spectral_norm(_lib.ptr(wm), O, K, _lib.ptr(module.weight_u), _lib.ptr(module.weight_v), int(bool(update)),
+                                                 1e-12, _lib.ptr(scratch), _lib.ptr(sigma), _lib.stream_ptr()), "eml_spectral_norm")
+        if update:
+            torch.autograd.graph.increment_version(module.weight_u)
+            torch.autograd.graph.increment_version(module.weight_v)
+    return sigma[0]
+
+
 def _spectral_sigma(module, w):
     """sigma of torch.nn.utils.spectral_norm: in training mode ONE power iteration first (u, v updated in place, eps 1e-12), in eval
     mode the stored vectors (GenProjector/models/networks/architecture.py:37-40, normalization.py:29 wrap their convs with it)."""
     wm = w.reshape(w.shape[0], -1)
+    if _sn_kernel_ok(wm):
+        return _sn_sigma_kernel(module, wm, module.training)
     if module.training:
         v = nn.functional.normalize(torch.mv(wm.t(), module.weight_u), dim=0, eps=1e-12)
         u = nn.functional.normalize(torch.mv(wm, v), dim=0, eps=1e-12)

@@ -33,7 +33,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import gp_ops as ops
-from .genprojector import _RED_COS, _RED_HINGE_FAKE, _RED_HINGE_REAL, _RED_L1, _RED_L1_MASKED, _RED_SUM, _up4
+from .genprojector import _RED_COS, _RED_HINGE_FAKE, _RED_HINGE_REAL, _RED_L1, _RED_L1_MASKED, _RED_SUM, _sn_kernel_ok, _sn_sigma_kernel, _up4
 
 
 
@@ -115,6 +115,9 @@ def spectral_weight(module, update):
     w = module.weight_orig.detach()
     wm = w.reshape(w.shape[0], -1)
     with torch.no_grad():
+        if _sn_kernel_ok(wm):
+            sigma = _sn_sigma_kernel(module, wm, update)
+            return w / sigma, sigma, module.weight_u.clone(), module.weight_v.clone()
         if update:
             v = F.normalize(torch.mv(wm.t(), module.weight_u), dim=0, eps=1e-12)
             u = F.normalize(torch.mv(wm, v), dim=0, eps=1e-12)

@@ -232,6 +232,12 @@ int eml_gemm_bf16_slices(const void *A_hi, const void *A_lo, long M, int Kp, con
  * ksplit of eml_gemm_bf16_slices: 1, or the split-K factor of eml_gemm_bf16_splitk (then `out` must be ZERO on entry). */
 int eml_gemm_pack_slices(const float *w, void *wpack, int nslices, int rows, int K, long slice_bytes, void *stream);
 
+/* torch.nn.utils.spectral_norm's sigma for a weight viewed as (O, K) row-major (architecture.py:37-40, normalization.py:29 wrap every
+ * generator / discriminator convolution): training != 0 runs ONE power iteration first, in place on the module's buffers --
+ * v <- normalize(W^T u), u <- normalize(W v), eps as in torch (1e-12) -- then *sigma = u . (W v); training == 0 uses the stored u, v.
+ * scratch: K + O floats.  Deterministic (fixed summation order). */
+int eml_spectral_norm(const float *w, int O, int K, float *u, float *v, int training, float eps, float *scratch, float *sigma, void *stream);
+
 /* SPADE.forward (models/networks/normalization.py:101-115) after the gamma/beta convolutions:
  *   out = ((x - mean[c]) * inv_std[c]) * (1 + gamma + bias_gamma[c]) + (beta + bias_beta[c]), optional LeakyReLU(0.2);
  * gamma_beta (M, gb_pitch) holds gamma in channels [0,C) and beta in [C,2C) (one GEMM with concatenated weights). */

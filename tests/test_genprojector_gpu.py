@@ -190,3 +190,35 @@ def test_im2col_bf16_operand_equals_fp32_im2col(cuda, B, h, w, C, stride, kind, 
         gh, gl = gp_ops.im2col_t(x, B, h, w, C, (idx, wgt, ho, wo), bias, act)                      # the host wrapper: transform + pad zeroing
         assert torch.equal(gh[:, :M], hi[:, :K].t()) and torch.equal(gl[:, :M], lo[:, :K].t())
         assert float(gh[:, M:].float().abs().sum()) == 0.0 and float(gl[:, M:].float().abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("O,K", [(64, 27), (1024, 9216), (3, 576), (128, 1152), (37, 1001)])
+def test_spectral_norm_kernel_equals_the_tensor_formulation(cuda, O, K):
+    """eml_spectral_norm == torch.nn.utils.spectral_norm's arithmetic (architecture.py:37-40): v <- normalize(W^T u), u <- normalize(W v),
+    sigma = u . (W v) in training mode (buffers updated in place), stored vectors in eval mode."""
+    from emlight_b200 import _lib
+    import torch.nn.functional as F
+    lib, P, st = _lib.load(), _lib.ptr, _lib.stream_ptr()
+    gen = torch.Generator().manual_seed(O + K)
+    W = torch.randn(O, K, generator=gen).to(cuda)
+    u0 = F.normalize(torch.randn(O, generator=gen), dim=0).to(cuda)
+    v0 = F.normalize(torch.randn(K, generator=gen), dim=0).to(cuda)
+    Wd = W.double()
+    v_ref = F.normalize(Wd.t() @ u0.double(), dim=0, eps=1e-12)
+    u_ref = F.normalize(Wd @ v_ref, dim=0, eps=1e-12)
+    s_ref = torch.dot(u_ref, Wd @ v_ref)
+    u, v = u0.clone(), v0.clone()
+    scratch = torch.empty(O + K + 1, device=cuda)
+    _lib.check(lib.eml_spectral_norm(P(W), O, K, P(u), P(v), 1, 1e-12, P(scratch), P(scratch[O + K:]), st), "eml_spectral_norm")
+    assert float((v.double() - v_ref).abs().max()) <= 2e-6 and float((u.double() - u_ref).abs().max()) <= 2e-6
+    assert abs(float(scratch[O + K]) - float(s_ref)) <= 2e-6 * float(s_ref)
+    # eval mode: buffers untouched, sigma from the stored vectors
+    u2, v2 = u0.clone(), v0.clone()
+    _lib.check(lib.eml_spectral_norm(P(W), O, K, P(u2), P(v2), 0, 1e-12, P(scratch), P(scratch[O + K:]), st), "eml_spectral_norm")
+    assert torch.equal(u2, u0) and torch.equal(v2, v0)
+    s_eval = torch.dot(u0.double(), Wd @ v0.double())
+    assert abs(float(scratch[O + K]) - float(s_eval)) <= 1e-5 * max(1.0, abs(float(s_eval)))
+    # a second run from the same state gives the same bits (fixed summation order)
+    u3, v3 = u0.clone(), v0.clone()
+    _lib.check(lib.eml_spectral_norm(P(W), O, K, P(u3), P(v3), 1, 1e-12, P(scratch), P(scratch[O + K:]), st), "eml_spectral_norm")
+    assert torch.equal(u3, u) and torch.equal(v3, v)

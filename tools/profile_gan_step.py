@@ -69,3 +69,15 @@ for _ in range(3):
 c1.record(); host = (time.perf_counter() - t0) / 3
 torch.cuda.synchronize()
 print(json.dumps({"clean_ms_per_iteration": c0.elapsed_time(c1) / 3, "host_enqueue_ms": host * 1e3}))
+if os.environ.get("EML_CPROFILE") == "1":
+    # where the HOST time of one iteration goes (the step is enqueue-bound): top functions by own time and by cumulative time
+    import cProfile, pstats, io
+    pr = cProfile.Profile()
+    pr.enable()
+    iteration()
+    pr.disable()
+    torch.cuda.synchronize()
+    for key in ("tottime", "cumtime"):
+        buf = io.StringIO()
+        pstats.Stats(pr, stream=buf).sort_stats(key).print_stats(28)
+        print("\n".join(l[:170] for l in buf.getvalue().splitlines()[4:]))
