@@ -118,14 +118,31 @@ __device__ __forceinline__ void bn_eval4(const BnArgs &a, const Bn4 &p, const fl
     }
 }
 
+// thread -> (channel quad q, row lane rl).  Wide tensors (more than 32 quads): a warp = 32 consecutive quads of one row, 8 row lanes,
+// block column blockIdx.x.  Narrow ones (the 48-channel bottleneck of every dense layer: 12 quads) would leave 20 of 32 lanes idle that
+// way -- there the block's 256 threads are dealt as (256 / nq) row lanes x nq quads, one block column.
+struct BnMap { int c, rl, rows, nq, q; bool active; };
+__device__ __forceinline__ BnMap bn_map(const BnArgs &a) {
+    BnMap m;
+    const int cq = (a.C + 3) >> 2;
+    if (cq <= 32) {
+        m.nq = cq; m.rows = 256 / cq; m.q = threadIdx.x % cq; m.rl = threadIdx.x / cq;
+        m.c = m.q * 4; m.active = m.rl < m.rows;
+    } else {
+        m.nq = 32; m.rows = 8; m.q = threadIdx.x & 31; m.rl = threadIdx.x >> 5;
+        m.c = (blockIdx.x * 32 + m.q) * 4; m.active = m.c < a.C;
+    }
+    return m;
+}
+
 __global__ void __launch_bounds__(256) bn_bwd_reduce4_kernel(const BnArgs a, double *sums, long stride) {
-    __shared__ double s1[8][128], s2[8][128];
-    const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
-    const int c = (blockIdx.x * 32 + lane) * 4;
+    __shared__ double s1[256][4], s2[256][4];
+    const BnMap mp = bn_map(a);
+    const int c = mp.c, rl = mp.rl;
     double a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
-    if (c < a.C) {
+    if (mp.active) {
         Bn4 p; bn_load4(a, c, p);
-        for (long m0 = (blockIdx.y * 8L + rl) * 4; m0 < a.M; m0 += gridDim.y * 32L) {
+        for (long m0 = (static_cast<long>(blockIdx.y) * mp.rows + rl) * 4; m0 < a.M; m0 += static_cast<long>(gridDim.y) * mp.rows * 4) {
             float4 xv[4], gv[4]; float gs[4]; bool ok[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -147,13 +164,14 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce4_kernel(const BnArgs a, dou
         }
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { s1[rl][lane * 4 + e] = a1[e]; s2[rl][lane * 4 + e] = a2[e]; }
+    for (int e = 0; e < 4; ++e) { s1[threadIdx.x][e] = a1[e]; s2[threadIdx.x][e] = a2[e]; }      // idle threads hold zeros
     __syncthreads();
-    if (threadIdx.x < 128) {
-        const int cc = blockIdx.x * 128 + threadIdx.x;
+    if (threadIdx.x < mp.nq * 4) {
+        const int q = threadIdx.x >> 2, e = threadIdx.x & 3;
+        const int cc = (mp.nq == 32 && ((a.C + 3) >> 2) > 32 ? blockIdx.x * 128 : 0) + q * 4 + e;
         if (cc < a.C) {
             double t1 = 0.0, t2 = 0.0;
-            for (int r = 0; r < 8; ++r) { t1 += s1[r][threadIdx.x]; t2 += s2[r][threadIdx.x]; }
+            for (int r = 0; r < mp.rows; ++r) { t1 += s1[r * mp.nq + q][e]; t2 += s2[r * mp.nq + q][e]; }
             atomicAdd(sums + cc, t1);
             atomicAdd(sums + stride + cc, t2);
         }
@@ -162,9 +180,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce4_kernel(const BnArgs a, dou
 
 __global__ void __launch_bounds__(256) bn_bwd_apply4_kernel(const BnArgs a, const double *sums, long stride, float *out, int o_pitch,
                                                             int accumulate, int to_stored) {
-    const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
-    const int c = (blockIdx.x * 32 + lane) * 4;
-    if (c >= a.C) return;
+    const BnMap mp = bn_map(a);
+    const int c = mp.c, rl = mp.rl;
+    if (!mp.active) return;
     Bn4 p; bn_load4(a, c, p);
     const double invM = 1.0 / static_cast<double>(a.M);
     float k[4], m1[4], m2[4];
@@ -176,7 +194,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply4_kernel(const BnArgs a, cons
         k[e] = p.gamma[e] * p.inv[e] * (to_stored ? p.pa[e] : 1.f);
     }
     const bool full = c + 3 < a.C;
-    for (long m0 = (blockIdx.y * 8L + rl) * 4; m0 < a.M; m0 += gridDim.y * 32L) {
+    for (long m0 = (static_cast<long>(blockIdx.y) * mp.rows + rl) * 4; m0 < a.M; m0 += static_cast<long>(gridDim.y) * mp.rows * 4) {
         float4 xv[4], gv[4], ov[4]; float gs[4]; bool ok[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -399,8 +417,10 @@ extern "C" int eml_bn_bwd_reduce(const float *grad, int g_pitch, const float *x,
     if (M <= 0 || C <= 0 || x_pitch < C || g_pitch < C || (pool && (H <= 0 || W <= 0 || ((H | W) & 1)))) return EML_E_SHAPE;
     const BnArgs a = make_bn(grad, g_pitch, x, x_pitch, pre_a, pre_b, mean, inv_std, gamma, beta, relu, pool, H, W, M, C);
     if (bn_vec_ok(a, nullptr, 0)) {
-        long gy = (M + 32 * 16 - 1) / (32 * 16);
-        const int gx = (C + 127) / 128;
+        const int cq = (C + 3) / 4;
+        const int gx = cq <= 32 ? 1 : (C + 127) / 128;                   // bn_map: narrow tensors use one block column
+        const int rows4 = (cq <= 32 ? 256 / cq : 8) * 4;                 // rows per block and pass
+        long gy = (M + rows4 * 16 - 1) / (rows4 * 16);
         const long cap = (148L * 8 + gx - 1) / gx;
         if (gy > cap) gy = cap;
         dim3 grid(gx, static_cast<unsigned>(gy < 1 ? 1 : gy));
@@ -423,8 +443,10 @@ extern "C" int eml_bn_bwd_apply(const float *grad, int g_pitch, const float *x, 
     if (M <= 0 || C <= 0 || x_pitch < C || g_pitch < C || out_pitch < C) return EML_E_SHAPE;
     const BnArgs a = make_bn(grad, g_pitch, x, x_pitch, pre_a, pre_b, mean, inv_std, gamma, beta, relu, pool, H, W, M, C);
     if (bn_vec_ok(a, out, out_pitch)) {
-        long gy4 = (M + 32 * 4 - 1) / (32 * 4);
-        const int gx = (C + 127) / 128;
+        const int cq = (C + 3) / 4;
+        const int gx = cq <= 32 ? 1 : (C + 127) / 128;
+        const int rows4 = (cq <= 32 ? 256 / cq : 8) * 4;
+        long gy4 = (M + rows4 * 4 - 1) / (rows4 * 4);
         const long cap = (148L * 16 + gx - 1) / gx;
         if (gy4 > cap) gy4 = cap;
         dim3 grid4(gx, static_cast<unsigned>(gy4 < 1 ? 1 : gy4));

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) wgrad1x1_tc_kernel(const WArgs a
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_bar[2 * W_STAGES + 1];
     __shared__ uint32_t s_tmem;
+    __shared__ __align__(16) float s_sc[256], s_sh[256];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     // stage: X blocks hi [nblk][8 KB] | X blocks lo | G block hi [8 KB] | G block lo
     const int x_img = a.nblk * W_BLK;
@@ -65,6 +66,10 @@ __global__ void __launch_bounds__(W_THREADS, 1) wgrad1x1_tc_kernel(const WArgs a
     const int mt = a.nblk / 2;                                      // 128-channel M tiles
     const int N_pad = (a.N + 15) & ~15;
 
+    for (int i = tid; i < 256; i += W_THREADS) {                    // channels of this launch's range (<= 256); identity behind C
+        s_sc[i] = (i < a.C && a.scale) ? a.scale[i] : 1.f;
+        s_sh[i] = (i < a.C && a.shift) ? a.shift[i] : 0.f;
+    }
     if (tid == 0) {
         for (int s = 0; s < W_STAGES; ++s) { mbar_init(bar_full + 8 * s, W_PWARPS); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_done, 1);
@@ -131,12 +136,11 @@ __global__ void __launch_bounds__(W_THREADS, 1) wgrad1x1_tc_kernel(const WArgs a
                     const int ch = b * 64 + sub * 4;
                     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (rok[i] && ch < a.C) {
-                        float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (ch + e < a.C) { if (a.scale) sc[e] = a.scale[ch + e]; if (a.shift) sh[e] = a.shift[ch + e]; }
-                        o.x = fmaf(xv[i][b].x, sc[0], sh[0]); o.y = fmaf(xv[i][b].y, sc[1], sh[1]);
-                        o.z = fmaf(xv[i][b].z, sc[2], sh[2]); o.w = fmaf(xv[i][b].w, sc[3], sh[3]);
+                        // folded BatchNorm affine from shared memory (two broadcast LDS.128; it was 8 predicated scalar global loads per
+                        // quad and tile -- the producers were issue / LSU-bound, profiles/r02_ncu_train_kernels_metrics.csv)
+                        const float4 sc = *reinterpret_cast<const float4 *>(s_sc + ch), sh = *reinterpret_cast<const float4 *>(s_sh + ch);
+                        o.x = fmaf(xv[i][b].x, sc.x, sh.x); o.y = fmaf(xv[i][b].y, sc.y, sh.y);
+                        o.z = fmaf(xv[i][b].z, sc.z, sh.z); o.w = fmaf(xv[i][b].w, sc.w, sh.w);
                         if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                         if (ch + 1 >= a.C) o.y = 0.f;
                         if (ch + 2 >= a.C) o.z = 0.f;
