@@ -5,7 +5,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_lon
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libemlight_b200.so")
-ABI_VERSION = 22
+ABI_VERSION = 23
 
 EML_CONV_1x1, EML_CONV_3x3, EML_CONV_POOL2 = 0, 1, 2
 EML_PREC_BF16, EML_PREC_BF16X3, EML_PREC_FP32 = 0, 1, 2
@@ -17,13 +17,13 @@ class ConvParams(Structure):
                 ("wpack", c_void_p), ("out", c_void_p), ("stats", c_void_p), ("stats_stride", c_long),
                 ("B", c_int), ("H", c_int), ("W", c_int), ("C_in", c_int), ("in_pitch", c_int),
                 ("C_out", c_int), ("out_pitch", c_int), ("out_choff", c_int),
-                ("mode", c_int), ("relu", c_int), ("precision", c_int)]
+                ("mode", c_int), ("relu", c_int), ("precision", c_int), ("plane_pixels", c_long)]
 
 
 class DenseLayerParams(Structure):
     _fields_ = [("in_", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("wpack", c_void_p), ("bias9", c_void_p),
                 ("out", c_void_p), ("B", c_int), ("H", c_int), ("W", c_int), ("C_in", c_int), ("in_pitch", c_int),
-                ("growth", c_int), ("out_pitch", c_int), ("out_choff", c_int), ("precision", c_int)]
+                ("growth", c_int), ("out_pitch", c_int), ("out_choff", c_int), ("precision", c_int), ("plane_pixels", c_long)]
 
 
 # name -> (restype, argtypes); must list every symbol include/emlight_b200.h declares
@@ -43,6 +43,7 @@ SIGNATURES = {
     "eml_conv_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "eml_conv_forward": (c_int, [POINTER(ConvParams), c_void_p]),
     "eml_dense_layer_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    "eml_transition_planes_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "eml_dense_layer_forward": (c_int, [POINTER(DenseLayerParams), c_void_p]),
     "eml_dense_layer_wpack_bytes": (c_size_t, [c_int]),
     "eml_dense_layer_compose": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -1,7 +1,7 @@
 // Version / error-string / device-check entry points of the C ABI.
 #include "common.cuh"
 
-extern "C" int eml_version(void) { return 22; }
+extern "C" int eml_version(void) { return 23; }
 
 extern "C" const char *eml_error_string(int code) {
     switch (code) {

@@ -459,7 +459,9 @@ extern "C" int eml_conv_forward(const eml_conv_params *p, void *stream) {
     EML_CHECK_PTR(p); EML_CHECK_PTR(p->in); EML_CHECK_PTR(p->out);
     if (p->B <= 0 || p->H <= 0 || p->W <= 0 || p->C_in <= 0 || p->C_out <= 0 || p->C_out > 256) return EML_E_SHAPE;
     if (p->mode < 0 || p->mode > 2) return EML_E_ARG;
-    if ((p->in_pitch & 3) || p->in_pitch < p->C_in) return EML_E_ALIGN;
+    if (p->plane_pixels > 0) {                               // channel-plane input (header): only the TMA transition reads it
+        if (p->precision == EML_PREC_FP32 || p->wpack == nullptr || !eml_dense_pool_supported(p)) return EML_E_SHAPE;
+    } else if ((p->in_pitch & 3) || p->in_pitch < p->C_in) return EML_E_ALIGN;
     if (p->out_pitch < p->out_choff + p->C_out || p->out_choff < 0) return EML_E_SHAPE;
     if (p->mode == EML_CONV_POOL2 && ((p->H | p->W) & 1)) return EML_E_SHAPE;
     EML_CHECK_ALIGN16(p->in);
@@ -472,6 +474,7 @@ extern "C" int eml_conv_forward(const eml_conv_params *p, void *stream) {
     EML_CHECK_ALIGN16(p->wpack);
     if (static_cast<long>(p->B) * p->H * p->W >= (1L << 31)) return EML_E_SHAPE;
     if (eml_dense_pool_supported(p)) return eml_dense_pool_forward(p, st);
+    if (p->plane_pixels > 0) return EML_E_SHAPE;             // channel-plane input: the TMA transition only
     if (eml_persist_supported(p) && !eml_env_flag("EML_NO_PERSIST")) return eml_persist_forward(p, st);
     if (eml_rows_supported(p))
         return eml_rows_forward(p, static_cast<const unsigned char *>(p->wpack) + generic_wpack_bytes(p->C_out, p->C_in, 9), st);

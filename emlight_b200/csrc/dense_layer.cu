@@ -103,6 +103,9 @@ struct FArgs {
                                  // the tensor core (vertical half of the 2x2 average), epilogue = horizontal pair sum, x 0.25, N channels out
     int n_out;                   // pool mode: output channels
     int pair;                    // W == 64: a tile is row r of image 2k (pixels 0-63) next to row r of image 2k+1 (pixels 64-127)
+    long gstride;                // > 0: channel-PLANE input ("grouped" slab): plane g = channels [32g, 32g+32) of every pixel as 128-byte
+                                 // rows, planes gstride pixels apart -- a stage's box is one contiguous 16 KB run.  0: NHWC pixel records.
+    long ogstride;               // the same for the output (dense mode, wide == 3)
 };
 
 __device__ __forceinline__ void f_mbar_arrive(uint32_t bar) {
@@ -453,7 +456,9 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
                         const uint32_t dst = smem_u32(smem + static_cast<size_t>(s) * F_STAGE_BYTES);
                         mbar_wait(bar_empty + 8 * s, ph ^ 1);
                         mbar_expect_tx(bar_full + 8 * s, F_STAGE_BYTES);
-                        if (a.pair) {                 // two boxes of 64 pixels: the same row of two consecutive images
+                        if (a.gstride > 0) {          // channel planes: stage j = plane j, rows = pixels
+                            f_tma_load_2d(dst, &tmap, 0, static_cast<int>(j * a.gstride + mrow), bar_full + 8 * s);
+                        } else if (a.pair) {          // two boxes of 64 pixels: the same row of two consecutive images
                             f_tma_load_2d(dst, &tmap, j * F_STAGE_C, mrow, bar_full + 8 * s);
                             f_tma_load_2d(dst + F_STAGE_BYTES / 2, &tmap, j * F_STAGE_C, mrow + a.H * a.W, bar_full + 8 * s);
                         } else {
@@ -739,7 +744,26 @@ __global__ void __launch_bounds__(f_threads(NCW), 1) dense_layer_kernel(const __
                         asm volatile("bar.sync 1, %0;" ::"r"(nE) : "memory");     // the whole row is staged
                         const int rc = orow == 0 ? 0 : (orow == a.H - 1 ? 2 : 1);
                         float *obase = a.out + ((img * a.H + orow) * a.W) * a.out_pitch + a.out_choff;
-                        if (a.wide == 2) {
+                        if (a.wide == 3) {
+                            // channel-plane output: quad cq = out_choff / 4 + qd of pixel m lives at plane cq / 8, row m, 16-byte slot cq % 8
+                            // (the 12 new channels may straddle two planes); consecutive pixels = consecutive 128-byte rows
+                            const long mbase = (img * a.H + orow) * static_cast<long>(a.W);
+                            const int cq0 = a.out_choff >> 2;
+                            for (int f = et; f < a.W * 3; f += nE) {
+                                const int x = f / 3, qd = f - x * 3;
+                                const float *s0 = s_row + x * F_SROW + qd * 4;
+                                const float4 v0 = *reinterpret_cast<const float4 *>(s0);
+                                const float4 v1 = *reinterpret_cast<const float4 *>(s0 + F_SROW + F_G);
+                                const float4 v2 = *reinterpret_cast<const float4 *>(s0 + 2 * F_SROW + 2 * F_G);
+                                const int cc = x == 0 ? 0 : (x == a.W - 1 ? 2 : 1);
+                                const float4 bb = *reinterpret_cast<const float4 *>(&s_bias[(rc * 3 + cc) * F_G + qd * 4]);
+                                float4 o;
+                                o.x = v0.x + v1.x + v2.x + bb.x; o.y = v0.y + v1.y + v2.y + bb.y;
+                                o.z = v0.z + v1.z + v2.z + bb.z; o.w = v0.w + v1.w + v2.w + bb.w;
+                                const int cq = cq0 + qd;
+                                *reinterpret_cast<float4 *>(a.out + ((cq >> 3) * a.ogstride + mbase + x) * 32 + (cq & 7) * 4) = o;
+                            }
+                        } else if (a.wide == 2) {
                             // 64 bytes per pixel starting 4 channels IN FRONT of the new ones: [4 stashed raw channels | 12 new channels]
                             const float4 *srow4 = s_stash + ((pass == 0 ? rseq - 1 : rseq) % static_cast<uint32_t>(a.stash_rows)) * a.W;
                             for (int f = et; f < a.W * 4; f += nE) {
@@ -872,10 +896,14 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
     if (p->B <= 0 || !eml_dense_layer_supported(p->H, p->W, p->C_in, p->growth, p->precision)) return EML_E_SHAPE;
     const bool pair = p->W == 64;                            // two images side by side in one 128-pixel tile
     if (pair && (p->B & 1)) return EML_E_SHAPE;
-    if ((p->in_pitch & 3) || p->in_pitch < p->C_in || (p->out_pitch & 3) || (p->out_choff & (pair ? 1 : 3)) || p->out_choff < 0 ||
-        p->out_pitch < p->out_choff + F_G)
-        return EML_E_ALIGN;
     const long npix = static_cast<long>(p->B) * p->H * p->W;
+    const bool grouped = p->plane_pixels > 0;                // channel-plane slab (header): in == out, planes of 32 channels
+    if (grouped) {
+        if (pair || p->in != p->out || p->plane_pixels < npix || (p->out_choff & 3) || p->out_choff < 0) return EML_E_SHAPE;
+        if (((p->C_in + 31) / 32) * p->plane_pixels >= (1L << 31)) return EML_E_SHAPE;
+    } else if ((p->in_pitch & 3) || p->in_pitch < p->C_in || (p->out_pitch & 3) || (p->out_choff & (pair ? 1 : 3)) || p->out_choff < 0 ||
+               p->out_pitch < p->out_choff + F_G)
+        return EML_E_ALIGN;
     if (npix >= (1L << 31)) return EML_E_SHAPE;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -898,8 +926,10 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
     if (enc == nullptr) return EML_E_ARG;
     CUtensorMap tmap;
     {
-        const cuuint64_t dims[2] = {static_cast<cuuint64_t>(p->C_in), static_cast<cuuint64_t>(npix)};
-        const cuuint64_t strides[1] = {static_cast<cuuint64_t>(p->in_pitch) * 4};
+        // grouped: ceil(C_in / 32) planes of (plane_pixels x 32 floats) seen as ONE 2-D tensor of 128-byte rows
+        const cuuint64_t dims[2] = {static_cast<cuuint64_t>(grouped ? F_STAGE_C : p->C_in),
+                                    static_cast<cuuint64_t>(grouped ? ((p->C_in + 31) / 32) * p->plane_pixels : npix)};
+        const cuuint64_t strides[1] = {static_cast<cuuint64_t>(grouped ? F_STAGE_C : p->in_pitch) * 4};
         const cuuint32_t box[2] = {F_STAGE_C, static_cast<cuuint32_t>(pair ? 64 : F_TILE_M)};
         const cuuint32_t estr[2] = {1, 1};
         if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p->in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -917,7 +947,8 @@ extern "C" int eml_dense_layer_forward(const eml_dense_layer_params *p, void *st
     a.nbands = static_cast<long>(pair ? p->B / 2 : p->B) * (p->H / R);
     // full-sector stores (see the output pass): possible when every pixel record starts on a 32-byte boundary
     a.wide = 0;
-    if ((reinterpret_cast<uintptr_t>(p->out) & 31u) == 0 && (p->out_pitch & 7) == 0 && !eml_env_flag("EML_DENSE_NARROW_STORE")) {
+    if (grouped) { a.gstride = p->plane_pixels; a.ogstride = p->plane_pixels; a.wide = 3; }
+    else if ((reinterpret_cast<uintptr_t>(p->out) & 31u) == 0 && (p->out_pitch & 7) == 0 && !eml_env_flag("EML_DENSE_NARROW_STORE")) {
         if (!pair && (p->out_choff & 7) == 0 && p->out_choff + F_G + 4 <= p->out_pitch) a.wide = 1;
     }
     a.wbytes = static_cast<int>(dense_wbytes(p->C_in));
@@ -1050,6 +1081,15 @@ bool eml_dense_pool_supported(const eml_conv_params *p) {
     return fused_stages(pool_wbytes(p->C_in), p->W) >= 4;
 }
 
+// Can transition (C_in -> C_out, 2x2 average) at H x W read the block's slab as channel planes (eml_conv_params.plane_pixels)?
+extern "C" int eml_transition_planes_supported(int H, int W, int C_in, int C_out, int precision) {
+    eml_conv_params p{};
+    static const float one = 1.f;
+    p.mode = EML_CONV_POOL2; p.relu = 1; p.precision = precision; p.H = H; p.W = W; p.C_in = C_in; p.C_out = C_out;
+    p.out_pitch = (C_out + 3) & ~3; p.out_choff = 0; p.scale = &one; p.shift = &one;
+    return eml_dense_pool_supported(&p) ? 1 : 0;
+}
+
 int eml_dense_pool_forward(const eml_conv_params *p, cudaStream_t st) {
     const long npix = static_cast<long>(p->B) * p->H * p->W;
     int dev = 0, sms = 148;
@@ -1065,10 +1105,13 @@ int eml_dense_pool_forward(const eml_conv_params *p, cudaStream_t st) {
     }
     EncodeTiledFn enc = f_get_encode();
     if (enc == nullptr) return EML_E_ARG;
+    const bool grouped = p->plane_pixels > 0;                // the block's slab as channel planes (eml_dense_layer_forward)
+    if (grouped && (p->plane_pixels < npix || ((p->C_in + 31) / 32) * p->plane_pixels >= (1L << 31))) return EML_E_SHAPE;
     CUtensorMap tmap;
     {
-        const cuuint64_t dims[2] = {static_cast<cuuint64_t>(p->C_in), static_cast<cuuint64_t>(npix)};
-        const cuuint64_t strides[1] = {static_cast<cuuint64_t>(p->in_pitch) * 4};
+        const cuuint64_t dims[2] = {static_cast<cuuint64_t>(grouped ? F_STAGE_C : p->C_in),
+                                    static_cast<cuuint64_t>(grouped ? ((p->C_in + 31) / 32) * p->plane_pixels : npix)};
+        const cuuint64_t strides[1] = {static_cast<cuuint64_t>(grouped ? F_STAGE_C : p->in_pitch) * 4};
         const cuuint32_t box[2] = {F_STAGE_C, F_TILE_M};
         const cuuint32_t estr[2] = {1, 1};
         if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p->in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1083,6 +1126,7 @@ int eml_dense_pool_forward(const eml_conv_params *p, cudaStream_t st) {
     a.nwchunks = (p->C_in + 63) / 64;
     a.nstg = (p->C_in + F_STAGE_C - 1) / F_STAGE_C;
     a.pool = 1; a.n_out = p->C_out;
+    a.gstride = grouped ? p->plane_pixels : 0;
     a.wbytes = static_cast<int>(pool_wbytes(p->C_in));
     a.stages = fused_stages(a.wbytes, p->W);
     if (!eml_env_flag("EML_DENSE_SMEM_A")) a.stages &= ~3;          // TS: ring depth a multiple of the 4 converter warpgroups (see eml_dense_layer_forward)

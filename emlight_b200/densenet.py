@@ -330,7 +330,7 @@ class DenseNet(nn.Module):
                 c["fused"][(b, l)] = (buf, bias_all[i])
                 i += 1
 
-    def _dense_layer(self, c, key, slab, pitch, h, w, B, ci):
+    def _dense_layer(self, c, key, slab, pitch, h, w, B, ci, plane_pixels=0):
         lib = _lib.load()
         buf, bias9 = c["fused"][key]
         sc, sh = self._aff(c, "b%d.l%d.norm1" % key)
@@ -340,6 +340,7 @@ class DenseNet(nn.Module):
         p.B, p.H, p.W, p.C_in, p.in_pitch = B, h, w, ci, pitch
         p.growth, p.out_pitch, p.out_choff = self.growth_rate, pitch, ci
         p.precision = _lib.PRECISIONS[self.precision]
+        p.plane_pixels = plane_pixels                      # > 0: `slab` is the channel-plane form (G, B*h*w, 32), see _planes_ok
         if self.launch_log is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -350,6 +351,21 @@ class DenseNet(nn.Module):
             M = B * h * w
             # algorithmic bytes: the slab channels read once + the 12 new channels written once; flops of the reference layer
             self.launch_log.append(("dense_layer", "b%d.l%d" % key, 4 * M * (ci + g), 2 * M * (ci * nb + 9 * nb * g), e0, e1))
+
+    def _planes_ok(self, c, ws, B):
+        """Block 1 can keep its slab as channel planes when every one of its layers runs as the one-kernel dense layer and transition 1 on
+        the TMA pipeline (eval mode, tensor-core precision, W in {128, 256}); EML_DENSE_PLANES=0 keeps the NHWC records."""
+        if os.environ.get("EML_DENSE_PLANES") == "0" or self.precision == "fp32":
+            return False
+        lib = _lib.load()
+        b, c_in, c_out, c_tr = self._plan[0]
+        h, w = ws["geom"][0]
+        prec = _lib.PRECISIONS[self.precision]
+        nl = (c_out - c_in) // self.growth_rate
+        if w not in (128, 256) or any((b, l) not in c.get("fused", ()) or
+                                      not lib.eml_dense_layer_supported(h, w, c_in + l * self.growth_rate, self.growth_rate, prec) for l in range(nl)):
+            return False
+        return bool(lib.eml_transition_planes_supported(h, w, c_out, c_tr, prec)) and ("t%d.conv" % b) in c["wpack"]
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, B, H, W, device):
@@ -392,7 +408,7 @@ class DenseNet(nn.Module):
         return ws
 
     # ------------------------------------------------------------------ execution
-    def _conv(self, c, name, src, src_pitch, H, W, B, c_in, dst, dst_pitch, choff, c_out, mode, relu, aff, stats, stride):
+    def _conv(self, c, name, src, src_pitch, H, W, B, c_in, dst, dst_pitch, choff, c_out, mode, relu, aff, stats, stride, plane_pixels=0):
         lib = _lib.load()
         p = ConvParams()
         p.in_ = src.data_ptr()
@@ -407,6 +423,7 @@ class DenseNet(nn.Module):
         p.C_in, p.in_pitch = c_in, src_pitch
         p.C_out, p.out_pitch, p.out_choff = c_out, dst_pitch, choff
         p.mode, p.relu, p.precision = mode, relu, _lib.PRECISIONS[self.precision]
+        p.plane_pixels = plane_pixels
         if self.launch_log is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -458,9 +475,16 @@ class DenseNet(nn.Module):
             if os.environ.get("EML_RECOMPUTE_BOTTLENECK") != "1" and need - have < 0.5 * free:
                 keep = ws.setdefault("bott_keep", {})
         ws["bott_kept"] = keep is not None
+        # ---- block 1 as channel planes (eval): (G, B*H*W, 32) instead of (B, H, W, pitch) -- §4.0 of DESIGN.md
+        planes0 = 0
+        if not train and self._planes_ok(c, ws, B):
+            planes0 = B * H * W
+            if "slab_planes0" not in ws:
+                groups = (self._plan[0][2] + 31) // 32
+                ws["slab_planes0"] = torch.zeros(groups, planes0, 32, dtype=torch.float32, device=dev)   # zeroed: unwritten channels stay finite
         # ---- stem (DenseNet.py:89-92)
-        slab = ws["slab"][0]
-        pitch = slab.shape[3]
+        slab = ws["slab_planes0"] if planes0 else ws["slab"][0]
+        pitch = 32 if planes0 else slab.shape[3]
         s1 = stats[so["slab1"]:]
         if train:
             raw = stats[so["stem_raw"]:]
@@ -475,8 +499,9 @@ class DenseNet(nn.Module):
         # ---- dense blocks + transitions
         pre = None
         for bi, (b, c_in, c_out, c_tr) in enumerate(self._plan):
-            slab = ws["slab"][bi]
-            pitch = slab.shape[3]
+            planes = planes0 if bi == 0 else 0
+            slab = ws["slab_planes0"] if planes else ws["slab"][bi]
+            pitch = 32 if planes else slab.shape[3]
             h, w = ws["geom"][bi]
             count = B * h * w
             sstat = stats[so["slab%d" % b]:]
@@ -487,8 +512,9 @@ class DenseNet(nn.Module):
                 mid = stats[so["b%d.l%d.mid" % (b, l)]:]
                 if (not train and (b, l) in c.get("fused", ()) and (w != 64 or B % 2 == 0) and    # W = 64 tiles hold a row of two images
                         lib.eml_dense_layer_supported(h, w, ci, self.growth_rate, _lib.PRECISIONS[self.precision])):
-                    self._dense_layer(c, (b, l), slab, pitch, h, w, B, ci)
+                    self._dense_layer(c, (b, l), slab, pitch, h, w, B, ci, planes)
                     continue
+                assert not planes, "channel-plane slab: every layer of the block must take the one-kernel path (_planes_ok)"
                 if train:
                     self._fold(c, n1, layer.norm1, stats=sstat, stride=pitch, count=count, pre=pre, mean_var=mv(layer.norm1, count))
                 bott = ws["bott"]
@@ -511,7 +537,7 @@ class DenseNet(nn.Module):
             dpitch = dst.shape[3]
             dstat = stats[so["t_last"]:] if last else stats[so["slab%d" % (b + 1)]:]
             self._conv(c, "t%d.conv" % b, slab, pitch, h, w, B, c_out, dst, dpitch, 0, c_tr, _lib.EML_CONV_POOL2, 1,
-                       self._aff(c, tn), dstat if train else None, dpitch)
+                       self._aff(c, tn), dstat if train else None, dpitch, planes)
             ln = getattr(f, "last_norm%d" % b)
             if train:
                 cnt2 = B * (h // 2) * (w // 2)

@@ -110,6 +110,8 @@ typedef struct eml_conv_params {
     int mode;               /* EML_CONV_1x1, EML_CONV_3x3, EML_CONV_POOL2 (act -> 2x2 average -> 1x1) */
     int relu;               /* 1: act = ReLU, 0: identity */
     int precision;          /* EML_PREC_BF16 (1 MMA pass), EML_PREC_BF16X3 (hi/lo split, fp32-grade), EML_PREC_FP32 (SIMT) */
+    long plane_pixels;      /* 0: `in` is NHWC.  > 0 (EML_CONV_POOL2 on the TMA pipeline only, i.e. transition 1): `in` is the channel-plane
+                             * slab of eml_dense_layer_params.plane_pixels; in_pitch is ignored.  Other modes reject it. */
 } eml_conv_params;
 
 #define EML_CONV_1x1 0
@@ -152,8 +154,17 @@ typedef struct eml_dense_layer_params {
     int C_in, in_pitch;
     int growth, out_pitch, out_choff;
     int precision;
+    long plane_pixels;      /* 0: NHWC pixel records (above).  > 0: CHANNEL-PLANE slab, in == out: plane g holds channels [32g, 32g+32) of
+                             * every pixel as 128-byte rows, consecutive planes plane_pixels rows apart (>= B*H*W); in_pitch / out_pitch are
+                             * ignored.  A stage's TMA box is then one contiguous 16 KB run and the 12 new channels are written into
+                             * consecutive rows instead of 64 bytes every in_pitch*4 bytes.  Channels the block has not produced yet must
+                             * hold FINITE values (allocate the slab zeroed): they are multiplied by zero weights, not skipped.  W = 64
+                             * (image-pair tiles) is not supported in this layout. */
 } eml_dense_layer_params;
 int eml_dense_layer_supported(int H, int W, int C_in, int growth, int precision);
+/* 1 when eml_conv_forward(EML_CONV_POOL2, relu) for this transition runs on the TMA pipeline and therefore accepts a channel-plane
+ * input (eml_conv_params.plane_pixels > 0) -- the caller's test before laying a block's slab out as planes. */
+int eml_transition_planes_supported(int H, int W, int C_in, int C_out, int precision);
 int eml_dense_layer_forward(const eml_dense_layer_params *p, void *stream);
 /* The composite operands of eml_dense_layer_forward, built on the device once per parameter version (fp64 accumulation):
  *   w1 (nb, C_in) = conv1.weight (DenseNet.py:37), w2 (growth, nb, 3, 3) = conv2.weight (:42), scale2 / shift2 (nb) = folded norm2 (:41)

@@ -140,3 +140,27 @@ def test_densenet_backward_contract(cuda):
     net(torch.rand(2, 3, 192, 256, device=cuda))           # a second forward overwrites the workspace the first backward needs
     with pytest.raises(RuntimeError, match="must follow"):
         a["distribution"].sum().backward()
+
+
+@pytest.mark.parametrize("B", [1, 3, 8])
+def test_channel_plane_slab_equals_pixel_records(cuda, B, monkeypatch):
+    """Block 1's slab as channel planes (eml_dense_layer_params.plane_pixels: contiguous TMA boxes, row-contiguous writes) is only a
+    different ADDRESSING of the same computation: outputs are bit-identical to the NHWC pixel-record layout, also after the workspace
+    has been used by a previous batch (stale channels behind C_in are multiplied by zero weights) and next to a training-mode call."""
+    g = np.load(os.path.join(GOLDEN, "densenet.npz"))
+    net = _net(cuda, "bf16x3", g).eval()
+    gen = torch.Generator().manual_seed(B)
+    x1 = torch.rand(B, 3, 192, 256, generator=gen).to(cuda)
+    x2 = torch.rand(B, 3, 192, 256, generator=gen).to(cuda) * 3.0
+    with torch.no_grad():
+        monkeypatch.setenv("EML_DENSE_PLANES", "0")
+        want1 = [t.clone() for t in net(x1).values()]
+        want2 = [t.clone() for t in net(x2).values()]
+        monkeypatch.delenv("EML_DENSE_PLANES")
+        got1 = [t.clone() for t in net(x1).values()]
+        ws = next(iter(net._ws.values()))
+        assert "slab_planes0" in ws                                   # the plane path really ran
+        got2 = [t.clone() for t in net(x2).values()]                  # second batch on the same (now dirty) planes
+        got1b = [t.clone() for t in net(x1).values()]
+    for a, b in zip(want1 + want2 + want1, got1 + got2 + got1b):
+        assert torch.equal(a, b)

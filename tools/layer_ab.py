@@ -10,6 +10,9 @@ import emlight_b200 as E
 
 VARIANTS = [("smemA_r1", {"EML_DENSE_SMEM_A": "1"}), ("zstencil_all", {"EML_DENSE_RS_MAX_C": "0"}), ("rowsum<=96", {"EML_DENSE_RS_MAX_C": "96"}),
             ("rowsum<=144", {"EML_DENSE_RS_MAX_C": "144"}), ("rowsum_all", {"EML_DENSE_RS_MAX_C": "400"})]
+if os.environ.get("EML_AB_SET") == "planes":          # block-1 slab layout (NHWC records vs channel planes) x epilogue choice
+    VARIANTS = [("records", {"EML_DENSE_PLANES": "0"}), ("planes", {}), ("planes_zst", {"EML_DENSE_RS_MAX_C": "0"}),
+                ("planes_rs<=96", {"EML_DENSE_RS_MAX_C": "96"}), ("planes_rs<=144", {"EML_DENSE_RS_MAX_C": "144"})]
 KEYS = sorted({k for _, env in VARIANTS for k in env})
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
