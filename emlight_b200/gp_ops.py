@@ -313,9 +313,7 @@ def im2col_t(x, B, H, W, C, lut_, bias_in, act, split=True):
     Mp = (M + 63) // 64 * 64
     if (bias_in is not None or act) and C == Cp and x.shape[-1] % 4 == 0:
         # the input transform once per value, then the tiled (shared-memory transposed) form of the gather
-        xt = torch.empty(B, H, W, Cp, dtype=torch.float32, device=x.device)
-        _lib.check(_fn("eml_bias_act")(_lib.ptr(x), x.shape[-1], _lib.ptr(bias_in), int(act), _lib.ptr(xt), Cp, B * H * W, C, _st()), "eml_bias_act")
-        x, bias_in, act = xt, None, 0
+        x, bias_in, act = bias_act(x, bias_in, int(act), B * H * W, C), None, 0
     hi = torch.empty(9 * Cp, Mp, dtype=torch.bfloat16, device=x.device)
     lo = torch.empty_like(hi) if split else None
     if Mp > M:                                                     # the K padding of the weight-gradient GEMM
