@@ -128,3 +128,44 @@ def test_wgrad_3x3(cuda, lib, B, H, W, N, precision, tol):
     # accumulates into dW (the caller zeroes): a second call doubles it
     _lib.check(lib.eml_wgrad_3x3(P(dY), 16, N, P(b), 48, 48, P(sc), P(sh), P(dW), B, H, W, _lib.PRECISIONS[precision], st), "eml_wgrad_3x3")
     assert float((dW.double() - 2 * w.grad).abs().max()) <= 2 * tol * float(w.grad.abs().max())
+
+
+@pytest.mark.parametrize("M,C,relu,pre,accumulate", [(1000, 48, 1, False, 0), (4099, 48, 0, True, 1), (777, 12, 1, True, 0), (2048, 128, 1, False, 1),
+                                                      (1500, 132, 1, True, 0), (900, 342, 1, False, 0), (64, 216, 0, True, 1)])
+def test_bn_backward_reduce_and_apply(cuda, lib, M, C, relu, pre, accumulate):
+    """eml_bn_bwd_reduce / eml_bn_bwd_apply (BatchNorm2d under batch statistics + ReLU, DenseNet.py:32-41 backward) against fp64 autograd:
+    narrow tensors (compact row-lane x quad mapping: C = 12, 48, 128), wide ones (block columns: 132, 216, 342 with a ragged last quad),
+    with and without the composed pre-affine u = a*x + b, writing and accumulating."""
+    from emlight_b200 import _lib
+    P, st = _lib.ptr, _lib.stream_ptr()
+    gen = torch.Generator().manual_seed(M + C)
+    pitch = (C + 7) // 8 * 8
+    x = torch.randn(M, pitch, generator=gen).to(cuda)
+    g = torch.randn(M, pitch, generator=gen).to(cuda)
+    pa = (torch.rand(C, generator=gen) + 0.5).to(cuda) if pre else None
+    pb = torch.randn(C, generator=gen).to(cuda) if pre else None
+    gamma, beta = (torch.rand(C, generator=gen) + 0.5).to(cuda), (0.3 * torch.randn(C, generator=gen)).to(cuda)
+    xr = x[:, :C].double().clone().requires_grad_()
+    u = xr * pa.double() + pb.double() if pre else xr
+    mean, var = u.mean(0), u.var(0, unbiased=False)
+    inv = torch.rsqrt(var + 1e-5)
+    y = (u - mean) * inv * gamma.double() + beta.double()
+    if relu:
+        y = torch.relu(y)
+    (y * g[:, :C].double()).sum().backward()
+    mean32, inv32 = mean.detach().float().contiguous(), inv.detach().float().contiguous()
+    sums = torch.zeros(2 * pitch, dtype=torch.float64, device=cuda)
+    _lib.check(lib.eml_bn_bwd_reduce(P(g), pitch, P(x), pitch, P(pa), P(pb), P(mean32), P(inv32), P(gamma), P(beta), relu, 0, 0, 0, M, C,
+                                     P(sums), pitch, st), "eml_bn_bwd_reduce")
+    base = torch.randn(M, pitch, generator=gen).to(cuda)
+    out = base.clone()
+    _lib.check(lib.eml_bn_bwd_apply(P(g), pitch, P(x), pitch, P(pa), P(pb), P(mean32), P(inv32), P(gamma), P(beta), relu, 0, 0, 0, M, C,
+                                    P(sums), pitch, P(out), pitch, accumulate, 1, st), "eml_bn_bwd_apply")
+    want = xr.grad + (base[:, :C].double() if accumulate else 0)
+    assert float((out[:, :C].double() - want).abs().max()) <= 2e-4 * float(xr.grad.abs().max())
+    assert torch.equal(out[:, C:], base[:, C:])                                       # pitch padding untouched
+    # the two sums are what the affine parameters' gradients are built from: d beta = S1, d gamma = S2
+    yhat = ((u - mean) * inv).detach()
+    gm = g[:, :C].double() * ((yhat * gamma.double() + beta.double() > 0) if relu else 1.0)
+    assert float((sums[:C] - gm.sum(0)).abs().max()) <= 1e-4 * float(gm.sum(0).abs().max() + 1)
+    assert float((sums[pitch:pitch + C] - (gm * yhat).sum(0)).abs().max()) <= 1e-4 * float((gm * yhat).sum(0).abs().max() + 1)
