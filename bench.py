@@ -482,7 +482,7 @@ def main():
                 "frac": round(achieved / hbm_peak, 4), "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                 "traffic": traffic, "traffic_source": traffic_src, "families": roofs,
                 "note": "achieved = algorithmic bytes (inputs read once + outputs written once, fp32) / CUDA-event time, summed over the family's launches in one step"}
-    fc_launches = 5 if (args.precision != "fp32" and B >= 32) else 1               # bf16 split + 4 GEMM slices, or the SIMT linear
+    fc_launches = 2 if (args.precision != "fp32" and B >= 32) else 1               # bf16 split + ONE 4-slice GEMM launch, or the SIMT linear
     launches_per_step = 1 + sum(v["launches"] for v in fam.values()) + 1 + fc_launches + 1 + 1   # stem + convs + head_pool + fc + heads + render
 
     # ---- secondary workloads (reported, not the headline).  The TRAINING steps run at every N: they are the workloads with a real
