@@ -220,8 +220,10 @@ def train_workloads(E, parallel, dev, rank, world, gen, timed, args):
             warnings.simplefilter("ignore")                     # VGG19 weights: none on the box (random features; timing only)
             gm = E.Pix2PixModel(gopt)
         gm.train()
-        og = parallel.FlatAdam(gm.netG.named_parameters(), lr=gopt.lr / 2, betas=(gopt.beta1, gopt.beta2))     # TTUR, pix2pix_model.py:62-66
-        od = parallel.FlatAdam(gm.netD.named_parameters(), lr=gopt.lr * 2, betas=(gopt.beta1, gopt.beta2))
+        # the tape hands over its gradients when backward() returns, so there is nothing to overlap with: few large buckets (the
+        # 8 MB default is sized for buckets that are reduced WHILE the backward runs; 27 of them are launch-latency-bound at 8 GPUs)
+        og = parallel.FlatAdam(gm.netG.named_parameters(), lr=gopt.lr / 2, betas=(gopt.beta1, gopt.beta2), bucket_bytes=256 << 20)     # TTUR, pix2pix_model.py:62-66
+        od = parallel.FlatAdam(gm.netD.named_parameters(), lr=gopt.lr * 2, betas=(gopt.beta1, gopt.beta2), bucket_bytes=256 << 20)
         Bg = 4
         gd = gan_batch(Bg, gen, dev)
 
