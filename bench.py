@@ -139,10 +139,11 @@ def train_workloads(E, parallel, dev, rank, world, gen, timed, args):
     from train_regression_synthetic import synthetic_batch
     out = {}
 
-    def med(fn, n=5):
-        """Median (and min, max) of n single-step timings: a secondary workload's step time should not hinge on one slow step (the
-        boxes' power-capped clocks and the host's enqueue jitter gave 125-150 ms for the same 3-step mean on different runs)."""
-        ts = sorted(timed(fn, 1) for _ in range(n))
+    def med(fn, n=3, k=3):
+        """Median (and min, max) over n samples of the mean of k BACK-TO-BACK steps (the host runs ahead of the device inside a sample, as
+        in a training loop; single-step samples start from an idle GPU and expose the host's enqueue time).  A secondary workload's step
+        time should not hinge on one slow sample: the same 3-step mean gave 125-150 ms on different runs (power-capped clocks, host jitter)."""
+        ts = sorted(timed(fn, k) / k for _ in range(n))
         return ts[n // 2], ts[0], ts[-1]
 
     def comm_alone(opts, reps=5):
@@ -183,7 +184,7 @@ def train_workloads(E, parallel, dev, rank, world, gen, timed, args):
     wait_ms = opt.exposed_ms()                                   # compute stream waiting for the NCCL stream inside step()
     opt.measure = False
     ar = comm_alone([opt])
-    entry = {"ms_per_step": round(ms_tr, 3), "ms_per_step_min_max_of_5": [round(ms_tr_min, 3), round(ms_tr_max, 3)],
+    entry = {"ms_per_step": round(ms_tr, 3), "ms_per_step_min_max_of_3x3": [round(ms_tr_min, 3), round(ms_tr_max, 3)],
              "maps_per_s": round(Bt * world / ms_tr * 1e3, 1), "batch_per_gpu": Bt,
              "allreduce_bytes": opt.comm_bytes, "allreduce_buckets": len(opt.buckets),
              "buckets_launched_inside_backward": opt.early_buckets, "allreduce_alone_ms": round(ar, 3)}
@@ -245,7 +246,7 @@ def train_workloads(E, parallel, dev, rank, world, gen, timed, args):
         og.measure = od.measure = False
         ar = comm_alone([og, od], reps=3)
         out["config3_genprojector_G_step_plus_D_step_b4_per_gpu"] = {
-            "ms_per_iteration": round(ms_g, 3), "ms_per_iteration_min_max_of_5": [round(ms_g_min, 3), round(ms_g_max, 3)],
+            "ms_per_iteration": round(ms_g, 3), "ms_per_iteration_min_max_of_3x3": [round(ms_g_min, 3), round(ms_g_max, 3)],
             "maps_per_s": round(Bg * world / ms_g * 1e3, 2), "batch_per_gpu": Bg, "ngf": 64,
             "allreduce_bytes": og.comm_bytes + od.comm_bytes, "allreduce_buckets": len(og.buckets) + len(od.buckets),
             "allreduce_alone_ms": round(ar, 3), "allreduce_algbw_GBps": round((og.comm_bytes + od.comm_bytes) / ar / 1e6, 1) if ar > 0 else None,
@@ -259,7 +260,7 @@ def train_workloads(E, parallel, dev, rank, world, gen, timed, args):
                 gm.criterionVGG.vgg.precision = "bf16"
             for _ in range(2):
                 gan_iter()
-            ms_b = med(gan_iter, 3)[0]
+            ms_b = med(gan_iter, 3, 2)[0]
             out["config3_genprojector_G_step_plus_D_step_b4_per_gpu"]["bf16_single_pass_ms_per_iteration"] = round(ms_b, 3)
             out["config3_genprojector_G_step_plus_D_step_b4_per_gpu"]["bf16_single_pass_maps_per_s"] = round(Bg * world / ms_b * 1e3, 2)
         except Exception as e:                          # noqa: BLE001
