@@ -119,3 +119,22 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith(".py"):
                 assert "oracle" not in open(os.path.join(d, f)).read(), f
+
+
+def test_support_queries_answer_without_a_gpu():
+    """The host-side shape rules that decide the execution plan (no device work): every block-1 / block-2 layer of the 192x256 network
+    takes the one-kernel path, C_in = 330 (block 3, layer 16) does not; transition 1 reads channel planes, transitions 2 / 3 (C_out =
+    160 / 171: not on the TMA pipeline) do not; fp32 never does."""
+    from emlight_b200 import _lib
+    lib = _lib.load()
+    P = _lib.PRECISIONS
+    assert all(lib.eml_dense_layer_supported(192, 256, 24 + 12 * l, 12, P["bf16x3"]) == 1 for l in range(16))
+    assert all(lib.eml_dense_layer_supported(96, 128, 108 + 12 * l, 12, P["bf16"]) == 1 for l in range(16))
+    assert lib.eml_dense_layer_supported(48, 64, 330, 12, P["bf16x3"]) == 0
+    assert lib.eml_dense_layer_supported(192, 256, 24, 12, P["fp32"]) == 0
+    assert lib.eml_dense_layer_supported(192, 200, 24, 12, P["bf16x3"]) == 0           # W must be 64, 128 or 256
+    assert lib.eml_transition_planes_supported(192, 256, 216, 108, P["bf16x3"]) == 1
+    assert lib.eml_transition_planes_supported(96, 128, 320, 160, P["bf16x3"]) == 0
+    assert lib.eml_transition_planes_supported(48, 64, 342, 171, P["bf16x3"]) == 0
+    assert lib.eml_transition_planes_supported(192, 256, 216, 108, P["fp32"]) == 0
+    assert lib.eml_dense_layer_wpack_bytes(24) > 0 and lib.eml_conv_wpack_bytes(256, 1152, 1) == 18 * 2 * 256 * 128
