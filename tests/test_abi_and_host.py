@@ -72,6 +72,13 @@ def test_new_entry_points_validate_arguments_without_a_gpu(lib):
     assert lib.eml_needlet_sparsify(None, 1, 1, 1, None, 1, 0.1, None) == -1
     assert lib.eml_gemm_bf16_splitk(None, None, 1, 64, None, 1, None, None, 4, 0, 1, 1, None) == -1
     assert lib.eml_channel_stats(None, 4, 1, 4, None, None) == -1
+    # round-2 entry points: NULL pointers are refused before anything is launched
+    assert lib.eml_gemm_bf16_slices(None, None, 1, 64, None, 0, 2, 16, None, None, 36, 0, 1, 1, None) == -1
+    assert lib.eml_gemm_pack_slices(None, None, 2, 16, 64, 4096, None) == -1
+    assert lib.eml_spectral_norm(None, 4, 4, None, None, 1, 1e-12, None, None, None) == -1
+    assert lib.eml_bias_act(None, 4, None, 1, None, 4, 1, 4, None) == -1
+    assert lib.eml_wgrad_3x3(None, 16, 12, None, 48, 48, None, None, None, 1, 4, 64, 1, None) == -1
+    assert lib.eml_dense_layer_compose(None, None, None, None, 48, 24, 12, None, None, None) == -1
     assert lib.eml_extract_params(None, None, None, 1, 128, 256, 64, None, None, None, None, None, None) == -1
     assert lib.eml_tonemap_hdr(None, None, None, 1, 1, 2.4, 50.0, 0.5, 1, 1, 0, None) == -1
 
