@@ -478,10 +478,14 @@ class DenseNet(nn.Module):
         # ---- block 1 as channel planes (eval): (G, B*H*W, 32) instead of (B, H, W, pitch) -- §4.0 of DESIGN.md
         planes0 = 0
         if not train and self._planes_ok(c, ws, B):
-            planes0 = B * H * W
             if "slab_planes0" not in ws:
                 groups = (self._plan[0][2] + 31) // 32
-                ws["slab_planes0"] = torch.zeros(groups, planes0, 32, dtype=torch.float32, device=dev)   # zeroed: unwritten channels stay finite
+                free, _total = torch.cuda.mem_get_info(dev)
+                # a second copy of block 1's buffer (the NHWC one stays for training): only when memory is plentiful
+                ws["slab_planes0"] = (torch.zeros(groups, B * H * W, 32, dtype=torch.float32, device=dev)     # zeroed: unwritten channels stay finite
+                                      if groups * B * H * W * 128 < 0.5 * free else None)
+            if ws["slab_planes0"] is not None:
+                planes0 = B * H * W
         # ---- stem (DenseNet.py:89-92)
         slab = ws["slab_planes0"] if planes0 else ws["slab"][0]
         pitch = 32 if planes0 else slab.shape[3]
