@@ -64,8 +64,14 @@ def sphere_grid(h, w, stride=1):
     return torch.from_numpy(g.astype(np.float32))
 
 
+_GRIDS = {}
+
+
 def sphere_conv(x, weight, bias, stride=1):
-    grid = sphere_grid(x.shape[2], x.shape[3], stride).repeat(x.shape[0], 1, 1, 1).to(x.dtype)   # fp32 coordinates (as the reference); cast only for the fp64 debug runs
+    key = (x.shape[2], x.shape[3], stride, str(x.device), x.dtype)          # the reference module keeps its grid too (sphere_cnn.py:111-118)
+    if key not in _GRIDS:
+        _GRIDS[key] = sphere_grid(x.shape[2], x.shape[3], stride).to(device=x.device, dtype=x.dtype)   # fp32 coordinates (as the reference); cast only for the fp64 debug runs
+    grid = _GRIDS[key].expand(x.shape[0], -1, -1, -1)
     s = F.grid_sample(x, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
     return F.conv2d(s, weight, bias, stride=3)
 

@@ -13,6 +13,7 @@ ap.add_argument("--precision", default="bf16x3")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--profile", action="store_true")
 ap.add_argument("--graph", action="store_true")
+ap.add_argument("--eager", action="store_true", help="also time the reference ops (CPU restatement run on cuda: grid_sample + conv2d, fp32, TF32 off)")
 args = ap.parse_args()
 opt = argparse.Namespace(ngf=args.ngf, norm_G="spectralspadesyncbatch3x3", norm_E="spectralinstance", semantic_nc=3,
                          num_upsampling_layers="normal", crop_size=256, aspect_ratio=2.0)
@@ -68,3 +69,21 @@ flops = 154.1e9 * args.batch * (args.ngf / 64) ** 2
 print(json.dumps({"workload": "SPADEGenerator forward (eval)", "ngf": args.ngf, "batch": args.batch, "precision": args.precision,
                   "ms_per_step": ms, "maps_per_s": args.batch / ms * 1e3, "useful_TFLOPs": flops / ms / 1e9,
                   "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30}))
+if args.eager:
+    # PyTorch eager on the same GPU: the reference's formulation (9x grid_sample blow-up + stride-3 conv2d, cuDNN / cuBLAS fp32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = {k: v.to(dev) for k, v in GO.init_generator_state_dict(0, args.ngf).items()}
+    with torch.no_grad():
+        for _ in range(2):
+            ref = GO.generator_forward(sd, guide, crop, args.ngf)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            ref = GO.generator_forward(sd, guide, crop, args.ngf)
+        e1.record(); torch.cuda.synchronize()
+    ems = e0.elapsed_time(e1) / args.steps
+    err = float((out - ref).abs().max() / ref.abs().max())
+    print(json.dumps({"workload": "the same forward, PyTorch eager (reference ops) on cuda:0", "ms_per_step": ems, "maps_per_s": args.batch / ems * 1e3,
+                      "ours_over_eager": ems / ms, "max_rel_diff_ours_vs_eager": err, "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30}))
+
